@@ -1,0 +1,147 @@
+"""ctypes binding of include/zfista_b200.h (the C-ABI drop-in boundary).
+
+The library is the product: if ``libzfista_b200.so`` is missing, or no CUDA device is
+visible when a compute entry point is called, the call fails loudly.  There is no
+CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+ZF_MAX_OBJECTIVES = 4
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzfista_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int64_p = C.POINTER(C.c_int64)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class ZfProblem(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("n_features", C.c_int32), ("n_objectives", C.c_int32),
+        ("has_l1", C.c_int32),
+        ("l1_ratios", C.c_double * ZF_MAX_OBJECTIVES),
+        ("l1_shifts", C.c_double * ZF_MAX_OBJECTIVES),
+        ("has_bounds", C.c_int32), ("bounds_are_arrays", C.c_int32),
+        ("lower", C.c_double), ("upper", C.c_double),
+        ("lower_v", C.c_void_p), ("upper_v", C.c_void_p),
+        ("A", C.c_void_p), ("b", C.c_void_p),
+        ("n_rows", C.c_int32), ("reserved", C.c_int32),
+        ("scale", C.c_double), ("l1", C.c_double),
+    ]
+
+
+class ZfOptions(C.Structure):
+    _fields_ = [
+        ("lr", C.c_double), ("tol", C.c_double), ("tol_internal", C.c_double),
+        ("max_iter", C.c_int64),
+        ("max_iter_internal", C.c_int32), ("max_backtrack_iter", C.c_int32),
+        ("warm_start", C.c_int32), ("nesterov", C.c_int32),
+        ("decay_rate", C.c_double), ("nesterov_a", C.c_double), ("nesterov_b", C.c_double),
+        ("deprecated", C.c_int32), ("dual_solver", C.c_int32),
+        ("trace_capacity", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class ZfResult(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("fun", C.c_void_p), ("nit", C.c_void_p), ("status", C.c_void_p),
+        ("lr", C.c_void_p), ("nfev", C.c_void_p), ("n_dual", C.c_void_p), ("err", C.c_void_p),
+        ("allerrs", C.c_void_p), ("allfuns", C.c_void_p), ("allvecs", C.c_void_p),
+    ]
+
+
+# every symbol include/zfista_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    "zf_abi_version", "zf_last_error", "zf_device_count", "zf_default_options",
+    "zf_solve_batched_device", "zf_solve_batched_host", "zf_solve_subproblem_host",
+    "zf_problem_eval_host",
+    "zf_lasso_create", "zf_lasso_destroy", "zf_lasso_solve", "zf_lasso_begin",
+    "zf_lasso_grad", "zf_lasso_partial", "zf_lasso_step", "zf_lasso_finish",
+    "zf_lasso_gradient_device",
+]
+
+
+class ZfError(RuntimeError):
+    """A zfista_b200 C-ABI call failed (code, message from zf_last_error())."""
+
+    def __init__(self, code, message):
+        super().__init__(f"zfista_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} not found: build the CUDA library first "
+            "(python -m zfista_b200.build, or __graft_entry__.build()). "
+            "zfista_b200 has no CPU fallback.")
+    L = C.CDLL(_LIB_PATH)
+    L.zf_abi_version.restype = C.c_int
+    L.zf_last_error.restype = C.c_char_p
+    L.zf_device_count.restype = C.c_int
+    L.zf_launch_count.restype = C.c_int64
+    L.zf_default_options.argtypes = [C.POINTER(ZfOptions)]
+    L.zf_default_options.restype = None
+    L.zf_solve_batched_device.argtypes = [
+        C.POINTER(ZfProblem), C.POINTER(ZfOptions), C.c_int64, C.c_void_p, C.c_void_p,
+        C.POINTER(ZfResult), C.c_void_p]
+    L.zf_solve_batched_host.argtypes = [
+        C.POINTER(ZfProblem), C.POINTER(ZfOptions), C.c_int64, C.c_void_p, C.c_void_p,
+        C.POINTER(ZfResult)]
+    L.zf_solve_subproblem_host.argtypes = [
+        C.POINTER(ZfProblem), C.POINTER(ZfOptions), C.c_int64, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.zf_problem_eval_host.argtypes = [
+        C.POINTER(ZfProblem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p]
+    for name in ("zf_solve_batched_device", "zf_solve_batched_host",
+                 "zf_solve_subproblem_host", "zf_problem_eval_host"):
+        getattr(L, name).restype = C.c_int
+    # large-n LASSO handle API
+    L.zf_lasso_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_int64, C.c_double, C.c_double, C.c_void_p]
+    L.zf_lasso_create.restype = C.c_int
+    L.zf_lasso_destroy.argtypes = [C.c_void_p]
+    L.zf_lasso_destroy.restype = None
+    L.zf_lasso_solve.argtypes = [C.c_void_p, C.POINTER(ZfOptions), C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.zf_lasso_solve.restype = C.c_int
+    L.zf_lasso_begin.argtypes = [C.c_void_p, C.POINTER(ZfOptions), C.c_void_p]
+    L.zf_lasso_begin.restype = C.c_int
+    L.zf_lasso_grad.argtypes = [C.c_void_p, C.c_int]
+    L.zf_lasso_grad.restype = C.c_int
+    L.zf_lasso_partial.argtypes = [C.c_void_p, c_int64_p]
+    L.zf_lasso_partial.restype = C.c_void_p
+    L.zf_lasso_step.argtypes = [C.c_void_p, c_int32_p]
+    L.zf_lasso_step.restype = C.c_int
+    L.zf_lasso_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.zf_lasso_finish.restype = C.c_int
+    L.zf_lasso_gradient_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.zf_lasso_gradient_device.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise ZfError(code, lib().zf_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    """Kernels launched by the library in this process (bench.py's gpu_launches)."""
+    return int(lib().zf_launch_count())
+
+
+def default_options() -> ZfOptions:
+    o = ZfOptions()
+    lib().zf_default_options(C.byref(o))
+    return o

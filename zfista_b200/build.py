@@ -1,0 +1,97 @@
+"""In-tree build of libzfista_b200.so with nvcc for sm_100a.
+
+    python -m zfista_b200.build [--force] [--verbose]
+
+Every .cu under zfista_b200/csrc is compiled (in parallel) with
+``-gencode arch=compute_100a,code=sm_100a -lineinfo`` and linked into
+``zfista_b200/libzfista_b200.so``.  The .so is git-ignored but travels to the GPU
+box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+BUILD_DIR = os.path.join(PKG_DIR, "build")
+LIB_PATH = os.path.join(PKG_DIR, "libzfista_b200.so")
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC",
+    "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for d in (CSRC, os.path.join(ROOT, "include")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(d, f), "rb") as fh:
+                    h.update(f.encode())
+                    h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    stamp = os.path.join(BUILD_DIR, "fingerprint.txt")
+    fp = _fingerprint()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            if fh.read().strip() == fp:
+                return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+
+    def compile_one(src):
+        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr, flush=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as fh:
+        fh.write(fp)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose))
+    sys.exit(0)

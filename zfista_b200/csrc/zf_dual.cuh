@@ -1,0 +1,457 @@
+// Device solvers for the dual of the multi-objective proximal subproblem
+// (proximal_gradient.py:61-76, 161-209).  One warp solves one subproblem; the
+// n-dimensional work is strided over the lanes and every scalar decision is taken
+// redundantly (and identically) by all 32 lanes.
+//
+//   max_{w in simplex}  D(w) = sum_i w_i g_i(p) + ||p - v||^2 / (2 lr)
+//                              - lr/2 ||J^T w||^2 + w . c
+//   v = y - lr J^T w,   p = prox_{lr sum_i w_i g_i}(v),   c_i = f_i(y) - F_i(x^{k-1})
+//
+// The reference minimises -D:
+//   m = 2 : scipy minimize_scalar(bounds=(0,1))      -> DualBrent   (same sequence)
+//   m >= 3: scipy trust-constr on the simplex        -> DualNewton  (exact optimum)
+#pragma once
+#include "zf_problems.cuh"
+
+namespace zf {
+
+template <int M>
+struct DualData {
+  double lr;
+  double c[M];        // F_prev - f_y added to -D  (0 when deprecated): c[i] = f_y - F_prev
+  bool use_c;         // !deprecated
+};
+
+// ------------------------------------------------------------------------------------
+// -D(w) exactly as _dual_minimized_fun_jac (proximal_gradient.py:161-177) forms it.
+// ------------------------------------------------------------------------------------
+template <int M>
+__device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
+                                 const double (&w)[M]) {
+  double wt[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) wt[i] = d.lr * w[i];
+  constexpr int NS = M + 2;
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  const bool lsq = (P.kind == ZF_LSQ_L1);
+  for (int j = c.lane; j < c.n; j += 32) {
+    double wj = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + j];
+    const double v = c.y[j] - d.lr * wj;
+    double alpha, eps[M];
+    const double p = prox_elem<M, false>(P, j, v, wt, alpha, eps);
+    if (lsq) {
+      s[0] += fabs(p);
+    } else if (P.has_l1) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) s[i] += fabs(p - P.l1_shifts[i]);
+    }
+    s[M] += (p - v) * (p - v);
+    s[M + 1] += wj * wj;
+  }
+  warp_sum_k<NS>(s);
+  double wg = 0.0;
+  if (lsq) {
+    const double gl = P.l1 * s[0];
+#pragma unroll
+    for (int i = 0; i < M; ++i) wg += w[i] * gl;
+  } else if (P.has_l1) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) wg += w[i] * (P.l1_ratios[i] * s[i]);
+  }
+  double fun = -wg - norm_sq_like_numpy(s[M]) / 2.0 / d.lr +
+               d.lr / 2.0 * norm_sq_like_numpy(s[M + 1]);
+  if (d.use_c) {
+    double wc = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) wc += w[i] * (-d.c[i]);   // inner(w, F_prev - f_y)
+    fun += wc;
+  }
+  return fun;
+}
+
+// x = prox_wsum_g(lr * w, y - lr * w @ J)   (proximal_gradient.py:206)
+template <int M>
+__device__ void primal_from_weights(const zf_problem& P, const WarpCtx& c, double lr,
+                                    const double (&w)[M], double* out) {
+  double wt[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) wt[i] = lr * w[i];
+  for (int j = c.lane; j < c.n; j += 32) {
+    double wj = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + j];
+    const double v = c.y[j] - lr * wj;
+    double alpha, eps[M];
+    out[j] = prox_elem<M, false>(P, j, v, wt, alpha, eps);
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------
+// Bounded Brent on [0, 1] ("fmin", Forsythe-Malcolm-Moler / Brent 1973) with the
+// tolerances and update order of scipy's _minimize_scalar_bounded, which is what
+// minimize_scalar(bounds=(0, 1), options={"maxiter", "xatol"}) runs
+// (proximal_gradient.py:184-188).  Returns xf; *fmin = -D(xf); *nfev evaluations.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double sgn_plus(double v) {
+  // np.sign(v) + (v == 0)
+  return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : (v == 0.0 ? 1.0 : v));
+}
+
+__device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualData<2>& d,
+                             double xatol, int maxfun, double* fmin, int* nfev) {
+  const double sqrt_eps = sqrt(2.2e-16);
+  const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
+  double a = 0.0, b = 1.0;
+  double fulc = a + golden_mean * (b - a);
+  double nfc = fulc, xf = fulc;
+  double rat = 0.0, e = 0.0;
+  double x = xf;
+  double w2[2] = {x, 1.0 - x};
+  double fx = neg_dual_value<2>(P, c, d, w2);
+  int num = 1;
+  double fu = CUDART_INF;
+  double ffulc = fx, fnfc = fx;
+  double xm = 0.5 * (a + b);
+  double tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+  double tol2 = 2.0 * tol1;
+  while (fabs(xf - xm) > (tol2 - 0.5 * (b - a))) {
+    bool golden = true;
+    if (fabs(e) > tol1) {
+      golden = false;
+      double r = (xf - nfc) * (fx - ffulc);
+      double q = (xf - fulc) * (fx - fnfc);
+      double p = (xf - fulc) * q - (xf - nfc) * r;
+      q = 2.0 * (q - r);
+      if (q > 0.0) p = -p;
+      q = fabs(q);
+      r = e;
+      e = rat;
+      if ((fabs(p) < fabs(0.5 * q * r)) && (p > q * (a - xf)) && (p < q * (b - xf))) {
+        rat = (p + 0.0) / q;
+        x = xf + rat;
+        if (((x - a) < tol2) || ((b - x) < tol2)) {
+          rat = tol1 * sgn_plus(xm - xf);
+        }
+      } else {
+        golden = true;
+      }
+    }
+    if (golden) {
+      e = (xf >= xm) ? (a - xf) : (b - xf);
+      rat = golden_mean * e;
+    }
+    x = xf + sgn_plus(rat) * fmax(fabs(rat), tol1);
+    w2[0] = x;
+    w2[1] = 1.0 - x;
+    fu = neg_dual_value<2>(P, c, d, w2);
+    num += 1;
+    if (fu <= fx) {
+      if (x >= xf) a = xf; else b = xf;
+      fulc = nfc; ffulc = fnfc;
+      nfc = xf; fnfc = fx;
+      xf = x; fx = fu;
+    } else {
+      if (x < xf) a = x; else b = x;
+      if ((fu <= fnfc) || (nfc == xf)) {
+        fulc = nfc; ffulc = fnfc;
+        nfc = x; fnfc = fu;
+      } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
+        fulc = x; ffulc = fu;
+      }
+    }
+    xm = 0.5 * (a + b);
+    tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+    tol2 = 2.0 * tol1;
+    if (num >= maxfun) break;
+  }
+  *fmin = fx;
+  *nfev = num;
+  return xf;
+}
+
+// ------------------------------------------------------------------------------------
+// Simplex semi-smooth Newton.  D is concave and piecewise quadratic; on the current
+// piece  grad D = G,  hess D = -Qm  with  Qm = lr * Mm Mm^T,
+//   Mm[i][j] = alpha_j (J[i][j] + l1_ratios_i eps_ij).
+// One pass over the coordinates gives D, G (M sums) and Qm (M(M+1)/2 sums); the QP
+//   max_{w' in simplex}  (G + Qm w) . w' - 1/2 w'^T Qm w'
+// is then solved exactly in registers by enumerating the 2^M - 1 faces.
+// ------------------------------------------------------------------------------------
+template <int M>
+struct DualPoint {
+  double D;
+  double G[M];
+  double Q[M][M];
+};
+
+template <int M>
+__device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
+                          const double (&w)[M], DualPoint<M>& out) {
+  double wt[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) wt[i] = d.lr * w[i];
+  constexpr int NQ = M * (M + 1) / 2;
+  constexpr int NS = 2 * M + 2 + NQ;   // |p - s_i| sums, J_i.(p-y), ||p-v||^2, ||wj||^2, Q
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  const bool lsq = (P.kind == ZF_LSQ_L1);
+  for (int j = c.lane; j < c.n; j += 32) {
+    double Jc[M];
+    double wj = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      Jc[i] = c.J[i * c.n + j];
+      wj += w[i] * Jc[i];
+    }
+    const double yj = c.y[j];
+    const double v = yj - d.lr * wj;
+    double alpha, eps[M];
+    const double p = prox_elem<M, true>(P, j, v, wt, alpha, eps);
+    double mcol[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      double lam = 0.0, shift = 0.0;
+      if (lsq) lam = P.l1;
+      else if (P.has_l1) { lam = P.l1_ratios[i]; shift = P.l1_shifts[i]; }
+      s[i] += fabs(p - shift);
+      s[M + i] += Jc[i] * (p - yj);
+      mcol[i] = alpha * (Jc[i] + lam * eps[i]);
+    }
+    s[2 * M] += (p - v) * (p - v);
+    s[2 * M + 1] += wj * wj;
+    int k = 2 * M + 2;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+      for (int l = i; l < M; ++l) s[k++] += mcol[i] * mcol[l];
+    }
+  }
+  warp_sum_k<NS>(s);
+  double Dv = s[2 * M] / 2.0 / d.lr - d.lr / 2.0 * s[2 * M + 1];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    double gi = 0.0;
+    if (lsq) gi = P.l1 * s[i];
+    else if (P.has_l1) gi = P.l1_ratios[i] * s[i];
+    const double ci = d.use_c ? d.c[i] : 0.0;
+    out.G[i] = gi + s[M + i] + ci;
+    Dv += w[i] * (gi + ci);
+  }
+  out.D = Dv;
+  int k = 2 * M + 2;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+#pragma unroll
+    for (int l = i; l < M; ++l) {
+      const double q = d.lr * s[k++];
+      out.Q[i][l] = q;
+      out.Q[l][i] = q;
+    }
+  }
+}
+
+constexpr __host__ __device__ int zf_popcount(int v) {
+  int c = 0;
+  while (v) { c += v & 1; v >>= 1; }
+  return c;
+}
+constexpr __host__ __device__ int zf_nth_bit(int mask, int r) {
+  int seen = 0;
+  for (int b = 0; b < 8; ++b) {
+    if (mask & (1 << b)) {
+      if (seen == r) return b;
+      ++seen;
+    }
+  }
+  return -1;
+}
+
+// One face of the simplex (support = MASK): stationary point of the local model
+//   G.d - 1/2 d^T Q d,  d = w' - w,
+// restricted to the face's affine hull via w'_S = e_0 + Z z, LDL^T on the (K-1)x(K-1)
+// reduced PSD matrix.  Everything is expressed in the step d: G is O(1) while Q w can
+// reach 1e12 (FDS, n = 100), so G + Q w must never be formed.  A (near-)singular
+// reduced matrix means the restricted optimum is not unique or lies on the face's
+// boundary, i.e. on a smaller face that is enumerated anyway -- skip.
+template <int M, int MASK>
+__device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&G)[M],
+                                        const double (&wc)[M], double pivot_floor,
+                                        double (&best_w)[M], double& best_val) {
+  constexpr int K = zf_popcount(MASK);
+  constexpr int S0 = zf_nth_bit(MASK, 0);
+  double w[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) w[i] = 0.0;
+  if constexpr (K == 1) {
+    w[S0] = 1.0;
+  } else {
+    constexpr int R = K - 1;
+    // u = Q (e_S0 - w)
+    double u[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < M; ++l) acc += Q[i][l] * ((l == S0 ? 1.0 : 0.0) - wc[l]);
+      u[i] = acc;
+    }
+    double A[R][R];
+    double rhs[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      const int ia = zf_nth_bit(MASK, a + 1);
+      rhs[a] = (G[ia] - u[ia]) - (G[S0] - u[S0]);
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        const int ib = zf_nth_bit(MASK, b + 1);
+        A[a][b] = Q[ia][ib] - Q[ia][S0] - Q[S0][ib] + Q[S0][S0];
+      }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const double piv = A[k][k];
+      if (!(piv > pivot_floor)) ok = false;
+      const double inv = ok ? 1.0 / piv : 0.0;
+#pragma unroll
+      for (int r = k + 1; r < R; ++r) {
+        const double fct = A[r][k] * inv;
+#pragma unroll
+        for (int cc = k + 1; cc < R; ++cc) A[r][cc] -= fct * A[k][cc];
+        rhs[r] -= fct * rhs[k];
+      }
+    }
+    if (!ok) return;
+    double z[R];
+#pragma unroll
+    for (int k = R - 1; k >= 0; --k) {
+      double acc = rhs[k];
+#pragma unroll
+      for (int cc = k + 1; cc < R; ++cc) acc -= A[k][cc] * z[cc];
+      z[k] = acc / A[k][k];
+    }
+    double zs = 0.0;
+    bool feas = true;
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      zs += z[a];
+      feas = feas && (z[a] >= 0.0);
+      w[zf_nth_bit(MASK, a + 1)] = z[a];
+    }
+    const double w0 = 1.0 - zs;
+    feas = feas && (w0 >= 0.0);
+    if (!feas) return;
+    w[S0] = w0;
+  }
+  double dvec[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) dvec[i] = w[i] - wc[i];
+  double val = 0.0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    double qd = 0.0;
+#pragma unroll
+    for (int l = 0; l < M; ++l) qd += Q[i][l] * dvec[l];
+    val += dvec[i] * (G[i] - 0.5 * qd);
+  }
+  if (val > best_val) {
+    best_val = val;
+#pragma unroll
+    for (int i = 0; i < M; ++i) best_w[i] = w[i];
+  }
+}
+
+template <int M, int MASK>
+struct QpFaces {
+  __device__ __forceinline__ static void run(const double (&Q)[M][M], const double (&G)[M],
+                                             const double (&wc)[M], double pf, double (&bw)[M],
+                                             double& bv) {
+    qp_face<M, MASK>(Q, G, wc, pf, bw, bv);
+    QpFaces<M, MASK - 1>::run(Q, G, wc, pf, bw, bv);
+  }
+};
+template <int M>
+struct QpFaces<M, 0> {
+  __device__ __forceinline__ static void run(const double (&)[M][M], const double (&)[M],
+                                             const double (&)[M], double, double (&)[M],
+                                             double&) {}
+};
+
+// w_out = argmax over the simplex of the local model around wc
+template <int M>
+__device__ void simplex_qp(const double (&Q)[M][M], const double (&G)[M],
+                           const double (&wc)[M], double (&w_out)[M]) {
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) tr += Q[i][i];
+  const double pivot_floor = 1e-13 * tr;
+  double best_val = -CUDART_INF;
+#pragma unroll
+  for (int i = 0; i < M; ++i) w_out[i] = wc[i];
+  QpFaces<M, (1 << M) - 1>::run(Q, G, wc, pivot_floor, w_out, best_val);
+}
+
+// Returns D(w*); w is in/out (initial guess -> maximiser); *nfev dual evaluations.
+// Each step solves the QP of the current quadratic piece exactly.  When the model's
+// predicted gain drops below the rounding level of D the step is taken on trust and
+// the iteration stops (oracle/dual_model.py:simplex_newton is the CPU statement).
+template <int M>
+__device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
+                              double (&w)[M], int max_iter, int* nfev) {
+  DualPoint<M> cur, trial;
+  dual_full<M>(P, c, d, w, cur);
+  int evals = 1;
+  for (int it = 0; it < max_iter; ++it) {
+    double gabs = 0.0;
+    double wn[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) gabs = fmax(gabs, fabs(cur.G[i]));
+    simplex_qp<M>(cur.Q, cur.G, w, wn);
+    double dmax = 0.0, dir[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      dir[i] = wn[i] - w[i];
+      dmax = fmax(dmax, fabs(dir[i]));
+    }
+    if (dmax == 0.0) break;
+    double pred = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      double qd = 0.0;
+#pragma unroll
+      for (int l = 0; l < M; ++l) qd += cur.Q[i][l] * dir[l];
+      pred += dir[i] * (cur.G[i] - 0.5 * qd);
+    }
+    if (pred <= 1e-15 * (fabs(cur.D) + gabs)) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) w[i] = wn[i];
+      cur.D += pred;
+      break;
+    }
+    double step = 1.0;
+    bool accepted = false;
+    double wt[M];
+    for (int bt = 0; bt < 30; ++bt) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) wt[i] = (step == 1.0) ? wn[i] : w[i] + step * dir[i];
+      dual_full<M>(P, c, d, wt, trial);
+      ++evals;
+      if (trial.D >= cur.D) { accepted = true; break; }
+      step *= 0.5;
+    }
+    if (!accepted) break;
+#pragma unroll
+    for (int i = 0; i < M; ++i) w[i] = wt[i];
+    cur = trial;
+  }
+  *nfev = evals;
+  return cur.D;
+}
+
+}  // namespace zf
