@@ -92,3 +92,72 @@ def fixture_problems():
         "FDS_n10_box": ("FDS", dict(n_features=10, bounds=(0, np.inf))),
         "FDS_n100_l1": ("FDS", dict(n_features=100, **l1(100, 3))),
     }
+
+
+# ---------------------------------------------------------------------------------------
+# Rounding sensitivity of the REFERENCE itself.
+#
+# For two objectives the reference finds the dual weight with scipy's bounded Brent, whose
+# resolution is sqrt(eps)*|w| ~ 1.5e-8 and whose path depends on comparisons of function
+# values that differ in the last bit.  On problems with L1 terms (kinks) or flat directions
+# (TOI4) the outer FISTA loop amplifies that: perturbing the reference's own dual function
+# by ONE ulp changes its iteration count by +-10 % and its final x by up to ~1e-3 (see
+# tests/test_oracle_golden.py::test_reference_is_rounding_sensitive_on_l1_cases).  The
+# reference's numbers on such cases are therefore one draw from an envelope (they also
+# depend on the BLAS build numpy links to); a different summation order -- any GPU -- is
+# another draw.  `oracle_noise_envelope` measures that envelope with the oracle so that a
+# test can require "the device is as close to the reference as the reference is to itself".
+# ---------------------------------------------------------------------------------------
+def noisy_brent_subproblem(noise, seed):
+    """oracle subproblem (m = 2, restated Brent) whose dual value carries `noise` relative
+    rounding noise; noise = 0 reproduces the reference bit for bit."""
+    from oracle import dual_model as dm
+    from oracle import zfista_oracle as zo
+
+    rng = np.random.RandomState(seed)
+
+    def sub(spec, lr, x_prev, y, w_init, tol=1e-12, max_iter=1000, deprecated=False):
+        fy = zo.f(spec, y)
+        F_prev = zo.f(spec, x_prev) + zo.g(spec, x_prev)
+        Jy = zo.jac_f(spec, y)
+
+        def neg_dual(ws):
+            w = np.array([ws, 1 - ws])
+            wj = w @ Jy
+            v = y - lr * wj
+            p = zo.prox_wsum_g(spec, lr * w, v)
+            val = (-np.inner(w, zo.g(spec, p)) - np.linalg.norm(p - v) ** 2 / 2 / lr
+                   + lr / 2 * np.linalg.norm(wj) ** 2)
+            if not deprecated:
+                val += np.inner(w, F_prev - fy)
+            return val * (1 + noise * rng.uniform(-1, 1))
+
+        xf, fx, nfev = dm.fmin_bounded(neg_dual, 0.0, 1.0, xatol=tol, maxfun=max_iter)
+        weight = np.array([xf, 1 - xf])
+        x = zo.prox_wsum_g(spec, lr * weight, y - lr * weight @ Jy)
+        return x, -fx, weight, nfev
+
+    return sub
+
+
+def oracle_noise_envelope(spec, X0, x_ref, fun_ref, nit_ref, opts, n_starts=4, seeds=(0, 1, 2),
+                          noise=1.1e-16):
+    """max deviation of the (1-ulp perturbed) oracle from the reference's stored result over
+    the first `n_starts` starts: dict(dx, dF (relative), dnit)."""
+    import warnings
+
+    from oracle import zfista_oracle as zo
+
+    dx = dF = 0.0
+    dnit = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(min(n_starts, len(X0))):
+            for s in seeds:
+                r = zo.minimize_proximal_gradient(
+                    spec, X0[i], subproblem=noisy_brent_subproblem(noise, s), **opts)
+                dx = max(dx, float(np.max(np.abs(r["x"] - x_ref[i]))))
+                dF = max(dF, float(np.max(np.abs(r["fun"] - fun_ref[i])
+                                          / np.maximum(1.0, np.abs(fun_ref[i])))))
+                dnit = max(dnit, abs(int(r["nit"]) - int(nit_ref[i])))
+    return dict(dx=dx, dF=dF, dnit=dnit)

@@ -1,0 +1,146 @@
+"""GPU parity tests of the large-n LASSO path (DESIGN.md row c): csrc/zf_lasso.cu through
+zfista_b200.lasso.DenseLasso, against the reference's golden runs and the CPU oracle."""
+import warnings
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+REL = 1e-8
+
+
+def _close(a, b, rel=REL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    np.testing.assert_allclose(a, b, rtol=rel, atol=rel * max(1.0, float(np.max(np.abs(b)))))
+
+
+def test_gradient_matches_numpy(gpu):
+    """jac_f = A.T @ (A @ x - b) * (2*scale), f = ||A x - b||^2 * scale; vector (even n_cols)
+    and scalar (odd n_cols) kernels, ragged row / column counts."""
+    from zfista_b200.lasso import DenseLasso
+
+    rng = np.random.RandomState(0)
+    for n_rows, n_cols in [(1, 1), (3, 1), (7, 2), (50, 200), (257, 1023), (1000, 2050),
+                           (3001, 4098)]:
+        A = rng.standard_normal((n_rows, n_cols))
+        b = rng.standard_normal(n_rows)
+        x = rng.standard_normal(n_cols)
+        prob = DenseLasso(A, b, 0.1, scale=0.37)
+        grad, f = prob.gradient(x)
+        r = A @ x - b
+        _close(grad.cpu().numpy(), A.T @ r * (2 * 0.37), rel=1e-12)
+        _close(f.item(), np.linalg.norm(r) ** 2 * 0.37, rel=1e-13)
+        _close(prob.jac_f(x), A.T @ r * (2 * 0.37), rel=1e-12)
+
+
+def test_reference_toy_and_dataset_runs(gpu):
+    """The reference's own single-objective tests (tests/test_proximal_gradient.py:66-111 toy
+    problems, build_dataset() regression) and fixed-step FISTA in the cameraman notebook's
+    style (lr = 1/L, decay_rate = 1, custom (a, b)): same nit, x and F within 1e-8."""
+    from zfista_b200 import minimize_proximal_gradient
+    from zfista_b200.lasso import DenseLasso
+
+    d = helpers.load("lasso_single")
+    for l1, nest, x_ref, fun_ref, nit_ref in d["toy_rows"]:
+        prob = DenseLasso(d["toy_A"], d["toy_b"], l1, scale=1 / 6)
+        res = minimize_proximal_gradient(prob.f, prob.g, prob.jac_f, prob.prox_wsum_g,
+                                         d["toy_x0"], nesterov=bool(nest))
+        assert res.success and res.nit == int(nit_ref)
+        _close(res.x, [x_ref])
+        _close(res.fun, fun_ref)
+    prob = DenseLasso(d["ds_A"], d["ds_b"], float(d["ds_l1"]), scale=float(d["ds_scale"]))
+    L = float(d["ds_L"])
+    runs = {
+        "bt_ista": dict(nesterov=False),
+        "bt_fista": dict(nesterov=True),
+        "fixed_fista": dict(nesterov=True, lr=1 / L, decay_rate=1),
+        "fixed_fista_ab": dict(nesterov=True, lr=1 / L, decay_rate=1,
+                               nesterov_ratio=(0.5, 1 / 16)),
+    }
+    for tag, opts in runs.items():
+        res = prob.minimize_proximal_gradient(d["ds_x0"], max_iter=20000, return_all=True, **opts)
+        assert res.nit == int(d[f"ds_{tag}_nit"]), tag
+        _close(res.x, d[f"ds_{tag}_x"])
+        _close(res.fun, d[f"ds_{tag}_fun"])
+        _close(res.allerrs, d[f"ds_{tag}_allerrs"], rel=1e-6)
+        _close(np.ravel(res.allfuns), np.ravel(d[f"ds_{tag}_allfuns"]))
+        # without traces the fixed-step run skips the F evaluations but must land on the same x
+        res2 = prob.minimize_proximal_gradient(d["ds_x0"], max_iter=20000, **opts)
+        assert res2.nit == res.nit and res2.allerrs is None
+        np.testing.assert_array_equal(res2.x, res.x)
+        _close(res2.fun, res.fun, rel=1e-14)
+
+
+@pytest.mark.parametrize("n_rows,n_cols", [(300, 120), (200, 501)])
+def test_seeded_lasso_matches_oracle(gpu, n_rows, n_cols):
+    from oracle import zfista_oracle as zo
+    from zfista_b200.lasso import DenseLasso
+
+    rng = np.random.RandomState(n_rows + n_cols)
+    A = rng.standard_normal((n_rows, n_cols))
+    w = np.zeros(n_cols)
+    w[:10] = rng.standard_normal(10)
+    b = A @ w + 0.01 * rng.standard_normal(n_rows)
+    scale, l1 = 1 / (2 * n_rows), 0.05
+    spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
+    prob = DenseLasso(A, b, l1, scale=scale)
+    x0 = rng.standard_normal(n_cols) * 0.1
+    for opts in (dict(nesterov=True), dict(nesterov=False, max_iter=300),
+                 dict(nesterov=True, deprecated=True),
+                 dict(nesterov=True, nesterov_ratio=(0.25, 17 / 128), lr=4.0)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = zo.minimize_proximal_gradient(spec, x0, **opts)
+            res = prob.minimize_proximal_gradient(x0, **opts)
+        assert res.nit == ref["nit"] and res.success == ref["success"]
+        _close(res.x, ref["x"])
+        _close(res.fun, ref["fun"])
+
+
+def test_backtracking_failure_and_max_iter(gpu):
+    from zfista_b200.lasso import DenseLasso
+
+    rng = np.random.RandomState(1)
+    A = rng.standard_normal((40, 30)) * 100
+    b = rng.standard_normal(40)
+    prob = DenseLasso(A, b, 0.1)
+    x0 = np.ones(30)
+    res = prob.minimize_proximal_gradient(x0, lr=1e6, max_backtrack_iter=2)
+    assert res.status == -1 and not res.success and res.nit == 0
+    np.testing.assert_array_equal(res.x, x0)
+    with pytest.warns(UserWarning, match="Maximum number of iterations"):
+        res = prob.minimize_proximal_gradient(x0, max_iter=4)
+    assert res.status == 0 and res.nit == 4
+
+
+def test_large_a_properties(gpu):
+    """A >> L2 (1.3 GB): properties that do not need a CPU pass over A.
+    * the gradient is affine in x:  J(x1 + x2) + J(0) == J(x1) + J(x2);
+    * f(x) >= 0 and f at the planted solution is the noise level;
+    * fixed-step FISTA decreases F and recovers the planted support."""
+    import torch
+    from zfista_b200.lasso import DenseLasso
+
+    n_rows, n_cols = 20000, 8192
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(n_rows, n_cols, dtype=torch.float64, device="cuda", generator=g)
+    w = torch.zeros(n_cols, dtype=torch.float64, device="cuda")
+    w[:32] = torch.randn(32, dtype=torch.float64, device="cuda", generator=g) + 3.0
+    b = A @ w
+    prob = DenseLasso(A, b, l1_ratio=1e-3, scale=1 / (2 * n_rows))
+    x1 = torch.randn(n_cols, dtype=torch.float64, device="cuda", generator=g)
+    x2 = torch.randn(n_cols, dtype=torch.float64, device="cuda", generator=g)
+    zero = torch.zeros_like(x1)
+    j12, j0 = prob.gradient(x1 + x2)[0], prob.gradient(zero)[0]
+    j1, j2 = prob.gradient(x1)[0], prob.gradient(x2)[0]
+    torch.testing.assert_close(j12 + j0, j1 + j2, rtol=1e-11, atol=1e-11)
+    torch.testing.assert_close(j1, (A.T @ (A @ x1 - b)) / n_rows, rtol=1e-11, atol=1e-11)
+    assert prob.f(w) < 1e-20
+    res = prob.minimize_proximal_gradient(zero, lr=0.4, decay_rate=1, nesterov=True,
+                                          max_iter=60, return_all=True)
+    F = np.array(res.allfuns)
+    assert F[-1] < 1e-3 * F[0]
+    x = np.asarray(res.x)
+    assert np.all(np.abs(x[:32]) > 1.0) and np.max(np.abs(x[32:])) < 0.05

@@ -211,3 +211,27 @@ def test_lasso_single_objective_matches_reference():
         assert r["nit"] == int(d[f"ds_{tag}_nit"])
         np.testing.assert_array_equal(r["x"], d[f"ds_{tag}_x"])
         np.testing.assert_array_equal(np.array(r["allerrs"]), d[f"ds_{tag}_allerrs"])
+
+
+def test_reference_is_rounding_sensitive_on_l1_cases():
+    """Evidence for the parity tiers of DESIGN.md: with zero noise the restated Brent route
+    reproduces the reference bit for bit; with ONE ulp of relative noise on the dual value
+    the reference's own iteration counts and final points move by far more than 1e-8 on an
+    L1 case, and not at all on a smooth one."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d = helpers.load("JOS1_n50_l1__fista")
+        spec = helpers.oracle_spec("JOS1", helpers.case_kwargs(d))
+        opts = helpers.case_options(d)
+        r0 = zo.minimize_proximal_gradient(
+            spec, d["x0"][0], subproblem=helpers.noisy_brent_subproblem(0.0, 0), **opts)
+        assert r0["nit"] == d["nit"][0]
+        np.testing.assert_allclose(r0["x"], d["x"][0], rtol=0, atol=1e-12)
+        env = helpers.oracle_noise_envelope(spec, d["x0"], d["x"], d["fun"], d["nit"], opts,
+                                            n_starts=3, seeds=(0, 1))
+        assert env["dnit"] >= 5 and env["dx"] > 1e-5
+        d = helpers.load("JOS1_n50__fista")
+        spec = helpers.oracle_spec("JOS1", helpers.case_kwargs(d))
+        env = helpers.oracle_noise_envelope(spec, d["x0"], d["x"], d["fun"], d["nit"],
+                                            helpers.case_options(d), n_starts=2, seeds=(0,))
+        assert env["dnit"] == 0 and env["dx"] < 1e-8

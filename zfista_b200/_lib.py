@@ -107,6 +107,12 @@ def lib():
                  "zf_solve_subproblem_host", "zf_problem_eval_host"):
         getattr(L, name).restype = C.c_int
     # large-n LASSO handle API
+    _bind_lasso(L)
+    _lib = L
+    return L
+
+
+def _bind_lasso(L):
     L.zf_lasso_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_double, C.c_double, C.c_void_p]
     L.zf_lasso_create.restype = C.c_int
@@ -127,8 +133,6 @@ def lib():
     L.zf_lasso_finish.restype = C.c_int
     L.zf_lasso_gradient_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.zf_lasso_gradient_device.restype = C.c_int
-    _lib = L
-    return L
 
 
 def check(code: int) -> None:

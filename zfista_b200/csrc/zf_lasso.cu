@@ -1,0 +1,782 @@
+// Large-n single-objective LASSO path:  F(x) = scale*||A x - b||^2 + l1*||x||_1
+// with dense row-major fp64 A streamed from HBM (north_star (c); replaces
+// minimize_proximal_gradient(f, g, jac_f, prox_wsum_g, x0, ...) driven by the dense numpy
+// closures of tests/test_proximal_gradient.py:49-63 at sizes where A >> L2).
+//
+// Per FISTA iteration the device does
+//   r = A y - b                      lasso_residual_kernel   (one pass over A)
+//   q = A^T r                        lasso_atr_kernel        (one pass over A)
+//   x = soft(y - lr*2*scale*q, lr*l1) + the four sums the line search / stop test need
+//                                    lasso_prox_kernel       (n_cols work)
+//   [line search]  ||A x - b||^2     lasso_residual_kernel   (one pass per trial)
+//   y = x + mom*(x - x_prev)         lasso_momentum_kernel
+// Every reduction has a fixed order (no floating-point atomics), so a solve is bit
+// reproducible run to run.  Scalars (lr, t_k, F values, accept/stop decisions) live on the
+// host: one small D2H copy + stream sync per trial, negligible against a >= 1 ms pass.
+//
+// Row-sharded multi-GPU: each rank owns a block of rows and the same replicated vectors;
+// the only exchange is the all-reduce of `partial` = [A^T r (n_cols) | sum r^2] between
+// zf_lasso_grad() and zf_lasso_step() (done by the caller, NCCL over NVLink).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "zf_common.cuh"
+#include "zf_host.h"
+
+namespace zf {
+
+// streaming 16 B load that does not displace the (reused) vectors from L1
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream1(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+constexpr int RES_THREADS = 256;
+constexpr int RES_ROWS_PER_WARP = 4;
+
+// r = A v - b for a block of rows per warp; sq_part[block] = sum over the block's rows of r^2.
+// A warp owns RES_ROWS_PER_WARP consecutive rows at a time: each v element it loads is used
+// for all of them, and the independent row streams give 16 outstanding 16 B loads per lane.
+template <bool VEC>
+__global__ void __launch_bounds__(RES_THREADS, 3)
+lasso_residual_kernel(const double* __restrict__ A, const double* __restrict__ b,
+                      const double* __restrict__ v, long long n_rows, long long n_cols,
+                      double* __restrict__ r, double* __restrict__ sq_part) {
+  constexpr int R = RES_ROWS_PER_WARP;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int WARPS = RES_THREADS / 32;
+  const long long n_groups = (n_rows + R - 1) / R;
+  const long long total_warps = (long long)gridDim.x * WARPS;
+  double ss = 0.0;
+  for (long long g = (long long)blockIdx.x * WARPS + warp; g < n_groups; g += total_warps) {
+    const long long row0 = g * R;
+    const double* rowp[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const long long row = (row0 + k < n_rows) ? row0 + k : n_rows - 1;   // clamp, masked below
+      rowp[k] = A + row * n_cols;
+    }
+    double acc[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) acc[k] = 0.0;
+    if (VEC) {
+      const long long n2 = n_cols >> 1;
+      long long c = lane;
+      for (; c + 96 < n2; c += 128) {       // 4 column steps x R rows = 16 loads in flight
+        double2 a[4][R];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < R; ++k) a[u][k] = ld_stream2(rowp[k] + 2 * (c + 32 * u));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2 vv = __ldg(reinterpret_cast<const double2*>(v) + c + 32 * u);
+#pragma unroll
+          for (int k = 0; k < R; ++k) acc[k] += a[u][k].x * vv.x + a[u][k].y * vv.y;
+        }
+      }
+      for (; c < n2; c += 32) {
+        const double2 vv = __ldg(reinterpret_cast<const double2*>(v) + c);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const double2 a = ld_stream2(rowp[k] + 2 * c);
+          acc[k] += a.x * vv.x + a.y * vv.y;
+        }
+      }
+    } else {
+      for (long long c = lane; c < n_cols; c += 32) {
+        const double vv = __ldg(v + c);
+#pragma unroll
+        for (int k = 0; k < R; ++k) acc[k] += ld_stream1(rowp[k] + c) * vv;
+      }
+    }
+    warp_sum_k<R>(acc);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (row0 + k < n_rows) {
+        const double d = acc[k] - b[row0 + k];
+        if (lane == 0) r[row0 + k] = d;
+        ss += d * d;
+      }
+    }
+  }
+  __shared__ double wsum[WARPS];
+  if (lane == 0) wsum[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) t += wsum[w];
+    sq_part[blockIdx.x] = t;
+  }
+}
+
+constexpr int ATR_THREADS = 256;
+constexpr int ATR_COLS_PER_THREAD = 4;                       // two 16 B column pairs
+constexpr int ATR_SLAB = ATR_THREADS * ATR_COLS_PER_THREAD;  // 1024 columns per CTA
+constexpr int ATR_ROW_UNROLL = 8;
+
+// gpart[rb][j] = sum over the rows of row-block rb of r_i * A[i][j].  CTA (slab, rb): threads own
+// columns (accumulators in registers), rows stream through; 16 outstanding 16 B loads/thread.
+template <bool VEC>
+__global__ void __launch_bounds__(ATR_THREADS, 2)
+lasso_atr_kernel(const double* __restrict__ A, const double* __restrict__ r, long long n_rows,
+                 long long n_cols, long long rows_per_block, double* __restrict__ gpart) {
+  const long long col_base = (long long)blockIdx.x * ATR_SLAB;
+  const long long rb = blockIdx.y;
+  const long long i0 = rb * rows_per_block;
+  const long long i1 = (i0 + rows_per_block < n_rows) ? i0 + rows_per_block : n_rows;
+  double* out = gpart + rb * n_cols;
+  if (VEC) {
+    const long long c0 = col_base + 2 * threadIdx.x;             // first pair
+    const long long c1 = c0 + 2 * ATR_THREADS;                   // second pair
+    const bool ok0 = c0 < n_cols, ok1 = c1 < n_cols;
+    // clamp addresses of inactive pairs onto a valid one; their results are never stored
+    const long long a0 = ok0 ? c0 : 0, a1 = ok1 ? c1 : 0;
+    double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
+    long long i = i0;
+    for (; i + ATR_ROW_UNROLL <= i1; i += ATR_ROW_UNROLL) {
+      double2 p[ATR_ROW_UNROLL], q[ATR_ROW_UNROLL];
+#pragma unroll
+      for (int u = 0; u < ATR_ROW_UNROLL; ++u) {
+        const double* row = A + (i + u) * n_cols;
+        p[u] = ld_stream2(row + a0);
+        q[u] = ld_stream2(row + a1);
+      }
+#pragma unroll
+      for (int u = 0; u < ATR_ROW_UNROLL; ++u) {
+        const double ri = __ldg(r + i + u);
+        s0.x += ri * p[u].x; s0.y += ri * p[u].y;
+        s1.x += ri * q[u].x; s1.y += ri * q[u].y;
+      }
+    }
+    for (; i < i1; ++i) {
+      const double* row = A + i * n_cols;
+      const double2 p = ld_stream2(row + a0), q = ld_stream2(row + a1);
+      const double ri = __ldg(r + i);
+      s0.x += ri * p.x; s0.y += ri * p.y;
+      s1.x += ri * q.x; s1.y += ri * q.y;
+    }
+    if (ok0) *reinterpret_cast<double2*>(out + c0) = s0;
+    if (ok1) *reinterpret_cast<double2*>(out + c1) = s1;
+  } else {
+    // scalar fallback (odd n_cols or unaligned A): thread owns columns tid + k*256
+    double s[ATR_COLS_PER_THREAD];
+    long long cj[ATR_COLS_PER_THREAD];
+    bool ok[ATR_COLS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < ATR_COLS_PER_THREAD; ++k) {
+      cj[k] = col_base + threadIdx.x + (long long)k * ATR_THREADS;
+      ok[k] = cj[k] < n_cols;
+      if (!ok[k]) cj[k] = 0;
+      s[k] = 0.0;
+    }
+    for (long long i = i0; i < i1; ++i) {
+      const double* row = A + i * n_cols;
+      const double ri = __ldg(r + i);
+#pragma unroll
+      for (int k = 0; k < ATR_COLS_PER_THREAD; ++k) s[k] += ri * ld_stream1(row + cj[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < ATR_COLS_PER_THREAD; ++k)
+      if (ok[k]) out[cj[k]] = s[k];
+  }
+}
+
+// partial[j] = sum_rb gpart[rb][j] (fixed order);  partial[n_cols] = sum_blk sq_part[blk]
+__global__ void __launch_bounds__(256)
+lasso_collect_kernel(const double* __restrict__ gpart, int n_rowblocks,
+                     const double* __restrict__ sq_part, int n_sq, long long n_cols,
+                     double* __restrict__ partial) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gpart && j < n_cols) {
+    double s = 0.0;
+    for (int rb = 0; rb < n_rowblocks; ++rb) s += gpart[(long long)rb * n_cols + j];
+    partial[j] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < n_sq; ++k) s += sq_part[k];
+    partial[n_cols] = s;
+  }
+}
+
+constexpr int VEC_THREADS = 256;
+constexpr int VEC_MAX_BLOCKS = 1024;
+
+// block partials: sums[0..2] added, sums[3] max-ed; final combine over blocks in index order
+struct StepSums { double gd, dd, abs1, maxd; };
+
+__device__ __forceinline__ void block_reduce_step(StepSums& s, StepSums* sh) {
+  s.gd = warp_sum(s.gd);
+  s.dd = warp_sum(s.dd);
+  s.abs1 = warp_sum(s.abs1);
+  s.maxd = warp_max(s.maxd);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    StepSums t = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      t.gd += sh[w].gd; t.dd += sh[w].dd; t.abs1 += sh[w].abs1; t.maxd = fmax(t.maxd, sh[w].maxd);
+    }
+    s = t;
+  }
+}
+
+// x = soft(y - lr*g, lr*l1), g = partial*(2*scale)  (test_proximal_gradient.py:55-63), plus
+//   gd = g.(x-y), dd = ||x-y||^2 (sum), abs1 = ||x||_1, maxd = max|x-y|
+// If y == nullptr only abs1 of x_in is produced (g(x0) at start-up).
+__global__ void __launch_bounds__(VEC_THREADS)
+lasso_prox_kernel(const double* __restrict__ y, const double* __restrict__ partial,
+                  double two_scale, double lr, double thresh, long long n,
+                  double* __restrict__ x, double* __restrict__ g_out,
+                  StepSums* __restrict__ block_sums, unsigned int* __restrict__ counter,
+                  StepSums* __restrict__ out) {
+  __shared__ StepSums sh[VEC_THREADS / 32];
+  __shared__ bool is_last;
+  StepSums s{0.0, 0.0, 0.0, 0.0};
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    if (y) {
+      const double gj = partial[j] * two_scale;
+      const double yj = y[j];
+      const double xj = soft_threshold(yj - lr * gj, thresh);
+      const double d = xj - yj;
+      x[j] = xj;
+      if (g_out) g_out[j] = gj;
+      s.gd += gj * d;
+      s.dd += d * d;
+      s.abs1 += fabs(xj);
+      s.maxd = fmax(s.maxd, fabs(d));
+    } else {
+      s.abs1 += fabs(x[j]);
+    }
+  }
+  block_reduce_step(s, sh);
+  if (threadIdx.x == 0) {
+    block_sums[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    StepSums t = block_sums[0];
+    for (unsigned int k = 1; k < gridDim.x; ++k) {
+      const StepSums u = block_sums[k];
+      t.gd += u.gd; t.dd += u.dd; t.abs1 += u.abs1; t.maxd = fmax(t.maxd, u.maxd);
+    }
+    *out = t;
+    *counter = 0u;
+  }
+}
+
+// y = x + mom*(x - x_prev)   (proximal_gradient.py:534)
+__global__ void __launch_bounds__(VEC_THREADS)
+lasso_momentum_kernel(const double* __restrict__ x, const double* __restrict__ xp, double mom,
+                      long long n, double* __restrict__ y) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double xj = x[j];
+    y[j] = xj + mom * (xj - xp[j]);
+  }
+}
+
+// grad = partial * (2*scale) (bench / zf_lasso_gradient_device)
+__global__ void __launch_bounds__(VEC_THREADS)
+lasso_scale_kernel(const double* __restrict__ partial, double two_scale, double scale,
+                   long long n, double* __restrict__ grad, double* __restrict__ f_out) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x)
+    grad[j] = partial[j] * two_scale;
+  if (f_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double nrm = sqrt(partial[n]);
+    *f_out = nrm * nrm * scale;
+  }
+}
+
+}  // namespace zf
+
+// =======================================================================================
+// handle
+// =======================================================================================
+enum LassoPhase { LP_IDLE = 0, LP_INIT, LP_GRAD, LP_FNEW, LP_FINAL, LP_DONE };
+
+struct zf_lasso {
+  const double* A = nullptr;
+  const double* b = nullptr;
+  long long n_rows = 0, n_cols = 0;
+  double scale = 1.0, l1 = 0.0;
+  cudaStream_t st = 0;
+  bool vec = false;
+  int n_sm = 148;
+  // device workspace
+  double* vecs = nullptr;       // 4 * n_cols: x_prev, x_new, y, g
+  double *xp = nullptr, *xn = nullptr, *y = nullptr, *g = nullptr;
+  double* r = nullptr;          // n_rows
+  double* gpart = nullptr;      // n_rowblocks * n_cols
+  double* sq_part = nullptr;    // res_blocks
+  double* partial = nullptr;    // n_cols + 1
+  zf::StepSums* block_sums = nullptr;
+  zf::StepSums* d_sums = nullptr;
+  unsigned int* counter = nullptr;
+  double* h_pin = nullptr;      // pinned: [StepSums (4) | ss]
+  int res_blocks = 0, n_slabs = 0, n_rowblocks = 0, vec_blocks = 0;
+  long long rows_per_block = 0;
+  // solver state (host scalars)
+  zf_options opt{};
+  int phase = LP_IDLE;
+  double lr = 1.0, t_prev = 1.0, F_prev = 0.0, F_x = 0.0, f_y = 0.0, sub_fun = 0.0, err = 0.0;
+  bool F_known = false, need_F = false;
+  long long nit = 0;
+  int status = 0, bt = 0;
+  zf::StepSums sums{};
+  bool result_is_prev = false;
+  double* h_allerrs = nullptr;
+  double* h_allfuns = nullptr;
+};
+
+namespace {
+
+#define ZF_CUDA(call)                                          \
+  do {                                                         \
+    cudaError_t _e = (call);                                   \
+    if (_e != cudaSuccess) return zf::zf_fail_cuda(_e, #call); \
+  } while (0)
+
+int launch_residual(zf_lasso* h, const double* v) {
+  if (h->vec)
+    zf::lasso_residual_kernel<true><<<h->res_blocks, zf::RES_THREADS, 0, h->st>>>(
+        h->A, h->b, v, h->n_rows, h->n_cols, h->r, h->sq_part);
+  else
+    zf::lasso_residual_kernel<false><<<h->res_blocks, zf::RES_THREADS, 0, h->st>>>(
+        h->A, h->b, v, h->n_rows, h->n_cols, h->r, h->sq_part);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int launch_atr(zf_lasso* h) {
+  dim3 grid((unsigned)h->n_slabs, (unsigned)h->n_rowblocks);
+  if (h->vec)
+    zf::lasso_atr_kernel<true><<<grid, zf::ATR_THREADS, 0, h->st>>>(
+        h->A, h->r, h->n_rows, h->n_cols, h->rows_per_block, h->gpart);
+  else
+    zf::lasso_atr_kernel<false><<<grid, zf::ATR_THREADS, 0, h->st>>>(
+        h->A, h->r, h->n_rows, h->n_cols, h->rows_per_block, h->gpart);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int launch_collect(zf_lasso* h, bool with_gradient) {
+  const int blocks = with_gradient ? (int)((h->n_cols + 255) / 256) : 1;
+  zf::lasso_collect_kernel<<<blocks, 256, 0, h->st>>>(with_gradient ? h->gpart : nullptr,
+                                                     h->n_rowblocks, h->sq_part, h->res_blocks,
+                                                     h->n_cols, h->partial);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+// x_new = prox(...) and its sums -> h->sums ; also fetches partial[n_cols] -> *ss
+int run_trial(zf_lasso* h, bool abs_only, const double* vec_for_abs, double* ss) {
+  if (abs_only)
+    zf::lasso_prox_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
+        nullptr, nullptr, 0.0, 0.0, 0.0, h->n_cols, const_cast<double*>(vec_for_abs), nullptr,
+        h->block_sums, h->counter, h->d_sums);
+  else
+    zf::lasso_prox_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
+        h->y, h->partial, 2.0 * h->scale, h->lr, h->l1 * h->lr, h->n_cols, h->xn, h->g,
+        h->block_sums, h->counter, h->d_sums);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  ZF_CUDA(cudaMemcpyAsync(h->h_pin, h->d_sums, sizeof(zf::StepSums), cudaMemcpyDeviceToHost,
+                          h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->h_pin + 4, h->partial + h->n_cols, sizeof(double),
+                          cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  std::memcpy(&h->sums, h->h_pin, sizeof(zf::StepSums));
+  if (ss) *ss = h->h_pin[4];
+  return ZF_OK;
+}
+
+int fetch_ss(zf_lasso* h, double* ss) {
+  ZF_CUDA(cudaMemcpyAsync(h->h_pin + 4, h->partial + h->n_cols, sizeof(double),
+                          cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  *ss = h->h_pin[4];
+  return ZF_OK;
+}
+
+// f = np.linalg.norm(A @ x - b) ** 2 * scale   (test_proximal_gradient.py:50)
+inline double f_from_ss(const zf_lasso* h, double ss) {
+  const double nrm = std::sqrt(ss);
+  return nrm * nrm * h->scale;
+}
+
+// proximal_gradient.py:149-155 for one objective
+inline double subproblem_fun(const zf_lasso* h) {
+  const double nrm = std::sqrt(h->sums.dd);
+  double fun = h->sums.gd + h->l1 * h->sums.abs1 + nrm * nrm / 2.0 / h->lr;
+  if (!h->opt.deprecated) fun += h->f_y - h->F_prev;
+  return fun;
+}
+
+void finish_state(zf_lasso* h, int status) {
+  h->status = status;
+  h->phase = LP_DONE;
+}
+
+// The candidate x_new was accepted by the line search: stop test, momentum, next iterate
+// (proximal_gradient.py:510-538).  Returns the next `which` (0 grad, 1 f-eval, 2 done).
+int accept_candidate(zf_lasso* h, int* next) {
+  h->err = h->sums.maxd;
+  const int cap = h->opt.trace_capacity;
+  if (cap > 0 && h->nit <= cap) {
+    if (h->h_allerrs) h->h_allerrs[h->nit - 1] = h->err;
+    if (h->h_allfuns && h->F_known) h->h_allfuns[h->nit] = h->F_x;
+  }
+  const bool converged = h->err < h->opt.tol;
+  if (converged || h->nit >= h->opt.max_iter) {
+    h->status = converged ? 1 : 0;
+    h->result_is_prev = false;
+    if (h->F_known) {
+      h->phase = LP_DONE;
+      *next = 2;
+    } else {
+      h->phase = LP_FINAL;   // one more pass for res.fun = F(x)
+      *next = 1;
+    }
+    return ZF_OK;
+  }
+  double mom = 0.0;
+  if (h->opt.nesterov) {
+    const double t = h->t_prev;
+    const double t_new = std::sqrt(t * t - h->opt.nesterov_a * t + h->opt.nesterov_b) + 0.5;
+    mom = (t - 1.0) / t_new;
+    h->t_prev = t_new;
+  }
+  zf::lasso_momentum_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(h->xn, h->xp, mom,
+                                                                        h->n_cols, h->y);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  double* t = h->xp;
+  h->xp = h->xn;
+  h->xn = t;
+  h->F_prev = h->F_x;
+  h->nit += 1;
+  h->phase = LP_GRAD;
+  *next = 0;
+  return ZF_OK;
+}
+
+}  // namespace
+
+extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* d_b,
+                               int64_t n_rows, int64_t n_cols, double scale, double l1,
+                               void* cuda_stream) {
+  if (!out || !d_A || !d_b) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  if (n_rows < 1 || n_cols < 1) return zf::zf_fail(ZF_ERR_INVALID, "n_rows and n_cols must be >= 1");
+  int rc = zf::zf_require_device();
+  if (rc != ZF_OK) return rc;
+  zf_lasso* h = new zf_lasso();
+  h->A = d_A;
+  h->b = d_b;
+  h->n_rows = n_rows;
+  h->n_cols = n_cols;
+  h->scale = scale;
+  h->l1 = l1;
+  h->st = (cudaStream_t)cuda_stream;
+  h->vec = (n_cols % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_A) & 15u) == 0);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (h->n_sm < 1) h->n_sm = 148;
+  // residual: 3 CTAs per SM, never more warps than row groups
+  const long long n_groups = (n_rows + zf::RES_ROWS_PER_WARP - 1) / zf::RES_ROWS_PER_WARP;
+  long long rb = (n_groups + 7) / 8;
+  if (rb > 3LL * h->n_sm) rb = 3LL * h->n_sm;
+  h->res_blocks = (int)(rb < 1 ? 1 : rb);
+  // A^T r: slabs x row blocks ~ 6 CTAs per SM, at least 64 rows per block
+  h->n_slabs = (int)((n_cols + zf::ATR_SLAB - 1) / zf::ATR_SLAB);
+  long long want = (6LL * h->n_sm + h->n_slabs - 1) / h->n_slabs;
+  long long max_rb = (n_rows + 63) / 64;
+  if (want > max_rb) want = max_rb;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  h->rows_per_block = (n_rows + want - 1) / want;
+  h->n_rowblocks = (int)((n_rows + h->rows_per_block - 1) / h->rows_per_block);
+  long long vb = (n_cols + zf::VEC_THREADS - 1) / zf::VEC_THREADS;
+  if (vb > zf::VEC_MAX_BLOCKS) vb = zf::VEC_MAX_BLOCKS;
+  h->vec_blocks = (int)vb;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  alloc((void**)&h->vecs, sizeof(double) * 4 * (size_t)n_cols);
+  alloc((void**)&h->r, sizeof(double) * (size_t)n_rows);
+  alloc((void**)&h->gpart, sizeof(double) * (size_t)h->n_rowblocks * (size_t)n_cols);
+  alloc((void**)&h->sq_part, sizeof(double) * (size_t)h->res_blocks);
+  alloc((void**)&h->partial, sizeof(double) * ((size_t)n_cols + 1));
+  alloc((void**)&h->block_sums, sizeof(zf::StepSums) * zf::VEC_MAX_BLOCKS);
+  alloc((void**)&h->d_sums, sizeof(zf::StepSums));
+  alloc((void**)&h->counter, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_pin, sizeof(double) * 8);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), h->st);
+  if (e != cudaSuccess) {
+    zf_lasso_destroy(h);
+    return zf::zf_fail_cuda(e, "zf_lasso_create allocation");
+  }
+  h->xp = h->vecs;
+  h->xn = h->vecs + n_cols;
+  h->y = h->vecs + 2 * n_cols;
+  h->g = h->vecs + 3 * n_cols;
+  *out = h;
+  return ZF_OK;
+}
+
+extern "C" void zf_lasso_destroy(zf_lasso* h) {
+  if (!h) return;
+  cudaFree(h->vecs);
+  cudaFree(h->r);
+  cudaFree(h->gpart);
+  cudaFree(h->sq_part);
+  cudaFree(h->partial);
+  cudaFree(h->block_sums);
+  cudaFree(h->d_sums);
+  cudaFree(h->counter);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  delete h;
+}
+
+static int lasso_check_options(const zf_options* o) {
+  if (!o) return zf::zf_fail(ZF_ERR_INVALID, "options is NULL");
+  if (!(o->lr > 0.0)) return zf::zf_fail(ZF_ERR_INVALID, "lr must be > 0");
+  if (o->max_iter < 1) return zf::zf_fail(ZF_ERR_INVALID, "max_iter must be >= 1");
+  if (o->max_backtrack_iter < 1) return zf::zf_fail(ZF_ERR_INVALID, "max_backtrack_iter must be >= 1");
+  if (!(o->decay_rate > 0.0 && o->decay_rate <= 1.0))
+    return zf::zf_fail(ZF_ERR_INVALID, "decay_rate must be in (0, 1]");
+  if (o->trace_capacity < 0) return zf::zf_fail(ZF_ERR_INVALID, "trace_capacity must be >= 0");
+  return ZF_OK;
+}
+
+static int lasso_begin_impl(zf_lasso* h, const zf_options* opt, const double* d_x0,
+                            double* h_allerrs, double* h_allfuns) {
+  if (!h || !d_x0) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int rc = lasso_check_options(opt);
+  if (rc != ZF_OK) return rc;
+  h->opt = *opt;
+  h->h_allerrs = h_allerrs;
+  h->h_allfuns = h_allfuns;
+  h->lr = opt->lr;
+  h->t_prev = 1.0;
+  h->nit = 0;
+  h->status = 0;
+  h->bt = 0;
+  h->err = INFINITY;
+  h->result_is_prev = false;
+  // F is needed by the line search, and by return_all's allfuns
+  h->need_F = (opt->decay_rate != 1.0) || (opt->trace_capacity > 0 && h_allfuns != nullptr);
+  h->F_known = false;
+  h->xp = h->vecs;
+  h->xn = h->vecs + h->n_cols;
+  const size_t nb = sizeof(double) * (size_t)h->n_cols;
+  ZF_CUDA(cudaMemcpyAsync(h->xp, d_x0, nb, cudaMemcpyDeviceToDevice, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->xn, d_x0, nb, cudaMemcpyDeviceToDevice, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->y, d_x0, nb, cudaMemcpyDeviceToDevice, h->st));
+  // F(x0): residual norm partial into `partial[n_cols]` (all-reduced by the caller if sharded)
+  rc = launch_residual(h, h->xp);
+  if (rc != ZF_OK) return rc;
+  rc = launch_collect(h, false);
+  if (rc != ZF_OK) return rc;
+  h->phase = LP_INIT;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_begin(zf_lasso* h, const zf_options* opt, const double* d_x0) {
+  return lasso_begin_impl(h, opt, d_x0, nullptr, nullptr);
+}
+
+extern "C" int zf_lasso_grad(zf_lasso* h, int which) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  int rc;
+  if (which == 0) {
+    if (h->phase != LP_GRAD) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_grad(0) out of order");
+    rc = launch_residual(h, h->y);
+    if (rc != ZF_OK) return rc;
+    rc = launch_atr(h);
+    if (rc != ZF_OK) return rc;
+    return launch_collect(h, true);
+  }
+  if (which == 1) {
+    if (h->phase != LP_FNEW && h->phase != LP_FINAL)
+      return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_grad(1) out of order");
+    rc = launch_residual(h, h->xn);
+    if (rc != ZF_OK) return rc;
+    return launch_collect(h, false);
+  }
+  return zf::zf_fail(ZF_ERR_INVALID, "which must be 0 or 1");
+}
+
+extern "C" double* zf_lasso_partial(zf_lasso* h, int64_t* n_values) {
+  if (!h) return nullptr;
+  if (n_values) *n_values = h->n_cols + 1;
+  return h->partial;
+}
+
+extern "C" int zf_lasso_step(zf_lasso* h, int32_t* h_next) {
+  if (!h || !h_next) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int next = 2;
+  int rc = ZF_OK;
+  double ss = 0.0;
+  switch (h->phase) {
+    case LP_INIT: {
+      // F(x0) = f(x0) + g(x0)   (proximal_gradient.py:466, 279)
+      rc = run_trial(h, true, h->xp, &ss);
+      if (rc != ZF_OK) return rc;
+      h->F_prev = f_from_ss(h, ss) + h->l1 * h->sums.abs1;
+      h->F_x = h->F_prev;
+      if (h->opt.trace_capacity > 0 && h->h_allfuns) h->h_allfuns[0] = h->F_prev;
+      h->nit = 1;
+      h->phase = LP_GRAD;
+      next = 0;
+      break;
+    }
+    case LP_GRAD: {
+      h->bt = 0;
+      rc = run_trial(h, false, nullptr, &ss);
+      if (rc != ZF_OK) return rc;
+      h->f_y = f_from_ss(h, ss);
+      h->sub_fun = subproblem_fun(h);
+      if (h->need_F) {
+        h->phase = LP_FNEW;
+        next = 1;
+      } else {
+        h->F_known = false;
+        rc = accept_candidate(h, &next);
+      }
+      break;
+    }
+    case LP_FNEW: {
+      rc = fetch_ss(h, &ss);
+      if (rc != ZF_OK) return rc;
+      const double f_x = f_from_ss(h, ss);
+      h->F_x = f_x + h->l1 * h->sums.abs1;
+      h->F_known = true;
+      bool ok;
+      if (h->opt.decay_rate == 1.0) ok = true;                      // proximal_gradient.py:298
+      else if (h->opt.deprecated) ok = (f_x - h->f_y <= h->sub_fun + h->opt.tol_internal);
+      else ok = (h->F_x - h->F_prev <= h->sub_fun + h->opt.tol_internal);
+      if (ok) {
+        rc = accept_candidate(h, &next);
+      } else {
+        h->lr *= h->opt.decay_rate;
+        h->bt += 1;
+        if (h->bt >= h->opt.max_backtrack_iter) {
+          // RuntimeError("Backtracking failed ...") -> x = x_prev, nit - 1 (493-509)
+          h->result_is_prev = true;
+          h->F_x = h->F_prev;
+          h->nit -= 1;
+          finish_state(h, -1);
+          next = 2;
+        } else {
+          // same gradient, smaller step: redo the prox from the stored g
+          zf::lasso_prox_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
+              h->y, h->g, 1.0, h->lr, h->l1 * h->lr, h->n_cols, h->xn, nullptr, h->block_sums,
+              h->counter, h->d_sums);
+          ZF_CUDA(cudaGetLastError());
+          zf::zf_count_launch();
+          ZF_CUDA(cudaMemcpyAsync(h->h_pin, h->d_sums, sizeof(zf::StepSums),
+                                  cudaMemcpyDeviceToHost, h->st));
+          ZF_CUDA(cudaStreamSynchronize(h->st));
+          std::memcpy(&h->sums, h->h_pin, sizeof(zf::StepSums));
+          h->sub_fun = subproblem_fun(h);
+          h->phase = LP_FNEW;
+          next = 1;
+        }
+      }
+      break;
+    }
+    case LP_FINAL: {
+      rc = fetch_ss(h, &ss);
+      if (rc != ZF_OK) return rc;
+      h->F_x = f_from_ss(h, ss) + h->l1 * h->sums.abs1;
+      h->F_known = true;
+      h->phase = LP_DONE;
+      next = 2;
+      break;
+    }
+    case LP_DONE:
+      next = 2;
+      break;
+    default:
+      return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_step called before zf_lasso_begin");
+  }
+  if (rc != ZF_OK) return rc;
+  *h_next = next;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
+                               int32_t* h_status) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (h->phase != LP_DONE) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_finish before the solve ended");
+  if (d_x) {
+    ZF_CUDA(cudaMemcpyAsync(d_x, h->result_is_prev ? h->xp : h->xn,
+                            sizeof(double) * (size_t)h->n_cols, cudaMemcpyDeviceToDevice, h->st));
+    ZF_CUDA(cudaStreamSynchronize(h->st));
+  }
+  if (h_fun) *h_fun = h->F_x;
+  if (h_nit) *h_nit = h->nit;
+  if (h_status) *h_status = h->status;
+  h->phase = LP_IDLE;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_solve(zf_lasso* h, const zf_options* opt, const double* d_x0,
+                              double* d_x, double* h_fun, int64_t* h_nit, int32_t* h_status,
+                              double* h_allerrs, double* h_allfuns) {
+  int rc = lasso_begin_impl(h, opt, d_x0, h_allerrs, h_allfuns);
+  if (rc != ZF_OK) return rc;
+  int32_t next = 0;
+  rc = zf_lasso_step(h, &next);
+  while (rc == ZF_OK && next != 2) {
+    rc = zf_lasso_grad(h, next);
+    if (rc != ZF_OK) break;
+    rc = zf_lasso_step(h, &next);
+  }
+  if (rc != ZF_OK) {
+    h->phase = LP_IDLE;
+    return rc;
+  }
+  return zf_lasso_finish(h, d_x, h_fun, h_nit, h_status);
+}
+
+extern "C" int zf_lasso_gradient_device(zf_lasso* h, const double* d_x, double* d_grad,
+                                        double* d_f) {
+  if (!h || !d_x || !d_grad) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int rc = launch_residual(h, d_x);
+  if (rc != ZF_OK) return rc;
+  rc = launch_atr(h);
+  if (rc != ZF_OK) return rc;
+  rc = launch_collect(h, true);
+  if (rc != ZF_OK) return rc;
+  zf::lasso_scale_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
+      h->partial, 2.0 * h->scale, h->scale, h->n_cols, d_grad, d_f);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}

@@ -211,6 +211,20 @@ def minimize_proximal_gradient(f, g, jac_f, prox_wsum_g, x0, lr=1, tol=1e-5,
     (bounded Brent for two objectives); ``"newton"`` uses the exact simplex Newton
     solver for every m >= 2.
     """
+    from .lasso import DenseLasso
+
+    owner = getattr(f, "__self__", None)
+    if isinstance(owner, DenseLasso):
+        # the large-n path: same four closures, bound to a DenseLasso
+        for name, fn in (("g", g), ("jac_f", jac_f), ("prox_wsum_g", prox_wsum_g)):
+            if getattr(fn, "__self__", None) is not owner or fn.__name__ != name:
+                raise TypeError("f, g, jac_f and prox_wsum_g must belong to the same DenseLasso")
+        return owner.minimize_proximal_gradient(
+            x0, lr=lr, tol=tol, tol_internal=tol_internal, max_iter=max_iter,
+            max_iter_internal=max_iter_internal, max_backtrack_iter=max_backtrack_iter,
+            warm_start=warm_start, decay_rate=decay_rate, nesterov=nesterov,
+            nesterov_ratio=nesterov_ratio, return_all=return_all, verbose=verbose,
+            deprecated=deprecated)
     if deprecated:
         warn("Using the deprecated option is not mathematically proven to converge. "
              "Please consider using the recommended condition instead.", stacklevel=2)
