@@ -1,0 +1,518 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for zfista_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload fds|jos1|sweep|lasso]
+
+Headline (default) workload, BASELINE.json configs[2]: FDS tri-objective, n = 100, with the
+L1 term of benchmarks/benchmark.py:439-440, FISTA (nesterov=True), tol_internal = 1e-11,
+max_iter = 1e8; 1024 uniform(-2, 2) starts PER GPU (weak scaling: starts are independent, no
+collective on the data path).  A "step" is one batched solve of a fresh batch of 1024
+starts.  metric = converged solves/sec (starts whose status is 1 / device time).
+
+  value : inputs resident in HBM, zf_solve_batched_device on torch's current stream, timed
+          with CUDA events per step, L2 flushed between steps, max over ranks.
+  e2e   : the public API call problem.minimize_proximal_gradient_batched(X0) on PINNED HOST
+          arrays: H2D of the starts and D2H of x / fun / nit / status inside the timed region.
+  roofline / also.lasso.roofline : see DESIGN.md "Measurement".
+  cpu_baseline : the oracle (numpy + scipy restatement of the reference, kind "port") on
+          the box's host cores, one start per core.
+
+--impl reference times that same CPU path as its own arm (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "converged solves/sec (batched starts)"
+UNIT = "solves/s"
+
+
+# --------------------------------------------------------------------------- workloads
+def workload_spec(name: str):
+    """-> dict(cls, kw, low, high, n_starts, opts, label)  (benchmarks/benchmark.py:463-471)."""
+    if name == "fds":
+        n = 100
+        return dict(cls="FDS", kw=dict(n_features=n, l1_ratios=(np.arange(3) + 1) / n,
+                                       l1_shifts=np.arange(3.0)),
+                    low=-2.0, high=2.0, n_starts=1024,
+                    opts=dict(nesterov=True, tol_internal=1e-11, max_iter=100000000),
+                    label="FDS tri-objective n=100 + L1, FISTA, 1024 starts per GPU")
+    if name == "jos1":
+        return dict(cls="JOS1", kw=dict(n_features=5), low=-2.0, high=4.0, n_starts=1000,
+                    opts=dict(nesterov=True, tol_internal=1e-11, max_iter=100000000),
+                    ref_sample=1000,
+                    label="JOS1 bi-objective n=5, FISTA, 1000 starts per GPU")
+    if name == "jos1_l1":
+        n = 50
+        return dict(cls="JOS1", kw=dict(n_features=n, l1_ratios=(np.arange(2) + 1) / n,
+                                        l1_shifts=np.arange(2.0)),
+                    low=-2.0, high=4.0, n_starts=1024,
+                    opts=dict(nesterov=True, tol_internal=1e-11, max_iter=100000000),
+                    ref_sample=128,
+                    label="JOS1 bi-objective n=50 + L1, FISTA, 1024 starts per GPU")
+    raise ValueError(name)
+
+
+def make_starts(spec, seed, n_features):
+    rng = np.random.RandomState(seed)
+    return rng.uniform(spec["low"], spec["high"], size=(spec["n_starts"], n_features))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _oracle_solve_one(args):
+    import warnings
+
+    from oracle import zfista_oracle as zo
+
+    cls, kw, x0, opts = args
+    warnings.simplefilter("ignore")
+    bounds = kw.pop("bounds", None) if "bounds" in kw else None
+    spec = zo.make_spec(cls, bounds=bounds, **kw)
+    t0 = time.time()
+    r = zo.minimize_proximal_gradient(spec, x0, **opts)
+    return bool(r["success"]), int(r["nit"]), time.time() - t0
+
+
+_POOL = None
+
+
+def _warm(_):
+    from oracle import zfista_oracle  # noqa: F401  (import scipy in the worker)
+
+    return os.getpid()
+
+
+def cpu_pool(cores):
+    """Worker processes for the CPU arm, started and warmed (imports done) outside any
+    timed region; the reference fans starts out over joblib workers the same way
+    (benchmarks/benchmark.py:320-372)."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ProcessPoolExecutor
+
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        _POOL = ProcessPoolExecutor(max_workers=cores)
+        list(_POOL.map(_warm, range(4 * cores)))
+    return _POOL
+
+
+def cpu_reference_step(spec, X0, cores):
+    """The reference's CPU path (oracle port: same numpy / scipy calls, one process per
+    start) on `len(X0)` starts.  Returns (converged, seconds, nits)."""
+    pool = cpu_pool(cores)
+    tasks = [(spec["cls"], dict(spec["kw"]), X0[i], spec["opts"]) for i in range(len(X0))]
+    t0 = time.time()
+    out = list(pool.map(_oracle_solve_one, tasks, chunksize=max(1, len(tasks) // (4 * cores))))
+    dt = time.time() - t0
+    return sum(o[0] for o in out), dt, [o[1] for o in out]
+
+
+def ref_sample_size(spec, args, cores):
+    """Starts per CPU step: a bounded sample of the step's batch (about 10-30 s of CPU work)."""
+    if args.ref_sample:
+        return max(1, min(spec["n_starts"], args.ref_sample))
+    return max(1, min(spec["n_starts"], spec.get("ref_sample") or cores))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    spec = workload_spec(args.workload)
+    cores = host_cores()
+    n_sample = ref_sample_size(spec, args, cores)
+    n_features = spec["kw"].get("n_features", 4)
+    times, conv, nits = [], 0, []
+    for step in range(args.warmup + args.steps):
+        X0 = make_starts(spec, 1000 + step, n_features)[:n_sample]
+        c, dt, ns = cpu_reference_step(spec, X0, cores)
+        if step >= args.warmup:
+            times.append(dt)
+            conv += c
+            nits += ns
+    total = sum(times)
+    value = conv / total if total > 0 else 0.0
+    sample = (f"{n_sample} starts per step of the same workload; "
+              f"oracle port of zfista (numpy + scipy trust-constr), one process per start")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": spec["label"], "options": _json_opts(spec["opts"]),
+                   "starts_per_step": n_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "nit_mean": float(np.mean(nits)) if nits else None,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def _json_opts(opts):
+    return {k: (v if not isinstance(v, (np.floating, np.integer)) else v.item())
+            for k, v in opts.items()}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from zfista_b200 import _lib
+    from zfista_b200 import build as zbuild
+    import zfista_b200.problems as zp
+    from zfista_b200.proximal_gradient import _make_options
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run "
+                             "(one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: zfista_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    zbuild.build()
+    L = _lib.lib()
+
+    spec = workload_spec(args.workload)
+    prob = getattr(zp, spec["cls"])(**spec["kw"])
+    n, m, S = prob.n_features, prob.n_objectives, spec["n_starts"]
+    total_steps = args.warmup + args.steps
+    # every step gets its own batch of starts; each rank its own slice of the seed space
+    host_batches = [make_starts(spec, 1000 + step * world + rank, n) for step in range(total_steps)]
+    dev_batches = [torch.from_numpy(b).to(dev) for b in host_batches]
+    out_x = torch.empty(S, n, dtype=torch.float64, device=dev)
+    out_fun = torch.empty(S, m, dtype=torch.float64, device=dev)
+    out_nit = torch.empty(S, dtype=torch.int64, device=dev)
+    out_status = torch.empty(S, dtype=torch.int32, device=dev)
+    out_ndual = torch.empty(S, dtype=torch.int64, device=dev)
+    out_nfev = torch.empty(S, dtype=torch.int64, device=dev)
+    res = _lib.ZfResult()
+    res.x, res.fun, res.nit, res.status = (out_x.data_ptr(), out_fun.data_ptr(),
+                                           out_nit.data_ptr(), out_status.data_ptr())
+    res.n_dual, res.nfev = out_ndual.data_ptr(), out_nfev.data_ptr()
+    o = spec["opts"]
+    opts = _make_options(1.0, 1e-5, o["tol_internal"], o["max_iter"], 100000, 100, False, 0.5,
+                         o.get("nesterov", False), (0, 0.25), False, "reference", 0)
+    desc, keep = prob.descriptor()
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i):
+        _lib.check(L.zf_solve_batched_device(
+            C.byref(desc), C.byref(opts), S, C.c_void_p(dev_batches[i].data_ptr()), None,
+            C.byref(res), C.c_void_p(stream.cuda_stream)))
+
+    # ---------------- value: device-resident, CUDA events per step, L2 flushed between steps
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    converged = 0
+    nit_sum = 0
+    ndual_sum = 0
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        device_step(args.warmup + k)
+        ev[k][1].record(stream)
+        ev[k][1].synchronize()
+        converged += int((out_status == 1).sum().item())
+        nit_sum += int(out_nit.sum().item())
+        ndual_sum += int(out_ndual.sum().item())
+    barrier()
+    launches = _lib.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- e2e: public API, pinned host arrays in, host arrays out
+    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
+    for i in range(min(args.warmup, 2)):
+        prob.minimize_proximal_gradient_batched(pinned[i].numpy(), **spec["opts"])
+    barrier()
+    e2e_s = 0.0
+    e2e_conv = 0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        br = prob.minimize_proximal_gradient_batched(pinned[args.warmup + k].numpy(),
+                                                     **spec["opts"])
+        e2e_s += time.perf_counter() - t0
+        e2e_conv += int((br.status == 1).sum())
+    h2d = S * n * 8
+    d2h = S * (n * 8 + m * 8 + 8 + 4 + 8 + 8 + 8 + 8)
+
+    # ---------------- reduce over ranks: time = max, counts = sum
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    c = torch.tensor([converged, e2e_conv, nit_sum, ndual_sum, launches], dtype=torch.float64,
+                     device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = t.tolist()
+    conv_all, e2e_conv_all, nit_all, ndual_all, launches_all = c.tolist()
+
+    line = None
+    if rank == 0:
+        value = conv_all / (dev_ms_max / 1e3)
+        e2e_value = e2e_conv_all / (e2e_ms_max / 1e3)
+        peaks = _measured_peaks()
+        # dominant kernel = batched_fista_kernel: one launch per step.  Algorithmic HBM bytes
+        # per start: x0 in; x, fun, nit, status, n_dual, nfev out (DESIGN.md "Measurement").
+        bytes_per_start = n * 8 + n * 8 + m * 8 + 8 + 4 + 8 + 8
+        ker_s = (dev_ms / 1e3) / args.steps
+        achieved = S * bytes_per_start / ker_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": spec["label"], "options": _json_opts(spec["opts"]),
+                       "starts_per_gpu": S, "l2": "flushed between steps (256 MiB memset)",
+                       "inner_solver": "bounded Brent (m=2) / simplex Newton (m>=3)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "nit_mean": nit_all / (S * world * args.steps),
+            "dual_evals_per_solve": ndual_all / (S * world * args.steps),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["source"],
+                "note": ("batched_fista_kernel keeps each start's state in shared memory and "
+                         "touches HBM only for x0 and the results; it is FP64-latency bound, "
+                         "not HBM bound (profiles/), so this fraction is tiny by design. The "
+                         "HBM-bound kernel of the path is the dense LASSO pass: also.lasso")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            ns = ref_sample_size(spec, args, cores)
+            cconv, cdt, cn = cpu_reference_step(spec, host_batches[args.warmup][:ns], cores)
+            line["cpu_baseline"] = {
+                "value": cconv / cdt if cdt > 0 else 0.0, "unit": UNIT, "cores": cores,
+                "kind": "port", "seconds": cdt, "nit": cn,
+                "sample": (f"{ns} starts of this step's batch, oracle port "
+                           "of zfista (numpy + scipy trust-constr), one process per start")}
+        else:
+            line["cpu_baseline"] = None
+    if rank == 0 or world > 1:
+        also = {}
+        if not args.no_extras:
+            try:
+                also["lasso"] = bench_lasso(args, dev, rank, world)
+            except Exception as e:  # extras must never lose the headline line
+                also["lasso"] = {"error": repr(e)}
+        if rank == 0:
+            line["also"] = also
+            print(json.dumps(line), flush=True)
+    del keep
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def bench_lasso(args, dev, rank, world):
+    """Dense LASSO gradient pass (the HBM-bound kernels): A rows x cols fp64 per GPU, rows
+    sharded over ranks (weak: every rank holds `rows` rows), A^T r all-reduced over NCCL.
+    Reports FISTA iterations/s of a fixed-step run and the roofline of one gradient."""
+    import torch
+    import torch.distributed as dist
+
+    from zfista_b200 import _lib
+    from zfista_b200.lasso import DenseLasso
+
+    rows, cols = args.lasso_rows, args.lasso_cols
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    A = torch.empty(rows, cols, dtype=torch.float64, device=dev)
+    chunk = max(1, (64 << 20) // (cols * 8))
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        A[r0:r1] = torch.randn(r1 - r0, cols, dtype=torch.float64, device=dev, generator=g)
+    w = torch.zeros(cols, dtype=torch.float64, device=dev)
+    w[:64] = 1.0
+    b = A @ w
+    prob = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows * world),
+                      distributed=world > 1)
+    x = torch.zeros(cols, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    a_bytes = rows * cols * 8
+    out = {"A": f"{rows}x{cols} fp64 per GPU ({a_bytes / 2**30:.1f} GiB, > L2)"}
+    if world == 1:
+        # kernel-level: one gradient = residual pass + A^T pass (2 x |A| from HBM)
+        for _ in range(3):
+            prob.gradient(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record(stream)
+        for _ in range(reps):
+            prob.gradient(x)
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        peaks = _measured_peaks()
+        # algorithmic bytes of one gradient as built: A read twice (A y, then A^T r) plus
+        # vectors; the one-pass bound (A read once) is reported beside it.
+        vec_bytes = (2 * cols + 2 * rows) * 8
+        two_pass = 2 * a_bytes + vec_bytes
+        ach = two_pass / (ms / 1e3) / 1e9
+        out["roofline"] = {
+            "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_gradient": ms,
+            "peak_source": peaks["source"],
+            "frac_of_one_pass_bound": (a_bytes + vec_bytes) / (ms / 1e3) / 1e9 / peaks["hbm_gbs"]}
+    # solver-level: fixed-step FISTA iterations per second (A stays resident)
+    iters = args.lasso_iters
+    lr = 0.5
+    prob.minimize_proximal_gradient(x, lr=lr, decay_rate=1, nesterov=True, max_iter=3, tol=0.0,
+                                    return_device=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    import warnings
+
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = prob.minimize_proximal_gradient(x, lr=lr, decay_rate=1, nesterov=True,
+                                              max_iter=iters, tol=0.0, return_device=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    out["fista_iters_per_s"] = res.nit / tt.item()
+    out["fista_iters"] = res.nit
+    out["global_rows"] = rows * world
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fds", choices=["fds", "jos1", "jos1_l1"])
+    ap.add_argument("--ref-sample", type=int, default=0,
+                    help="starts per CPU step (default: one per host core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--lasso-rows", type=int, default=65536)
+    ap.add_argument("--lasso-cols", type=int, default=16384)
+    ap.add_argument("--lasso-iters", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

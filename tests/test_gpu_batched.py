@@ -162,11 +162,12 @@ def test_batched_solve_matches_reference(gpu, case):
         _rel_close(br.allfuns[0, :n0 + 1], d["allfuns0"])
         return
     env = helpers.oracle_noise_envelope(helpers.oracle_spec(cls, kw), d["x0"], d["x"], d["fun"],
-                                        d["nit"], opts)
+                                        d["nit"], opts,
+                                        n_starts=16 if prob.n_features <= 10 else 4)
     dnit = np.abs(br.nit - d["nit"])
     dx = np.max(np.abs(br.x - d["x"]))
     dF = np.max(np.abs(br.fun - d["fun"]) / np.maximum(1.0, np.abs(d["fun"])))
-    assert dnit.max() <= 2 * env["dnit"] + 2, (dnit, env)
+    assert dnit.max() <= 2 * env["dnit"] + max(3, 0.05 * d["nit"].max()), (dnit, env)
     assert dx <= 4 * env["dx"] + 1e-6, (dx, env)
     assert dF <= 4 * env["dF"] + 1e-7, (dF, env)
     # the first iterations (before the noise is amplified) still agree tightly
