@@ -1,0 +1,70 @@
+"""Run under torchrun on N >= 2 GPUs (tests/test_gpu_multi.py launches it):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multigpu_check.py
+
+Checks, with NCCL: (1) the row-sharded DenseLasso gives the single-GPU result and the CPU
+oracle's; (2) starts sharded over ranks (no collective) give the single-GPU batch result."""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from oracle import zfista_oracle as zo
+    from zfista_b200 import distributed as zd
+    from zfista_b200.lasso import DenseLasso
+    import zfista_b200.problems as zp
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    rng = np.random.RandomState(11)
+    n_rows, n_cols = 403, 130
+    A = rng.standard_normal((n_rows, n_cols))
+    w = np.zeros(n_cols)
+    w[:8] = rng.standard_normal(8)
+    b = A @ w + 0.01 * rng.standard_normal(n_rows)
+    scale, l1, x0 = 1 / (2 * n_rows), 0.03, np.zeros(n_cols)
+    lo, hi = zd.shard_bounds(n_rows, rank, world)
+    sharded = DenseLasso(A[lo:hi], b[lo:hi], l1, scale=scale, distributed=True)
+    single = DenseLasso(A, b, l1, scale=scale)
+    spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
+    for opts in (dict(nesterov=True), dict(nesterov=False, max_iter=80),
+                 dict(nesterov=True, lr=0.2, decay_rate=1, nesterov_ratio=(0.25, 1 / 64))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r_sh = sharded.minimize_proximal_gradient(x0, **opts)
+            r_1 = single.minimize_proximal_gradient(x0, **opts)
+            ref = zo.minimize_proximal_gradient(spec, x0, **opts)
+        assert r_sh.nit == r_1.nit == ref["nit"], (r_sh.nit, r_1.nit, ref["nit"])
+        np.testing.assert_allclose(r_sh.x, r_1.x, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(r_sh.x, ref["x"], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(r_sh.fun, ref["fun"], rtol=1e-9)
+        # all ranks hold the same replicated x
+        xs = [None] * world
+        dist.all_gather_object(xs, r_sh.x)
+        for other in xs[1:]:
+            np.testing.assert_array_equal(other, xs[0])
+    prob = zp.JOS1(n_features=20)
+    X0 = np.random.RandomState(3).uniform(-2, 4, size=(101, 20))
+    full = zd.minimize_proximal_gradient_sharded(prob, X0, nesterov=True, tol_internal=1e-11)
+    one = prob.minimize_proximal_gradient_batched(X0, nesterov=True, tol_internal=1e-11)
+    np.testing.assert_array_equal(full.nit, one.nit)
+    np.testing.assert_array_equal(full.x, one.x)
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIGPU_OK world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,260 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic in zfista_b200.distributed:
+start sharding with no data-path collective, and the row-sharded LASSO protocol whose one
+exchange is the all-reduce of [A^T r | sum r^2].  The local compute is injected (the CPU
+oracle / a numpy model of the split protocol), the sharding + exchange code is the
+product's."""
+import os
+import socket
+import warnings
+
+import numpy as np
+import pytest
+
+import helpers
+from zfista_b200 import distributed as zd
+
+
+def test_shard_bounds_partition_everything_exactly_once():
+    for n in (0, 1, 7, 8, 1000, 1024, 15 * 1024):
+        for world in (1, 2, 3, 4, 8):
+            spans = [zd.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        zd.shard_bounds(4, 2, 2)
+
+
+def test_momentum_grid_layout():
+    X0 = np.arange(6.0).reshape(3, 2)
+    Xr, AB, si, gi = zd.momentum_grid(X0, helpers.AB_GRID)
+    G = len(helpers.AB_GRID)
+    assert Xr.shape == (3 * G, 2) and AB.shape == (3 * G, 2)
+    for s in range(3):
+        for g in range(G):
+            row = s * G + g
+            assert si[row] == s and gi[row] == g
+            np.testing.assert_array_equal(Xr[row], X0[s])
+            np.testing.assert_array_equal(AB[row], helpers.AB_GRID[g])
+
+
+# ----------------------------------------------------------------------------- workers
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_local_solver(problem, X0, nesterov_ratio=(0, 0.25), **kw):
+    """Stand-in for the CUDA batched solve: the CPU oracle, returning a BatchResult."""
+    from oracle import zfista_oracle as zo
+    from zfista_b200.proximal_gradient import BatchResult
+
+    spec = zo.make_spec(type(problem).__name__, n_features=problem.n_features)
+    ab = np.asarray(nesterov_ratio, dtype=np.float64)
+    rows = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(len(X0)):
+            pair = tuple(ab[i]) if ab.ndim == 2 else tuple(ab)
+            rows.append(zo.minimize_proximal_gradient(spec, X0[i], nesterov_ratio=pair, **kw))
+    n, m = problem.n_features, problem.n_objectives
+    S = len(rows)
+    return BatchResult(
+        x=np.array([r["x"] for r in rows]).reshape(S, n),
+        fun=np.array([r["fun"] for r in rows]).reshape(S, m),
+        nit=np.array([r["nit"] for r in rows], dtype=np.int64),
+        status=np.array([r["status"] for r in rows], dtype=np.int32),
+        lr=np.array([r["lr"] for r in rows], dtype=np.float64),
+        nfev=np.zeros(S, dtype=np.int64), n_dual=np.zeros(S, dtype=np.int64),
+        err=np.zeros(S), time=0.0)
+
+
+def _worker_starts(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    import zfista_b200.problems as zp
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    prob = zp.JOS1(n_features=5)
+    rng = np.random.RandomState(0)
+    X0 = rng.uniform(-2, 4, size=(7, 5))          # 7 starts over 2 ranks: ragged shards
+    Xg, AB, _, _ = zd.momentum_grid(X0[:3], helpers.AB_GRID[:3])
+    full = zd.minimize_proximal_gradient_sharded(prob, X0, nesterov=True, tol_internal=1e-11,
+                                                 local_solver=_oracle_local_solver)
+    mine = zd.minimize_proximal_gradient_sharded(prob, X0, nesterov=True, tol_internal=1e-11,
+                                                 gather=False, local_solver=_oracle_local_solver)
+    grid = zd.minimize_proximal_gradient_sharded(prob, Xg, nesterov_ratio=AB, nesterov=True,
+                                                 tol_internal=1e-11,
+                                                 local_solver=_oracle_local_solver)
+    np.savez(os.path.join(out_dir, f"starts_{rank}.npz"), x=full.x, nit=full.nit, fun=full.fun,
+             mine_x=mine.x, grid_nit=grid.nit, grid_x=grid.x)
+    dist.destroy_process_group()
+
+
+def test_sharded_starts_world2_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+
+    import zfista_b200.problems as zp
+
+    port = _free_port()
+    mp.spawn(_worker_starts, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    prob = zp.JOS1(n_features=5)
+    rng = np.random.RandomState(0)
+    X0 = rng.uniform(-2, 4, size=(7, 5))
+    ref = _oracle_local_solver(prob, X0, nesterov=True, tol_internal=1e-11)
+    Xg, AB, _, _ = zd.momentum_grid(X0[:3], helpers.AB_GRID[:3])
+    ref_grid = _oracle_local_solver(prob, Xg, nesterov_ratio=AB, nesterov=True, tol_internal=1e-11)
+    outs = [np.load(tmp_path / f"starts_{r}.npz") for r in range(2)]
+    for r, o in enumerate(outs):
+        np.testing.assert_array_equal(o["nit"], ref.nit)          # gathered, original order
+        np.testing.assert_array_equal(o["x"], ref.x)
+        np.testing.assert_array_equal(o["fun"], ref.fun)
+        lo, hi = zd.shard_bounds(7, r, 2)
+        np.testing.assert_array_equal(o["mine_x"], ref.x[lo:hi])  # gather=False: own slice only
+        np.testing.assert_array_equal(o["grid_nit"], ref_grid.nit)
+        np.testing.assert_array_equal(o["grid_x"], ref_grid.x)
+
+
+class NumpySplitLasso:
+    """numpy model of the zf_lasso_begin / grad / partial / step / finish state machine
+    (csrc/zf_lasso.cu) on ONE row shard; `partial` = [A^T r | sum r^2] is what gets reduced."""
+
+    def __init__(self, A, b, scale, l1, x0, opts):
+        self.A, self.b, self.scale, self.l1 = A, b, scale, l1
+        self.o = dict(lr=1.0, tol=1e-5, tol_internal=1e-12, max_iter=1000000,
+                      max_backtrack_iter=100, decay_rate=0.5, nesterov=False,
+                      nesterov_ratio=(0, 0.25), deprecated=False)
+        self.o.update(opts)
+        self.x0 = x0
+        self.partial = np.zeros(A.shape[1] + 1)
+
+    def _f(self, ss):
+        return np.sqrt(ss) ** 2 * self.scale
+
+    def begin(self):
+        self.xp = self.xn = self.y = self.x0.copy()
+        self.lr, self.t, self.nit, self.phase = self.o["lr"], 1.0, 0, "init"
+        r = self.A @ self.xp - self.b
+        self.partial[-1] = r @ r
+
+    def grad(self, which):
+        v = self.y if which == 0 else self.xn
+        r = self.A @ v - self.b
+        if which == 0:
+            self.partial[:-1] = self.A.T @ r
+        self.partial[-1] = r @ r
+
+    def _trial(self):
+        self.xn = np.sign(self.y - self.lr * self.g) * np.maximum(
+            np.abs(self.y - self.lr * self.g) - self.lr * self.l1, 0)
+        d = self.xn - self.y
+        self.gx = self.l1 * np.abs(self.xn).sum()
+        self.sub = self.g @ d + self.gx + np.sqrt(d @ d) ** 2 / 2 / self.lr
+        if not self.o["deprecated"]:
+            self.sub += self.f_y - self.F_prev
+        self.err = np.max(np.abs(d))
+
+    def _accept(self):
+        if self.err < self.o["tol"] or self.nit >= self.o["max_iter"]:
+            self.status = 1 if self.err < self.o["tol"] else 0
+            self.phase = "done"
+            return 2
+        mom = 0.0
+        if self.o["nesterov"]:
+            a, b = self.o["nesterov_ratio"]
+            t_new = np.sqrt(self.t ** 2 - a * self.t + b) + 0.5
+            mom, self.t = (self.t - 1) / t_new, t_new
+        self.y = self.xn + mom * (self.xn - self.xp)
+        self.xp, self.F_prev, self.nit, self.phase = self.xn, self.F_x, self.nit + 1, "grad"
+        return 0
+
+    def step(self):
+        ss = self.partial[-1]
+        if self.phase == "init":
+            self.F_prev = self.F_x = self._f(ss) + self.l1 * np.abs(self.xp).sum()
+            self.nit, self.phase = 1, "grad"
+            return 0
+        if self.phase == "grad":
+            self.g = self.partial[:-1] * (2 * self.scale)
+            self.f_y = self._f(ss)
+            self.bt = 0
+            self._trial()
+            self.phase = "fnew"
+            return 1
+        if self.phase == "fnew":
+            f_x = self._f(ss)
+            self.F_x = f_x + self.gx
+            ok = (f_x - self.f_y if self.o["deprecated"] else self.F_x - self.F_prev) \
+                <= self.sub + self.o["tol_internal"]
+            if ok or self.o["decay_rate"] == 1:
+                return self._accept()
+            self.lr *= self.o["decay_rate"]
+            self.bt += 1
+            if self.bt >= self.o["max_backtrack_iter"]:
+                self.status, self.phase, self.xn, self.nit = -1, "done", self.xp, self.nit - 1
+                return 2
+            self._trial()
+            return 1
+        return 2
+
+    def finish(self):
+        return dict(x=self.xn, fun=self.F_x, nit=self.nit, status=self.status)
+
+
+def _lasso_problem():
+    rng = np.random.RandomState(5)
+    A = rng.standard_normal((90, 40))
+    w = np.zeros(40)
+    w[:6] = rng.standard_normal(6)
+    b = A @ w + 0.01 * rng.standard_normal(90)
+    return A, b, 1 / 180, 0.05, np.zeros(40)
+
+
+def _worker_lasso(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    A, b, scale, l1, x0 = _lasso_problem()
+    lo, hi = zd.shard_bounds(len(A), rank, world)
+    for tag, opts in (("fista", dict(nesterov=True)), ("ista", dict(nesterov=False, max_iter=50))):
+        ops = NumpySplitLasso(A[lo:hi], b[lo:hi], scale, l1, x0, opts)
+        buf = torch.from_numpy(ops.partial)             # shares memory with ops.partial
+
+        def allreduce():
+            dist.all_reduce(buf)
+
+        res = zd.run_split_lasso(ops, allreduce)
+        np.savez(os.path.join(out_dir, f"lasso_{tag}_{rank}.npz"), **res)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_lasso_world2_matches_oracle(tmp_path):
+    import torch.multiprocessing as mp
+
+    from oracle import zfista_oracle as zo
+
+    port = _free_port()
+    mp.spawn(_worker_lasso, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    A, b, scale, l1, x0 = _lasso_problem()
+    spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
+    for tag, opts in (("fista", dict(nesterov=True)), ("ista", dict(nesterov=False, max_iter=50))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = zo.minimize_proximal_gradient(spec, x0, **opts)
+        outs = [np.load(tmp_path / f"lasso_{tag}_{r}.npz") for r in range(2)]
+        np.testing.assert_array_equal(outs[0]["x"], outs[1]["x"])      # ranks agree bit for bit
+        for o in outs:
+            assert int(o["nit"]) == ref["nit"]
+            assert int(o["status"]) == ref["status"]
+            np.testing.assert_allclose(o["x"], ref["x"], rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(float(o["fun"]), ref["fun"], rtol=1e-10)
+        # one process, one shard == the same protocol without an exchange
+        solo = zd.run_split_lasso(NumpySplitLasso(A, b, scale, l1, x0, opts), lambda: None)
+        assert solo["nit"] == ref["nit"]
+        np.testing.assert_allclose(solo["x"], ref["x"], rtol=1e-9, atol=1e-10)

@@ -10,6 +10,7 @@
 //   t_{k+1}(a, b), extrapolation y = x + (t_k - 1)/t_{k+1} (x - x_prev)
 // State (y, x_prev, x, J rows) lives in the warp's slice of shared memory.
 #include <cstdio>
+#include <mutex>
 
 #include "zf_dual.cuh"
 #include "zf_host.h"
@@ -492,30 +493,73 @@ extern "C" int zf_solve_batched_device(const zf_problem* problem, const zf_optio
 }
 
 namespace {
-// RAII device buffer used by the *_host entry points.
-struct DevBuf {
-  void* p = nullptr;
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
-  ~DevBuf() { if (p) cudaFree(p); }
-  template <class T> T* as() { return static_cast<T*>(p); }
-};
 #define ZF_CUDA(call)                                               \
   do {                                                              \
     cudaError_t _e = (call);                                        \
     if (_e != cudaSuccess) return zf::zf_fail_cuda(_e, #call);      \
   } while (0)
 
+// Device scratch of the *_host entry points: one grow-only block per process, carved per
+// call (cudaMalloc / cudaFree cost ~0.3 ms each and cudaFree synchronises; a 1024-start
+// solve is ~1 ms of kernel).  Calls through the host entry points are serialised by the lock.
+struct Arena {
+  std::mutex mu;
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  int device = -1;
+  int reset(size_t need) {
+    int dev = 0;
+    ZF_CUDA(cudaGetDevice(&dev));
+    if (dev != device || need > cap) {
+      if (base) {
+        cudaSetDevice(device);
+        cudaFree(base);
+        cudaSetDevice(dev);
+        base = nullptr;
+        cap = 0;
+      }
+      size_t want = need + (need >> 2) + (1u << 20);
+      ZF_CUDA(cudaMalloc((void**)&base, want));
+      cap = want;
+      device = dev;
+    }
+    off = 0;
+    return ZF_OK;
+  }
+  void* take(size_t bytes) {
+    void* p = base + off;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  }
+};
+Arena g_arena;
+inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// a slice of the arena (same interface the RAII buffers had)
+struct DevBuf {
+  void* p = nullptr;
+  void take(size_t bytes) { p = g_arena.take(bytes ? bytes : 8); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
 // copies the host-side pointer members of a zf_problem (bounds arrays, A, b) to device
 struct DevProblem {
   zf_problem P;
   DevBuf lo, hi, A, b;
+  static size_t bytes(const zf_problem& hp) {
+    size_t t = 0;
+    if (hp.has_bounds && hp.bounds_are_arrays) t += 2 * pad256((size_t)hp.n_features * 8);
+    if (hp.kind == ZF_LSQ_L1 && hp.n_rows > 0)
+      t += pad256((size_t)hp.n_rows * hp.n_features * 8) + pad256((size_t)hp.n_rows * 8);
+    return t + 1024;
+  }
   int upload(const zf_problem& hp, cudaStream_t st) {
     P = hp;
     const size_t nb = (size_t)hp.n_features * sizeof(double);
     if (hp.has_bounds && hp.bounds_are_arrays) {
       if (!hp.lower_v || !hp.upper_v) return zf::zf_fail(ZF_ERR_INVALID, "bounds arrays missing");
-      ZF_CUDA(lo.alloc(nb));
-      ZF_CUDA(hi.alloc(nb));
+      lo.take(nb);
+      hi.take(nb);
       ZF_CUDA(cudaMemcpyAsync(lo.p, hp.lower_v, nb, cudaMemcpyHostToDevice, st));
       ZF_CUDA(cudaMemcpyAsync(hi.p, hp.upper_v, nb, cudaMemcpyHostToDevice, st));
       P.lower_v = lo.as<double>();
@@ -525,8 +569,8 @@ struct DevProblem {
       if (!hp.A || !hp.b || hp.n_rows < 1) return zf::zf_fail(ZF_ERR_INVALID, "LSQ_L1 needs A, b");
       const size_t ab = (size_t)hp.n_rows * hp.n_features * sizeof(double);
       const size_t bb = (size_t)hp.n_rows * sizeof(double);
-      ZF_CUDA(A.alloc(ab));
-      ZF_CUDA(b.alloc(bb));
+      A.take(ab);
+      b.take(bb);
       ZF_CUDA(cudaMemcpyAsync(A.p, hp.A, ab, cudaMemcpyHostToDevice, st));
       ZF_CUDA(cudaMemcpyAsync(b.p, hp.b, bb, cudaMemcpyHostToDevice, st));
       P.A = A.as<double>();
@@ -552,42 +596,51 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
   cudaStream_t st = 0;
   const size_t N = (size_t)n_starts, n = problem->n_features, m = problem->n_objectives;
   const size_t cap = (size_t)opt->trace_capacity;
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  {
+    size_t total = DevProblem::bytes(*problem) + 2 * pad256(N * n * 8) + pad256(N * 16) +
+                   pad256(N * m * 8) + 6 * pad256(N * 8);
+    if (cap > 0)
+      total += pad256(N * cap * 8) + pad256(N * (cap + 1) * m * 8) + pad256(N * (cap + 1) * n * 8);
+    rc = g_arena.reset(total);
+    if (rc != ZF_OK) return rc;
+  }
   DevProblem dp;
   rc = dp.upload(*problem, st);
   if (rc != ZF_OK) return rc;
   DevBuf x0, ab, x, fun, nit, status, lr, nfev, ndual, err, allerrs, allfuns, allvecs;
-  ZF_CUDA(x0.alloc(N * n * 8));
+  x0.take(N * n * 8);
   ZF_CUDA(cudaMemcpyAsync(x0.p, h_x0, N * n * 8, cudaMemcpyHostToDevice, st));
   if (h_ab) {
-    ZF_CUDA(ab.alloc(N * 2 * 8));
+    ab.take(N * 2 * 8);
     ZF_CUDA(cudaMemcpyAsync(ab.p, h_ab, N * 2 * 8, cudaMemcpyHostToDevice, st));
   }
-  ZF_CUDA(x.alloc(N * n * 8));
-  ZF_CUDA(fun.alloc(N * m * 8));
-  ZF_CUDA(nit.alloc(N * 8));
-  ZF_CUDA(status.alloc(N * 4));
+  x.take(N * n * 8);
+  fun.take(N * m * 8);
+  nit.take(N * 8);
+  status.take(N * 4);
   zf_result R{};
   R.x = x.as<double>();
   R.fun = fun.as<double>();
   R.nit = nit.as<int64_t>();
   R.status = status.as<int32_t>();
-  if (h_out->lr) { ZF_CUDA(lr.alloc(N * 8)); R.lr = lr.as<double>(); }
-  if (h_out->nfev) { ZF_CUDA(nfev.alloc(N * 8)); R.nfev = nfev.as<int64_t>(); }
-  if (h_out->n_dual) { ZF_CUDA(ndual.alloc(N * 8)); R.n_dual = ndual.as<int64_t>(); }
-  if (h_out->err) { ZF_CUDA(err.alloc(N * 8)); R.err = err.as<double>(); }
+  if (h_out->lr) { lr.take(N * 8); R.lr = lr.as<double>(); }
+  if (h_out->nfev) { nfev.take(N * 8); R.nfev = nfev.as<int64_t>(); }
+  if (h_out->n_dual) { ndual.take(N * 8); R.n_dual = ndual.as<int64_t>(); }
+  if (h_out->err) { err.take(N * 8); R.err = err.as<double>(); }
   if (cap > 0) {
     if (h_out->allerrs) {
-      ZF_CUDA(allerrs.alloc(N * cap * 8));
+      allerrs.take(N * cap * 8);
       ZF_CUDA(cudaMemsetAsync(allerrs.p, 0, N * cap * 8, st));
       R.allerrs = allerrs.as<double>();
     }
     if (h_out->allfuns) {
-      ZF_CUDA(allfuns.alloc(N * (cap + 1) * m * 8));
+      allfuns.take(N * (cap + 1) * m * 8);
       ZF_CUDA(cudaMemsetAsync(allfuns.p, 0, N * (cap + 1) * m * 8, st));
       R.allfuns = allfuns.as<double>();
     }
     if (h_out->allvecs) {
-      ZF_CUDA(allvecs.alloc(N * (cap + 1) * n * 8));
+      allvecs.take(N * (cap + 1) * n * 8);
       ZF_CUDA(cudaMemsetAsync(allvecs.p, 0, N * (cap + 1) * n * 8, st));
       R.allvecs = allvecs.as<double>();
     }
@@ -623,21 +676,25 @@ extern "C" int zf_solve_subproblem_host(const zf_problem* problem, const zf_opti
   if (rc != ZF_OK) return rc;
   cudaStream_t st = 0;
   const size_t N = (size_t)n, nf = problem->n_features, m = problem->n_objectives;
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  rc = g_arena.reset(DevProblem::bytes(*problem) + 3 * pad256(N * nf * 8) + 3 * pad256(N * 8) +
+                     pad256(N * m * 8));
+  if (rc != ZF_OK) return rc;
   DevProblem dp;
   rc = dp.upload(*problem, st);
   if (rc != ZF_OK) return rc;
   DevBuf y, xo, lr, dep, x, fun, w;
-  ZF_CUDA(y.alloc(N * nf * 8));
-  ZF_CUDA(xo.alloc(N * nf * 8));
-  ZF_CUDA(lr.alloc(N * 8));
-  ZF_CUDA(x.alloc(N * nf * 8));
-  ZF_CUDA(fun.alloc(N * 8));
-  ZF_CUDA(w.alloc(N * m * 8));
+  y.take(N * nf * 8);
+  xo.take(N * nf * 8);
+  lr.take(N * 8);
+  x.take(N * nf * 8);
+  fun.take(N * 8);
+  w.take(N * m * 8);
   ZF_CUDA(cudaMemcpyAsync(y.p, h_y, N * nf * 8, cudaMemcpyHostToDevice, st));
   ZF_CUDA(cudaMemcpyAsync(xo.p, h_x_old, N * nf * 8, cudaMemcpyHostToDevice, st));
   ZF_CUDA(cudaMemcpyAsync(lr.p, h_lr, N * 8, cudaMemcpyHostToDevice, st));
   if (h_deprecated) {
-    ZF_CUDA(dep.alloc(N * 4));
+    dep.take(N * 4);
     ZF_CUDA(cudaMemcpyAsync(dep.p, h_deprecated, N * 4, cudaMemcpyHostToDevice, st));
   }
   LaunchArgs L{};
@@ -672,20 +729,24 @@ extern "C" int zf_problem_eval_host(const zf_problem* problem, int64_t n, const 
   if (rc != ZF_OK) return rc;
   cudaStream_t st = 0;
   const size_t N = (size_t)n, nf = problem->n_features, m = problem->n_objectives;
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  rc = g_arena.reset(DevProblem::bytes(*problem) + 2 * pad256(N * nf * 8) + 3 * pad256(N * m * 8) +
+                     pad256(N * m * nf * 8));
+  if (rc != ZF_OK) return rc;
   DevProblem dp;
   rc = dp.upload(*problem, st);
   if (rc != ZF_OK) return rc;
   DevBuf X, W, f, g, jac, prox;
-  ZF_CUDA(X.alloc(N * nf * 8));
+  X.take(N * nf * 8);
   ZF_CUDA(cudaMemcpyAsync(X.p, h_X, N * nf * 8, cudaMemcpyHostToDevice, st));
   if (h_W) {
-    ZF_CUDA(W.alloc(N * m * 8));
+    W.take(N * m * 8);
     ZF_CUDA(cudaMemcpyAsync(W.p, h_W, N * m * 8, cudaMemcpyHostToDevice, st));
   }
-  if (h_f) ZF_CUDA(f.alloc(N * m * 8));
-  if (h_g) ZF_CUDA(g.alloc(N * m * 8));
-  if (h_jac) ZF_CUDA(jac.alloc(N * m * nf * 8));
-  if (h_prox) ZF_CUDA(prox.alloc(N * nf * 8));
+  if (h_f) f.take(N * m * 8);
+  if (h_g) g.take(N * m * 8);
+  if (h_jac) jac.take(N * m * nf * 8);
+  if (h_prox) prox.take(N * nf * 8);
   LaunchArgs L{};
   L.op = Op::Eval;
   L.P = dp.P;

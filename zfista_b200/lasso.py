@@ -180,16 +180,27 @@ class DenseLasso:
             else:
                 if cap:
                     raise NotImplementedError("return_all is not available on the row-sharded path")
-                nxt = C.c_int32(0)
-                _lib.check(L.zf_lasso_begin(self._h, C.byref(opts), C.c_void_p(x0d.data_ptr())))
-                self._allreduce()
-                _lib.check(L.zf_lasso_step(self._h, C.byref(nxt)))
-                while nxt.value != 2:
-                    _lib.check(L.zf_lasso_grad(self._h, nxt.value))
-                    self._allreduce()
-                    _lib.check(L.zf_lasso_step(self._h, C.byref(nxt)))
-                _lib.check(L.zf_lasso_finish(self._h, C.c_void_p(xd.data_ptr()), C.byref(fun),
-                                             C.byref(nit), C.byref(status)))
+                from .distributed import run_split_lasso
+
+                h = self._h
+
+                class _Ops:
+                    def begin(self_):
+                        _lib.check(L.zf_lasso_begin(h, C.byref(opts), C.c_void_p(x0d.data_ptr())))
+
+                    def grad(self_, which):
+                        _lib.check(L.zf_lasso_grad(h, int(which)))
+
+                    def step(self_):
+                        nxt = C.c_int32(0)
+                        _lib.check(L.zf_lasso_step(h, C.byref(nxt)))
+                        return nxt.value
+
+                    def finish(self_):
+                        _lib.check(L.zf_lasso_finish(h, C.c_void_p(xd.data_ptr()), C.byref(fun),
+                                                     C.byref(nit), C.byref(status)))
+
+                run_split_lasso(_Ops(), self._allreduce)
         st, k = int(status.value), int(nit.value)
         res = OptimizeResult(
             x=xd if return_device else xd.cpu().numpy(), fun=float(fun.value), nit=k,
