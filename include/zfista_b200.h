@@ -174,6 +174,31 @@ int zf_lasso_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
 /* one gradient pass only (bench / roofline): grad = 2*scale*A^T(Ax-b), returns f */
 int zf_lasso_gradient_device(zf_lasso* h, const double* d_x, double* d_grad, double* d_f);
 
+/* ---- (c') cameraman-style deblurring:  ||R W x - b||^2 + l1*||x||_1 ----------------
+ * replaces minimize_proximal_gradient(f, g, jac_f, prox_wsum_g, x0, ...) with the closures of
+ * examples/cameraman.ipynb ("Objective function" cell): R = correlate2d(., kernel,
+ * mode="same", boundary="symm"), W = inverse single-level 2-D Haar transform of the
+ * coefficient vector [cA, cH, cV, cD] (each height/2 x width/2).  The notebook's joblib
+ * fan-out over (a, b) momentum pairs becomes n_runs runs of one call: x0 is one vector
+ * (x0_is_batched = 0) or n_runs x (height*width); ab is n_runs x 2 (host) or NULL.
+ * Results: x (n_runs x n), fun / nit / status / lr / err (n_runs), allerrs (n_runs x cap),
+ * allfuns (n_runs x (cap+1)); allvecs is not recorded.                                   */
+typedef struct zf_deblur zf_deblur;
+
+int zf_deblur_create(zf_deblur** out, int32_t height, int32_t width, const double* h_kernel,
+                     int32_t ksize, const double* h_observed, double l1, int32_t max_runs,
+                     void* cuda_stream);
+void zf_deblur_destroy(zf_deblur* h);
+int zf_deblur_solve_host(zf_deblur* h, const zf_options* opt, int64_t n_runs,
+                         const double* h_x0, int32_t x0_is_batched, const double* h_ab,
+                         const zf_result* h_out);
+int zf_deblur_solve_device(zf_deblur* h, const zf_options* opt, int64_t n_runs,
+                           const double* d_x0, int32_t x0_is_batched, const double* h_ab,
+                           const zf_result* d_out);
+/* the closures themselves at n_points <= max_runs points: f, g (n_points), jac (n_points x n) */
+int zf_deblur_eval_host(zf_deblur* h, int64_t n_points, const double* h_X, double* h_f,
+                        double* h_g, double* h_jac);
+
 #ifdef __cplusplus
 }
 #endif

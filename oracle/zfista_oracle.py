@@ -146,6 +146,8 @@ def f(spec: ProblemSpec, x):
         return (io * np.inner(jf, x) - 1) ** 2
     if k == "LeastSquaresL1":
         return np.linalg.norm(spec.A @ x - spec.b) ** 2 * spec.scale
+    if k == "Closures":        # caller-supplied numpy closures (oracle/deblur_oracle.py)
+        return spec.extra["f"](x)
     raise ValueError(k)
 
 
@@ -195,6 +197,8 @@ def jac_f(spec: ProblemSpec, x):
         return 2 * io[:, None] * jf * (io[:, None] * np.inner(jf, x) - 1)
     if k == "LeastSquaresL1":
         return spec.A.T @ (spec.A @ x - spec.b) * (2 * spec.scale)
+    if k == "Closures":
+        return spec.extra["jac_f"](x)
     raise ValueError(k)
 
 
@@ -209,6 +213,8 @@ def soft_threshold(x, t):
 def g(spec: ProblemSpec, x):
     if spec.kind == "LeastSquaresL1":
         return spec.l1 * np.linalg.norm(x, ord=1)
+    if spec.kind == "Closures":
+        return spec.extra["g"](x)
     m = spec.n_objectives
     if spec.has_bounds:
         if (x < spec.lower).any() or (x > spec.upper).any():
@@ -222,6 +228,8 @@ def g(spec: ProblemSpec, x):
 def prox_wsum_g(spec: ProblemSpec, weight, x):
     if spec.kind == "LeastSquaresL1":
         return soft_threshold(x, spec.l1 * weight)
+    if spec.kind == "Closures":
+        return spec.extra["prox_wsum_g"](weight, x)
     if spec.l1_ratios is not None:
         coef = weight * spec.l1_ratios
         s = spec.l1_shifts

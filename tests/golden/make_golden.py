@@ -253,6 +253,66 @@ def gen_lasso_cases(only, overwrite):
     np.savez(path, **save)
 
 
+def gen_deblur_cases(only, overwrite):
+    """Cameraman-notebook workload at small sizes: the UNMODIFIED reference solver
+    (zfista.minimize_proximal_gradient) driven by the notebook's closures as restated in
+    oracle/deblur_oracle.py (fixed step lr = 1/L, decay_rate = 1, several (a, b) pairs, and
+    one backtracking run)."""
+    from zfista import minimize_proximal_gradient
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import deblur_oracle as do
+
+    path = os.path.join(HERE, "deblur.npz")
+    if only and only not in "deblur":
+        return
+    if os.path.exists(path) and not overwrite:
+        return
+    warnings.simplefilter("ignore")
+    save = {}
+    for tag, (h, w, ks, sigma, l1) in {
+        "s32": (32, 32, 9, 4.0, 2e-5),
+        "s48x64": (48, 64, 5, 1.5, 1e-4),
+    }.items():
+        kernel = do.gaussian_kernel(ks, sigma)
+        kernel = kernel / kernel.sum()
+        img, obs, _ = do.synthetic_scene(h, w, seed=h + w, kernel=kernel)
+        f, g, jac_f, prox = do.closures(obs, kernel, l1)
+        x0 = do.dwt_array(obs)
+        L = do.lipschitz(kernel)
+        save[f"{tag}_observed"], save[f"{tag}_kernel"] = obs, kernel
+        save[f"{tag}_l1"], save[f"{tag}_L"], save[f"{tag}_x0"] = np.array(l1), np.array(L), x0
+        pairs = [AB_GRID[i] for i in (0, 2, 4, 8, 14)]
+        save[f"{tag}_pairs"] = np.array(pairs)
+        for i, ab in enumerate(pairs):
+            r = minimize_proximal_gradient(f, g, jac_f, prox, x0, lr=1 / L, decay_rate=1,
+                                           nesterov=True, nesterov_ratio=ab, return_all=True,
+                                           max_iter=400, tol=1e-5)
+            save[f"{tag}_fixed{i}_x"] = np.asarray(r.x)
+            save[f"{tag}_fixed{i}_fun"] = np.asarray(r.fun).reshape(-1)
+            save[f"{tag}_fixed{i}_nit"] = np.array(r.nit)
+            save[f"{tag}_fixed{i}_success"] = np.array(bool(r.success))
+            save[f"{tag}_fixed{i}_allerrs"] = np.asarray(r.allerrs)
+            save[f"{tag}_fixed{i}_allfuns"] = np.asarray(r.allfuns).reshape(-1)
+            print(f"[golden] deblur {tag} fixed ab={ab}: nit={r.nit} ok={r.success}", flush=True)
+        for name, opts in {"bt_fista": dict(nesterov=True), "bt_ista": dict(nesterov=False)}.items():
+            r = minimize_proximal_gradient(f, g, jac_f, prox, x0, return_all=True, max_iter=150,
+                                           **opts)
+            save[f"{tag}_{name}_x"] = np.asarray(r.x)
+            save[f"{tag}_{name}_fun"] = np.asarray(r.fun).reshape(-1)
+            save[f"{tag}_{name}_nit"] = np.array(r.nit)
+            save[f"{tag}_{name}_allerrs"] = np.asarray(r.allerrs)
+            save[f"{tag}_{name}_allfuns"] = np.asarray(r.allfuns).reshape(-1)
+            print(f"[golden] deblur {tag} {name}: nit={r.nit} ok={r.success}", flush=True)
+        # closure values at random points (pins W, W^T, R as used by the solver)
+        rng = np.random.RandomState(3)
+        X = rng.standard_normal((3, h * w)) * 0.1
+        save[f"{tag}_evalX"] = X
+        save[f"{tag}_evalf"] = np.array([f(x)[0] for x in X])
+        save[f"{tag}_evaljac"] = np.array([jac_f(x)[0] for x in X])
+    np.savez(path, **save)
+
+
 def gen_subproblem_cases(only, overwrite):
     """Direct fixtures of zfista.proximal_gradient._solve_subproblem (35-209):
     (yk, xk_old, lr) -> (weight, x, fun) for m = 2 (bounded Brent) and m >= 3
@@ -331,5 +391,6 @@ if __name__ == "__main__":
     a = ap.parse_args()
     gen_problem_eval_cases(a.only, a.overwrite)
     gen_lasso_cases(a.only, a.overwrite)
+    gen_deblur_cases(a.only, a.overwrite)
     gen_subproblem_cases(a.only, a.overwrite)
     gen_problem_cases(a.only, a.jobs, a.overwrite)

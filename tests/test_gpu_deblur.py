@@ -1,0 +1,127 @@
+"""GPU parity of the cameraman-style deblurring path (csrc/zf_deblur.cu via
+zfista_b200.deblur.HaarDeblurL1) against the reference-generated fixtures and the oracle."""
+import warnings
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rel=1e-8):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    np.testing.assert_allclose(a, b, rtol=rel, atol=rel * max(1.0, float(np.max(np.abs(b)))))
+
+
+def _problem(d, tag, max_runs=16):
+    from zfista_b200.deblur import HaarDeblurL1
+
+    return HaarDeblurL1(d[f"{tag}_observed"], d[f"{tag}_kernel"], float(d[f"{tag}_l1"]),
+                        max_runs=max_runs)
+
+
+@pytest.mark.parametrize("tag", ["s32", "s48x64"])
+def test_closures_match_reference_values(gpu, tag):
+    d = helpers.load("deblur")
+    prob = _problem(d, tag)
+    for k, x in enumerate(d[f"{tag}_evalX"]):
+        _close(prob.f(x), d[f"{tag}_evalf"][k], rel=1e-12)
+        _close(prob.jac_f(x)[0], d[f"{tag}_evaljac"][k], rel=1e-12)
+        _close(prob.g(x), float(d[f"{tag}_l1"]) * np.abs(x).sum(), rel=1e-13)
+    np.testing.assert_array_equal(prob.dwt_array(d[f"{tag}_observed"]), d[f"{tag}_x0"])
+
+
+@pytest.mark.parametrize("tag", ["s32", "s48x64"])
+def test_fixed_step_ab_sweep_matches_reference(gpu, tag):
+    """The notebook's run: lr = 1/L, decay_rate = 1, one run per (a, b) pair, all in one call:
+    the same nit per pair, x / F / traces within 1e-8."""
+    d = helpers.load("deblur")
+    prob = _problem(d, tag)
+    pairs, L, x0 = d[f"{tag}_pairs"], float(d[f"{tag}_L"]), d[f"{tag}_x0"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = prob.minimize_proximal_gradient_batched(x0, pairs, lr=1 / L, decay_rate=1,
+                                                      nesterov=True, return_all=True,
+                                                      max_iter=400, tol=1e-5)
+        fast = prob.minimize_proximal_gradient_batched(x0, pairs, lr=1 / L, decay_rate=1,
+                                                       nesterov=True, max_iter=400, tol=1e-5)
+    for i, r in enumerate(res):
+        assert r.nit == int(d[f"{tag}_fixed{i}_nit"]), i
+        assert r.success == bool(d[f"{tag}_fixed{i}_success"])
+        _close(r.x, d[f"{tag}_fixed{i}_x"])
+        _close(r.fun, d[f"{tag}_fixed{i}_fun"])
+        _close(r.allerrs, d[f"{tag}_fixed{i}_allerrs"], rel=1e-6)
+        _close(np.ravel(r.allfuns), d[f"{tag}_fixed{i}_allfuns"])
+        # without traces F is only evaluated once at the end; x must be bit-identical
+        assert fast[i].nit == r.nit and fast[i].allerrs is None
+        np.testing.assert_array_equal(fast[i].x, r.x)
+        _close(fast[i].fun, r.fun, rel=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["s32", "s48x64"])
+def test_backtracking_runs_match_reference(gpu, tag):
+    d = helpers.load("deblur")
+    prob = _problem(d, tag)
+    x0 = d[f"{tag}_x0"]
+    for name, nest in (("bt_fista", True), ("bt_ista", False)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = prob.minimize_proximal_gradient(x0, nesterov=nest, return_all=True, max_iter=150)
+        assert r.nit == int(d[f"{tag}_{name}_nit"])
+        _close(r.x, d[f"{tag}_{name}_x"])
+        _close(r.fun, d[f"{tag}_{name}_fun"])
+        _close(r.allerrs, d[f"{tag}_{name}_allerrs"], rel=1e-6)
+        _close(np.ravel(r.allfuns), d[f"{tag}_{name}_allfuns"])
+
+
+@pytest.mark.parametrize("shape,ks", [((20, 36), 3), ((70, 34), 7), ((64, 96), 9)])
+def test_seeded_scenes_match_oracle(gpu, shape, ks):
+    """Ragged tiles (sides not multiples of 32), every supported kernel radius."""
+    from oracle import deblur_oracle as do
+    from zfista_b200.deblur import HaarDeblurL1
+
+    kernel = do.gaussian_kernel(ks, ks / 3.0)
+    kernel /= kernel.sum()
+    _, obs, _ = do.synthetic_scene(*shape, seed=ks, kernel=kernel)
+    prob = HaarDeblurL1(obs, kernel, 1e-4)
+    x0 = do.dwt_array(obs)
+    L = do.lipschitz(kernel)
+    opts = dict(lr=1 / L, decay_rate=1, nesterov=True, nesterov_ratio=(0.25, 1 / 64),
+                max_iter=120, tol=1e-6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = do.minimize(obs, kernel, 1e-4, x0, **opts)
+        res = prob.minimize_proximal_gradient(x0, **opts)
+    assert res.nit == ref["nit"]
+    _close(res.x, ref["x"])
+    _close(res.fun, ref["fun"])
+
+
+def test_cameraman_size_properties(gpu):
+    """256 x 256, 9 x 9 blur, the notebook's 15 (a, b) pairs in one call (BASELINE
+    configs[1] shape): runs are independent of their batch (bit-identical alone), F
+    decreases from F(x0), and the deblurred image is closer to the truth than the input."""
+    from oracle import deblur_oracle as do
+    from zfista_b200.deblur import HaarDeblurL1
+
+    kernel = do.gaussian_kernel(9, 4.0)
+    kernel /= kernel.sum()
+    img, obs, _ = do.synthetic_scene(256, 256, seed=1, kernel=kernel)
+    prob = HaarDeblurL1(obs, kernel, 2e-5)
+    x0 = prob.dwt_array(obs)
+    L = do.lipschitz(kernel)
+    pairs = np.array(helpers.AB_GRID)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = prob.minimize_proximal_gradient_batched(x0, pairs, lr=1 / L, decay_rate=1,
+                                                      max_iter=300, return_all=True)
+        alone = prob.minimize_proximal_gradient_batched(x0, pairs[4:5], lr=1 / L, decay_rate=1,
+                                                        max_iter=300)
+    np.testing.assert_array_equal(alone[0].x, res[4].x)
+    for r in res:
+        F = np.ravel(r.allfuns)
+        assert F[-1] < F[0]
+        rec = prob.idwt_array(r.x)
+        assert np.linalg.norm(rec - img) < np.linalg.norm(obs - img)

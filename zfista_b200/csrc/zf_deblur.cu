@@ -1,0 +1,704 @@
+// Cameraman-style deblurring (examples/cameraman.ipynb "Objective function" cell):
+//     f(x) = || R W x - b ||^2,  g(x) = l1 ||x||_1,  jac_f(x) = 2 W^T R (R W x - b)
+// R = correlate2d(., K, mode="same", boundary="symm") with an odd K up to 9x9,
+// W = inverse single-level 2-D Haar transform of the coefficient vector [cA,cH,cV,cD].
+// The notebook runs minimize_proximal_gradient once per (a, b) momentum pair under joblib;
+// here every pair is a RUN of one batched solve.  A run's state machine (line search, stop
+// test, t_k, momentum) lives in device memory, so a whole round
+//     grad (tile kernel) -> prox (elementwise) -> [F(candidate) (tile kernel)] -> decide
+// is replayed without any host round trip; the host only polls "runs still active" once per
+// chunk of rounds.  All reductions have a fixed order: runs are bit reproducible.
+//
+// Tile kernel: CTA = 32x32 image tile of one run.  U = W y on the tile + 2R halo (computed
+// from the coefficient vectors, y = x + mom (x - x_prev) formed on the fly), V = R U - b on
+// tile + R halo (symmetric reflection at the image border), then R V on the tile and the
+// forward Haar transform of each 2x2 block -> gradient coefficients.  Everything between the
+// coefficient loads and the gradient store stays in shared memory.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "zf_common.cuh"
+#include "zf_host.h"
+
+namespace zf {
+
+constexpr int DB_T = 32;
+constexpr int DB_THREADS = 256;
+constexpr int DB_MAXR = 4;
+constexpr int DB_UR = DB_T + 4 * DB_MAXR;   // 48
+constexpr int DB_VR = DB_T + 2 * DB_MAXR;   // 40
+
+enum DeblurPhase { DP_INIT = 0, DP_NEW = 1, DP_RETRY = 2, DP_FINAL = 3, DP_DONE = 4 };
+
+struct DeblurRun {
+  double lr, t_prev, mom, F_prev, F_x, f_y, sub_fun, err, na, nb, abs_cand;
+  long long nit;
+  int status, phase, cur, bt, res_buf, pad;
+};
+
+struct DeblurDims {
+  int H, W, h2, w2, tiles_x, tiles_y, n_tiles, R;
+  long long n;        // H * W
+  int prox_blocks;
+};
+
+struct DeblurSums { double gd, dd, abs1, maxd; };
+
+__constant__ double c_kernel[81];
+
+__device__ __forceinline__ int db_reflect(int i, int n) {
+  int r = i < 0 ? -i - 1 : (i >= n ? 2 * n - i - 1 : i);
+  return r < 0 ? 0 : (r >= n ? n - 1 : r);
+}
+
+// y = x + mom * (x - x_prev) with numpy's rounding (mul and add separately; identical at
+// every site that forms y)
+__device__ __forceinline__ double db_extrap(double x, double xp, double mom) {
+  return __dadd_rn(x, __dmul_rn(mom, __dsub_rn(x, xp)));
+}
+
+// MODE 0: gradient round (U halo 2R, V halo R, writes Y, G, f(y) partial)
+// MODE 1: F evaluation   (U halo R, V tile only, f partial + ||x||_1 partial)
+template <int R, int MODE>
+__global__ void __launch_bounds__(DB_THREADS)
+deblur_tile_kernel(DeblurDims d, const DeblurRun* __restrict__ runs, double* __restrict__ X0,
+                   double* __restrict__ X1, double* __restrict__ Y, double* __restrict__ G,
+                   const double* __restrict__ b, double* __restrict__ f_part,
+                   double* __restrict__ abs_part) {
+  constexpr int T = DB_T;
+  constexpr int HV = (MODE == 0) ? R : 0;         // halo of V
+  // halo of U, rounded up to even so that the region is aligned to the 2x2 Haar blocks
+  constexpr int HU = (((MODE == 0) ? 2 * R : R) + 1) & ~1;
+  constexpr int OFF = HU - HV - R;                // U index of tap (0,0) of V position (0,0)
+  constexpr int UR = T + 2 * HU, VR = T + 2 * HV;
+  constexpr int K = 2 * R + 1;
+  const int run = blockIdx.y;
+  const DeblurRun st = runs[run];
+  const double *xa, *xb;
+  double mom = 0.0;
+  if (MODE == 0) {
+    if (st.phase != DP_NEW) return;
+    xa = (st.cur ? X1 : X0) + (long long)run * d.n;
+    xb = (st.cur ? X0 : X1) + (long long)run * d.n;
+    mom = st.mom;
+  } else {
+    int buf;
+    if (st.phase == DP_INIT) buf = st.cur;
+    else if (st.phase == DP_NEW || st.phase == DP_RETRY) buf = 1 - st.cur;
+    else if (st.phase == DP_FINAL) buf = st.res_buf;
+    else return;
+    xa = (buf ? X1 : X0) + (long long)run * d.n;
+    xb = xa;
+  }
+  __shared__ double U[DB_UR][DB_UR + 1];
+  __shared__ double V[DB_VR][DB_VR + 1];
+  __shared__ double red[2][DB_THREADS / 32];
+  const int tid = threadIdx.x;
+  const int tyo = (blockIdx.x / d.tiles_x) * T, txo = (blockIdx.x % d.tiles_x) * T;
+  const long long q = (long long)d.h2 * d.w2;
+  double abs_acc = 0.0;
+  // ---- 1. U = W y on the halo region, by 2x2 blocks (one coefficient quadruple each)
+  constexpr int UB = UR / 2;
+  for (int blk = tid; blk < UB * UB; blk += DB_THREADS) {
+    const int lbi = blk / UB, lbj = blk % UB;
+    const int i0 = tyo - HU + 2 * lbi, j0 = txo - HU + 2 * lbj;
+    const int gi0 = db_reflect(i0, d.H), gi1 = db_reflect(i0 + 1, d.H);
+    const int gj0 = db_reflect(j0, d.W), gj1 = db_reflect(j0 + 1, d.W);
+    const long long o = (long long)(gi0 >> 1) * d.w2 + (gj0 >> 1);
+    double ca = xa[o], ch = xa[q + o], cv = xa[2 * q + o], cd = xa[3 * q + o];
+    if (MODE == 0) {
+      ca = db_extrap(ca, xb[o], mom);
+      ch = db_extrap(ch, xb[q + o], mom);
+      cv = db_extrap(cv, xb[2 * q + o], mom);
+      cd = db_extrap(cd, xb[3 * q + o], mom);
+    }
+    const bool interior = (i0 >= tyo) && (i0 < tyo + T) && (j0 >= txo) && (j0 < txo + T) &&
+                          (i0 < d.H) && (j0 < d.W);
+    if (interior) {
+      if (MODE == 0) {
+        double* y = Y + (long long)run * d.n;
+        y[o] = ca; y[q + o] = ch; y[2 * q + o] = cv; y[3 * q + o] = cd;
+      } else {
+        abs_acc += fabs(ca) + fabs(ch) + fabs(cv) + fabs(cd);
+      }
+    }
+#pragma unroll
+    for (int di = 0; di < 2; ++di) {
+      const int gi = di ? gi1 : gi0;
+      const double sh = (gi & 1) ? -1.0 : 1.0;
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj) {
+        const int gj = dj ? gj1 : gj0;
+        const double sv = (gj & 1) ? -1.0 : 1.0;
+        // idwt2 (haar): (cA +- cH +- cV +- cD) / 2, summed left to right
+        U[2 * lbi + di][2 * lbj + dj] = (((ca + sh * ch) + sv * cv) + (sh * sv) * cd) / 2.0;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 2. V = R U - b at the in-image positions of the V region (vertical strips of 4)
+  double fsum = 0.0;
+  constexpr int VS = (VR + 3) / 4;
+  for (int task = tid; task < VS * VR; task += DB_THREADS) {
+    const int li0 = 4 * (task / VR), lj = task % VR;
+    const int gj = txo - HV + lj;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int v = 0; v < K; ++v) {
+      double col[4 + 2 * R];
+#pragma unroll
+      for (int k = 0; k < 4 + 2 * R; ++k) col[k] = U[li0 + k + OFF][lj + v + OFF];
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        const double w = c_kernel[u * K + v];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] += w * col[o + u];
+      }
+    }
+    if (gj >= 0 && gj < d.W) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int li = li0 + o, gi = tyo - HV + li;
+        if (li < VR && gi >= 0 && gi < d.H) {
+          const double val = acc[o] - b[(long long)gi * d.W + gj];
+          V[li][lj] = val;
+          if (li >= HV && li < HV + T && lj >= HV && lj < HV + T) fsum += val * val;
+        }
+      }
+    }
+  }
+  // block reduction of the f partial (and ||x||_1 partial), fixed order
+  fsum = warp_sum(fsum);
+  abs_acc = warp_sum(abs_acc);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = fsum; red[1][tid >> 5] = abs_acc; }
+  __syncthreads();
+  if (tid == 0) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < DB_THREADS / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; }
+    f_part[(long long)run * d.n_tiles + blockIdx.x] = t0;
+    if (MODE == 1) abs_part[(long long)run * d.n_tiles + blockIdx.x] = t1;
+  }
+  if (MODE == 1) return;
+  // ---- 3. symmetric reflection of V into the out-of-image halo positions
+  for (int idx = tid; idx < VR * VR; idx += DB_THREADS) {
+    const int li = idx / VR, lj = idx % VR;
+    const int gi = tyo - HV + li, gj = txo - HV + lj;
+    if (gi < 0 || gi >= d.H || gj < 0 || gj >= d.W) {
+      const int si = db_reflect(gi, d.H) - (tyo - HV), sj = db_reflect(gj, d.W) - (txo - HV);
+      if (si >= 0 && si < VR && sj >= 0 && sj < VR) V[li][lj] = V[si][sj];
+      else V[li][lj] = 0.0;   // never read by an in-image output
+    }
+  }
+  __syncthreads();
+  // ---- 4. Wimg = R V on the tile (one vertical strip of 4 per thread), into U's storage
+  {
+    const int li0 = 4 * (tid / T), lj = tid % T;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int v = 0; v < K; ++v) {
+      double col[4 + 2 * R];
+#pragma unroll
+      for (int k = 0; k < 4 + 2 * R; ++k) col[k] = V[li0 + k][lj + v];
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        const double w = c_kernel[u * K + v];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] += w * col[o + u];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) U[li0 + o][lj] = acc[o];
+  }
+  __syncthreads();
+  // ---- 5. gradient coefficients = 2 * dwt2(Wimg) per 2x2 block
+  {
+    const int bi = tid / (T / 2), bj = tid % (T / 2);
+    const int gi = tyo + 2 * bi, gj = txo + 2 * bj;
+    if (gi < d.H && gj < d.W) {
+      const double p00 = U[2 * bi][2 * bj], p01 = U[2 * bi][2 * bj + 1];
+      const double p10 = U[2 * bi + 1][2 * bj], p11 = U[2 * bi + 1][2 * bj + 1];
+      const long long o = (long long)(gi >> 1) * d.w2 + (gj >> 1);
+      double* g = G + (long long)run * d.n;
+      g[o] = 2.0 * ((((p00 + p01) + p10) + p11) / 2.0);
+      g[q + o] = 2.0 * ((((p00 + p01) - p10) - p11) / 2.0);
+      g[2 * q + o] = 2.0 * ((((p00 - p01) + p10) - p11) / 2.0);
+      g[3 * q + o] = 2.0 * ((((p00 - p01) - p10) + p11) / 2.0);
+    }
+  }
+}
+
+// candidate x = soft(y - lr g, lr l1) into the run's spare buffer + block partials
+__global__ void __launch_bounds__(DB_THREADS)
+deblur_prox_kernel(DeblurDims d, const DeblurRun* __restrict__ runs, double l1,
+                   double* __restrict__ X0, double* __restrict__ X1,
+                   const double* __restrict__ Y, const double* __restrict__ G,
+                   DeblurSums* __restrict__ psum) {
+  const int run = blockIdx.y;
+  const DeblurRun st = runs[run];
+  if (st.phase != DP_NEW && st.phase != DP_RETRY) return;
+  double* xn = (st.cur ? X0 : X1) + (long long)run * d.n;     // buffer 1 - cur
+  const double* y = Y + (long long)run * d.n;
+  const double* g = G + (long long)run * d.n;
+  const double lr = st.lr, thr = l1 * lr;
+  DeblurSums s{0.0, 0.0, 0.0, 0.0};
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < d.n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double gj = g[j], yj = y[j];
+    const double xj = soft_threshold(yj - lr * gj, thr);
+    const double dd = xj - yj;
+    xn[j] = xj;
+    s.gd += gj * dd;
+    s.dd += dd * dd;
+    s.abs1 += fabs(xj);
+    s.maxd = fmax(s.maxd, fabs(dd));
+  }
+  __shared__ DeblurSums sh[DB_THREADS / 32];
+  s.gd = warp_sum(s.gd);
+  s.dd = warp_sum(s.dd);
+  s.abs1 = warp_sum(s.abs1);
+  s.maxd = warp_max(s.maxd);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    DeblurSums t = sh[0];
+    for (int w = 1; w < DB_THREADS / 32; ++w) {
+      t.gd += sh[w].gd; t.dd += sh[w].dd; t.abs1 += sh[w].abs1; t.maxd = fmax(t.maxd, sh[w].maxd);
+    }
+    psum[(long long)run * d.prox_blocks + blockIdx.x] = t;
+  }
+}
+
+struct DeblurCtl {
+  double tol, tol_internal, decay_rate, l1;
+  long long max_iter;
+  int max_backtrack, nesterov, deprecated, need_F, cap;
+};
+
+// One warp per run: fixed-order reduction of the round's partials, then the reference's
+// scalar logic (proximal_gradient.py:149-155, 279-308, 510-538) by lane 0.
+__global__ void __launch_bounds__(32)
+deblur_decide_kernel(DeblurDims d, DeblurCtl c, DeblurRun* __restrict__ runs,
+                     const double* __restrict__ fy_part, const double* __restrict__ fx_part,
+                     const double* __restrict__ abs_part, const DeblurSums* __restrict__ psum,
+                     double* __restrict__ allerrs, double* __restrict__ allfuns,
+                     unsigned int* __restrict__ n_active) {
+  const int run = blockIdx.x, lane = threadIdx.x;
+  DeblurRun st = runs[run];
+  if (st.phase == DP_DONE) return;
+  double fy = 0.0, fx = 0.0, ax = 0.0;
+  for (int t = lane; t < d.n_tiles; t += 32) {
+    fy += fy_part[(long long)run * d.n_tiles + t];
+    fx += fx_part[(long long)run * d.n_tiles + t];
+    ax += abs_part[(long long)run * d.n_tiles + t];
+  }
+  fy = warp_sum(fy); fx = warp_sum(fx); ax = warp_sum(ax);
+  DeblurSums s{0.0, 0.0, 0.0, 0.0};
+  for (int t = lane; t < d.prox_blocks; t += 32) {
+    const DeblurSums u = psum[(long long)run * d.prox_blocks + t];
+    s.gd += u.gd; s.dd += u.dd; s.abs1 += u.abs1; s.maxd = fmax(s.maxd, u.maxd);
+  }
+  s.gd = warp_sum(s.gd); s.dd = warp_sum(s.dd); s.abs1 = warp_sum(s.abs1);
+  s.maxd = warp_max(s.maxd);
+  if (lane != 0) return;
+  // f = np.linalg.norm(.)**2 : sqrt, then square
+  const double fyv = norm_sq_like_numpy(fy), fxv = norm_sq_like_numpy(fx);
+  bool accepted = false;
+  if (st.phase == DP_INIT) {
+    st.F_prev = fxv + c.l1 * ax;
+    st.F_x = st.F_prev;
+    if (c.cap > 0 && allfuns) allfuns[(long long)run * (c.cap + 1)] = st.F_prev;
+    st.nit = 1;
+    st.phase = DP_NEW;
+  } else if (st.phase == DP_FINAL) {
+    st.F_x = fxv + c.l1 * ax;
+    st.phase = DP_DONE;
+  } else {
+    if (st.phase == DP_NEW) { st.f_y = fyv; st.bt = 0; }
+    double fun = s.gd + c.l1 * s.abs1 + norm_sq_like_numpy(s.dd) / 2.0 / st.lr;
+    if (!c.deprecated) fun += st.f_y - st.F_prev;
+    st.sub_fun = fun;
+    if (c.need_F) {
+      const double Fx = fxv + c.l1 * s.abs1;
+      bool ok;
+      if (c.decay_rate == 1.0) ok = true;
+      else if (c.deprecated) ok = (fxv - st.f_y <= fun + c.tol_internal);
+      else ok = (Fx - st.F_prev <= fun + c.tol_internal);
+      if (ok) { st.F_x = Fx; accepted = true; }
+      else {
+        st.lr *= c.decay_rate;
+        st.bt += 1;
+        if (st.bt >= c.max_backtrack) {          // RuntimeError path: x = x_prev, nit - 1
+          st.status = -1; st.res_buf = st.cur; st.F_x = st.F_prev; st.nit -= 1;
+          st.phase = DP_DONE;
+        } else st.phase = DP_RETRY;
+      }
+    } else accepted = true;
+  }
+  if (accepted) {
+    st.err = s.maxd;
+    if (c.cap > 0 && st.nit <= c.cap) {
+      if (allerrs) allerrs[(long long)run * c.cap + (st.nit - 1)] = st.err;
+      if (allfuns && c.need_F) allfuns[(long long)run * (c.cap + 1) + st.nit] = st.F_x;
+    }
+    const bool conv = st.err < c.tol;
+    if (conv || st.nit >= c.max_iter) {
+      st.status = conv ? 1 : 0;
+      st.res_buf = 1 - st.cur;
+      st.phase = c.need_F ? DP_DONE : DP_FINAL;
+    } else {
+      double mom = 0.0;
+      if (c.nesterov) {
+        const double t = st.t_prev;
+        const double t_new = sqrt(t * t - st.na * t + st.nb) + 0.5;
+        mom = (t - 1.0) / t_new;
+        st.t_prev = t_new;
+      }
+      st.mom = mom;
+      st.cur = 1 - st.cur;       // the candidate becomes x^k, the old x^k becomes x^{k-1}
+      st.F_prev = st.F_x;
+      st.nit += 1;
+      st.phase = DP_NEW;
+    }
+  }
+  runs[run] = st;
+  if (n_active && st.phase != DP_DONE && st.phase != DP_FINAL) atomicAdd(n_active, 1u);
+}
+
+__global__ void __launch_bounds__(DB_THREADS)
+deblur_gather_kernel(DeblurDims d, const DeblurRun* __restrict__ runs,
+                     const double* __restrict__ X0, const double* __restrict__ X1,
+                     double* __restrict__ out) {
+  const int run = blockIdx.y;
+  const double* src = (runs[run].res_buf ? X1 : X0) + (long long)run * d.n;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < d.n;
+       j += (long long)gridDim.x * blockDim.x)
+    out[(long long)run * d.n + j] = src[j];
+}
+
+}  // namespace zf
+
+// =======================================================================================
+struct zf_deblur {
+  zf::DeblurDims d{};
+  double l1 = 0.0;
+  int max_runs = 0;
+  double *b = nullptr, *X0 = nullptr, *X1 = nullptr, *Y = nullptr, *G = nullptr;
+  double *fy_part = nullptr, *fx_part = nullptr, *abs_part = nullptr;
+  zf::DeblurSums* psum = nullptr;
+  zf::DeblurRun* runs = nullptr;
+  unsigned int* n_active = nullptr;
+  unsigned int* h_active = nullptr;   // pinned
+  double *allerrs = nullptr, *allfuns = nullptr;
+  size_t trace_cap_alloc = 0;
+  cudaStream_t st = nullptr;
+  double kernel_host[81];
+  std::mutex mu;
+};
+
+namespace {
+#define ZF_CUDA(call)                                          \
+  do {                                                         \
+    cudaError_t _e = (call);                                   \
+    if (_e != cudaSuccess) return zf::zf_fail_cuda(_e, #call); \
+  } while (0)
+
+template <int MODE>
+int launch_tile(zf_deblur* h, int n_runs) {
+  dim3 grid((unsigned)h->d.n_tiles, (unsigned)n_runs);
+  double* fp = MODE == 0 ? h->fy_part : h->fx_part;
+  switch (h->d.R) {
+    case 1: zf::deblur_tile_kernel<1, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
+    case 2: zf::deblur_tile_kernel<2, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
+    case 3: zf::deblur_tile_kernel<3, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
+    default: zf::deblur_tile_kernel<4, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
+  }
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int launch_prox(zf_deblur* h, int n_runs) {
+  dim3 grid((unsigned)h->d.prox_blocks, (unsigned)n_runs);
+  zf::deblur_prox_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->l1, h->X0, h->X1,
+                                                            h->Y, h->G, h->psum);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int launch_decide(zf_deblur* h, int n_runs, const zf::DeblurCtl& c, bool count) {
+  zf::deblur_decide_kernel<<<n_runs, 32, 0, h->st>>>(h->d, c, h->runs, h->fy_part, h->fx_part,
+                                                    h->abs_part, h->psum,
+                                                    c.cap > 0 ? h->allerrs : nullptr,
+                                                    c.cap > 0 ? h->allfuns : nullptr,
+                                                    count ? h->n_active : nullptr);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int deblur_check_options(const zf_options* o) {
+  if (!o) return zf::zf_fail(ZF_ERR_INVALID, "options is NULL");
+  if (!(o->lr > 0.0)) return zf::zf_fail(ZF_ERR_INVALID, "lr must be > 0");
+  if (o->max_iter < 1) return zf::zf_fail(ZF_ERR_INVALID, "max_iter must be >= 1");
+  if (o->max_backtrack_iter < 1) return zf::zf_fail(ZF_ERR_INVALID, "max_backtrack_iter must be >= 1");
+  if (!(o->decay_rate > 0.0 && o->decay_rate <= 1.0))
+    return zf::zf_fail(ZF_ERR_INVALID, "decay_rate must be in (0, 1]");
+  if (o->trace_capacity < 0) return zf::zf_fail(ZF_ERR_INVALID, "trace_capacity must be >= 0");
+  return ZF_OK;
+}
+
+// Solve n_runs runs whose x0 is already in X0/X1 (both buffers) on the device.
+int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_ab,
+               bool want_funs) {
+  const int cap = opt->trace_capacity;
+  zf::DeblurCtl c{};
+  c.tol = opt->tol; c.tol_internal = opt->tol_internal; c.decay_rate = opt->decay_rate;
+  c.l1 = h->l1; c.max_iter = opt->max_iter; c.max_backtrack = opt->max_backtrack_iter;
+  c.nesterov = opt->nesterov; c.deprecated = opt->deprecated; c.cap = cap;
+  c.need_F = (opt->decay_rate != 1.0) || (cap > 0 && want_funs);
+  if (cap > 0) {
+    const size_t need = (size_t)n_runs * ((size_t)cap + 1);
+    if (need > h->trace_cap_alloc) {
+      cudaFree(h->allerrs); cudaFree(h->allfuns);
+      h->allerrs = h->allfuns = nullptr;
+      ZF_CUDA(cudaMalloc((void**)&h->allerrs, need * 8));
+      ZF_CUDA(cudaMalloc((void**)&h->allfuns, need * 8));
+      h->trace_cap_alloc = need;
+    }
+    ZF_CUDA(cudaMemsetAsync(h->allerrs, 0, (size_t)n_runs * cap * 8, h->st));
+    ZF_CUDA(cudaMemsetAsync(h->allfuns, 0, (size_t)n_runs * (cap + 1) * 8, h->st));
+  }
+  std::vector<zf::DeblurRun> init((size_t)n_runs);
+  for (int r = 0; r < n_runs; ++r) {
+    zf::DeblurRun& s = init[r];
+    std::memset(&s, 0, sizeof(s));
+    s.lr = opt->lr; s.t_prev = 1.0; s.mom = 0.0;
+    s.na = h_ab ? h_ab[2 * r] : opt->nesterov_a;
+    s.nb = h_ab ? h_ab[2 * r + 1] : opt->nesterov_b;
+    s.err = INFINITY;
+    s.nit = c.need_F ? 0 : 1;
+    s.phase = c.need_F ? zf::DP_INIT : zf::DP_NEW;
+    s.cur = 0; s.res_buf = 0;
+  }
+  ZF_CUDA(cudaMemcpyAsync(h->runs, init.data(), sizeof(zf::DeblurRun) * n_runs,
+                          cudaMemcpyHostToDevice, h->st));
+  const size_t part_bytes = sizeof(double) * (size_t)n_runs * h->d.n_tiles;
+  ZF_CUDA(cudaMemsetAsync(h->fy_part, 0, part_bytes, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->fx_part, 0, part_bytes, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->abs_part, 0, part_bytes, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->psum, 0, sizeof(zf::DeblurSums) * (size_t)n_runs * h->d.prox_blocks, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));   // `init` must outlive the copy
+  int rc;
+  auto round = [&](bool count) -> int {
+    if ((rc = launch_tile<0>(h, n_runs)) != ZF_OK) return rc;
+    if ((rc = launch_prox(h, n_runs)) != ZF_OK) return rc;
+    if (c.need_F && (rc = launch_tile<1>(h, n_runs)) != ZF_OK) return rc;
+    if (count) ZF_CUDA(cudaMemsetAsync(h->n_active, 0, sizeof(unsigned int), h->st));
+    return launch_decide(h, n_runs, c, count);
+  };
+  // chunks of rounds between polls; grows so that short solves do not over-run much and
+  // long ones poll rarely
+  int chunk = 8;
+  while (true) {
+    for (int k = 0; k < chunk; ++k)
+      if ((rc = round(k == chunk - 1)) != ZF_OK) return rc;
+    ZF_CUDA(cudaMemcpyAsync(h->h_active, h->n_active, sizeof(unsigned int),
+                            cudaMemcpyDeviceToHost, h->st));
+    ZF_CUDA(cudaStreamSynchronize(h->st));
+    if (*h->h_active == 0) break;
+    if (chunk < 64) chunk *= 2;
+  }
+  if (!c.need_F) {   // res.fun = F(x): one evaluation of the result buffer
+    if ((rc = launch_tile<1>(h, n_runs)) != ZF_OK) return rc;
+    if ((rc = launch_decide(h, n_runs, c, false)) != ZF_OK) return rc;
+  }
+  return ZF_OK;
+}
+}  // namespace
+
+extern "C" int zf_deblur_create(zf_deblur** out, int32_t height, int32_t width,
+                                const double* h_kernel, int32_t ksize, const double* h_observed,
+                                double l1, int32_t max_runs, void* cuda_stream) {
+  if (!out || !h_kernel || !h_observed) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  if (ksize < 3 || ksize > 9 || ksize % 2 == 0)
+    return zf::zf_fail(ZF_ERR_UNSUPPORTED, "kernel size must be odd, 3..9 (got %d)", ksize);
+  if (height < 2 * ksize || width < 2 * ksize || height % 2 || width % 2)
+    return zf::zf_fail(ZF_ERR_INVALID, "image sides must be even and >= 2*ksize");
+  if (max_runs < 1) return zf::zf_fail(ZF_ERR_INVALID, "max_runs must be >= 1");
+  int rc = zf::zf_require_device();
+  if (rc != ZF_OK) return rc;
+  zf_deblur* h = new zf_deblur();
+  zf::DeblurDims& d = h->d;
+  d.H = height; d.W = width; d.h2 = height / 2; d.w2 = width / 2;
+  d.tiles_x = (width + zf::DB_T - 1) / zf::DB_T;
+  d.tiles_y = (height + zf::DB_T - 1) / zf::DB_T;
+  d.n_tiles = d.tiles_x * d.tiles_y;
+  d.R = ksize / 2;
+  d.n = (long long)height * width;
+  long long pb = (d.n + zf::DB_THREADS * 4 - 1) / (zf::DB_THREADS * 4);
+  d.prox_blocks = (int)(pb > 256 ? 256 : pb);
+  h->l1 = l1;
+  h->max_runs = max_runs;
+  h->st = (cudaStream_t)cuda_stream;
+  std::memcpy(h->kernel_host, h_kernel, sizeof(double) * ksize * ksize);
+  const size_t vb = sizeof(double) * (size_t)max_runs * (size_t)d.n;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  alloc((void**)&h->b, sizeof(double) * (size_t)d.n);
+  alloc((void**)&h->X0, vb); alloc((void**)&h->X1, vb); alloc((void**)&h->Y, vb); alloc((void**)&h->G, vb);
+  alloc((void**)&h->fy_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
+  alloc((void**)&h->fx_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
+  alloc((void**)&h->abs_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
+  alloc((void**)&h->psum, sizeof(zf::DeblurSums) * (size_t)max_runs * d.prox_blocks);
+  alloc((void**)&h->runs, sizeof(zf::DeblurRun) * (size_t)max_runs);
+  alloc((void**)&h->n_active, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_active, sizeof(unsigned int));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h->b, h_observed, sizeof(double) * (size_t)d.n, cudaMemcpyHostToDevice, h->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+  if (e != cudaSuccess) {
+    zf_deblur_destroy(h);
+    return zf::zf_fail_cuda(e, "zf_deblur_create");
+  }
+  *out = h;
+  return ZF_OK;
+}
+
+extern "C" void zf_deblur_destroy(zf_deblur* h) {
+  if (!h) return;
+  cudaFree(h->b); cudaFree(h->X0); cudaFree(h->X1); cudaFree(h->Y); cudaFree(h->G);
+  cudaFree(h->fy_part); cudaFree(h->fx_part); cudaFree(h->abs_part); cudaFree(h->psum);
+  cudaFree(h->runs); cudaFree(h->n_active); cudaFree(h->allerrs); cudaFree(h->allfuns);
+  if (h->h_active) cudaFreeHost(h->h_active);
+  delete h;
+}
+
+static int deblur_load_kernel(zf_deblur* h) {
+  const int K = 2 * h->d.R + 1;
+  ZF_CUDA(cudaMemcpyToSymbolAsync(zf::c_kernel, h->kernel_host, sizeof(double) * K * K, 0,
+                                  cudaMemcpyHostToDevice, h->st));
+  return ZF_OK;
+}
+
+// x0: n_runs x n when x0_is_batched, else one vector shared by every run.
+static int deblur_solve_impl(zf_deblur* h, const zf_options* opt, int64_t n_runs,
+                             const double* x0, bool x0_on_device, int x0_is_batched,
+                             const double* h_ab, const zf_result* out, bool out_on_device) {
+  if (!h || !x0 || !out) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int rc = deblur_check_options(opt);
+  if (rc != ZF_OK) return rc;
+  if (n_runs < 0 || n_runs > h->max_runs)
+    return zf::zf_fail(ZF_ERR_INVALID, "n_runs=%lld outside 0..max_runs=%d", (long long)n_runs, h->max_runs);
+  if (n_runs == 0) return ZF_OK;
+  if (!out->x || !out->fun || !out->nit || !out->status)
+    return zf::zf_fail(ZF_ERR_INVALID, "result.x/fun/nit/status are required");
+  std::lock_guard<std::mutex> lock(h->mu);
+  rc = deblur_load_kernel(h);
+  if (rc != ZF_OK) return rc;
+  const size_t nb = sizeof(double) * (size_t)h->d.n;
+  const cudaMemcpyKind kin = x0_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int64_t r = 0; r < n_runs; ++r) {
+    const double* src = x0 + (x0_is_batched ? (size_t)r * h->d.n : 0);
+    ZF_CUDA(cudaMemcpyAsync(h->X0 + (size_t)r * h->d.n, src, nb, kin, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->X1 + (size_t)r * h->d.n, src, nb, kin, h->st));
+  }
+  rc = deblur_run(h, opt, (int)n_runs, h_ab, out->allfuns != nullptr);
+  if (rc != ZF_OK) return rc;
+  // results
+  const cudaMemcpyKind kout = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  dim3 grid((unsigned)h->d.prox_blocks, (unsigned)n_runs);
+  zf::deblur_gather_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  ZF_CUDA(cudaMemcpyAsync(out->x, h->Y, nb * (size_t)n_runs, kout, h->st));
+  std::vector<zf::DeblurRun> fin((size_t)n_runs);
+  ZF_CUDA(cudaMemcpyAsync(fin.data(), h->runs, sizeof(zf::DeblurRun) * n_runs, cudaMemcpyDeviceToHost, h->st));
+  const int cap = opt->trace_capacity;
+  if (cap > 0 && out->allerrs)
+    ZF_CUDA(cudaMemcpyAsync(out->allerrs, h->allerrs, (size_t)n_runs * cap * 8, kout, h->st));
+  if (cap > 0 && out->allfuns)
+    ZF_CUDA(cudaMemcpyAsync(out->allfuns, h->allfuns, (size_t)n_runs * (cap + 1) * 8, kout, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  if (out_on_device) {
+    // scalars are small: stage on host, copy up
+    std::vector<double> fun(n_runs), lr(n_runs), err(n_runs);
+    std::vector<int64_t> nit(n_runs);
+    std::vector<int32_t> status(n_runs);
+    for (int64_t r = 0; r < n_runs; ++r) {
+      fun[r] = fin[r].F_x; lr[r] = fin[r].lr; err[r] = fin[r].err; nit[r] = fin[r].nit; status[r] = fin[r].status;
+    }
+    ZF_CUDA(cudaMemcpyAsync(out->fun, fun.data(), 8 * n_runs, cudaMemcpyHostToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(out->nit, nit.data(), 8 * n_runs, cudaMemcpyHostToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(out->status, status.data(), 4 * n_runs, cudaMemcpyHostToDevice, h->st));
+    if (out->lr) ZF_CUDA(cudaMemcpyAsync(out->lr, lr.data(), 8 * n_runs, cudaMemcpyHostToDevice, h->st));
+    if (out->err) ZF_CUDA(cudaMemcpyAsync(out->err, err.data(), 8 * n_runs, cudaMemcpyHostToDevice, h->st));
+    ZF_CUDA(cudaStreamSynchronize(h->st));
+  } else {
+    for (int64_t r = 0; r < n_runs; ++r) {
+      out->fun[r] = fin[r].F_x;
+      out->nit[r] = fin[r].nit;
+      out->status[r] = fin[r].status;
+      if (out->lr) out->lr[r] = fin[r].lr;
+      if (out->err) out->err[r] = fin[r].err;
+    }
+  }
+  return ZF_OK;
+}
+
+extern "C" int zf_deblur_solve_host(zf_deblur* h, const zf_options* opt, int64_t n_runs,
+                                    const double* h_x0, int32_t x0_is_batched,
+                                    const double* h_ab, const zf_result* h_out) {
+  return deblur_solve_impl(h, opt, n_runs, h_x0, false, x0_is_batched, h_ab, h_out, false);
+}
+
+extern "C" int zf_deblur_solve_device(zf_deblur* h, const zf_options* opt, int64_t n_runs,
+                                      const double* d_x0, int32_t x0_is_batched,
+                                      const double* h_ab, const zf_result* d_out) {
+  return deblur_solve_impl(h, opt, n_runs, d_x0, true, x0_is_batched, h_ab, d_out, true);
+}
+
+extern "C" int zf_deblur_eval_host(zf_deblur* h, int64_t n_points, const double* h_X,
+                                   double* h_f, double* h_g, double* h_jac) {
+  if (!h || !h_X) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  if (n_points < 0 || n_points > h->max_runs)
+    return zf::zf_fail(ZF_ERR_INVALID, "n_points outside 0..max_runs");
+  if (n_points == 0) return ZF_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  int rc = deblur_load_kernel(h);
+  if (rc != ZF_OK) return rc;
+  const int n = (int)n_points;
+  const size_t nb = sizeof(double) * (size_t)h->d.n * n;
+  ZF_CUDA(cudaMemcpyAsync(h->X0, h_X, nb, cudaMemcpyHostToDevice, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->X1, h_X, nb, cudaMemcpyHostToDevice, h->st));
+  std::vector<zf::DeblurRun> init((size_t)n);
+  for (auto& s : init) { std::memset(&s, 0, sizeof(s)); s.phase = zf::DP_NEW; s.lr = 1.0; }
+  ZF_CUDA(cudaMemcpyAsync(h->runs, init.data(), sizeof(zf::DeblurRun) * n, cudaMemcpyHostToDevice, h->st));
+  rc = launch_tile<0>(h, n);           // G = jac_f(x), fy_part = f(x) partials
+  if (rc != ZF_OK) return rc;
+  for (auto& s : init) s.phase = zf::DP_INIT;
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->runs, init.data(), sizeof(zf::DeblurRun) * n, cudaMemcpyHostToDevice, h->st));
+  rc = launch_tile<1>(h, n);           // fx_part, abs_part of x
+  if (rc != ZF_OK) return rc;
+  std::vector<double> fp((size_t)n * h->d.n_tiles), ap((size_t)n * h->d.n_tiles);
+  ZF_CUDA(cudaMemcpyAsync(fp.data(), h->fx_part, fp.size() * 8, cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaMemcpyAsync(ap.data(), h->abs_part, ap.size() * 8, cudaMemcpyDeviceToHost, h->st));
+  if (h_jac) ZF_CUDA(cudaMemcpyAsync(h_jac, h->G, nb, cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  for (int r = 0; r < n; ++r) {
+    // same fixed order as deblur_decide_kernel: lane-strided partial sums, then butterfly
+    double lf[32] = {0}, la[32] = {0};
+    for (int t = 0; t < h->d.n_tiles; ++t) { lf[t & 31] += fp[(size_t)r * h->d.n_tiles + t]; la[t & 31] += ap[(size_t)r * h->d.n_tiles + t]; }
+    for (int o = 16; o > 0; o >>= 1)
+      for (int l = 0; l < o; ++l) { lf[l] += lf[l + o]; la[l] += la[l + o]; }
+    const double nrm = std::sqrt(lf[0]);
+    if (h_f) h_f[r] = nrm * nrm;
+    if (h_g) h_g[r] = h->l1 * la[0];
+  }
+  return ZF_OK;
+}
