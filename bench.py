@@ -396,10 +396,12 @@ def run_ours(args):
     if rank == 0 or world > 1:
         also = {}
         if not args.no_extras:
-            try:
-                also["lasso"] = bench_lasso(args, dev, rank, world)
-            except Exception as e:  # extras must never lose the headline line
-                also["lasso"] = {"error": repr(e)}
+            for name, fn in (("lasso", bench_lasso), ("cameraman", bench_cameraman),
+                             ("ab_sweep", bench_sweep)):
+                try:
+                    also[name] = fn(args, dev, rank, world)
+                except Exception as e:  # extras must never lose the headline line
+                    also[name] = {"error": repr(e)}
         if rank == 0:
             line["also"] = also
             print(json.dumps(line), flush=True)
@@ -494,6 +496,105 @@ def bench_lasso(args, dev, rank, world):
     return out
 
 
+AB_GRID = [
+    (0.0, 0.0), (0.0, 1 / 8), (0.0, 1 / 4), (1 / 6, 1 / 144), (1 / 6, 37 / 288), (1 / 6, 1 / 4),
+    (1 / 4, 1 / 64), (1 / 4, 17 / 128), (1 / 4, 1 / 4), (1 / 2, 1 / 16), (1 / 2, 5 / 32),
+    (1 / 2, 1 / 4), (3 / 4, 9 / 64), (3 / 4, 25 / 128), (3 / 4, 1 / 4),
+]
+
+
+def _cameraman_cpu_iters(args):
+    obs, kernel, l1, x0, L, ab, iters = args
+    import warnings
+
+    from oracle import deblur_oracle as do
+
+    warnings.simplefilter("ignore")
+    t0 = time.time()
+    r = do.minimize(obs, kernel, l1, x0, lr=1 / L, decay_rate=1, nesterov=True,
+                    nesterov_ratio=ab, max_iter=iters, tol=0.0)
+    return r["nit"], time.time() - t0
+
+
+def bench_cameraman(args, dev, rank, world):
+    """BASELINE configs[1]: 256x256 deblurring (9x9 Gaussian blur, Haar, l1 = 2e-5), the
+    notebook's 15 (a, b) pairs as 15 runs of one call, fixed step 1/L; every rank solves the
+    same 15 runs (replicas).  Capped at --cameraman-iters iterations per run so that the CPU
+    arm can time the identical work; reports FISTA iterations/s summed over the runs, timed
+    through the host entry point (x0 and the (a, b) table go H2D, x / fun / nit come D2H)."""
+    import warnings
+
+    import torch
+
+    from oracle import deblur_oracle as do
+    from zfista_b200.deblur import HaarDeblurL1
+
+    kernel = do.gaussian_kernel(9, 4.0)
+    kernel /= kernel.sum()
+    _, obs, _ = do.synthetic_scene(256, 256, seed=1, kernel=kernel)
+    l1 = 2e-5
+    prob = HaarDeblurL1(obs, kernel, l1)
+    x0 = prob.dwt_array(obs)
+    L = do.lipschitz(kernel)
+    pairs = np.array(AB_GRID)
+    iters = args.cameraman_iters
+    kw = dict(lr=1 / L, decay_rate=1, nesterov=True, max_iter=iters, tol=0.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        prob.minimize_proximal_gradient_batched(x0, pairs, **dict(kw, max_iter=20))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = prob.minimize_proximal_gradient_batched(x0, pairs, **kw)
+        dt = time.perf_counter() - t0
+    total = sum(r.nit for r in res)
+    out = {"workload": "256x256 Haar/9x9-blur deblurring, 15 (a,b) runs, fixed step, "
+                       f"{iters} iterations per run",
+           "fista_iters_per_s": total / dt, "seconds": dt, "iterations": total,
+           "us_per_round_of_15": 1e6 * dt / iters}
+    # algorithmic HBM bytes per run-iteration: x, x_prev in; y, g out; y, g in, x out; b in
+    out["algorithmic_GBps"] = total * 8 * 65536 * 8 / dt / 1e9
+    # FP64 work: two 81-tap correlations on (40^2 + 32^2) points per 32x32 tile
+    out["fp64_tflops"] = total * 64 * (1600 + 1024) * 81 * 2 / dt / 1e12
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cores = host_cores()
+        pool = cpu_pool(cores)
+        cpu_iters = 30
+        tasks = [(obs, kernel, l1, x0, L, tuple(ab), cpu_iters) for ab in AB_GRID]
+        t0 = time.time()
+        got = list(pool.map(_cameraman_cpu_iters, tasks))
+        cdt = time.time() - t0
+        out["cpu_fista_iters_per_s"] = sum(g[0] for g in got) / cdt
+        out["cpu_sample"] = (f"{cpu_iters} iterations of each of the 15 runs, oracle port "
+                             f"(scipy correlate2d + numpy Haar), {cores} cores")
+    return out
+
+
+def bench_sweep(args, dev, rank, world):
+    """BASELINE configs[4]: momentum (a, b) grid x 1024 starts on JOS1 (n = 50, +L1) as ONE
+    launch of 15 x 1024 = 15360 starts per GPU (per-start (a, b) table)."""
+    import torch
+
+    from zfista_b200.distributed import momentum_grid
+    import zfista_b200.problems as zp
+
+    n = 50
+    prob = zp.JOS1(n_features=n, l1_ratios=(1 / n, 1 / n / 2), l1_shifts=(0, 1))
+    rng = np.random.RandomState(77 + rank)
+    X0 = rng.uniform(-2, 4, size=(1024, n))
+    Xg, AB, _, _ = momentum_grid(X0, AB_GRID)
+    prob.minimize_proximal_gradient_batched(Xg[:64], nesterov=True, nesterov_ratio=AB[:64],
+                                            tol_internal=1e-11)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    br = prob.minimize_proximal_gradient_batched(Xg, nesterov=True, nesterov_ratio=AB,
+                                                 tol_internal=1e-11)
+    dt = time.perf_counter() - t0
+    return {"workload": "JOS1 n=50 +L1, 15 (a,b) pairs x 1024 starts in one launch (e2e call)",
+            "solves": int(len(Xg)), "converged": int((br.status == 1).sum()),
+            "solves_per_s": float((br.status == 1).sum() / dt), "seconds": dt,
+            "nit_mean": float(br.nit.mean())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -508,6 +609,7 @@ def main():
     ap.add_argument("--lasso-rows", type=int, default=65536)
     ap.add_argument("--lasso-cols", type=int, default=16384)
     ap.add_argument("--lasso-iters", type=int, default=20)
+    ap.add_argument("--cameraman-iters", type=int, default=300)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -275,7 +275,7 @@ deblur_prox_kernel(DeblurDims d, const DeblurRun* __restrict__ runs, double l1,
 struct DeblurCtl {
   double tol, tol_internal, decay_rate, l1;
   long long max_iter;
-  int max_backtrack, nesterov, deprecated, need_F, cap;
+  int max_backtrack, nesterov, deprecated, need_F, cap, finalize;
 };
 
 // One warp per run: fixed-order reduction of the round's partials, then the reference's
@@ -289,6 +289,7 @@ deblur_decide_kernel(DeblurDims d, DeblurCtl c, DeblurRun* __restrict__ runs,
   const int run = blockIdx.x, lane = threadIdx.x;
   DeblurRun st = runs[run];
   if (st.phase == DP_DONE) return;
+  if (st.phase == DP_FINAL && !c.finalize) return;   // waits for the host's final F pass
   double fy = 0.0, fx = 0.0, ax = 0.0;
   for (int t = lane; t < d.n_tiles; t += 32) {
     fy += fy_part[(long long)run * d.n_tiles + t];
@@ -515,6 +516,7 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
   }
   if (!c.need_F) {   // res.fun = F(x): one evaluation of the result buffer
     if ((rc = launch_tile<1>(h, n_runs)) != ZF_OK) return rc;
+    c.finalize = 1;
     if ((rc = launch_decide(h, n_runs, c, false)) != ZF_OK) return rc;
   }
   return ZF_OK;
