@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 ZF_MAX_OBJECTIVES = 4
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzfista_b200.so")
+_LIB_PATH = os.environ.get("ZFISTA_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "libzfista_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)

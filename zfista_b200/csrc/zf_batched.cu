@@ -38,6 +38,7 @@ __device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const
     // x = prox(lr, y - lr * jac); fun = jac.(x - y) + g(x) + ||x - y||^2 / 2 / lr (+ f_y - F_prev)
     double wt[1] = {lr};
     double s[2] = {0.0, 0.0};
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       const double yj = c.y[j];
       const double gj = c.J[j];
@@ -106,6 +107,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
        s += total_warps) {
     const double* xs = x0 + s * n;
     const int cap = O.trace_capacity;
+#pragma unroll 1
     for (int j = lane; j < n; j += 32) {
       const double v = xs[j];
       c.y[j] = v;
@@ -157,7 +159,11 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
         ++nfev;
 #pragma unroll
         for (int i = 0; i < M; ++i) Fx[i] = fx[i] + gx[i];
-        if (O.warm_start) {
+        // The reference passes w0 = 1/m to its inner solver unless warm_start is set.  The
+        // simplex Newton solver converges to the same (exact) maximiser from any start, so it
+        // always continues from the previous subproblem's weights: near convergence that is
+        // one or two dual evaluations instead of three or four.
+        if (O.warm_start || !(M == 2 && O.dual_solver == 0)) {
 #pragma unroll
           for (int i = 0; i < M; ++i) wwarm[i] = sub.w[i];
         }
@@ -180,6 +186,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
         break;
       }
       double e = 0.0;
+#pragma unroll 1
       for (int j = lane; j < n; j += 32) e = fmax(e, fabs(c.xn[j] - c.y[j]));
       err = warp_max(e);
       if (cap > 0 && it <= cap) {
@@ -189,6 +196,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
           for (int i = 0; i < M; ++i) R.allfuns[(s * (cap + 1) + it) * M + i] = Fx[i];
         }
         if (R.allvecs) {
+#pragma unroll 1
           for (int j = lane; j < n; j += 32) R.allvecs[(s * (cap + 1) + it) * n + j] = c.xn[j];
         }
       }
@@ -198,6 +206,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
       if (O.nesterov) {
         const double t_new = sqrt(t_prev * t_prev - na * t_prev + nb) + 0.5;
         const double mom = (t_prev - 1.0) / t_new;
+#pragma unroll 1
         for (int j = lane; j < n; j += 32) {
           const double xj = c.xn[j];
           c.y[j] = xj + mom * (xj - c.xp[j]);
@@ -206,6 +215,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
         double* tmp = c.xp; c.xp = c.xn; c.xn = tmp;
       } else {
         // y = x_prev = x^k
+#pragma unroll 1
         for (int j = lane; j < n; j += 32) c.y[j] = c.xn[j];
         double* tmp = c.xp; c.xp = c.xn; c.xn = tmp;
       }
@@ -220,6 +230,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
 #pragma unroll
       for (int i = 0; i < M; ++i) Fx[i] = Fprev[i];
     }
+#pragma unroll 1
     for (int j = lane; j < n; j += 32) R.x[s * n + j] = xres[j];
     if (lane == 0) {
 #pragma unroll
@@ -256,6 +267,7 @@ subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* _
   using F = Fn<KIND, M>;
   const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
   if (s >= n_items) return;
+#pragma unroll 1
   for (int j = lane; j < n; j += 32) {
     c.y[j] = Y[s * n + j];
     c.xp[j] = Xold[s * n + j];
@@ -273,6 +285,7 @@ subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* _
   for (int i = 0; i < M; ++i) sub.w[i] = 1.0 / (double)M;
   const bool deprecated = dep ? (dep[s] != 0) : (O.deprecated != 0);
   solve_subproblem<KIND, M>(P, O, c, LR[s], fy, Fprev, deprecated, sub);
+#pragma unroll 1
   for (int j = lane; j < n; j += 32) X[s * n + j] = c.xn[j];
   if (lane == 0) {
     FUN[s] = sub.fun;
@@ -301,6 +314,7 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
   using F = Fn<KIND, M>;
   const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
   if (s >= n_items) return;
+#pragma unroll 1
   for (int j = lane; j < n; j += 32) c.y[j] = Xin[s * n + j];
   __syncwarp();
   double fy[M], gy[M];
@@ -315,6 +329,7 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
     }
   }
   if (jo) {
+#pragma unroll 1
     for (int j = lane; j < n; j += 32) {
 #pragma unroll
       for (int i = 0; i < M; ++i) jo[(s * M + i) * n + j] = c.J[i * n + j];
@@ -324,6 +339,7 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
     double wt[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) wt[i] = Win[s * M + i];
+#pragma unroll 1
     for (int j = lane; j < n; j += 32) {
       double alpha, eps[M];
       po[s * n + j] = prox_elem<M, false>(P, j, c.y[j], wt, alpha, eps);

@@ -13,6 +13,13 @@
 #pragma once
 #include "zf_problems.cuh"
 
+#ifndef ZF_DUAL_UNROLL
+#define ZF_DUAL_UNROLL 1
+#endif
+#ifndef ZF_QP_BRANCHFREE
+#define ZF_QP_BRANCHFREE 0
+#endif
+
 namespace zf {
 
 template <int M>
@@ -36,6 +43,7 @@ __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const Du
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
   const bool lsq = (P.kind == ZF_LSQ_L1);
+#pragma unroll 1
   for (int j = c.lane; j < c.n; j += 32) {
     double wj = 0.0;
 #pragma unroll
@@ -80,6 +88,7 @@ __device__ void primal_from_weights(const zf_problem& P, const WarpCtx& c, doubl
   double wt[M];
 #pragma unroll
   for (int i = 0; i < M; ++i) wt[i] = lr * w[i];
+#pragma unroll 1
   for (int j = c.lane; j < c.n; j += 32) {
     double wj = 0.0;
 #pragma unroll
@@ -201,35 +210,47 @@ __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
   const bool lsq = (P.kind == ZF_LSQ_L1);
-  for (int j = c.lane; j < c.n; j += 32) {
-    double Jc[M];
-    double wj = 0.0;
+  // Two coordinates per trip: the prox chain of one coordinate is a long dependent sequence
+  // and the kernel is latency bound, so the second, independent chain is almost free.  The
+  // out-of-range slot works on coordinate 0 and contributes exact zeros, which keeps every
+  // partial sum bit-identical to the one-coordinate-per-trip order.
+#pragma unroll 1
+  for (int j0 = c.lane; j0 < c.n; j0 += 32 * ZF_DUAL_UNROLL) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
-      Jc[i] = c.J[i * c.n + j];
-      wj += w[i] * Jc[i];
-    }
-    const double yj = c.y[j];
-    const double v = yj - d.lr * wj;
-    double alpha, eps[M];
-    const double p = prox_elem<M, true>(P, j, v, wt, alpha, eps);
-    double mcol[M];
+    for (int u = 0; u < ZF_DUAL_UNROLL; ++u) {
+      const int jr = j0 + 32 * u;
+      const bool live = jr < c.n;
+      const int j = live ? jr : 0;
+      double Jc[M];
+      double wj = 0.0;
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
-      double lam = 0.0, shift = 0.0;
-      if (lsq) lam = P.l1;
-      else if (P.has_l1) { lam = P.l1_ratios[i]; shift = P.l1_shifts[i]; }
-      s[i] += fabs(p - shift);
-      s[M + i] += Jc[i] * (p - yj);
-      mcol[i] = alpha * (Jc[i] + lam * eps[i]);
-    }
-    s[2 * M] += (p - v) * (p - v);
-    s[2 * M + 1] += wj * wj;
-    int k = 2 * M + 2;
+      for (int i = 0; i < M; ++i) {
+        Jc[i] = c.J[i * c.n + j];
+        wj += w[i] * Jc[i];
+      }
+      const double yj = c.y[j];
+      const double v = yj - d.lr * wj;
+      double alpha, eps[M];
+      const double p = prox_elem<M, true>(P, j, v, wt, alpha, eps);
+      const double keep = live ? 1.0 : 0.0;
+      double mcol[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
+      for (int i = 0; i < M; ++i) {
+        double lam = 0.0, shift = 0.0;
+        if (lsq) lam = P.l1;
+        else if (P.has_l1) { lam = P.l1_ratios[i]; shift = P.l1_shifts[i]; }
+        s[i] += keep * fabs(p - shift);
+        s[M + i] += keep * (Jc[i] * (p - yj));
+        mcol[i] = (keep * alpha) * (Jc[i] + lam * eps[i]);
+      }
+      s[2 * M] += keep * ((p - v) * (p - v));
+      s[2 * M + 1] += keep * (wj * wj);
+      int k = 2 * M + 2;
 #pragma unroll
-      for (int l = i; l < M; ++l) s[k++] += mcol[i] * mcol[l];
+      for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int l = i; l < M; ++l) s[k++] += mcol[i] * mcol[l];
+      }
     }
   }
   warp_sum_k<NS>(s);
@@ -286,6 +307,7 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
   constexpr int K = zf_popcount(MASK);
   constexpr int S0 = zf_nth_bit(MASK, 0);
   double w[M];
+  bool feas = true;
 #pragma unroll
   for (int i = 0; i < M; ++i) w[i] = 0.0;
   if constexpr (K == 1) {
@@ -313,12 +335,17 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
         A[a][b] = Q[ia][ib] - Q[ia][S0] - Q[S0][ib] + Q[S0][S0];
       }
     }
+    // branch free (a rejected face still runs to the end, its result is discarded): the
+    // 2^M - 1 faces are independent, so straight-line code lets them overlap
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const double piv = A[k][k];
-      if (!(piv > pivot_floor)) ok = false;
-      const double inv = ok ? 1.0 / piv : 0.0;
+      ok = ok && (piv > pivot_floor);
+#if !ZF_QP_BRANCHFREE
+      if (!ok) return;
+#endif
+      const double inv = 1.0 / (ok ? piv : 1.0);
 #pragma unroll
       for (int r = k + 1; r < R; ++r) {
         const double fct = A[r][k] * inv;
@@ -327,17 +354,15 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
         rhs[r] -= fct * rhs[k];
       }
     }
-    if (!ok) return;
     double z[R];
 #pragma unroll
     for (int k = R - 1; k >= 0; --k) {
       double acc = rhs[k];
 #pragma unroll
       for (int cc = k + 1; cc < R; ++cc) acc -= A[k][cc] * z[cc];
-      z[k] = acc / A[k][k];
+      z[k] = acc / (ok ? A[k][k] : 1.0);
     }
     double zs = 0.0;
-    bool feas = true;
 #pragma unroll
     for (int a = 0; a < R; ++a) {
       zs += z[a];
@@ -345,8 +370,10 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
       w[zf_nth_bit(MASK, a + 1)] = z[a];
     }
     const double w0 = 1.0 - zs;
-    feas = feas && (w0 >= 0.0);
+    feas = feas && ok && (w0 >= 0.0);
+#if !ZF_QP_BRANCHFREE
     if (!feas) return;
+#endif
     w[S0] = w0;
   }
   double dvec[M];
@@ -360,7 +387,7 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
     for (int l = 0; l < M; ++l) qd += Q[i][l] * dvec[l];
     val += dvec[i] * (G[i] - 0.5 * qd);
   }
-  if (val > best_val) {
+  if (feas && val > best_val) {
     best_val = val;
 #pragma unroll
     for (int i = 0; i < M; ++i) best_w[i] = w[i];
@@ -373,6 +400,9 @@ struct QpFaces {
                                              const double (&wc)[M], double pf, double (&bw)[M],
                                              double& bv) {
     qp_face<M, MASK>(Q, G, wc, pf, bw, bv);
+    // The first face is the whole simplex: if the maximiser over its affine hull is feasible
+    // it is the global maximiser of the concave model and the sub-faces need not be visited.
+    if (MASK == (1 << M) - 1 && bv > -CUDART_INF) return;
     QpFaces<M, MASK - 1>::run(Q, G, wc, pf, bw, bv);
   }
 };
@@ -404,16 +434,37 @@ __device__ void simplex_qp(const double (&Q)[M][M], const double (&G)[M],
 template <int M>
 __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
                               double (&w)[M], int max_iter, int* nfev) {
-  DualPoint<M> cur, trial;
-  dual_full<M>(P, c, d, w, cur);
-  int evals = 1;
-  for (int it = 0; it < max_iter; ++it) {
-    double gabs = 0.0;
-    double wn[M];
+  // One evaluation site and one QP site (code size: see zf_common.cuh): the loop body is
+  // "evaluate the point under test, then either accept it and take the next Newton step from
+  // it, or halve the step".
+  DualPoint<M> cur, pt;
+  double wt[M], dir[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) { wt[i] = w[i]; dir[i] = 0.0; }
+  double step = 1.0;
+  int evals = 0, it = 0, bt = 0;
+  bool first = true;
+  for (;;) {
+    dual_full<M>(P, c, d, wt, pt);
+    ++evals;
+    if (first || pt.D >= cur.D) {
+      first = false;
+#pragma unroll
+      for (int i = 0; i < M; ++i) w[i] = wt[i];
+      cur = pt;
+    } else {
+      step *= 0.5;
+      if (++bt >= 30) break;
+#pragma unroll
+      for (int i = 0; i < M; ++i) wt[i] = w[i] + step * dir[i];
+      continue;
+    }
+    if (++it > max_iter) break;
+    double gabs = 0.0, wn[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) gabs = fmax(gabs, fabs(cur.G[i]));
     simplex_qp<M>(cur.Q, cur.G, w, wn);
-    double dmax = 0.0, dir[M];
+    double dmax = 0.0;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       dir[i] = wn[i] - w[i];
@@ -429,26 +480,16 @@ __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualD
       pred += dir[i] * (cur.G[i] - 0.5 * qd);
     }
     if (pred <= 1e-15 * (fabs(cur.D) + gabs)) {
+      // below the rounding level of D: take the Newton step on trust and stop
 #pragma unroll
       for (int i = 0; i < M; ++i) w[i] = wn[i];
       cur.D += pred;
       break;
     }
-    double step = 1.0;
-    bool accepted = false;
-    double wt[M];
-    for (int bt = 0; bt < 30; ++bt) {
+    step = 1.0;
+    bt = 0;
 #pragma unroll
-      for (int i = 0; i < M; ++i) wt[i] = (step == 1.0) ? wn[i] : w[i] + step * dir[i];
-      dual_full<M>(P, c, d, wt, trial);
-      ++evals;
-      if (trial.D >= cur.D) { accepted = true; break; }
-      step *= 0.5;
-    }
-    if (!accepted) break;
-#pragma unroll
-    for (int i = 0; i < M; ++i) w[i] = wt[i];
-    cur = trial;
+    for (int i = 0; i < M; ++i) wt[i] = wn[i];
   }
   *nfev = evals;
   return cur.D;

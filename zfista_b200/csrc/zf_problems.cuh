@@ -20,6 +20,7 @@ struct Fn<ZF_JOS1, 2> {
   __device__ static void f(const zf_problem& P, const WarpCtx& c, const double* x,
                            double (&out)[2]) {
     double s[2] = {0.0, 0.0};
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       const double xj = x[j];
       s[0] += xj * xj;
@@ -33,6 +34,7 @@ struct Fn<ZF_JOS1, 2> {
                                double* J, double (&fy)[2]) {
     f(P, c, y, fy);
     const double dn = (double)c.n;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       const double yj = y[j];
       J[j] = 2.0 * yj / dn;
@@ -71,6 +73,7 @@ template <>
 struct Fn<ZF_FDS, 3> {
   __device__ static void moments(const WarpCtx& c, const double* x, double (&s)[4]) {
     s[0] = s[1] = s[2] = s[3] = 0.0;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       const double xj = x[j];
       const double idx = (double)(j + 1);
@@ -99,21 +102,33 @@ struct Fn<ZF_FDS, 3> {
   }
   __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const double* y,
                                double* J, double (&fy)[3]) {
+    // one pass: the moments of f and the Jacobian rows 1 and 3 share exp(-y_j); row 2 needs
+    // exp(mean(y)), known only after the reduction, and is filled by a second (cheap) pass
     double s[4], e;
-    moments(c, y, s);
-    finish(c, s, fy, e);
+    s[0] = s[1] = s[2] = s[3] = 0.0;
     const double dn = (double)c.n;
     const double c1 = 4.0 / (dn * dn);
     const double c3 = dn * (dn + 1.0);
-    const double e_over_n = e / dn;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       const double yj = y[j];
       const double idx = (double)(j + 1);
       const double d = yj - idx;
+      const double d2 = d * d;
+      const double conv = idx * (double)(c.n - j);
+      const double ex = exp(-yj);
+      s[0] += idx * (d2 * d2);
+      s[1] += yj;
+      s[2] += yj * yj;
+      s[3] += conv * ex;
       J[j] = c1 * idx * (d * d * d);
-      J[c.n + j] = e_over_n + 2.0 * yj;
-      J[2 * c.n + j] = -(idx * (double)(c.n - j)) * exp(-yj) / c3;
+      J[2 * c.n + j] = -conv * ex / c3;
     }
+    warp_sum_k<4>(s);
+    finish(c, s, fy, e);
+    const double e_over_n = e / dn;
+#pragma unroll 1
+    for (int j = c.lane; j < c.n; j += 32) J[c.n + j] = e_over_n + 2.0 * y[j];
   }
 };
 
@@ -122,6 +137,7 @@ template <>
 struct Fn<ZF_ZDT1, 2> {
   __device__ static double h_of(const WarpCtx& c, const double* x) {
     double s = 0.0;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) s += (j >= 1) ? x[j] : 0.0;
     s = warp_sum(s);
     return 1.0 + 9.0 / (double)(c.n - 1) * s;
@@ -141,6 +157,7 @@ struct Fn<ZF_ZDT1, 2> {
     fy[1] = h * (1.0 - sqrt(y0 / h));
     const double rest = 9.0 * (2.0 - sqrt(y0 / h)) / 2.0 / (double)(c.n - 1);
     const double first = -sqrt(h / y0) / 2.0;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       J[j] = (j == 0) ? 1.0 : 0.0;
       J[c.n + j] = (j == 0) ? first : rest;
@@ -208,6 +225,7 @@ template <int M>
 struct Fn<ZF_LFR1, M> {
   __device__ static double weighted_sum(const WarpCtx& c, const double* x) {
     double s = 0.0;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) s += (double)(j + 1) * x[j];
     return warp_sum(s);
   }
@@ -222,6 +240,7 @@ struct Fn<ZF_LFR1, M> {
     const double s = weighted_sum(c, y);
 #pragma unroll
     for (int i = 0; i < M; ++i) fy[i] = sq((double)(i + 1) * s - 1.0);
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
 #pragma unroll
       for (int i = 0; i < M; ++i) {
@@ -242,6 +261,7 @@ struct Fn<ZF_LSQ_L1, M> {
     for (int r = 0; r < P.n_rows; ++r) {
       const double* Ar = P.A + (size_t)r * c.n;
       double d = 0.0;
+#pragma unroll 1
       for (int j = c.lane; j < c.n; j += 32) d += Ar[j] * x[j];
       d = warp_sum(d) - P.b[r];
       if (c.lane == 0) c.scratch[r] = d;
@@ -262,6 +282,7 @@ struct Fn<ZF_LSQ_L1, M> {
 #pragma unroll
     for (int i = 0; i < M; ++i) fy[i] = v;
     const double two_scale = 2.0 * P.scale;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       double gsum = 0.0;
       for (int r = 0; r < P.n_rows; ++r) gsum += P.A[(size_t)r * c.n + j] * c.scratch[r];
@@ -289,6 +310,7 @@ __device__ void g_eval(const zf_problem& P, const WarpCtx& c, const double* x,
                        double (&out)[M]) {
   if (P.kind == ZF_LSQ_L1) {
     double s = 0.0;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) s += fabs(x[j]);
     s = warp_sum(s) * P.l1;
 #pragma unroll
@@ -297,6 +319,7 @@ __device__ void g_eval(const zf_problem& P, const WarpCtx& c, const double* x,
   }
   if (P.has_bounds) {
     int bad = 0;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       const double xj = x[j];
       bad |= (xj < lower_of(P, j)) || (xj > upper_of(P, j));
@@ -311,6 +334,7 @@ __device__ void g_eval(const zf_problem& P, const WarpCtx& c, const double* x,
     double s[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) s[i] = 0.0;
+#pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
       const double xj = x[j];
 #pragma unroll
