@@ -19,6 +19,7 @@
 // zf_lasso_grad() and zf_lasso_step() (done by the caller, NCCL over NVLink).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "zf_common.cuh"
@@ -193,6 +194,128 @@ lasso_atr_kernel(const double* __restrict__ A, const double* __restrict__ r, lon
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Fused gradient pass: A^T (A v - b) and sum r^2 with A read from HBM ONCE.
+// One persistent CTA per SM owns a contiguous block of rows and every column: v sits in
+// shared memory (8 * n_cols bytes), the CTA's partial A^T r sits in registers (each thread
+// owns PAIRS column pairs), and rows stream through two at a time:
+//   phase 1: load the two rows (HBM -> L2 -> registers), dot them with v, block-reduce;
+//   phase 2: load the same two rows again -- now L2 hits, marked evict-first -- and
+//            accumulate r_i * A[i][:] into the thread's columns.
+// HBM traffic is one pass over A; the second read is served by the 126 MB L2 (148 CTAs x 2
+// rows x 8 n_cols bytes = 47 MB in flight for n_cols = 20000).
+// ------------------------------------------------------------------------------------
+constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_ROWS = 2;
+constexpr int FUSED_CHUNK = 4;     // column pairs loaded per thread per step (x2 rows in flight)
+
+// L2 residency control through cache-hint policies (the plain .L2::evict_* qualifiers are
+// only accepted on 32-byte loads)
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double2 ld_hint2(const double* p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+               : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+
+template <int PAIRS>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+lasso_fused_kernel(const double* __restrict__ A, const double* __restrict__ b,
+                   const double* __restrict__ v, long long n_rows, long long n_cols,
+                   long long rows_per_cta, double* __restrict__ gpart,
+                   double* __restrict__ sq_part) {
+  extern __shared__ double vsm[];                       // n_cols doubles
+  __shared__ double red[2][FUSED_THREADS / 32][FUSED_ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n2 = n_cols >> 1;
+  for (long long p = tid; p < n2; p += FUSED_THREADS)
+    reinterpret_cast<double2*>(vsm)[p] = __ldg(reinterpret_cast<const double2*>(v) + p);
+  __syncthreads();
+  const unsigned long long keep_pol = l2_policy_evict_last();     // phase 1: stay in L2
+  const unsigned long long last_pol = l2_policy_evict_first();    // phase 2: last use
+  double2 q[PAIRS];
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) q[k] = make_double2(0.0, 0.0);
+  const long long i0 = (long long)blockIdx.x * rows_per_cta;
+  const long long i1 = (i0 + rows_per_cta < n_rows) ? i0 + rows_per_cta : n_rows;
+  double ss = 0.0;
+  int parity = 0;
+  for (long long i = i0; i < i1; i += FUSED_ROWS) {
+    const bool two = (i + 1 < i1);
+    const double* row0 = A + i * n_cols;
+    const double* row1 = two ? row0 + n_cols : row0;     // a lone last row is read twice, used once
+    // ---- phase 1: dot products
+    double acc[FUSED_ROWS] = {0.0, 0.0};
+#pragma unroll
+    for (int k0 = 0; k0 < PAIRS; k0 += FUSED_CHUNK) {
+      double2 a0[FUSED_CHUNK], a1[FUSED_CHUNK];
+#pragma unroll
+      for (int u = 0; u < FUSED_CHUNK; ++u) {
+        const long long p = tid + (long long)(k0 + u) * FUSED_THREADS;
+        const long long pc = (k0 + u < PAIRS && p < n2) ? p : 0;
+        a0[u] = ld_hint2(row0 + 2 * pc, keep_pol);
+        a1[u] = ld_hint2(row1 + 2 * pc, keep_pol);
+      }
+#pragma unroll
+      for (int u = 0; u < FUSED_CHUNK; ++u) {
+        const long long p = tid + (long long)(k0 + u) * FUSED_THREADS;
+        if (k0 + u < PAIRS && p < n2) {
+          const double2 vv = reinterpret_cast<const double2*>(vsm)[p];
+          acc[0] += a0[u].x * vv.x + a0[u].y * vv.y;
+          acc[1] += a1[u].x * vv.x + a1[u].y * vv.y;
+        }
+      }
+    }
+    warp_sum_k<FUSED_ROWS>(acc);
+    if (lane == 0) { red[parity][warp][0] = acc[0]; red[parity][warp][1] = acc[1]; }
+    __syncthreads();
+    double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < FUSED_THREADS / 32; ++w) { r0 += red[parity][w][0]; r1 += red[parity][w][1]; }
+    parity ^= 1;
+    r0 -= b[i];
+    r1 = two ? r1 - b[i + 1] : 0.0;
+    ss += r0 * r0;
+    ss += r1 * r1;
+    // ---- phase 2: rank-1 updates of the thread's columns (rows re-read from L2)
+#pragma unroll
+    for (int k0 = 0; k0 < PAIRS; k0 += FUSED_CHUNK) {
+      double2 a0[FUSED_CHUNK], a1[FUSED_CHUNK];
+#pragma unroll
+      for (int u = 0; u < FUSED_CHUNK; ++u) {
+        const long long p = tid + (long long)(k0 + u) * FUSED_THREADS;
+        const long long pc = (k0 + u < PAIRS && p < n2) ? p : 0;
+        a0[u] = ld_hint2(row0 + 2 * pc, last_pol);
+        a1[u] = ld_hint2(row1 + 2 * pc, last_pol);
+      }
+#pragma unroll
+      for (int u = 0; u < FUSED_CHUNK; ++u) {
+        if (k0 + u < PAIRS) {
+          q[k0 + u].x += r0 * a0[u].x; q[k0 + u].y += r0 * a0[u].y;
+          q[k0 + u].x += r1 * a1[u].x; q[k0 + u].y += r1 * a1[u].y;
+        }
+      }
+    }
+  }
+  double* out = gpart + (long long)blockIdx.x * n_cols;
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) {
+    const long long p = tid + (long long)k * FUSED_THREADS;
+    if (p < n2) reinterpret_cast<double2*>(out)[p] = q[k];
+  }
+  if (tid == 0) sq_part[blockIdx.x] = ss;
+}
+
 // partial[j] = sum_rb gpart[rb][j] (fixed order);  partial[n_cols] = sum_blk sq_part[blk]
 __global__ void __launch_bounds__(256)
 lasso_collect_kernel(const double* __restrict__ gpart, int n_rowblocks,
@@ -335,6 +458,10 @@ struct zf_lasso {
   double* h_pin = nullptr;      // pinned: [StepSums (4) | ss]
   int res_blocks = 0, n_slabs = 0, n_rowblocks = 0, vec_blocks = 0;
   long long rows_per_block = 0;
+  // fused one-pass gradient (0 = not applicable)
+  int fused_pairs = 0, fused_ctas = 0;
+  long long fused_rows_per_cta = 0;
+  size_t gpart_rows = 0;
   // solver state (host scalars)
   zf_options opt{};
   int phase = LP_IDLE;
@@ -376,6 +503,52 @@ int launch_atr(zf_lasso* h) {
   else
     zf::lasso_atr_kernel<false><<<grid, zf::ATR_THREADS, 0, h->st>>>(
         h->A, h->r, h->n_rows, h->n_cols, h->rows_per_block, h->gpart);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+template <int PAIRS>
+int launch_fused_t(zf_lasso* h, const double* v) {
+  auto k = zf::lasso_fused_kernel<PAIRS>;
+  const size_t smem = sizeof(double) * (size_t)h->n_cols;
+  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<h->fused_ctas, zf::FUSED_THREADS, smem, h->st>>>(h->A, h->b, v, h->n_rows, h->n_cols,
+                                                       h->fused_rows_per_cta, h->gpart, h->sq_part);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+// gradient pass at v: leaves the A^T r partials in gpart (n_gpart_rows x n_cols) and the
+// sum r^2 partials in sq_part (n_sq), by the fused kernel when it applies
+int launch_gradient_pass(zf_lasso* h, const double* v, int* n_gpart_rows, int* n_sq) {
+  if (h->fused_pairs > 0) {
+    int rc;
+    switch (h->fused_pairs) {
+      case 4: rc = launch_fused_t<4>(h, v); break;
+      case 8: rc = launch_fused_t<8>(h, v); break;
+      case 12: rc = launch_fused_t<12>(h, v); break;
+      case 16: rc = launch_fused_t<16>(h, v); break;
+      default: rc = launch_fused_t<20>(h, v); break;
+    }
+    *n_gpart_rows = h->fused_ctas;
+    *n_sq = h->fused_ctas;
+    return rc;
+  }
+  int rc = launch_residual(h, v);
+  if (rc != ZF_OK) return rc;
+  rc = launch_atr(h);
+  *n_gpart_rows = h->n_rowblocks;
+  *n_sq = h->res_blocks;
+  return rc;
+}
+
+int launch_collect_n(zf_lasso* h, bool with_gradient, int n_gpart_rows, int n_sq) {
+  const int blocks = with_gradient ? (int)((h->n_cols + 255) / 256) : 1;
+  zf::lasso_collect_kernel<<<blocks, 256, 0, h->st>>>(with_gradient ? h->gpart : nullptr,
+                                                     n_gpart_rows, h->sq_part, n_sq, h->n_cols,
+                                                     h->partial);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -522,14 +695,39 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   long long vb = (n_cols + zf::VEC_THREADS - 1) / zf::VEC_THREADS;
   if (vb > zf::VEC_MAX_BLOCKS) vb = zf::VEC_MAX_BLOCKS;
   h->vec_blocks = (int)vb;
+  // fused one-pass gradient: v in shared memory (8 n_cols B), <= 20 column pairs per thread
+  h->gpart_rows = (size_t)h->n_rowblocks;
+  size_t sq_rows = (size_t)h->res_blocks;
+  {
+    // Measured on B200: the fused pass beats the two-pass form up to 8 column
+    // pairs per thread (n_cols <= 8192: 2.12 vs 2.48 ms on 131072 x 8192) and loses beyond
+    // (register pressure: 2.91 vs 2.29 ms on 49152 x 20000), so it is the default only there.
+    // ZF_LASSO_FUSED=1 / 0 forces it on (where it fits) / off.
+    const char* env = getenv("ZF_LASSO_FUSED");
+    const long long n2 = n_cols / 2;
+    const long long pairs = (n2 + zf::FUSED_THREADS - 1) / zf::FUSED_THREADS;
+    const bool enabled = env ? (env[0] != '0') : (pairs <= 8);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (enabled && h->vec && pairs <= 20 && (size_t)n_cols * 8 + 1024 <= (size_t)max_smem &&
+        n_rows >= 4LL * h->n_sm) {
+      h->fused_pairs = (int)(((pairs + 3) / 4) * 4);
+      h->fused_ctas = h->n_sm;
+      h->fused_rows_per_cta = (n_rows + h->fused_ctas - 1) / h->fused_ctas;
+      if (h->fused_rows_per_cta % 2) h->fused_rows_per_cta += 1;     // whole row pairs
+      h->fused_ctas = (int)((n_rows + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
+      if ((size_t)h->fused_ctas > h->gpart_rows) h->gpart_rows = (size_t)h->fused_ctas;
+      if ((size_t)h->fused_ctas > sq_rows) sq_rows = (size_t)h->fused_ctas;
+    }
+  }
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
   alloc((void**)&h->vecs, sizeof(double) * 4 * (size_t)n_cols);
   alloc((void**)&h->r, sizeof(double) * (size_t)n_rows);
-  alloc((void**)&h->gpart, sizeof(double) * (size_t)h->n_rowblocks * (size_t)n_cols);
-  alloc((void**)&h->sq_part, sizeof(double) * (size_t)h->res_blocks);
+  alloc((void**)&h->gpart, sizeof(double) * h->gpart_rows * (size_t)n_cols);
+  alloc((void**)&h->sq_part, sizeof(double) * sq_rows);
   alloc((void**)&h->partial, sizeof(double) * ((size_t)n_cols + 1));
   alloc((void**)&h->block_sums, sizeof(zf::StepSums) * zf::VEC_MAX_BLOCKS);
   alloc((void**)&h->d_sums, sizeof(zf::StepSums));
@@ -615,11 +813,10 @@ extern "C" int zf_lasso_grad(zf_lasso* h, int which) {
   int rc;
   if (which == 0) {
     if (h->phase != LP_GRAD) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_grad(0) out of order");
-    rc = launch_residual(h, h->y);
+    int ng = 0, ns = 0;
+    rc = launch_gradient_pass(h, h->y, &ng, &ns);
     if (rc != ZF_OK) return rc;
-    rc = launch_atr(h);
-    if (rc != ZF_OK) return rc;
-    return launch_collect(h, true);
+    return launch_collect_n(h, true, ng, ns);
   }
   if (which == 1) {
     if (h->phase != LP_FNEW && h->phase != LP_FINAL)
@@ -768,11 +965,10 @@ extern "C" int zf_lasso_solve(zf_lasso* h, const zf_options* opt, const double* 
 extern "C" int zf_lasso_gradient_device(zf_lasso* h, const double* d_x, double* d_grad,
                                         double* d_f) {
   if (!h || !d_x || !d_grad) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
-  int rc = launch_residual(h, d_x);
+  int ng = 0, ns = 0;
+  int rc = launch_gradient_pass(h, d_x, &ng, &ns);
   if (rc != ZF_OK) return rc;
-  rc = launch_atr(h);
-  if (rc != ZF_OK) return rc;
-  rc = launch_collect(h, true);
+  rc = launch_collect_n(h, true, ng, ns);
   if (rc != ZF_OK) return rc;
   zf::lasso_scale_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
       h->partial, 2.0 * h->scale, h->scale, h->n_cols, d_grad, d_f);
