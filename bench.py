@@ -375,7 +375,7 @@ def run_ours(args):
             "dual_evals_per_solve": ndual_all / (S * world * args.steps),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": 1239808.0,
                 "peak_source": peaks["source"],
                 "note": ("batched_fista_kernel keeps each start's state in shared memory and "
                          "touches HBM only for x0 and the results; it is FP64-latency bound, "
@@ -465,9 +465,21 @@ def bench_lasso(args, dev, rank, world):
         vec_bytes = (2 * cols + 2 * rows) * 8
         two_pass = 2 * a_bytes + vec_bytes
         ach = two_pass / (ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):        # ncu-measured DRAM bytes / algorithmic bytes, per kernel
+            with open(tp) as fh:
+                tj = json.load(fh)
+            ratio = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"])
+                        / tj[k]["algorithmic_bytes"]
+                        for k in ("lasso_residual_kernel", "lasso_atr_kernel")) / 2
+            traffic = two_pass * ratio
         out["roofline"] = {
             "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_gradient": ms,
+            "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+            "traffic_source": "ncu dram bytes / algorithmic bytes measured at 32768x16384 "
+                              "(profiles/r01_traffic.json), scaled to this A",
+            "ms_per_gradient": ms,
             "peak_source": peaks["source"],
             "frac_of_one_pass_bound": (a_bytes + vec_bytes) / (ms / 1e3) / 1e9 / peaks["hbm_gbs"]}
     # solver-level: fixed-step FISTA iterations per second (A stays resident)
