@@ -26,7 +26,8 @@
 namespace zf {
 
 constexpr int DB_T = 32;
-constexpr int DB_THREADS = 256;
+constexpr int DB_THREADS = 128;
+constexpr int DB_STRIP = 8;        // outputs per thread in a vertical strip
 constexpr int DB_MAXR = 4;
 constexpr int DB_UR = DB_T + 4 * DB_MAXR;   // 48
 constexpr int DB_VR = DB_T + 2 * DB_MAXR;   // 40
@@ -141,26 +142,35 @@ deblur_tile_kernel(DeblurDims d, const DeblurRun* __restrict__ runs, double* __r
   __syncthreads();
   // ---- 2. V = R U - b at the in-image positions of the V region (vertical strips of 4)
   double fsum = 0.0;
-  constexpr int VS = (VR + 3) / 4;
+  // A thread owns DB_STRIP vertically adjacent outputs: per kernel column it loads
+  // DB_STRIP + 2R values of U once and reuses them for all K kernel rows (8 x K DFMA per
+  // 8 + 2R shared-memory loads; neighbouring lanes read neighbouring columns, conflict free).
+  constexpr int S = DB_STRIP;
+  constexpr int VS = (VR + S - 1) / S;
   for (int task = tid; task < VS * VR; task += DB_THREADS) {
-    const int li0 = 4 * (task / VR), lj = task % VR;
+    const int li0 = S * (task / VR), lj = task % VR;
     const int gj = txo - HV + lj;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[S];
+#pragma unroll
+    for (int o = 0; o < S; ++o) acc[o] = 0.0;
 #pragma unroll
     for (int v = 0; v < K; ++v) {
-      double col[4 + 2 * R];
+      double col[S + 2 * R];
 #pragma unroll
-      for (int k = 0; k < 4 + 2 * R; ++k) col[k] = U[li0 + k + OFF][lj + v + OFF];
+      for (int k = 0; k < S + 2 * R; ++k) {
+        const int row = li0 + k + OFF;
+        col[k] = U[row < DB_UR ? row : DB_UR - 1][lj + v + OFF];
+      }
 #pragma unroll
       for (int u = 0; u < K; ++u) {
         const double w = c_kernel[u * K + v];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) acc[o] += w * col[o + u];
+        for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
       }
     }
     if (gj >= 0 && gj < d.W) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
+      for (int o = 0; o < S; ++o) {
         const int li = li0 + o, gi = tyo - HV + li;
         if (li < VR && gi >= 0 && gi < d.H) {
           const double val = acc[o] - b[(long long)gi * d.W + gj];
@@ -194,29 +204,31 @@ deblur_tile_kernel(DeblurDims d, const DeblurRun* __restrict__ runs, double* __r
     }
   }
   __syncthreads();
-  // ---- 4. Wimg = R V on the tile (one vertical strip of 4 per thread), into U's storage
-  {
-    const int li0 = 4 * (tid / T), lj = tid % T;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  // ---- 4. Wimg = R V on the tile (vertical strips of DB_STRIP), into U's storage
+  for (int task = tid; task < (T / S) * T; task += DB_THREADS) {
+    const int li0 = S * (task / T), lj = task % T;
+    double acc[S];
+#pragma unroll
+    for (int o = 0; o < S; ++o) acc[o] = 0.0;
 #pragma unroll
     for (int v = 0; v < K; ++v) {
-      double col[4 + 2 * R];
+      double col[S + 2 * R];
 #pragma unroll
-      for (int k = 0; k < 4 + 2 * R; ++k) col[k] = V[li0 + k][lj + v];
+      for (int k = 0; k < S + 2 * R; ++k) col[k] = V[li0 + k][lj + v];
 #pragma unroll
       for (int u = 0; u < K; ++u) {
         const double w = c_kernel[u * K + v];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) acc[o] += w * col[o + u];
+        for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
       }
     }
 #pragma unroll
-    for (int o = 0; o < 4; ++o) U[li0 + o][lj] = acc[o];
+    for (int o = 0; o < S; ++o) U[li0 + o][lj] = acc[o];
   }
   __syncthreads();
   // ---- 5. gradient coefficients = 2 * dwt2(Wimg) per 2x2 block
-  {
-    const int bi = tid / (T / 2), bj = tid % (T / 2);
+  for (int blk = tid; blk < (T / 2) * (T / 2); blk += DB_THREADS) {
+    const int bi = blk / (T / 2), bj = blk % (T / 2);
     const int gi = tyo + 2 * bi, gj = txo + 2 * bj;
     if (gi < d.H && gj < d.W) {
       const double p00 = U[2 * bi][2 * bj], p01 = U[2 * bi][2 * bj + 1];
@@ -396,6 +408,9 @@ struct zf_deblur {
   double *allerrs = nullptr, *allfuns = nullptr;
   size_t trace_cap_alloc = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t own_st = nullptr;     // created when the caller passes no stream (graphs cannot
+                                     // be captured on the legacy default stream)
+  bool capturing = false;
   double kernel_host[81];
   std::mutex mu;
 };
@@ -418,7 +433,7 @@ int launch_tile(zf_deblur* h, int n_runs) {
     default: zf::deblur_tile_kernel<4, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
   }
   ZF_CUDA(cudaGetLastError());
-  zf::zf_count_launch();
+  if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
 }
 
@@ -427,7 +442,7 @@ int launch_prox(zf_deblur* h, int n_runs) {
   zf::deblur_prox_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->l1, h->X0, h->X1,
                                                             h->Y, h->G, h->psum);
   ZF_CUDA(cudaGetLastError());
-  zf::zf_count_launch();
+  if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
 }
 
@@ -438,7 +453,7 @@ int launch_decide(zf_deblur* h, int n_runs, const zf::DeblurCtl& c, bool count) 
                                                     c.cap > 0 ? h->allfuns : nullptr,
                                                     count ? h->n_active : nullptr);
   ZF_CUDA(cudaGetLastError());
-  zf::zf_count_launch();
+  if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
 }
 
@@ -502,18 +517,56 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
     if (count) ZF_CUDA(cudaMemsetAsync(h->n_active, 0, sizeof(unsigned int), h->st));
     return launch_decide(h, n_runs, c, count);
   };
-  // chunks of rounds between polls; grows so that short solves do not over-run much and
-  // long ones poll rarely
-  int chunk = 8;
+  // Chunks of rounds between polls (8, 16, 32, 64, 64, ...: short solves do not over-run much,
+  // long ones poll rarely).  A chunk is captured once into a CUDA graph and replayed: every
+  // kernel argument is constant during a solve (all state is in device memory), and a round
+  // is ~4 small kernels, so per-launch CPU cost would otherwise rival the GPU time.
+  const int kernels_per_round = 3 + (c.need_F ? 1 : 0);
+  cudaGraphExec_t execs[4] = {nullptr, nullptr, nullptr, nullptr};
+  auto build_graph = [&](int chunk, cudaGraphExec_t* out) -> int {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return ZF_ERR_CUDA;
+    }
+    h->capturing = true;
+    int r2 = ZF_OK;
+    for (int k = 0; k < chunk && r2 == ZF_OK; ++k) r2 = round(k == chunk - 1);
+    if (r2 == ZF_OK &&
+        cudaMemcpyAsync(h->h_active, h->n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                        h->st) != cudaSuccess)
+      r2 = ZF_ERR_CUDA;
+    h->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(h->st, &graph);
+    if (r2 != ZF_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return ZF_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return ZF_ERR_CUDA; }
+    return ZF_OK;
+  };
+  int chunk = 8, slot = 0;
+  bool use_graph = true;
+  rc = ZF_OK;
   while (true) {
-    for (int k = 0; k < chunk; ++k)
-      if ((rc = round(k == chunk - 1)) != ZF_OK) return rc;
-    ZF_CUDA(cudaMemcpyAsync(h->h_active, h->n_active, sizeof(unsigned int),
-                            cudaMemcpyDeviceToHost, h->st));
-    ZF_CUDA(cudaStreamSynchronize(h->st));
+    if (use_graph && !execs[slot] && build_graph(chunk, &execs[slot]) != ZF_OK) use_graph = false;
+    if (use_graph) {
+      if (cudaGraphLaunch(execs[slot], h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "cudaGraphLaunch failed"); break; }
+      zf::zf_count_launch((int64_t)kernels_per_round * chunk);
+    } else {
+      for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = round(k == chunk - 1);
+      if (rc != ZF_OK) break;
+      if (cudaMemcpyAsync(h->h_active, h->n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "memcpy failed"); break; }
+    }
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "stream sync failed"); break; }
     if (*h->h_active == 0) break;
-    if (chunk < 64) chunk *= 2;
+    if (chunk < 64) { chunk *= 2; ++slot; }
   }
+  for (auto& ex : execs) if (ex) cudaGraphExecDestroy(ex);
+  if (rc != ZF_OK) return rc;
   if (!c.need_F) {   // res.fun = F(x): one evaluation of the result buffer
     if ((rc = launch_tile<1>(h, n_runs)) != ZF_OK) return rc;
     c.finalize = 1;
@@ -547,6 +600,13 @@ extern "C" int zf_deblur_create(zf_deblur** out, int32_t height, int32_t width,
   h->l1 = l1;
   h->max_runs = max_runs;
   h->st = (cudaStream_t)cuda_stream;
+  if (!h->st) {
+    if (cudaStreamCreate(&h->own_st) != cudaSuccess) {
+      delete h;
+      return zf::zf_fail(ZF_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    h->st = h->own_st;
+  }
   std::memcpy(h->kernel_host, h_kernel, sizeof(double) * ksize * ksize);
   const size_t vb = sizeof(double) * (size_t)max_runs * (size_t)d.n;
   cudaError_t e = cudaSuccess;
@@ -577,6 +637,7 @@ extern "C" void zf_deblur_destroy(zf_deblur* h) {
   cudaFree(h->fy_part); cudaFree(h->fx_part); cudaFree(h->abs_part); cudaFree(h->psum);
   cudaFree(h->runs); cudaFree(h->n_active); cudaFree(h->allerrs); cudaFree(h->allfuns);
   if (h->h_active) cudaFreeHost(h->h_active);
+  if (h->own_st) cudaStreamDestroy(h->own_st);
   delete h;
 }
 
