@@ -637,11 +637,15 @@ def main():
     ap.add_argument("--lasso-rows", type=int, default=65536)
     ap.add_argument("--lasso-cols", type=int, default=16384)
     ap.add_argument("--lasso-iters", type=int, default=20)
-    ap.add_argument("--cameraman-iters", type=int, default=300)
+    ap.add_argument("--cameraman-iters", type=int, default=2000)
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_ours(args)
+    try:
+        if args.impl == "reference":
+            return run_reference_arm(args)
+        return run_ours(args)
+    finally:
+        if _POOL is not None:       # join the CPU-arm workers before interpreter shutdown
+            _POOL.shutdown(wait=True, cancel_futures=True)
 
 
 if __name__ == "__main__":

@@ -4,10 +4,13 @@
 // W = inverse single-level 2-D Haar transform of the coefficient vector [cA,cH,cV,cD].
 // The notebook runs minimize_proximal_gradient once per (a, b) momentum pair under joblib;
 // here every pair is a RUN of one batched solve.  A run's state machine (line search, stop
-// test, t_k, momentum) lives in device memory, so a whole round
-//     grad (tile kernel) -> prox (elementwise) -> [F(candidate) (tile kernel)] -> decide
-// is replayed without any host round trip; the host only polls "runs still active" once per
-// chunk of rounds.  All reductions have a fixed order: runs are bit reproducible.
+// test, t_k, momentum) lives in device memory and is advanced by the LAST CTA of the run to
+// finish a round, so a round is
+//     fixed step, no F trace :  ONE kernel   (gradient + prox + decision)
+//     line search / F trace  :  gradient+prox -> [retry prox] -> F(candidate)+decision
+// replayed from a CUDA graph without any host round trip; the host only polls "runs still
+// active" once per chunk of rounds.  All reductions have a fixed order: runs are bit
+// reproducible.
 //
 // Tile kernel: CTA = 32x32 image tile of one run.  U = W y on the tile + 2R halo (computed
 // from the coefficient vectors, y = x + mom (x - x_prev) formed on the fly), V = R U - b on
@@ -35,9 +38,10 @@ constexpr int DB_VR = DB_T + 2 * DB_MAXR;   // 40
 enum DeblurPhase { DP_INIT = 0, DP_NEW = 1, DP_RETRY = 2, DP_FINAL = 3, DP_DONE = 4 };
 
 struct DeblurRun {
-  double lr, t_prev, mom, F_prev, F_x, f_y, sub_fun, err, na, nb, abs_cand;
+  double lr, t_prev, mom, F_prev, F_x, f_y, sub_fun, err, na, nb;
   long long nit;
-  int status, phase, cur, bt, res_buf, pad;
+  int status, phase, bt, res_buf;
+  int cur, prev, nxt, pad;     // rotating roles of the three coefficient buffers
 };
 
 struct DeblurDims {
@@ -47,6 +51,25 @@ struct DeblurDims {
 };
 
 struct DeblurSums { double gd, dd, abs1, maxd; };
+
+struct DeblurCtl {
+  double tol, tol_internal, decay_rate, l1;
+  long long max_iter;
+  int max_backtrack, nesterov, deprecated, need_F, cap, finalize, store_yg, pad;
+};
+
+struct DeblurBufs {
+  double* X[3];
+  double *Y, *G;
+  const double* b;
+  double *fy_part, *fx_part, *abs_part;     // [run][tile]
+  DeblurSums* tsum;                         // [run][tile]  prox sums of the gradient kernel
+  DeblurSums* psum;                         // [run][block] prox sums of the retry kernel
+  DeblurRun* runs;
+  unsigned int* tickets;                    // [run]
+  double *allerrs, *allfuns;
+  unsigned int* n_active;
+};
 
 __constant__ double c_kernel[81];
 
@@ -61,257 +84,27 @@ __device__ __forceinline__ double db_extrap(double x, double xp, double mom) {
   return __dadd_rn(x, __dmul_rn(mom, __dsub_rn(x, xp)));
 }
 
-// MODE 0: gradient round (U halo 2R, V halo R, writes Y, G, f(y) partial)
-// MODE 1: F evaluation   (U halo R, V tile only, f partial + ||x||_1 partial)
-template <int R, int MODE>
-__global__ void __launch_bounds__(DB_THREADS)
-deblur_tile_kernel(DeblurDims d, const DeblurRun* __restrict__ runs, double* __restrict__ X0,
-                   double* __restrict__ X1, double* __restrict__ Y, double* __restrict__ G,
-                   const double* __restrict__ b, double* __restrict__ f_part,
-                   double* __restrict__ abs_part) {
-  constexpr int T = DB_T;
-  constexpr int HV = (MODE == 0) ? R : 0;         // halo of V
-  // halo of U, rounded up to even so that the region is aligned to the 2x2 Haar blocks
-  constexpr int HU = (((MODE == 0) ? 2 * R : R) + 1) & ~1;
-  constexpr int OFF = HU - HV - R;                // U index of tap (0,0) of V position (0,0)
-  constexpr int UR = T + 2 * HU, VR = T + 2 * HV;
-  constexpr int K = 2 * R + 1;
-  const int run = blockIdx.y;
-  const DeblurRun st = runs[run];
-  const double *xa, *xb;
-  double mom = 0.0;
-  if (MODE == 0) {
-    if (st.phase != DP_NEW) return;
-    xa = (st.cur ? X1 : X0) + (long long)run * d.n;
-    xb = (st.cur ? X0 : X1) + (long long)run * d.n;
-    mom = st.mom;
-  } else {
-    int buf;
-    if (st.phase == DP_INIT) buf = st.cur;
-    else if (st.phase == DP_NEW || st.phase == DP_RETRY) buf = 1 - st.cur;
-    else if (st.phase == DP_FINAL) buf = st.res_buf;
-    else return;
-    xa = (buf ? X1 : X0) + (long long)run * d.n;
-    xb = xa;
-  }
-  __shared__ double U[DB_UR][DB_UR + 1];
-  __shared__ double V[DB_VR][DB_VR + 1];
-  __shared__ double red[2][DB_THREADS / 32];
-  const int tid = threadIdx.x;
-  const int tyo = (blockIdx.x / d.tiles_x) * T, txo = (blockIdx.x % d.tiles_x) * T;
-  const long long q = (long long)d.h2 * d.w2;
-  double abs_acc = 0.0;
-  // ---- 1. U = W y on the halo region, by 2x2 blocks (one coefficient quadruple each)
-  constexpr int UB = UR / 2;
-  for (int blk = tid; blk < UB * UB; blk += DB_THREADS) {
-    const int lbi = blk / UB, lbj = blk % UB;
-    const int i0 = tyo - HU + 2 * lbi, j0 = txo - HU + 2 * lbj;
-    const int gi0 = db_reflect(i0, d.H), gi1 = db_reflect(i0 + 1, d.H);
-    const int gj0 = db_reflect(j0, d.W), gj1 = db_reflect(j0 + 1, d.W);
-    const long long o = (long long)(gi0 >> 1) * d.w2 + (gj0 >> 1);
-    double ca = xa[o], ch = xa[q + o], cv = xa[2 * q + o], cd = xa[3 * q + o];
-    if (MODE == 0) {
-      ca = db_extrap(ca, xb[o], mom);
-      ch = db_extrap(ch, xb[q + o], mom);
-      cv = db_extrap(cv, xb[2 * q + o], mom);
-      cd = db_extrap(cd, xb[3 * q + o], mom);
-    }
-    const bool interior = (i0 >= tyo) && (i0 < tyo + T) && (j0 >= txo) && (j0 < txo + T) &&
-                          (i0 < d.H) && (j0 < d.W);
-    if (interior) {
-      if (MODE == 0) {
-        double* y = Y + (long long)run * d.n;
-        y[o] = ca; y[q + o] = ch; y[2 * q + o] = cv; y[3 * q + o] = cd;
-      } else {
-        abs_acc += fabs(ca) + fabs(ch) + fabs(cv) + fabs(cd);
-      }
-    }
-#pragma unroll
-    for (int di = 0; di < 2; ++di) {
-      const int gi = di ? gi1 : gi0;
-      const double sh = (gi & 1) ? -1.0 : 1.0;
-#pragma unroll
-      for (int dj = 0; dj < 2; ++dj) {
-        const int gj = dj ? gj1 : gj0;
-        const double sv = (gj & 1) ? -1.0 : 1.0;
-        // idwt2 (haar): (cA +- cH +- cV +- cD) / 2, summed left to right
-        U[2 * lbi + di][2 * lbj + dj] = (((ca + sh * ch) + sv * cv) + (sh * sv) * cd) / 2.0;
-      }
-    }
-  }
-  __syncthreads();
-  // ---- 2. V = R U - b at the in-image positions of the V region (vertical strips of 4)
-  double fsum = 0.0;
-  // A thread owns DB_STRIP vertically adjacent outputs: per kernel column it loads
-  // DB_STRIP + 2R values of U once and reuses them for all K kernel rows (8 x K DFMA per
-  // 8 + 2R shared-memory loads; neighbouring lanes read neighbouring columns, conflict free).
-  constexpr int S = DB_STRIP;
-  constexpr int VS = (VR + S - 1) / S;
-  for (int task = tid; task < VS * VR; task += DB_THREADS) {
-    const int li0 = S * (task / VR), lj = task % VR;
-    const int gj = txo - HV + lj;
-    double acc[S];
-#pragma unroll
-    for (int o = 0; o < S; ++o) acc[o] = 0.0;
-#pragma unroll
-    for (int v = 0; v < K; ++v) {
-      double col[S + 2 * R];
-#pragma unroll
-      for (int k = 0; k < S + 2 * R; ++k) {
-        const int row = li0 + k + OFF;
-        col[k] = U[row < DB_UR ? row : DB_UR - 1][lj + v + OFF];
-      }
-#pragma unroll
-      for (int u = 0; u < K; ++u) {
-        const double w = c_kernel[u * K + v];
-#pragma unroll
-        for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
-      }
-    }
-    if (gj >= 0 && gj < d.W) {
-#pragma unroll
-      for (int o = 0; o < S; ++o) {
-        const int li = li0 + o, gi = tyo - HV + li;
-        if (li < VR && gi >= 0 && gi < d.H) {
-          const double val = acc[o] - b[(long long)gi * d.W + gj];
-          V[li][lj] = val;
-          if (li >= HV && li < HV + T && lj >= HV && lj < HV + T) fsum += val * val;
-        }
-      }
-    }
-  }
-  // block reduction of the f partial (and ||x||_1 partial), fixed order
-  fsum = warp_sum(fsum);
-  abs_acc = warp_sum(abs_acc);
-  if ((tid & 31) == 0) { red[0][tid >> 5] = fsum; red[1][tid >> 5] = abs_acc; }
-  __syncthreads();
-  if (tid == 0) {
-    double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-    for (int w = 0; w < DB_THREADS / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; }
-    f_part[(long long)run * d.n_tiles + blockIdx.x] = t0;
-    if (MODE == 1) abs_part[(long long)run * d.n_tiles + blockIdx.x] = t1;
-  }
-  if (MODE == 1) return;
-  // ---- 3. symmetric reflection of V into the out-of-image halo positions
-  for (int idx = tid; idx < VR * VR; idx += DB_THREADS) {
-    const int li = idx / VR, lj = idx % VR;
-    const int gi = tyo - HV + li, gj = txo - HV + lj;
-    if (gi < 0 || gi >= d.H || gj < 0 || gj >= d.W) {
-      const int si = db_reflect(gi, d.H) - (tyo - HV), sj = db_reflect(gj, d.W) - (txo - HV);
-      if (si >= 0 && si < VR && sj >= 0 && sj < VR) V[li][lj] = V[si][sj];
-      else V[li][lj] = 0.0;   // never read by an in-image output
-    }
-  }
-  __syncthreads();
-  // ---- 4. Wimg = R V on the tile (vertical strips of DB_STRIP), into U's storage
-  for (int task = tid; task < (T / S) * T; task += DB_THREADS) {
-    const int li0 = S * (task / T), lj = task % T;
-    double acc[S];
-#pragma unroll
-    for (int o = 0; o < S; ++o) acc[o] = 0.0;
-#pragma unroll
-    for (int v = 0; v < K; ++v) {
-      double col[S + 2 * R];
-#pragma unroll
-      for (int k = 0; k < S + 2 * R; ++k) col[k] = V[li0 + k][lj + v];
-#pragma unroll
-      for (int u = 0; u < K; ++u) {
-        const double w = c_kernel[u * K + v];
-#pragma unroll
-        for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
-      }
-    }
-#pragma unroll
-    for (int o = 0; o < S; ++o) U[li0 + o][lj] = acc[o];
-  }
-  __syncthreads();
-  // ---- 5. gradient coefficients = 2 * dwt2(Wimg) per 2x2 block
-  for (int blk = tid; blk < (T / 2) * (T / 2); blk += DB_THREADS) {
-    const int bi = blk / (T / 2), bj = blk % (T / 2);
-    const int gi = tyo + 2 * bi, gj = txo + 2 * bj;
-    if (gi < d.H && gj < d.W) {
-      const double p00 = U[2 * bi][2 * bj], p01 = U[2 * bi][2 * bj + 1];
-      const double p10 = U[2 * bi + 1][2 * bj], p11 = U[2 * bi + 1][2 * bj + 1];
-      const long long o = (long long)(gi >> 1) * d.w2 + (gj >> 1);
-      double* g = G + (long long)run * d.n;
-      g[o] = 2.0 * ((((p00 + p01) + p10) + p11) / 2.0);
-      g[q + o] = 2.0 * ((((p00 + p01) - p10) - p11) / 2.0);
-      g[2 * q + o] = 2.0 * ((((p00 - p01) + p10) - p11) / 2.0);
-      g[3 * q + o] = 2.0 * ((((p00 - p01) - p10) + p11) / 2.0);
-    }
-  }
-}
-
-// candidate x = soft(y - lr g, lr l1) into the run's spare buffer + block partials
-__global__ void __launch_bounds__(DB_THREADS)
-deblur_prox_kernel(DeblurDims d, const DeblurRun* __restrict__ runs, double l1,
-                   double* __restrict__ X0, double* __restrict__ X1,
-                   const double* __restrict__ Y, const double* __restrict__ G,
-                   DeblurSums* __restrict__ psum) {
-  const int run = blockIdx.y;
-  const DeblurRun st = runs[run];
-  if (st.phase != DP_NEW && st.phase != DP_RETRY) return;
-  double* xn = (st.cur ? X0 : X1) + (long long)run * d.n;     // buffer 1 - cur
-  const double* y = Y + (long long)run * d.n;
-  const double* g = G + (long long)run * d.n;
-  const double lr = st.lr, thr = l1 * lr;
-  DeblurSums s{0.0, 0.0, 0.0, 0.0};
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < d.n;
-       j += (long long)gridDim.x * blockDim.x) {
-    const double gj = g[j], yj = y[j];
-    const double xj = soft_threshold(yj - lr * gj, thr);
-    const double dd = xj - yj;
-    xn[j] = xj;
-    s.gd += gj * dd;
-    s.dd += dd * dd;
-    s.abs1 += fabs(xj);
-    s.maxd = fmax(s.maxd, fabs(dd));
-  }
-  __shared__ DeblurSums sh[DB_THREADS / 32];
-  s.gd = warp_sum(s.gd);
-  s.dd = warp_sum(s.dd);
-  s.abs1 = warp_sum(s.abs1);
-  s.maxd = warp_max(s.maxd);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    DeblurSums t = sh[0];
-    for (int w = 1; w < DB_THREADS / 32; ++w) {
-      t.gd += sh[w].gd; t.dd += sh[w].dd; t.abs1 += sh[w].abs1; t.maxd = fmax(t.maxd, sh[w].maxd);
-    }
-    psum[(long long)run * d.prox_blocks + blockIdx.x] = t;
-  }
-}
-
-struct DeblurCtl {
-  double tol, tol_internal, decay_rate, l1;
-  long long max_iter;
-  int max_backtrack, nesterov, deprecated, need_F, cap, finalize;
-};
-
-// One warp per run: fixed-order reduction of the round's partials, then the reference's
-// scalar logic (proximal_gradient.py:149-155, 279-308, 510-538) by lane 0.
-__global__ void __launch_bounds__(32)
-deblur_decide_kernel(DeblurDims d, DeblurCtl c, DeblurRun* __restrict__ runs,
-                     const double* __restrict__ fy_part, const double* __restrict__ fx_part,
-                     const double* __restrict__ abs_part, const DeblurSums* __restrict__ psum,
-                     double* __restrict__ allerrs, double* __restrict__ allfuns,
-                     unsigned int* __restrict__ n_active) {
-  const int run = blockIdx.x, lane = threadIdx.x;
-  DeblurRun st = runs[run];
+// One warp: fixed-order reduction of the round's partials, then the reference's scalar logic
+// (proximal_gradient.py:149-155, 279-308, 510-538) by lane 0.
+__device__ void deblur_decide(const DeblurDims& d, const DeblurCtl& c, const DeblurBufs& B, int run,
+                              int lane, bool count) {
+  DeblurRun st = B.runs[run];
   if (st.phase == DP_DONE) return;
   if (st.phase == DP_FINAL && !c.finalize) return;   // waits for the host's final F pass
   double fy = 0.0, fx = 0.0, ax = 0.0;
   for (int t = lane; t < d.n_tiles; t += 32) {
-    fy += fy_part[(long long)run * d.n_tiles + t];
-    fx += fx_part[(long long)run * d.n_tiles + t];
-    ax += abs_part[(long long)run * d.n_tiles + t];
+    fy += B.fy_part[(long long)run * d.n_tiles + t];
+    fx += B.fx_part[(long long)run * d.n_tiles + t];
+    ax += B.abs_part[(long long)run * d.n_tiles + t];
   }
   fy = warp_sum(fy); fx = warp_sum(fx); ax = warp_sum(ax);
   DeblurSums s{0.0, 0.0, 0.0, 0.0};
-  for (int t = lane; t < d.prox_blocks; t += 32) {
-    const DeblurSums u = psum[(long long)run * d.prox_blocks + t];
+  const bool from_tiles = (st.phase == DP_NEW);
+  const int n_part = from_tiles ? d.n_tiles : d.prox_blocks;
+  const DeblurSums* part = from_tiles ? B.tsum + (long long)run * d.n_tiles
+                                      : B.psum + (long long)run * d.prox_blocks;
+  for (int t = lane; t < n_part; t += 32) {
+    const DeblurSums u = part[t];
     s.gd += u.gd; s.dd += u.dd; s.abs1 += u.abs1; s.maxd = fmax(s.maxd, u.maxd);
   }
   s.gd = warp_sum(s.gd); s.dd = warp_sum(s.dd); s.abs1 = warp_sum(s.abs1);
@@ -323,7 +116,7 @@ deblur_decide_kernel(DeblurDims d, DeblurCtl c, DeblurRun* __restrict__ runs,
   if (st.phase == DP_INIT) {
     st.F_prev = fxv + c.l1 * ax;
     st.F_x = st.F_prev;
-    if (c.cap > 0 && allfuns) allfuns[(long long)run * (c.cap + 1)] = st.F_prev;
+    if (c.cap > 0 && B.allfuns) B.allfuns[(long long)run * (c.cap + 1)] = st.F_prev;
     st.nit = 1;
     st.phase = DP_NEW;
   } else if (st.phase == DP_FINAL) {
@@ -354,13 +147,13 @@ deblur_decide_kernel(DeblurDims d, DeblurCtl c, DeblurRun* __restrict__ runs,
   if (accepted) {
     st.err = s.maxd;
     if (c.cap > 0 && st.nit <= c.cap) {
-      if (allerrs) allerrs[(long long)run * c.cap + (st.nit - 1)] = st.err;
-      if (allfuns && c.need_F) allfuns[(long long)run * (c.cap + 1) + st.nit] = st.F_x;
+      if (B.allerrs) B.allerrs[(long long)run * c.cap + (st.nit - 1)] = st.err;
+      if (B.allfuns && c.need_F) B.allfuns[(long long)run * (c.cap + 1) + st.nit] = st.F_x;
     }
     const bool conv = st.err < c.tol;
     if (conv || st.nit >= c.max_iter) {
       st.status = conv ? 1 : 0;
-      st.res_buf = 1 - st.cur;
+      st.res_buf = st.nxt;
       st.phase = c.need_F ? DP_DONE : DP_FINAL;
     } else {
       double mom = 0.0;
@@ -371,22 +164,293 @@ deblur_decide_kernel(DeblurDims d, DeblurCtl c, DeblurRun* __restrict__ runs,
         st.t_prev = t_new;
       }
       st.mom = mom;
-      st.cur = 1 - st.cur;       // the candidate becomes x^k, the old x^k becomes x^{k-1}
+      // the candidate becomes x^k, x^k becomes x^{k-1}, the old x^{k-1} is the next candidate
+      const int old_prev = st.prev;
+      st.prev = st.cur; st.cur = st.nxt; st.nxt = old_prev;
       st.F_prev = st.F_x;
       st.nit += 1;
       st.phase = DP_NEW;
     }
   }
-  runs[run] = st;
-  if (n_active && st.phase != DP_DONE && st.phase != DP_FINAL) atomicAdd(n_active, 1u);
+  B.runs[run] = st;
+  if (count && st.phase != DP_DONE && st.phase != DP_FINAL) atomicAdd(B.n_active, 1u);
+}
+
+// MODE 0: gradient round.  U = W y on tile + 2R halo, V = R U - b on tile + R halo, R V on the
+//         tile, gradient coefficients per 2x2 block, and immediately the prox candidate
+//         x = soft(y - lr g, lr l1) of those coefficients into the run's spare buffer, with
+//         the four sums of the subproblem value.
+// MODE 1: F evaluation of a buffer (U halo R, V tile only): f partial + ||x||_1 partial.
+// The last CTA of a run to finish (ticket counter) advances the run's state machine when
+// `decide` is set.
+template <int R, int MODE>
+__global__ void __launch_bounds__(DB_THREADS)
+deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int count) {
+  constexpr int T = DB_T;
+  constexpr int HV = (MODE == 0) ? R : 0;         // halo of V
+  // halo of U, rounded up to even so that the region is aligned to the 2x2 Haar blocks
+  constexpr int HU = (((MODE == 0) ? 2 * R : R) + 1) & ~1;
+  constexpr int OFF = HU - HV - R;                // U index of tap (0,0) of V position (0,0)
+  constexpr int UR = T + 2 * HU, VR = T + 2 * HV;
+  constexpr int K = 2 * R + 1;
+  const int run = blockIdx.y;
+  const DeblurRun st = B.runs[run];
+  const double *xa, *xb;
+  double mom = 0.0;
+  if (MODE == 0) {
+    if (st.phase != DP_NEW) return;
+    xa = B.X[st.cur] + (long long)run * d.n;
+    xb = B.X[st.prev] + (long long)run * d.n;
+    mom = st.mom;
+  } else {
+    int buf;
+    if (st.phase == DP_INIT) buf = st.cur;
+    else if (st.phase == DP_NEW || st.phase == DP_RETRY) buf = st.nxt;
+    else if (st.phase == DP_FINAL && c.finalize) buf = st.res_buf;
+    else return;
+    xa = B.X[buf] + (long long)run * d.n;
+    xb = xa;
+  }
+  __shared__ double U[DB_UR][DB_UR + 1];
+  __shared__ double V[DB_VR][DB_VR + 1];
+  __shared__ double red[6][DB_THREADS / 32];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  const int tyo = (blockIdx.x / d.tiles_x) * T, txo = (blockIdx.x % d.tiles_x) * T;
+  const long long q = (long long)d.h2 * d.w2;
+  double abs_acc = 0.0;
+  // ---- 1. U = W y on the halo region, by 2x2 blocks (one coefficient quadruple each)
+  constexpr int UB = UR / 2;
+  for (int blk = tid; blk < UB * UB; blk += DB_THREADS) {
+    const int lbi = blk / UB, lbj = blk % UB;
+    const int i0 = tyo - HU + 2 * lbi, j0 = txo - HU + 2 * lbj;
+    const int gi0 = db_reflect(i0, d.H), gi1 = db_reflect(i0 + 1, d.H);
+    const int gj0 = db_reflect(j0, d.W), gj1 = db_reflect(j0 + 1, d.W);
+    const long long o = (long long)(gi0 >> 1) * d.w2 + (gj0 >> 1);
+    double ca = xa[o], ch = xa[q + o], cv = xa[2 * q + o], cd = xa[3 * q + o];
+    if (MODE == 0) {
+      ca = db_extrap(ca, xb[o], mom);
+      ch = db_extrap(ch, xb[q + o], mom);
+      cv = db_extrap(cv, xb[2 * q + o], mom);
+      cd = db_extrap(cd, xb[3 * q + o], mom);
+    } else {
+      const bool interior = (i0 >= tyo) && (i0 < tyo + T) && (j0 >= txo) && (j0 < txo + T) &&
+                            (i0 < d.H) && (j0 < d.W);
+      if (interior) abs_acc += fabs(ca) + fabs(ch) + fabs(cv) + fabs(cd);
+    }
+#pragma unroll
+    for (int di = 0; di < 2; ++di) {
+      const int gi = di ? gi1 : gi0;
+      const double sh = (gi & 1) ? -1.0 : 1.0;
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj) {
+        const int gj = dj ? gj1 : gj0;
+        const double sv = (gj & 1) ? -1.0 : 1.0;
+        // idwt2 (haar): (cA +- cH +- cV +- cD) / 2, summed left to right
+        U[2 * lbi + di][2 * lbj + dj] = (((ca + sh * ch) + sv * cv) + (sh * sv) * cd) / 2.0;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 2. V = R U - b at the in-image positions of the V region.
+  // A thread owns DB_STRIP vertically adjacent outputs: per kernel column it loads
+  // DB_STRIP + 2R values of U once and reuses them for all K kernel rows (8 x K DFMA per
+  // 8 + 2R shared-memory loads; neighbouring lanes read neighbouring columns, conflict free).
+  double fsum = 0.0;
+  constexpr int S = DB_STRIP;
+  constexpr int VS = (VR + S - 1) / S;
+  for (int task = tid; task < VS * VR; task += DB_THREADS) {
+    const int li0 = S * (task / VR), lj = task % VR;
+    const int gj = txo - HV + lj;
+    double acc[S];
+#pragma unroll
+    for (int o = 0; o < S; ++o) acc[o] = 0.0;
+#pragma unroll
+    for (int v = 0; v < K; ++v) {
+      double col[S + 2 * R];
+#pragma unroll
+      for (int k = 0; k < S + 2 * R; ++k) {
+        const int row = li0 + k + OFF;
+        col[k] = U[row < DB_UR ? row : DB_UR - 1][lj + v + OFF];
+      }
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        const double w = c_kernel[u * K + v];
+#pragma unroll
+        for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
+      }
+    }
+    if (gj >= 0 && gj < d.W) {
+#pragma unroll
+      for (int o = 0; o < S; ++o) {
+        const int li = li0 + o, gi = tyo - HV + li;
+        if (li < VR && gi >= 0 && gi < d.H) {
+          const double val = acc[o] - B.b[(long long)gi * d.W + gj];
+          V[li][lj] = val;
+          if (li >= HV && li < HV + T && lj >= HV && lj < HV + T) fsum += val * val;
+        }
+      }
+    }
+  }
+  DeblurSums ps{0.0, 0.0, 0.0, 0.0};
+  if (MODE == 0) {
+    __syncthreads();
+    // ---- 3. symmetric reflection of V into the out-of-image halo positions
+    for (int idx = tid; idx < VR * VR; idx += DB_THREADS) {
+      const int li = idx / VR, lj = idx % VR;
+      const int gi = tyo - HV + li, gj = txo - HV + lj;
+      if (gi < 0 || gi >= d.H || gj < 0 || gj >= d.W) {
+        const int si = db_reflect(gi, d.H) - (tyo - HV), sj = db_reflect(gj, d.W) - (txo - HV);
+        if (si >= 0 && si < VR && sj >= 0 && sj < VR) V[li][lj] = V[si][sj];
+        else V[li][lj] = 0.0;   // never read by an in-image output
+      }
+    }
+    __syncthreads();
+    // ---- 4. Wimg = R V on the tile (vertical strips of DB_STRIP), into U's storage
+    for (int task = tid; task < (T / S) * T; task += DB_THREADS) {
+      const int li0 = S * (task / T), lj = task % T;
+      double acc[S];
+#pragma unroll
+      for (int o = 0; o < S; ++o) acc[o] = 0.0;
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        double col[S + 2 * R];
+#pragma unroll
+        for (int k = 0; k < S + 2 * R; ++k) col[k] = V[li0 + k][lj + v];
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+          const double w = c_kernel[u * K + v];
+#pragma unroll
+          for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < S; ++o) U[li0 + o][lj] = acc[o];
+    }
+    __syncthreads();
+    // ---- 5. gradient coefficients = 2 * dwt2(Wimg) per 2x2 block, and the prox candidate
+    double* xn = B.X[st.nxt] + (long long)run * d.n;
+    const double lr = st.lr, thr = c.l1 * lr;
+    for (int blk = tid; blk < (T / 2) * (T / 2); blk += DB_THREADS) {
+      const int bi = blk / (T / 2), bj = blk % (T / 2);
+      const int gi = tyo + 2 * bi, gj = txo + 2 * bj;
+      if (gi < d.H && gj < d.W) {
+        const double p00 = U[2 * bi][2 * bj], p01 = U[2 * bi][2 * bj + 1];
+        const double p10 = U[2 * bi + 1][2 * bj], p11 = U[2 * bi + 1][2 * bj + 1];
+        const long long o = (long long)(gi >> 1) * d.w2 + (gj >> 1);
+        double g4[4];
+        g4[0] = 2.0 * ((((p00 + p01) + p10) + p11) / 2.0);
+        g4[1] = 2.0 * ((((p00 + p01) - p10) - p11) / 2.0);
+        g4[2] = 2.0 * ((((p00 - p01) + p10) - p11) / 2.0);
+        g4[3] = 2.0 * ((((p00 - p01) - p10) + p11) / 2.0);
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb) {
+          const long long oo = sb * q + o;
+          const double yj = db_extrap(xa[oo], xb[oo], mom);
+          const double gj4 = g4[sb];
+          const double xj = soft_threshold(yj - lr * gj4, thr);
+          const double dd = xj - yj;
+          xn[oo] = xj;
+          if (c.store_yg) {
+            B.Y[(long long)run * d.n + oo] = yj;
+            B.G[(long long)run * d.n + oo] = gj4;
+          }
+          ps.gd += gj4 * dd;
+          ps.dd += dd * dd;
+          ps.abs1 += fabs(xj);
+          ps.maxd = fmax(ps.maxd, fabs(dd));
+        }
+      }
+    }
+  }
+  // ---- block reduction of the partials (fixed order), ticket, decision by the last CTA
+  fsum = warp_sum(fsum);
+  abs_acc = warp_sum(abs_acc);
+  ps.gd = warp_sum(ps.gd);
+  ps.dd = warp_sum(ps.dd);
+  ps.abs1 = warp_sum(ps.abs1);
+  ps.maxd = warp_max(ps.maxd);
+  if ((tid & 31) == 0) {
+    const int w = tid >> 5;
+    red[0][w] = fsum; red[1][w] = abs_acc;
+    red[2][w] = ps.gd; red[3][w] = ps.dd; red[4][w] = ps.abs1; red[5][w] = ps.maxd;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int w = 0; w < DB_THREADS / 32; ++w) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) t[k] += red[k][w];
+      t[5] = fmax(t[5], red[5][w]);
+    }
+    const long long slot = (long long)run * d.n_tiles + blockIdx.x;
+    if (MODE == 0) {
+      B.fy_part[slot] = t[0];
+      B.tsum[slot] = DeblurSums{t[2], t[3], t[4], t[5]};
+    } else {
+      B.fx_part[slot] = t[0];
+      B.abs_part[slot] = t[1];
+    }
+    int last = 0;
+    if (decide) {
+      __threadfence();
+      const unsigned int done = atomicAdd(&B.tickets[run], 1u);
+      last = (done == (unsigned int)d.n_tiles - 1u);
+      if (last) B.tickets[run] = 0u;
+    }
+    is_last = last;
+  }
+  __syncthreads();
+  if (decide && is_last && tid < 32) {
+    __threadfence();
+    deblur_decide(d, c, B, run, tid, count != 0);
+  }
+}
+
+// Line-search retry: the same gradient, a smaller step.  x = soft(y - lr g, lr l1) from the
+// stored y and g into the run's spare buffer + block partials.
+__global__ void __launch_bounds__(DB_THREADS)
+deblur_prox_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B) {
+  const int run = blockIdx.y;
+  const DeblurRun st = B.runs[run];
+  if (st.phase != DP_RETRY) return;
+  double* xn = B.X[st.nxt] + (long long)run * d.n;
+  const double* y = B.Y + (long long)run * d.n;
+  const double* g = B.G + (long long)run * d.n;
+  const double lr = st.lr, thr = c.l1 * lr;
+  DeblurSums s{0.0, 0.0, 0.0, 0.0};
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < d.n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double gj = g[j], yj = y[j];
+    const double xj = soft_threshold(yj - lr * gj, thr);
+    const double dd = xj - yj;
+    xn[j] = xj;
+    s.gd += gj * dd;
+    s.dd += dd * dd;
+    s.abs1 += fabs(xj);
+    s.maxd = fmax(s.maxd, fabs(dd));
+  }
+  __shared__ DeblurSums sh[DB_THREADS / 32];
+  s.gd = warp_sum(s.gd);
+  s.dd = warp_sum(s.dd);
+  s.abs1 = warp_sum(s.abs1);
+  s.maxd = warp_max(s.maxd);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    DeblurSums t = sh[0];
+    for (int w = 1; w < DB_THREADS / 32; ++w) {
+      t.gd += sh[w].gd; t.dd += sh[w].dd; t.abs1 += sh[w].abs1; t.maxd = fmax(t.maxd, sh[w].maxd);
+    }
+    B.psum[(long long)run * d.prox_blocks + blockIdx.x] = t;
+  }
 }
 
 __global__ void __launch_bounds__(DB_THREADS)
-deblur_gather_kernel(DeblurDims d, const DeblurRun* __restrict__ runs,
-                     const double* __restrict__ X0, const double* __restrict__ X1,
-                     double* __restrict__ out) {
+deblur_gather_kernel(DeblurDims d, DeblurBufs B, double* __restrict__ out) {
   const int run = blockIdx.y;
-  const double* src = (runs[run].res_buf ? X1 : X0) + (long long)run * d.n;
+  const double* src = B.X[B.runs[run].res_buf] + (long long)run * d.n;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < d.n;
        j += (long long)gridDim.x * blockDim.x)
     out[(long long)run * d.n + j] = src[j];
@@ -397,15 +461,11 @@ deblur_gather_kernel(DeblurDims d, const DeblurRun* __restrict__ runs,
 // =======================================================================================
 struct zf_deblur {
   zf::DeblurDims d{};
+  zf::DeblurBufs B{};
   double l1 = 0.0;
   int max_runs = 0;
-  double *b = nullptr, *X0 = nullptr, *X1 = nullptr, *Y = nullptr, *G = nullptr;
-  double *fy_part = nullptr, *fx_part = nullptr, *abs_part = nullptr;
-  zf::DeblurSums* psum = nullptr;
-  zf::DeblurRun* runs = nullptr;
-  unsigned int* n_active = nullptr;
   unsigned int* h_active = nullptr;   // pinned
-  double *allerrs = nullptr, *allfuns = nullptr;
+  double* scratch = nullptr;          // max_runs x n: gathered results
   size_t trace_cap_alloc = 0;
   cudaStream_t st = nullptr;
   cudaStream_t own_st = nullptr;     // created when the caller passes no stream (graphs cannot
@@ -423,35 +483,23 @@ namespace {
   } while (0)
 
 template <int MODE>
-int launch_tile(zf_deblur* h, int n_runs) {
+int launch_tile(zf_deblur* h, int n_runs, const zf::DeblurCtl& c, bool decide, bool count) {
   dim3 grid((unsigned)h->d.n_tiles, (unsigned)n_runs);
-  double* fp = MODE == 0 ? h->fy_part : h->fx_part;
+  const int dd = decide ? 1 : 0, cc = count ? 1 : 0;
   switch (h->d.R) {
-    case 1: zf::deblur_tile_kernel<1, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
-    case 2: zf::deblur_tile_kernel<2, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
-    case 3: zf::deblur_tile_kernel<3, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
-    default: zf::deblur_tile_kernel<4, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y, h->G, h->b, fp, h->abs_part); break;
+    case 1: zf::deblur_tile_kernel<1, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
+    case 2: zf::deblur_tile_kernel<2, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
+    case 3: zf::deblur_tile_kernel<3, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
+    default: zf::deblur_tile_kernel<4, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
   }
   ZF_CUDA(cudaGetLastError());
   if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
 }
 
-int launch_prox(zf_deblur* h, int n_runs) {
+int launch_prox(zf_deblur* h, int n_runs, const zf::DeblurCtl& c) {
   dim3 grid((unsigned)h->d.prox_blocks, (unsigned)n_runs);
-  zf::deblur_prox_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->l1, h->X0, h->X1,
-                                                            h->Y, h->G, h->psum);
-  ZF_CUDA(cudaGetLastError());
-  if (!h->capturing) zf::zf_count_launch();
-  return ZF_OK;
-}
-
-int launch_decide(zf_deblur* h, int n_runs, const zf::DeblurCtl& c, bool count) {
-  zf::deblur_decide_kernel<<<n_runs, 32, 0, h->st>>>(h->d, c, h->runs, h->fy_part, h->fx_part,
-                                                    h->abs_part, h->psum,
-                                                    c.cap > 0 ? h->allerrs : nullptr,
-                                                    c.cap > 0 ? h->allfuns : nullptr,
-                                                    count ? h->n_active : nullptr);
+  zf::deblur_prox_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B);
   ZF_CUDA(cudaGetLastError());
   if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
@@ -468,7 +516,18 @@ int deblur_check_options(const zf_options* o) {
   return ZF_OK;
 }
 
-// Solve n_runs runs whose x0 is already in X0/X1 (both buffers) on the device.
+int zero_partials(zf_deblur* h, int n_runs) {
+  const size_t part_bytes = sizeof(double) * (size_t)n_runs * h->d.n_tiles;
+  ZF_CUDA(cudaMemsetAsync(h->B.fy_part, 0, part_bytes, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->B.fx_part, 0, part_bytes, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->B.abs_part, 0, part_bytes, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->B.tsum, 0, sizeof(zf::DeblurSums) * (size_t)n_runs * h->d.n_tiles, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->B.psum, 0, sizeof(zf::DeblurSums) * (size_t)n_runs * h->d.prox_blocks, h->st));
+  ZF_CUDA(cudaMemsetAsync(h->B.tickets, 0, sizeof(unsigned int) * (size_t)n_runs, h->st));
+  return ZF_OK;
+}
+
+// Solve n_runs runs whose x0 is already in all three X buffers on the device.
 int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_ab,
                bool want_funs) {
   const int cap = opt->trace_capacity;
@@ -477,17 +536,19 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
   c.l1 = h->l1; c.max_iter = opt->max_iter; c.max_backtrack = opt->max_backtrack_iter;
   c.nesterov = opt->nesterov; c.deprecated = opt->deprecated; c.cap = cap;
   c.need_F = (opt->decay_rate != 1.0) || (cap > 0 && want_funs);
+  c.store_yg = (opt->decay_rate != 1.0);
   if (cap > 0) {
     const size_t need = (size_t)n_runs * ((size_t)cap + 1);
     if (need > h->trace_cap_alloc) {
-      cudaFree(h->allerrs); cudaFree(h->allfuns);
-      h->allerrs = h->allfuns = nullptr;
-      ZF_CUDA(cudaMalloc((void**)&h->allerrs, need * 8));
-      ZF_CUDA(cudaMalloc((void**)&h->allfuns, need * 8));
+      cudaFree(h->B.allerrs); cudaFree(h->B.allfuns);
+      h->B.allerrs = h->B.allfuns = nullptr;
+      h->trace_cap_alloc = 0;
+      ZF_CUDA(cudaMalloc((void**)&h->B.allerrs, need * 8));
+      ZF_CUDA(cudaMalloc((void**)&h->B.allfuns, need * 8));
       h->trace_cap_alloc = need;
     }
-    ZF_CUDA(cudaMemsetAsync(h->allerrs, 0, (size_t)n_runs * cap * 8, h->st));
-    ZF_CUDA(cudaMemsetAsync(h->allfuns, 0, (size_t)n_runs * (cap + 1) * 8, h->st));
+    ZF_CUDA(cudaMemsetAsync(h->B.allerrs, 0, (size_t)n_runs * cap * 8, h->st));
+    ZF_CUDA(cudaMemsetAsync(h->B.allfuns, 0, (size_t)n_runs * (cap + 1) * 8, h->st));
   }
   std::vector<zf::DeblurRun> init((size_t)n_runs);
   for (int r = 0; r < n_runs; ++r) {
@@ -499,29 +560,26 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
     s.err = INFINITY;
     s.nit = c.need_F ? 0 : 1;
     s.phase = c.need_F ? zf::DP_INIT : zf::DP_NEW;
-    s.cur = 0; s.res_buf = 0;
+    s.cur = 0; s.prev = 1; s.nxt = 2; s.res_buf = 0;
   }
-  ZF_CUDA(cudaMemcpyAsync(h->runs, init.data(), sizeof(zf::DeblurRun) * n_runs,
+  ZF_CUDA(cudaMemcpyAsync(h->B.runs, init.data(), sizeof(zf::DeblurRun) * n_runs,
                           cudaMemcpyHostToDevice, h->st));
-  const size_t part_bytes = sizeof(double) * (size_t)n_runs * h->d.n_tiles;
-  ZF_CUDA(cudaMemsetAsync(h->fy_part, 0, part_bytes, h->st));
-  ZF_CUDA(cudaMemsetAsync(h->fx_part, 0, part_bytes, h->st));
-  ZF_CUDA(cudaMemsetAsync(h->abs_part, 0, part_bytes, h->st));
-  ZF_CUDA(cudaMemsetAsync(h->psum, 0, sizeof(zf::DeblurSums) * (size_t)n_runs * h->d.prox_blocks, h->st));
+  int rc = zero_partials(h, n_runs);
+  if (rc != ZF_OK) return rc;
   ZF_CUDA(cudaStreamSynchronize(h->st));   // `init` must outlive the copy
-  int rc;
+  // one round; `count`: the deciding kernel also counts the runs that remain active
   auto round = [&](bool count) -> int {
-    if ((rc = launch_tile<0>(h, n_runs)) != ZF_OK) return rc;
-    if ((rc = launch_prox(h, n_runs)) != ZF_OK) return rc;
-    if (c.need_F && (rc = launch_tile<1>(h, n_runs)) != ZF_OK) return rc;
-    if (count) ZF_CUDA(cudaMemsetAsync(h->n_active, 0, sizeof(unsigned int), h->st));
-    return launch_decide(h, n_runs, c, count);
+    int r2;
+    if (count) ZF_CUDA(cudaMemsetAsync(h->B.n_active, 0, sizeof(unsigned int), h->st));
+    if (!c.need_F) return launch_tile<0>(h, n_runs, c, true, count);
+    if ((r2 = launch_tile<0>(h, n_runs, c, false, false)) != ZF_OK) return r2;
+    if (c.store_yg && (r2 = launch_prox(h, n_runs, c)) != ZF_OK) return r2;
+    return launch_tile<1>(h, n_runs, c, true, count);
   };
   // Chunks of rounds between polls (8, 16, 32, 64, 64, ...: short solves do not over-run much,
   // long ones poll rarely).  A chunk is captured once into a CUDA graph and replayed: every
-  // kernel argument is constant during a solve (all state is in device memory), and a round
-  // is ~4 small kernels, so per-launch CPU cost would otherwise rival the GPU time.
-  const int kernels_per_round = 3 + (c.need_F ? 1 : 0);
+  // kernel argument is constant during a solve (all state is in device memory).
+  const int kernels_per_round = c.need_F ? (c.store_yg ? 3 : 2) : 1;
   cudaGraphExec_t execs[4] = {nullptr, nullptr, nullptr, nullptr};
   auto build_graph = [&](int chunk, cudaGraphExec_t* out) -> int {
     cudaGraph_t graph = nullptr;
@@ -533,7 +591,7 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
     int r2 = ZF_OK;
     for (int k = 0; k < chunk && r2 == ZF_OK; ++k) r2 = round(k == chunk - 1);
     if (r2 == ZF_OK &&
-        cudaMemcpyAsync(h->h_active, h->n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+        cudaMemcpyAsync(h->h_active, h->B.n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost,
                         h->st) != cudaSuccess)
       r2 = ZF_ERR_CUDA;
     h->capturing = false;
@@ -559,7 +617,7 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
     } else {
       for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = round(k == chunk - 1);
       if (rc != ZF_OK) break;
-      if (cudaMemcpyAsync(h->h_active, h->n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "memcpy failed"); break; }
+      if (cudaMemcpyAsync(h->h_active, h->B.n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "memcpy failed"); break; }
     }
     if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "stream sync failed"); break; }
     if (*h->h_active == 0) break;
@@ -568,9 +626,8 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
   for (auto& ex : execs) if (ex) cudaGraphExecDestroy(ex);
   if (rc != ZF_OK) return rc;
   if (!c.need_F) {   // res.fun = F(x): one evaluation of the result buffer
-    if ((rc = launch_tile<1>(h, n_runs)) != ZF_OK) return rc;
     c.finalize = 1;
-    if ((rc = launch_decide(h, n_runs, c, false)) != ZF_OK) return rc;
+    if ((rc = launch_tile<1>(h, n_runs, c, true, false)) != ZF_OK) return rc;
   }
   return ZF_OK;
 }
@@ -611,17 +668,23 @@ extern "C" int zf_deblur_create(zf_deblur** out, int32_t height, int32_t width,
   const size_t vb = sizeof(double) * (size_t)max_runs * (size_t)d.n;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-  alloc((void**)&h->b, sizeof(double) * (size_t)d.n);
-  alloc((void**)&h->X0, vb); alloc((void**)&h->X1, vb); alloc((void**)&h->Y, vb); alloc((void**)&h->G, vb);
-  alloc((void**)&h->fy_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
-  alloc((void**)&h->fx_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
-  alloc((void**)&h->abs_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
-  alloc((void**)&h->psum, sizeof(zf::DeblurSums) * (size_t)max_runs * d.prox_blocks);
-  alloc((void**)&h->runs, sizeof(zf::DeblurRun) * (size_t)max_runs);
-  alloc((void**)&h->n_active, sizeof(unsigned int));
+  zf::DeblurBufs& B = h->B;
+  double* bimg = nullptr;
+  alloc((void**)&bimg, sizeof(double) * (size_t)d.n);
+  B.b = bimg;
+  for (int k = 0; k < 3; ++k) alloc((void**)&B.X[k], vb);
+  alloc((void**)&B.Y, vb); alloc((void**)&B.G, vb); alloc((void**)&h->scratch, vb);
+  alloc((void**)&B.fy_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
+  alloc((void**)&B.fx_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
+  alloc((void**)&B.abs_part, sizeof(double) * (size_t)max_runs * d.n_tiles);
+  alloc((void**)&B.tsum, sizeof(zf::DeblurSums) * (size_t)max_runs * d.n_tiles);
+  alloc((void**)&B.psum, sizeof(zf::DeblurSums) * (size_t)max_runs * d.prox_blocks);
+  alloc((void**)&B.runs, sizeof(zf::DeblurRun) * (size_t)max_runs);
+  alloc((void**)&B.tickets, sizeof(unsigned int) * (size_t)max_runs);
+  alloc((void**)&B.n_active, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_active, sizeof(unsigned int));
   if (e == cudaSuccess)
-    e = cudaMemcpyAsync(h->b, h_observed, sizeof(double) * (size_t)d.n, cudaMemcpyHostToDevice, h->st);
+    e = cudaMemcpyAsync(bimg, h_observed, sizeof(double) * (size_t)d.n, cudaMemcpyHostToDevice, h->st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
   if (e != cudaSuccess) {
     zf_deblur_destroy(h);
@@ -633,9 +696,13 @@ extern "C" int zf_deblur_create(zf_deblur** out, int32_t height, int32_t width,
 
 extern "C" void zf_deblur_destroy(zf_deblur* h) {
   if (!h) return;
-  cudaFree(h->b); cudaFree(h->X0); cudaFree(h->X1); cudaFree(h->Y); cudaFree(h->G);
-  cudaFree(h->fy_part); cudaFree(h->fx_part); cudaFree(h->abs_part); cudaFree(h->psum);
-  cudaFree(h->runs); cudaFree(h->n_active); cudaFree(h->allerrs); cudaFree(h->allfuns);
+  zf::DeblurBufs& B = h->B;
+  cudaFree(const_cast<double*>(B.b));
+  for (int k = 0; k < 3; ++k) cudaFree(B.X[k]);
+  cudaFree(B.Y); cudaFree(B.G); cudaFree(h->scratch);
+  cudaFree(B.fy_part); cudaFree(B.fx_part); cudaFree(B.abs_part); cudaFree(B.tsum);
+  cudaFree(B.psum); cudaFree(B.runs); cudaFree(B.tickets); cudaFree(B.n_active);
+  cudaFree(B.allerrs); cudaFree(B.allfuns);
   if (h->h_active) cudaFreeHost(h->h_active);
   if (h->own_st) cudaStreamDestroy(h->own_st);
   delete h;
@@ -667,25 +734,26 @@ static int deblur_solve_impl(zf_deblur* h, const zf_options* opt, int64_t n_runs
   const cudaMemcpyKind kin = x0_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   for (int64_t r = 0; r < n_runs; ++r) {
     const double* src = x0 + (x0_is_batched ? (size_t)r * h->d.n : 0);
-    ZF_CUDA(cudaMemcpyAsync(h->X0 + (size_t)r * h->d.n, src, nb, kin, h->st));
-    ZF_CUDA(cudaMemcpyAsync(h->X1 + (size_t)r * h->d.n, src, nb, kin, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->B.X[0] + (size_t)r * h->d.n, src, nb, kin, h->st));
   }
+  // x^0 = x^{-1} = x0 (proximal_gradient.py:463-465); the third buffer is the first candidate
+  ZF_CUDA(cudaMemcpyAsync(h->B.X[1], h->B.X[0], nb * (size_t)n_runs, cudaMemcpyDeviceToDevice, h->st));
   rc = deblur_run(h, opt, (int)n_runs, h_ab, out->allfuns != nullptr);
   if (rc != ZF_OK) return rc;
   // results
   const cudaMemcpyKind kout = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   dim3 grid((unsigned)h->d.prox_blocks, (unsigned)n_runs);
-  zf::deblur_gather_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->runs, h->X0, h->X1, h->Y);
+  zf::deblur_gather_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, h->B, h->scratch);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
-  ZF_CUDA(cudaMemcpyAsync(out->x, h->Y, nb * (size_t)n_runs, kout, h->st));
+  ZF_CUDA(cudaMemcpyAsync(out->x, h->scratch, nb * (size_t)n_runs, kout, h->st));
   std::vector<zf::DeblurRun> fin((size_t)n_runs);
-  ZF_CUDA(cudaMemcpyAsync(fin.data(), h->runs, sizeof(zf::DeblurRun) * n_runs, cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaMemcpyAsync(fin.data(), h->B.runs, sizeof(zf::DeblurRun) * n_runs, cudaMemcpyDeviceToHost, h->st));
   const int cap = opt->trace_capacity;
   if (cap > 0 && out->allerrs)
-    ZF_CUDA(cudaMemcpyAsync(out->allerrs, h->allerrs, (size_t)n_runs * cap * 8, kout, h->st));
+    ZF_CUDA(cudaMemcpyAsync(out->allerrs, h->B.allerrs, (size_t)n_runs * cap * 8, kout, h->st));
   if (cap > 0 && out->allfuns)
-    ZF_CUDA(cudaMemcpyAsync(out->allfuns, h->allfuns, (size_t)n_runs * (cap + 1) * 8, kout, h->st));
+    ZF_CUDA(cudaMemcpyAsync(out->allfuns, h->B.allfuns, (size_t)n_runs * (cap + 1) * 8, kout, h->st));
   ZF_CUDA(cudaStreamSynchronize(h->st));
   if (out_on_device) {
     // scalars are small: stage on host, copy up
@@ -736,25 +804,32 @@ extern "C" int zf_deblur_eval_host(zf_deblur* h, int64_t n_points, const double*
   if (rc != ZF_OK) return rc;
   const int n = (int)n_points;
   const size_t nb = sizeof(double) * (size_t)h->d.n * n;
-  ZF_CUDA(cudaMemcpyAsync(h->X0, h_X, nb, cudaMemcpyHostToDevice, h->st));
-  ZF_CUDA(cudaMemcpyAsync(h->X1, h_X, nb, cudaMemcpyHostToDevice, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->B.X[0], h_X, nb, cudaMemcpyHostToDevice, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->B.X[1], h_X, nb, cudaMemcpyHostToDevice, h->st));
+  rc = zero_partials(h, n);
+  if (rc != ZF_OK) return rc;
+  zf::DeblurCtl c{};
+  c.l1 = h->l1; c.decay_rate = 0.5; c.need_F = 1; c.store_yg = 1;
   std::vector<zf::DeblurRun> init((size_t)n);
-  for (auto& s : init) { std::memset(&s, 0, sizeof(s)); s.phase = zf::DP_NEW; s.lr = 1.0; }
-  ZF_CUDA(cudaMemcpyAsync(h->runs, init.data(), sizeof(zf::DeblurRun) * n, cudaMemcpyHostToDevice, h->st));
-  rc = launch_tile<0>(h, n);           // G = jac_f(x), fy_part = f(x) partials
+  for (auto& s : init) {
+    std::memset(&s, 0, sizeof(s));
+    s.phase = zf::DP_NEW; s.lr = 1.0; s.cur = 0; s.prev = 1; s.nxt = 2;
+  }
+  ZF_CUDA(cudaMemcpyAsync(h->B.runs, init.data(), sizeof(zf::DeblurRun) * n, cudaMemcpyHostToDevice, h->st));
+  rc = launch_tile<0>(h, n, c, false, false);      // G = jac_f(x) (no state change)
   if (rc != ZF_OK) return rc;
   for (auto& s : init) s.phase = zf::DP_INIT;
   ZF_CUDA(cudaStreamSynchronize(h->st));
-  ZF_CUDA(cudaMemcpyAsync(h->runs, init.data(), sizeof(zf::DeblurRun) * n, cudaMemcpyHostToDevice, h->st));
-  rc = launch_tile<1>(h, n);           // fx_part, abs_part of x
+  ZF_CUDA(cudaMemcpyAsync(h->B.runs, init.data(), sizeof(zf::DeblurRun) * n, cudaMemcpyHostToDevice, h->st));
+  rc = launch_tile<1>(h, n, c, false, false);      // fx_part, abs_part of x
   if (rc != ZF_OK) return rc;
   std::vector<double> fp((size_t)n * h->d.n_tiles), ap((size_t)n * h->d.n_tiles);
-  ZF_CUDA(cudaMemcpyAsync(fp.data(), h->fx_part, fp.size() * 8, cudaMemcpyDeviceToHost, h->st));
-  ZF_CUDA(cudaMemcpyAsync(ap.data(), h->abs_part, ap.size() * 8, cudaMemcpyDeviceToHost, h->st));
-  if (h_jac) ZF_CUDA(cudaMemcpyAsync(h_jac, h->G, nb, cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaMemcpyAsync(fp.data(), h->B.fx_part, fp.size() * 8, cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaMemcpyAsync(ap.data(), h->B.abs_part, ap.size() * 8, cudaMemcpyDeviceToHost, h->st));
+  if (h_jac) ZF_CUDA(cudaMemcpyAsync(h_jac, h->B.G, nb, cudaMemcpyDeviceToHost, h->st));
   ZF_CUDA(cudaStreamSynchronize(h->st));
   for (int r = 0; r < n; ++r) {
-    // same fixed order as deblur_decide_kernel: lane-strided partial sums, then butterfly
+    // same fixed order as deblur_decide: lane-strided partial sums, then butterfly
     double lf[32] = {0}, la[32] = {0};
     for (int t = 0; t < h->d.n_tiles; ++t) { lf[t & 31] += fp[(size_t)r * h->d.n_tiles + t]; la[t & 31] += ap[(size_t)r * h->d.n_tiles + t]; }
     for (int o = 16; o > 0; o >>= 1)
