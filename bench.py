@@ -320,6 +320,7 @@ def run_ours(args):
     converged = 0
     nit_sum = 0
     ndual_sum = 0
+    nit_max = 0
     barrier()
     for k in range(args.steps):
         flush.zero_()
@@ -329,6 +330,7 @@ def run_ours(args):
         ev[k][1].synchronize()
         converged += int((out_status == 1).sum().item())
         nit_sum += int(out_nit.sum().item())
+        nit_max = max(nit_max, int(out_nit.max().item()))
         ndual_sum += int(out_ndual.sum().item())
     barrier()
     launches = _lib.launch_count() - launches0
@@ -385,7 +387,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "nit_mean": nit_all / (S * world * args.steps),
+            "nit_mean": nit_all / (S * world * args.steps), "nit_max_rank0": nit_max,
             "dual_evals_per_solve": ndual_all / (S * world * args.steps),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -411,7 +413,7 @@ def run_ours(args):
         also = {}
         if not args.no_extras:
             for name, fn in (("lasso", bench_lasso), ("cameraman", bench_cameraman),
-                             ("ab_sweep", bench_sweep)):
+                             ("ab_sweep", bench_sweep), ("batch_scaling", bench_batch_scaling)):
                 try:
                     also[name] = fn(args, dev, rank, world)
                 except Exception as e:  # extras must never lose the headline line
@@ -592,6 +594,55 @@ def bench_cameraman(args, dev, rank, world):
         out["cpu_fista_iters_per_s"] = sum(g[0] for g in got) / cdt
         out["cpu_sample"] = (f"{cpu_iters} iterations of each of the 15 runs, oracle port "
                              f"(scipy correlate2d + numpy Haar), {cores} cores")
+    return out
+
+
+def bench_batch_scaling(args, dev, rank, world):
+    """The headline problem at larger batches per GPU (device-resident, CUDA events): the
+    kernel is latency bound at 1024 starts (7 % of the warp slots), so solves/s keeps growing
+    with the batch until the FP64 pipe saturates."""
+    import torch
+
+    from zfista_b200 import _lib
+    import zfista_b200.problems as zp
+    from zfista_b200.proximal_gradient import _make_options
+
+    spec = workload_spec(args.workload)
+    prob = getattr(zp, spec["cls"])(**spec["kw"])
+    n, m = prob.n_features, prob.n_objectives
+    o = spec["opts"]
+    opts = _make_options(1.0, 1e-5, o["tol_internal"], o["max_iter"],
+                         o.get("max_iter_internal", 100000), 100, False, 0.5,
+                         o.get("nesterov", False), (0, 0.25), False, "reference", 0)
+    desc, keep = prob.descriptor()
+    L = _lib.lib()
+    stream = torch.cuda.current_stream()
+    out = {}
+    for S in (1024, 4096, 16384, 65536):
+        rng = np.random.RandomState(5 + rank)
+        X0 = torch.from_numpy(rng.uniform(spec["low"], spec["high"], size=(S, n))).to(dev)
+        x = torch.empty(S, n, dtype=torch.float64, device=dev)
+        fun = torch.empty(S, m, dtype=torch.float64, device=dev)
+        nit = torch.empty(S, dtype=torch.int64, device=dev)
+        status = torch.empty(S, dtype=torch.int32, device=dev)
+        res = _lib.ZfResult()
+        res.x, res.fun, res.nit, res.status = (x.data_ptr(), fun.data_ptr(), nit.data_ptr(),
+                                               status.data_ptr())
+
+        def step():
+            _lib.check(L.zf_solve_batched_device(C.byref(desc), C.byref(opts), S,
+                                                 C.c_void_p(X0.data_ptr()), None, C.byref(res),
+                                                 C.c_void_p(stream.cuda_stream)))
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        out[str(S)] = {"ms": ms, "solves_per_s": float((status == 1).sum().item()) / (ms / 1e3)}
+    del keep
     return out
 
 

@@ -129,3 +129,41 @@ def test_cameraman_size_properties(gpu):
         assert F[-1] < F[0]
         rec = prob.idwt_array(r.x)
         assert np.linalg.norm(rec - img) < np.linalg.norm(obs - img)
+
+
+def test_device_entry_point(gpu):
+    """zf_deblur_solve_device (device x0 / results) == the host entry point."""
+    import ctypes as C
+
+    import torch
+
+    from zfista_b200 import _lib
+    from zfista_b200.proximal_gradient import _make_options
+
+    d = helpers.load("deblur")
+    tag = "s48x64"
+    prob = _problem(d, tag)
+    pairs, L, x0 = d[f"{tag}_pairs"][:3], float(d[f"{tag}_L"]), d[f"{tag}_x0"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        host = prob.minimize_proximal_gradient_batched(x0, pairs, lr=1 / L, decay_rate=1,
+                                                       nesterov=True, max_iter=400)
+    n = x0.shape[0]
+    dev = torch.device("cuda", 0)
+    x0d = torch.from_numpy(x0).to(dev)
+    x = torch.empty(3, n, dtype=torch.float64, device=dev)
+    fun = torch.empty(3, dtype=torch.float64, device=dev)
+    nit = torch.empty(3, dtype=torch.int64, device=dev)
+    status = torch.empty(3, dtype=torch.int32, device=dev)
+    res = _lib.ZfResult()
+    res.x, res.fun, res.nit, res.status = x.data_ptr(), fun.data_ptr(), nit.data_ptr(), status.data_ptr()
+    opts = _make_options(1 / L, 1e-5, 1e-12, 400, 100000, 100, False, 1.0, True, (0, 0.25), False,
+                         "reference", 0)
+    ab = np.ascontiguousarray(pairs, dtype=np.float64)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().zf_deblur_solve_device(prob._h, C.byref(opts), 3, C.c_void_p(x0d.data_ptr()),
+                                                 0, ab.ctypes.data_as(C.c_void_p), C.byref(res)))
+    for i in range(3):
+        assert int(nit[i]) == host[i].nit and int(status[i]) == host[i].status
+        np.testing.assert_array_equal(x[i].cpu().numpy(), host[i].x)
+        assert float(fun[i]) == float(host[i].fun[0])
