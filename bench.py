@@ -544,6 +544,23 @@ def _cameraman_cpu_iters(args):
     return r["nit"], time.time() - t0
 
 
+def synthetic_observation(h, w, kernel, seed=0, noise=1e-3):
+    """Synthetic stand-in for the notebook's blurred + noisy cameraman image (no network for
+    skimage.data): a piecewise-smooth scene in [0, 1], blurred with `kernel` (symmetric
+    boundary) plus N(0, noise^2)."""
+    from scipy.signal import correlate2d
+
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 0.5 + 0.25 * np.sin(2 * np.pi * xx / w * 1.5) * np.cos(2 * np.pi * yy / h)
+    for _ in range(6):
+        cy, cx = rng.uniform(0, h), rng.uniform(0, w)
+        ry, rx = rng.uniform(h / 16, h / 4), rng.uniform(w / 16, w / 4)
+        img[((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1] = rng.uniform(0, 1)
+    img = np.clip(img, 0, 1)
+    return correlate2d(img, kernel, mode="same", boundary="symm") + rng.standard_normal((h, w)) * noise
+
+
 def bench_cameraman(args, dev, rank, world):
     """BASELINE configs[1]: 256x256 deblurring (9x9 Gaussian blur, Haar, l1 = 2e-5), the
     notebook's 15 (a, b) pairs as 15 runs of one call, fixed step 1/L; every rank solves the
@@ -554,16 +571,15 @@ def bench_cameraman(args, dev, rank, world):
 
     import torch
 
-    from oracle import deblur_oracle as do
-    from zfista_b200.deblur import HaarDeblurL1
+    from zfista_b200.deblur import HaarDeblurL1, gaussian_kernel, lipschitz_constant
 
-    kernel = do.gaussian_kernel(9, 4.0)
+    kernel = gaussian_kernel(9, 4.0)
     kernel /= kernel.sum()
-    _, obs, _ = do.synthetic_scene(256, 256, seed=1, kernel=kernel)
+    obs = synthetic_observation(256, 256, kernel, seed=1)
     l1 = 2e-5
     prob = HaarDeblurL1(obs, kernel, l1)
     x0 = prob.dwt_array(obs)
-    L = do.lipschitz(kernel)
+    L = lipschitz_constant(kernel)
     pairs = np.array(AB_GRID)
     iters = args.cameraman_iters
     kw = dict(lr=1 / L, decay_rate=1, nesterov=True, max_iter=iters, tol=0.0)

@@ -5,16 +5,16 @@ import warnings
 import numpy as np
 
 sys.path.insert(0, ".")
-from oracle import deblur_oracle as do  # noqa: E402  (scene generation only)
-from zfista_b200.deblur import HaarDeblurL1  # noqa: E402
+from bench import synthetic_observation  # noqa: E402
+from zfista_b200.deblur import HaarDeblurL1, gaussian_kernel, lipschitz_constant  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 24
-kernel = do.gaussian_kernel(9, 4.0)
+kernel = gaussian_kernel(9, 4.0)
 kernel /= kernel.sum()
-_, obs, _ = do.synthetic_scene(256, 256, seed=1, kernel=kernel)
+obs = synthetic_observation(256, 256, kernel, seed=1)
 prob = HaarDeblurL1(obs, kernel, 2e-5)
 x0 = prob.dwt_array(obs)
-L = do.lipschitz(kernel)
+L = lipschitz_constant(kernel)
 grid = [(0.0, 0.0), (0.0, 1 / 8), (0.0, 1 / 4), (1 / 6, 1 / 144), (1 / 6, 37 / 288), (1 / 6, 1 / 4),
         (1 / 4, 1 / 64), (1 / 4, 17 / 128), (1 / 4, 1 / 4), (1 / 2, 1 / 16), (1 / 2, 5 / 32),
         (1 / 2, 1 / 4), (3 / 4, 9 / 64), (3 / 4, 25 / 128), (3 / 4, 1 / 4)]

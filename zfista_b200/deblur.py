@@ -24,6 +24,26 @@ from . import _lib
 from .problems import _as_f64, _ptr
 
 
+def gaussian_kernel(size: int = 9, sigma: float = 4.0) -> np.ndarray:
+    """Radial Gaussian blur kernel (what the notebook's ``skimage.filters.window(("gaussian",
+    4), (9, 9))`` approximates); not normalised."""
+    c = (size - 1) / 2
+    i = np.arange(size) - c
+    return np.exp(-(i[:, None] ** 2 + i[None, :] ** 2) / (2 * sigma ** 2))
+
+
+def lipschitz_constant(kernel) -> float:
+    """The notebook's ``L = 2 * max|dctn(K) / dctn(unit)|**2`` (Hansen et al. 2006): the
+    Lipschitz constant of grad f for the symmetric-boundary blur; the fixed step is 1 / L."""
+    from scipy.fftpack import dctn
+
+    kernel = np.asarray(kernel, dtype=np.float64)
+    unit = np.zeros(kernel.shape)
+    unit[0, 0] = 1
+    spectrum = dctn(kernel) / dctn(unit)
+    return float(2 * np.max(np.abs(spectrum)) ** 2)
+
+
 class HaarDeblurL1:
     n_objectives = 1
 
