@@ -211,6 +211,8 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
     xa = B.X[buf] + (long long)run * d.n;
     xb = xa;
   }
+  // 48 physical rows cover every strip overhang: the last strip of the V region reads rows up
+  // to S*(VS-1) + S + 2R - 1 + OFF <= 47 for every R <= 4 and both modes
   __shared__ double U[DB_UR][DB_UR + 1];
   __shared__ double V[DB_VR][DB_VR + 1];
   __shared__ double red[6][DB_THREADS / 32];
@@ -221,6 +223,9 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
   double abs_acc = 0.0;
   // ---- 1. U = W y on the halo region, by 2x2 blocks (one coefficient quadruple each)
   constexpr int UB = UR / 2;
+  // fully unrolled (<= 5 trips): all of a thread's coefficient loads are in flight at once --
+  // this gather from L2 is the latency the round-1 profile showed the kernel waiting on
+#pragma unroll
   for (int blk = tid; blk < UB * UB; blk += DB_THREADS) {
     const int lbi = blk / UB, lbj = blk % UB;
     const int i0 = tyo - HU + 2 * lbi, j0 = txo - HU + 2 * lbj;
@@ -262,17 +267,19 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
   for (int task = tid; task < VS * VR; task += DB_THREADS) {
     const int li0 = S * (task / VR), lj = task % VR;
     const int gj = txo - HV + lj;
-    double acc[S];
+    const bool col_ok = (gj >= 0 && gj < d.W);
+    double acc[S], bv[S];
 #pragma unroll
-    for (int o = 0; o < S; ++o) acc[o] = 0.0;
+    for (int o = 0; o < S; ++o) {       // observed image values: loaded before the FMA loop
+      const int gi = tyo - HV + li0 + o;
+      acc[o] = 0.0;
+      bv[o] = (col_ok && li0 + o < VR && gi >= 0 && gi < d.H) ? B.b[(long long)gi * d.W + gj] : 0.0;
+    }
 #pragma unroll
     for (int v = 0; v < K; ++v) {
       double col[S + 2 * R];
 #pragma unroll
-      for (int k = 0; k < S + 2 * R; ++k) {
-        const int row = li0 + k + OFF;
-        col[k] = U[row < DB_UR ? row : DB_UR - 1][lj + v + OFF];
-      }
+      for (int k = 0; k < S + 2 * R; ++k) col[k] = U[li0 + k + OFF][lj + v + OFF];
 #pragma unroll
       for (int u = 0; u < K; ++u) {
         const double w = c_kernel[u * K + v];
@@ -280,12 +287,12 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
         for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
       }
     }
-    if (gj >= 0 && gj < d.W) {
+    if (col_ok) {
 #pragma unroll
       for (int o = 0; o < S; ++o) {
         const int li = li0 + o, gi = tyo - HV + li;
         if (li < VR && gi >= 0 && gi < d.H) {
-          const double val = acc[o] - B.b[(long long)gi * d.W + gj];
+          const double val = acc[o] - bv[o];
           V[li][lj] = val;
           if (li >= HV && li < HV + T && lj >= HV && lj < HV + T) fsum += val * val;
         }
@@ -295,7 +302,10 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
   DeblurSums ps{0.0, 0.0, 0.0, 0.0};
   if (MODE == 0) {
     __syncthreads();
-    // ---- 3. symmetric reflection of V into the out-of-image halo positions
+    // ---- 3. symmetric reflection of V into the out-of-image halo positions (border tiles only)
+    const bool touches_border = (tyo - HV < 0) || (txo - HV < 0) || (tyo + T + HV > d.H) ||
+                                (txo + T + HV > d.W);
+    if (touches_border)
     for (int idx = tid; idx < VR * VR; idx += DB_THREADS) {
       const int li = idx / VR, lj = idx % VR;
       const int gi = tyo - HV + li, gj = txo - HV + lj;
