@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cooperative_groups.h>
+
 #include "zf_common.cuh"
 #include "zf_host.h"
 
@@ -316,6 +318,142 @@ lasso_fused_kernel(const double* __restrict__ A, const double* __restrict__ b,
   if (tid == 0) sq_part[blockIdx.x] = ss;
 }
 
+// ------------------------------------------------------------------------------------
+// Cluster form of the fused pass for wide A.  The columns are split over the CTAs of a thread
+// block cluster (2 or 4 SMs): each CTA keeps only its slice of v in shared memory and its slice
+// of the A^T r partial in registers (PAIRS <= 10 column pairs per thread: no spills at 20000
+// columns), computes the partial dot products of a row pair over its slice, and the CTAs
+// exchange those partials through distributed shared memory (one cluster barrier per row
+// pair).  The row stream is software pipelined: the loads of pair k+1 for the dot products are
+// issued before the rank-1 update of pair k, so the HBM pipe never drains at the barrier.
+// ------------------------------------------------------------------------------------
+template <int PAIRS, int THREADS, int CHUNK>
+__global__ void __launch_bounds__(THREADS, 1)
+lasso_fused_cluster_kernel(const double* __restrict__ A, const double* __restrict__ b,
+                           const double* __restrict__ v, long long n_rows, long long n_cols,
+                           long long rows_per_cluster, long long pairs_per_cta,
+                           double* __restrict__ gpart, double* __restrict__ sq_part) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+  const long long cid = blockIdx.x / csize;                 // cluster index = row block
+  extern __shared__ double vsm[];                           // this CTA's slice of v
+  __shared__ double red[THREADS / 32][FUSED_ROWS];
+  __shared__ double xch[2][FUSED_ROWS][8];                   // [parity][row][cluster rank]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n2 = n_cols >> 1;
+  const long long p_lo = (long long)crank * pairs_per_cta;
+  const long long p_hi = (p_lo + pairs_per_cta < n2) ? p_lo + pairs_per_cta : n2;
+  const long long my_pairs = p_hi > p_lo ? p_hi - p_lo : 0;
+  for (long long p = tid; p < my_pairs; p += THREADS)
+    reinterpret_cast<double2*>(vsm)[p] = __ldg(reinterpret_cast<const double2*>(v) + p_lo + p);
+  __syncthreads();
+  const unsigned long long keep_pol = l2_policy_evict_last();
+  const unsigned long long last_pol = l2_policy_evict_first();
+  double2 q[PAIRS];
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) q[k] = make_double2(0.0, 0.0);
+  const long long i0 = cid * rows_per_cluster;
+  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
+  double ss = 0.0;
+  int parity = 0;
+  // column-pair offsets of this thread (clamped: inactive slots read pair 0 and are masked)
+  auto dots = [&](const double* row0, const double* row1, double (&acc)[FUSED_ROWS]) {
+    acc[0] = acc[1] = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < PAIRS; k0 += CHUNK) {
+      double2 a0[CHUNK], a1[CHUNK];
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        if (k0 + u < PAIRS) {          // compile time: no load is issued for a slot past PAIRS
+          const long long p = tid + (long long)(k0 + u) * THREADS;
+          const long long pc = (p < my_pairs) ? p : 0;
+          a0[u] = ld_hint2(row0 + 2 * (p_lo + pc), keep_pol);
+          a1[u] = ld_hint2(row1 + 2 * (p_lo + pc), keep_pol);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        const long long p = tid + (long long)(k0 + u) * THREADS;
+        if (k0 + u < PAIRS && p < my_pairs) {
+          const double2 vv = reinterpret_cast<const double2*>(vsm)[p];
+          acc[0] += a0[u].x * vv.x + a0[u].y * vv.y;
+          acc[1] += a1[u].x * vv.x + a1[u].y * vv.y;
+        }
+      }
+    }
+  };
+  double acc[FUSED_ROWS];
+  if (i0 < i1) {
+    const double* r0p = A + i0 * n_cols;
+    dots(r0p, (i0 + 1 < i1) ? r0p + n_cols : r0p, acc);
+  }
+  for (long long i = i0; i < i1; i += FUSED_ROWS) {
+    const bool two = (i + 1 < i1);
+    const double* row0 = A + i * n_cols;
+    const double* row1 = two ? row0 + n_cols : row0;
+    // ---- CTA partial dots of this pair -> every CTA of the cluster
+    warp_sum_k<FUSED_ROWS>(acc);
+    if (lane == 0) { red[warp][0] = acc[0]; red[warp][1] = acc[1]; }
+    __syncthreads();
+    if (tid < csize) {
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int w = 0; w < THREADS / 32; ++w) { p0 += red[w][0]; p1 += red[w][1]; }
+      double* remote = cluster.map_shared_rank(&xch[0][0][0], tid);
+      remote[(parity * FUSED_ROWS + 0) * 8 + crank] = p0;
+      remote[(parity * FUSED_ROWS + 1) * 8 + crank] = p1;
+    }
+    // ---- prefetch: dot-product loads of the NEXT pair are in flight across the barrier
+    double nacc[FUSED_ROWS] = {0.0, 0.0};
+    const long long in = i + FUSED_ROWS;
+    if (in < i1) {
+      const double* n0 = A + in * n_cols;
+      dots(n0, (in + 1 < i1) ? n0 + n_cols : n0, nacc);
+    }
+    cluster.sync();
+    double r0 = 0.0, r1 = 0.0;
+    for (int c = 0; c < csize; ++c) { r0 += xch[parity][0][c]; r1 += xch[parity][1][c]; }
+    parity ^= 1;
+    r0 -= b[i];
+    r1 = two ? r1 - b[i + 1] : 0.0;
+    ss += r0 * r0;
+    ss += r1 * r1;
+    // ---- rank-1 updates of the thread's columns (rows re-read from L2)
+#pragma unroll
+    for (int k0 = 0; k0 < PAIRS; k0 += CHUNK) {
+      double2 a0[CHUNK], a1[CHUNK];
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        if (k0 + u < PAIRS) {
+          const long long p = tid + (long long)(k0 + u) * THREADS;
+          const long long pc = (p < my_pairs) ? p : 0;
+          a0[u] = ld_hint2(row0 + 2 * (p_lo + pc), last_pol);
+          a1[u] = ld_hint2(row1 + 2 * (p_lo + pc), last_pol);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        if (k0 + u < PAIRS) {
+          q[k0 + u].x += r0 * a0[u].x; q[k0 + u].y += r0 * a0[u].y;
+          q[k0 + u].x += r1 * a1[u].x; q[k0 + u].y += r1 * a1[u].y;
+        }
+      }
+    }
+    acc[0] = nacc[0];
+    acc[1] = nacc[1];
+  }
+  double* out = gpart + cid * n_cols;
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) {
+    const long long p = tid + (long long)k * THREADS;
+    if (p < my_pairs) reinterpret_cast<double2*>(out)[p_lo + p] = q[k];
+  }
+  if (tid == 0 && crank == 0) sq_part[cid] = ss;
+  cluster.sync();        // no CTA may exit while a peer can still write into its shared memory
+}
+
 // partial[j] = sum_rb gpart[rb][j] (fixed order);  partial[n_cols] = sum_blk sq_part[blk]
 __global__ void __launch_bounds__(256)
 lasso_collect_kernel(const double* __restrict__ gpart, int n_rowblocks,
@@ -461,6 +599,9 @@ struct zf_lasso {
   // fused one-pass gradient (0 = not applicable)
   int fused_pairs = 0, fused_ctas = 0;
   long long fused_rows_per_cta = 0;
+  int fused_cluster = 1;              // CTAs per cluster (1: single-CTA kernel)
+  int fused_threads = 512;            // threads per CTA of the cluster form
+  long long fused_pairs_per_cta = 0;  // column pairs per CTA (cluster form)
   size_t gpart_rows = 0;
   // solver state (host scalars)
   zf_options opt{};
@@ -520,9 +661,56 @@ int launch_fused_t(zf_lasso* h, const double* v) {
   return ZF_OK;
 }
 
+template <int PAIRS, int THREADS, int CHUNK>
+int launch_fused_cluster_t(zf_lasso* h, const double* v) {
+  auto k = zf::lasso_fused_cluster_kernel<PAIRS, THREADS, CHUNK>;
+  const size_t smem = sizeof(double) * 2 * (size_t)h->fused_pairs_per_cta;
+  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)h->fused_ctas);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)h->fused_cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const long long rows_per_cluster = h->fused_rows_per_cta;
+  ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, rows_per_cluster,
+                             h->fused_pairs_per_cta, h->gpart, h->sq_part));
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
 // gradient pass at v: leaves the A^T r partials in gpart (n_gpart_rows x n_cols) and the
 // sum r^2 partials in sq_part (n_sq), by the fused kernel when it applies
 int launch_gradient_pass(zf_lasso* h, const double* v, int* n_gpart_rows, int* n_sq) {
+  if (h->fused_pairs > 0 && h->fused_cluster > 1) {
+    int rc;
+    if (h->fused_threads == 1024) {
+      switch (h->fused_pairs) {
+        case 1: rc = launch_fused_cluster_t<1, 1024, 1>(h, v); break;
+        case 2: rc = launch_fused_cluster_t<2, 1024, 2>(h, v); break;
+        case 3: rc = launch_fused_cluster_t<3, 1024, 3>(h, v); break;
+        case 4: rc = launch_fused_cluster_t<4, 1024, 2>(h, v); break;
+        default: rc = launch_fused_cluster_t<5, 1024, 3>(h, v); break;
+      }
+    } else {
+      switch (h->fused_pairs) {
+        case 2: rc = launch_fused_cluster_t<2, 512, 2>(h, v); break;
+        case 4: rc = launch_fused_cluster_t<4, 512, 4>(h, v); break;
+        case 6: rc = launch_fused_cluster_t<6, 512, 4>(h, v); break;
+        case 8: rc = launch_fused_cluster_t<8, 512, 4>(h, v); break;
+        default: rc = launch_fused_cluster_t<10, 512, 4>(h, v); break;
+      }
+    }
+    *n_gpart_rows = h->fused_ctas / h->fused_cluster;
+    *n_sq = h->fused_ctas / h->fused_cluster;
+    return rc;
+  }
   if (h->fused_pairs > 0) {
     int rc;
     switch (h->fused_pairs) {
@@ -699,18 +887,46 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   h->gpart_rows = (size_t)h->n_rowblocks;
   size_t sq_rows = (size_t)h->res_blocks;
   {
-    // Measured on B200: the fused pass beats the two-pass form up to 8 column
-    // pairs per thread (n_cols <= 8192: 2.12 vs 2.48 ms on 131072 x 8192) and loses beyond
-    // (register pressure: 2.91 vs 2.29 ms on 49152 x 20000), so it is the default only there.
-    // ZF_LASSO_FUSED=1 / 0 forces it on (where it fits) / off.
+    // Measured on B200: the single-CTA fused pass beats the two-pass form up to
+    // 8 column pairs per thread (n_cols <= 8192: 2.12 vs 2.48 ms on 131072 x 8192) and loses
+    // beyond (register pressure: 2.91 vs 2.29 ms on 49152 x 20000); from there to 20480
+    // columns the 2-CTA cluster form takes over (1.71 vs 2.49 ms on 65536 x 16384); wider
+    // matrices use the two-pass kernels.  ZF_LASSO_FUSED=0 forces two-pass,
+    // ZF_LASSO_CLUSTER=2|4 forces the cluster form.
     const char* env = getenv("ZF_LASSO_FUSED");
     const long long n2 = n_cols / 2;
     const long long pairs = (n2 + zf::FUSED_THREADS - 1) / zf::FUSED_THREADS;
     const bool enabled = env ? (env[0] != '0') : (pairs <= 8);
+    // cluster form (ZF_LASSO_CLUSTER=2|4, or automatically beyond 8 pairs per thread): the
+    // columns are split over 2 or 4 CTAs so that a thread owns at most 10 pairs
+    int cluster = 1;
+    if (const char* cenv = getenv("ZF_LASSO_CLUSTER")) cluster = atoi(cenv);
+    else if (pairs > 8 && pairs <= 20 && !(env && env[0] == '0')) cluster = 2;
+    if (cluster == 2 || cluster == 4) {
+      const long long ppc = ((n2 + cluster - 1) / cluster);           // pairs per CTA
+      long long ppt = (ppc + zf::FUSED_THREADS - 1) / zf::FUSED_THREADS;
+      int threads = 512;
+      if (const char* tenv = getenv("ZF_LASSO_THREADS")) threads = atoi(tenv) == 1024 ? 1024 : 512;
+      else if (ppt > 8) threads = 1024;      // 9-10 pairs per thread spill at 512 threads
+      if (threads == 1024) ppt = (ppc + 1023) / 1024;
+      if (h->vec && ppt <= (threads == 1024 ? 5 : 10) && n_rows >= 4LL * h->n_sm) {
+        h->fused_cluster = cluster;
+        h->fused_threads = threads;
+        h->fused_pairs_per_cta = ppc;
+        h->fused_pairs = threads == 1024 ? (int)ppt : (int)(((ppt + 1) / 2) * 2);
+        const int n_clusters = h->n_sm / cluster;
+        h->fused_rows_per_cta = (n_rows + n_clusters - 1) / n_clusters;   // rows per cluster
+        if (h->fused_rows_per_cta % 2) h->fused_rows_per_cta += 1;
+        const int used = (int)((n_rows + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
+        h->fused_ctas = used * cluster;
+        if ((size_t)used > h->gpart_rows) h->gpart_rows = (size_t)used;
+        if ((size_t)used > sq_rows) sq_rows = (size_t)used;
+      }
+    }
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (enabled && h->vec && pairs <= 20 && (size_t)n_cols * 8 + 1024 <= (size_t)max_smem &&
-        n_rows >= 4LL * h->n_sm) {
+    if (h->fused_cluster == 1 && enabled && h->vec && pairs <= 20 &&
+        (size_t)n_cols * 8 + 1024 <= (size_t)max_smem && n_rows >= 4LL * h->n_sm) {
       h->fused_pairs = (int)(((pairs + 3) / 4) * 4);
       h->fused_ctas = h->n_sm;
       h->fused_rows_per_cta = (n_rows + h->fused_ctas - 1) / h->fused_ctas;
