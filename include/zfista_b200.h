@@ -171,6 +171,9 @@ double* zf_lasso_partial(zf_lasso* h, int64_t* n_values); /* device buffer to al
 int zf_lasso_step(zf_lasso* h, int32_t* h_done);           /* prox, line search, momentum */
 int zf_lasso_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
                     int32_t* h_status);
+/* how many times one gradient evaluation reads A from HBM with this handle's kernel choice:
+ * 1 (fused A^T(Av-b) kernels) or 2 (residual pass + A^T pass); for the roofline accounting */
+int zf_lasso_passes(zf_lasso* h);
 /* one gradient pass only (bench / roofline): grad = 2*scale*A^T(Ax-b), returns f */
 int zf_lasso_gradient_device(zf_lasso* h, const double* d_x, double* d_grad, double* d_f);
 

@@ -60,7 +60,7 @@ EXPORTED_SYMBOLS = [
     "zf_problem_eval_host",
     "zf_lasso_create", "zf_lasso_destroy", "zf_lasso_solve", "zf_lasso_begin",
     "zf_lasso_grad", "zf_lasso_partial", "zf_lasso_step", "zf_lasso_finish",
-    "zf_lasso_gradient_device",
+    "zf_lasso_gradient_device", "zf_lasso_passes",
     "zf_deblur_create", "zf_deblur_destroy", "zf_deblur_solve_host", "zf_deblur_solve_device",
     "zf_deblur_eval_host",
 ]
@@ -136,6 +136,8 @@ def _bind_lasso(L):
     L.zf_lasso_finish.restype = C.c_int
     L.zf_lasso_gradient_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.zf_lasso_gradient_device.restype = C.c_int
+    L.zf_lasso_passes.argtypes = [C.c_void_p]
+    L.zf_lasso_passes.restype = C.c_int
     # deblurring handle API
     L.zf_deblur_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_void_p]

@@ -1178,6 +1178,11 @@ extern "C" int zf_lasso_solve(zf_lasso* h, const zf_options* opt, const double* 
   return zf_lasso_finish(h, d_x, h_fun, h_nit, h_status);
 }
 
+extern "C" int zf_lasso_passes(zf_lasso* h) {
+  if (!h) return 0;
+  return h->fused_pairs > 0 ? 1 : 2;
+}
+
 extern "C" int zf_lasso_gradient_device(zf_lasso* h, const double* d_x, double* d_grad,
                                         double* d_f) {
   if (!h || !d_x || !d_grad) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");

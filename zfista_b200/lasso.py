@@ -106,6 +106,10 @@ class DenseLasso:
 
             dist.all_reduce(self._partial, group=self.group)
 
+    def hbm_passes_per_gradient(self) -> int:
+        """1 if this shape uses a fused one-pass A^T(Av - b) kernel, 2 for the two-pass form."""
+        return int(_lib.lib().zf_lasso_passes(self._h))
+
     def gradient(self, x):
         """(grad f(x), f(x)) as device tensors: one residual pass + one A^T pass."""
         torch = _torch()
