@@ -454,6 +454,175 @@ lasso_fused_cluster_kernel(const double* __restrict__ A, const double* __restric
   cluster.sync();        // no CTA may exit while a peer can still write into its shared memory
 }
 
+// ------------------------------------------------------------------------------------
+// TMA form of the fused pass: the row pair never leaves the chip between the dot products and
+// the rank-1 update.  The columns are split over a cluster of CS CTAs; each CTA keeps its
+// slice of v, and a ring of NS stages, each one row PAIR's slice, in shared memory.  One
+// elected thread streams the stages in with 1-D bulk TMA copies (cp.async.bulk ->
+// mbarrier complete_tx); all threads wait on the stage's mbarrier, form the partial dot
+// products from shared memory, exchange them across the cluster through distributed shared
+// memory (one cluster barrier per pair), apply the rank-1 update from the SAME shared-memory
+// stage, and hand the stage back for the pair NS ahead.  HBM sees A once, L2 is not re-read.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && spin > (1u << 26)) __trap();
+  }
+}
+
+constexpr int TMA_THREADS = 512;
+
+// NS: stages of the ring; PIPE: form the dot products of pair k+1 between the cluster barrier's
+// arrive and wait of pair k (needs NS >= 3 to keep a full pair in flight meanwhile)
+template <int PAIRS, int NS, bool PIPE>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ b,
+                       const double* __restrict__ v, long long n_rows, long long n_cols,
+                       long long rows_per_cluster, long long pairs_per_cta,
+                       double* __restrict__ gpart, double* __restrict__ sq_part) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+  const long long cid = blockIdx.x / csize;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ double red[TMA_THREADS / 32][FUSED_ROWS];
+  __shared__ double xch[2][FUSED_ROWS][8];
+  __shared__ __align__(8) unsigned long long full[NS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n2 = n_cols >> 1;
+  const long long p_lo = (long long)crank * pairs_per_cta;
+  const long long p_hi = (p_lo + pairs_per_cta < n2) ? p_lo + pairs_per_cta : n2;
+  const long long my_pairs = p_hi > p_lo ? p_hi - p_lo : 0;
+  const unsigned slice_bytes = (unsigned)(my_pairs * 16);
+  const size_t slice_stride = (size_t)pairs_per_cta * 16;        // bytes reserved per row slice
+  double2* vsm = reinterpret_cast<double2*>(dyn);
+  unsigned char* ring = dyn + slice_stride;                      // NS x 2 row slices
+  for (long long p = tid; p < my_pairs; p += TMA_THREADS)
+    vsm[p] = __ldg(reinterpret_cast<const double2*>(v) + p_lo + p);
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long i0 = cid * rows_per_cluster;
+  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
+  const long long n_pairs = (i1 > i0) ? (i1 - i0 + 1) / 2 : 0;
+  auto issue = [&](long long k) {        // elected thread: stream pair k into stage k % NS
+    const int s = (int)(k % NS);
+    const long long i = i0 + 2 * k;
+    const double* row0 = A + i * n_cols + 2 * p_lo;
+    const double* row1 = (i + 1 < i1) ? row0 + n_cols : row0;
+    unsigned char* dst = ring + (size_t)s * 2 * slice_stride;
+    mbar_expect_tx(&full[s], 2 * slice_bytes);
+    tma_load_1d(dst, row0, slice_bytes, &full[s]);
+    tma_load_1d(dst + slice_stride, row1, slice_bytes, &full[s]);
+  };
+  if (tid == 0 && my_pairs > 0)
+    for (long long k = 0; k < NS && k < n_pairs; ++k) issue(k);
+  double2 q[PAIRS];
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) q[k] = make_double2(0.0, 0.0);
+  double ss = 0.0;
+  int parity = 0;
+  // partial dot products of pair k over this CTA's columns, from its shared-memory stage
+  auto dots = [&](long long k, double (&acc)[FUSED_ROWS]) {
+    const int s = (int)(k % NS);
+    const double2* a0 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride);
+    const double2* a1 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride + slice_stride);
+    if (my_pairs > 0) mbar_wait(&full[s], (unsigned)((k / NS) & 1));
+    acc[0] = acc[1] = 0.0;
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const long long p = tid + (long long)u * TMA_THREADS;
+      if (p < my_pairs) {
+        const double2 vv = vsm[p], x0 = a0[p], x1 = a1[p];
+        acc[0] += x0.x * vv.x + x0.y * vv.y;
+        acc[1] += x1.x * vv.x + x1.y * vv.y;
+      }
+    }
+  };
+  double acc[FUSED_ROWS] = {0.0, 0.0};
+  if (n_pairs > 0) dots(0, acc);
+  for (long long k = 0; k < n_pairs; ++k) {
+    const int s = (int)(k % NS);
+    const long long i = i0 + 2 * k;
+    const bool two = (i + 1 < i1);
+    const double2* a0 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride);
+    const double2* a1 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride + slice_stride);
+    // ---- this CTA's partials of pair k -> every CTA of the cluster (DSMEM), barrier ARRIVE
+    warp_sum_k<FUSED_ROWS>(acc);
+    if (lane == 0) { red[warp][0] = acc[0]; red[warp][1] = acc[1]; }
+    __syncthreads();
+    if (tid < csize) {
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int w = 0; w < TMA_THREADS / 32; ++w) { p0 += red[w][0]; p1 += red[w][1]; }
+      double* remote = cluster.map_shared_rank(&xch[0][0][0], tid);
+      remote[(parity * FUSED_ROWS + 0) * 8 + crank] = p0;
+      remote[(parity * FUSED_ROWS + 1) * 8 + crank] = p1;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    // ---- while the barrier completes: the dot products of pair k+1 (nothing of it depends
+    //      on pair k)
+    double nacc[FUSED_ROWS] = {0.0, 0.0};
+    if (PIPE && k + 1 < n_pairs) dots(k + 1, nacc);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    double r0 = 0.0, r1 = 0.0;
+    for (int c = 0; c < csize; ++c) { r0 += xch[parity][0][c]; r1 += xch[parity][1][c]; }
+    parity ^= 1;
+    r0 -= b[i];
+    r1 = two ? r1 - b[i + 1] : 0.0;
+    ss += r0 * r0;
+    ss += r1 * r1;
+    // ---- phase 2: rank-1 update from the same shared-memory stage
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const long long p = tid + (long long)u * TMA_THREADS;
+      if (p < my_pairs) {
+        const double2 x0 = a0[p], x1 = a1[p];
+        q[u].x += r0 * x0.x; q[u].y += r0 * x0.y;
+        q[u].x += r1 * x1.x; q[u].y += r1 * x1.y;
+      }
+    }
+    __syncthreads();                      // every thread is done with stage s
+    if (tid == 0 && my_pairs > 0 && k + NS < n_pairs) issue(k + NS);
+    if (PIPE) { acc[0] = nacc[0]; acc[1] = nacc[1]; }
+    else if (k + 1 < n_pairs) dots(k + 1, acc);
+  }
+  double* out = gpart + cid * n_cols;
+#pragma unroll
+  for (int u = 0; u < PAIRS; ++u) {
+    const long long p = tid + (long long)u * TMA_THREADS;
+    if (p < my_pairs) reinterpret_cast<double2*>(out)[p_lo + p] = q[u];
+  }
+  if (tid == 0 && crank == 0) sq_part[cid] = ss;
+  cluster.sync();
+}
+
 // partial[j] = sum_rb gpart[rb][j] (fixed order);  partial[n_cols] = sum_blk sq_part[blk]
 __global__ void __launch_bounds__(256)
 lasso_collect_kernel(const double* __restrict__ gpart, int n_rowblocks,
@@ -601,6 +770,9 @@ struct zf_lasso {
   long long fused_rows_per_cta = 0;
   int fused_cluster = 1;              // CTAs per cluster (1: single-CTA kernel)
   int fused_threads = 512;            // threads per CTA of the cluster form
+  bool fused_tma = false;             // TMA / shared-memory-resident form
+  int tma_stages = 2;
+  bool tma_pipe = false;
   long long fused_pairs_per_cta = 0;  // column pairs per CTA (cluster form)
   size_t gpart_rows = 0;
   // solver state (host scalars)
@@ -685,9 +857,65 @@ int launch_fused_cluster_t(zf_lasso* h, const double* v) {
   return ZF_OK;
 }
 
+template <int PAIRS, int NS, bool PIPE>
+int launch_fused_tma_t(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+  auto k = zf::lasso_fused_tma_kernel<PAIRS, NS, PIPE>;
+  const size_t smem = (size_t)h->fused_pairs_per_cta * 16 * (1 + 2 * NS);
+  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (h->fused_cluster > 8) ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)h->fused_ctas);
+  cfg.blockDim = dim3(zf::TMA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)h->fused_cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (query_only) {
+    ZF_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, k, &cfg));
+    return ZF_OK;
+  }
+  const long long rows_per_cluster = h->fused_rows_per_cta;
+  ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, rows_per_cluster,
+                             h->fused_pairs_per_cta, h->gpart, h->sq_part));
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+template <int NS, bool PIPE>
+int launch_fused_tma_p(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+  switch (h->fused_pairs) {
+    case 1: return launch_fused_tma_t<1, NS, PIPE>(h, v, query_only, max_clusters);
+    case 2: return launch_fused_tma_t<2, NS, PIPE>(h, v, query_only, max_clusters);
+    case 3: return launch_fused_tma_t<3, NS, PIPE>(h, v, query_only, max_clusters);
+    case 4: return launch_fused_tma_t<4, NS, PIPE>(h, v, query_only, max_clusters);
+    case 5: return launch_fused_tma_t<5, NS, PIPE>(h, v, query_only, max_clusters);
+    case 6: return launch_fused_tma_t<6, NS, PIPE>(h, v, query_only, max_clusters);
+    default: return launch_fused_tma_t<8, NS, PIPE>(h, v, query_only, max_clusters);
+  }
+}
+
+int launch_fused_tma(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+  if (h->tma_stages == 3)
+    return h->tma_pipe ? launch_fused_tma_p<3, true>(h, v, query_only, max_clusters)
+                       : launch_fused_tma_p<3, false>(h, v, query_only, max_clusters);
+  return h->tma_pipe ? launch_fused_tma_p<2, true>(h, v, query_only, max_clusters)
+                     : launch_fused_tma_p<2, false>(h, v, query_only, max_clusters);
+}
+
 // gradient pass at v: leaves the A^T r partials in gpart (n_gpart_rows x n_cols) and the
 // sum r^2 partials in sq_part (n_sq), by the fused kernel when it applies
 int launch_gradient_pass(zf_lasso* h, const double* v, int* n_gpart_rows, int* n_sq) {
+  if (h->fused_pairs > 0 && h->fused_tma) {
+    const int rc = launch_fused_tma(h, v, false, nullptr);
+    *n_gpart_rows = h->fused_ctas / h->fused_cluster;
+    *n_sq = h->fused_ctas / h->fused_cluster;
+    return rc;
+  }
   if (h->fused_pairs > 0 && h->fused_cluster > 1) {
     int rc;
     if (h->fused_threads == 1024) {
@@ -883,50 +1111,74 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   long long vb = (n_cols + zf::VEC_THREADS - 1) / zf::VEC_THREADS;
   if (vb > zf::VEC_MAX_BLOCKS) vb = zf::VEC_MAX_BLOCKS;
   h->vec_blocks = (int)vb;
-  // fused one-pass gradient: v in shared memory (8 n_cols B), <= 20 column pairs per thread
+  // ---- which kernels compute A^T(A v - b) for this shape.  Measured on B200 (DESIGN.md 3.3,
+  // fraction of the one-pass HBM bound): single-CTA fused 0.62 at 8192 columns; 2-CTA cluster
+  // with L2 re-read 0.77 at 16384, 0.69 at 12000, 0.64 at 20000; TMA / shared-memory-resident
+  // form 0.73 at 8192 (cluster 2) and 0.72 at 20000 (cluster 4) but 0.66 at 16384; two-pass
+  // kernels 0.53 everywhere.  Environment overrides for experiments:
+  //   ZF_LASSO_FUSED=0 (two-pass), ZF_LASSO_CLUSTER=2|4, ZF_LASSO_THREADS=512|1024,
+  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_STAGES=2|3, ZF_LASSO_TMA_PIPE=0|1.
   h->gpart_rows = (size_t)h->n_rowblocks;
   size_t sq_rows = (size_t)h->res_blocks;
   {
-    // Measured on B200: the single-CTA fused pass beats the two-pass form up to
-    // 8 column pairs per thread (n_cols <= 8192: 2.12 vs 2.48 ms on 131072 x 8192) and loses
-    // beyond (register pressure: 2.91 vs 2.29 ms on 49152 x 20000); from there to 20480
-    // columns the 2-CTA cluster form takes over (1.71 vs 2.49 ms on 65536 x 16384); wider
-    // matrices use the two-pass kernels.  ZF_LASSO_FUSED=0 forces two-pass,
-    // ZF_LASSO_CLUSTER=2|4 forces the cluster form.
-    const char* env = getenv("ZF_LASSO_FUSED");
     const long long n2 = n_cols / 2;
-    const long long pairs = (n2 + zf::FUSED_THREADS - 1) / zf::FUSED_THREADS;
-    const bool enabled = env ? (env[0] != '0') : (pairs <= 8);
-    // cluster form (ZF_LASSO_CLUSTER=2|4, or automatically beyond 8 pairs per thread): the
-    // columns are split over 2 or 4 CTAs so that a thread owns at most 10 pairs
-    int cluster = 1;
-    if (const char* cenv = getenv("ZF_LASSO_CLUSTER")) cluster = atoi(cenv);
-    else if (pairs > 8 && pairs <= 20 && !(env && env[0] == '0')) cluster = 2;
-    if (cluster == 2 || cluster == 4) {
-      const long long ppc = ((n2 + cluster - 1) / cluster);           // pairs per CTA
+    const long long pairs = (n2 + zf::FUSED_THREADS - 1) / zf::FUSED_THREADS;  // per thread, 1 CTA
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const bool big_enough = h->vec && n_rows >= 4LL * h->n_sm;
+    const char* env_fused = getenv("ZF_LASSO_FUSED");
+    const char* env_cluster = getenv("ZF_LASSO_CLUSTER");
+    const char* env_tma = getenv("ZF_LASSO_TMA");
+    const bool off = env_fused && env_fused[0] == '0';
+    auto finish_cluster_grid = [&](int cluster, int n_clusters) {
+      h->fused_rows_per_cta = (n_rows + n_clusters - 1) / n_clusters;      // rows per cluster
+      if (h->fused_rows_per_cta % 2) h->fused_rows_per_cta += 1;
+      const int used = (int)((n_rows + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
+      h->fused_ctas = used * cluster;
+      if ((size_t)used > h->gpart_rows) h->gpart_rows = (size_t)used;
+      if ((size_t)used > sq_rows) sq_rows = (size_t)used;
+    };
+    auto try_tma = [&](int c) -> bool {
+      if (!(c == 2 || c == 4 || c == 8) || !big_enough) return false;
+      const long long ppc = (n2 + c - 1) / c;
+      const long long ppt = (ppc + zf::TMA_THREADS - 1) / zf::TMA_THREADS;
+      h->tma_stages = 2;
+      h->tma_pipe = false;
+      if (const char* e2 = getenv("ZF_LASSO_TMA_STAGES")) h->tma_stages = atoi(e2) == 3 ? 3 : 2;
+      if (const char* e3 = getenv("ZF_LASSO_TMA_PIPE")) h->tma_pipe = atoi(e3) != 0;
+      const size_t smem = (size_t)ppc * 16 * (1 + 2 * h->tma_stages);
+      if (ppt > 8 || smem + 2048 > (size_t)max_smem) return false;
+      h->fused_tma = true;
+      h->fused_cluster = c;
+      h->fused_pairs_per_cta = ppc;
+      h->fused_pairs = (int)(ppt == 7 ? 8 : ppt);
+      int n_clusters = h->n_sm / c;
+      h->fused_ctas = n_clusters * c;
+      h->fused_rows_per_cta = 2;
+      int active = 0;
+      if (launch_fused_tma(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
+        n_clusters = active;              // only clusters that can be co-resident: one wave
+      finish_cluster_grid(c, n_clusters);
+      return true;
+    };
+    auto try_cluster = [&](int c) -> bool {
+      if (!(c == 2 || c == 4) || !big_enough) return false;
+      const long long ppc = (n2 + c - 1) / c;
       long long ppt = (ppc + zf::FUSED_THREADS - 1) / zf::FUSED_THREADS;
       int threads = 512;
       if (const char* tenv = getenv("ZF_LASSO_THREADS")) threads = atoi(tenv) == 1024 ? 1024 : 512;
       else if (ppt > 8) threads = 1024;      // 9-10 pairs per thread spill at 512 threads
       if (threads == 1024) ppt = (ppc + 1023) / 1024;
-      if (h->vec && ppt <= (threads == 1024 ? 5 : 10) && n_rows >= 4LL * h->n_sm) {
-        h->fused_cluster = cluster;
-        h->fused_threads = threads;
-        h->fused_pairs_per_cta = ppc;
-        h->fused_pairs = threads == 1024 ? (int)ppt : (int)(((ppt + 1) / 2) * 2);
-        const int n_clusters = h->n_sm / cluster;
-        h->fused_rows_per_cta = (n_rows + n_clusters - 1) / n_clusters;   // rows per cluster
-        if (h->fused_rows_per_cta % 2) h->fused_rows_per_cta += 1;
-        const int used = (int)((n_rows + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
-        h->fused_ctas = used * cluster;
-        if ((size_t)used > h->gpart_rows) h->gpart_rows = (size_t)used;
-        if ((size_t)used > sq_rows) sq_rows = (size_t)used;
-      }
-    }
-    int max_smem = 0;
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (h->fused_cluster == 1 && enabled && h->vec && pairs <= 20 &&
-        (size_t)n_cols * 8 + 1024 <= (size_t)max_smem && n_rows >= 4LL * h->n_sm) {
+      if (ppt > (threads == 1024 ? 5 : 10) || (size_t)ppc * 16 + 2048 > (size_t)max_smem) return false;
+      h->fused_cluster = c;
+      h->fused_threads = threads;
+      h->fused_pairs_per_cta = ppc;
+      h->fused_pairs = threads == 1024 ? (int)ppt : (int)(((ppt + 1) / 2) * 2);
+      finish_cluster_grid(c, h->n_sm / c);
+      return true;
+    };
+    auto try_single = [&]() -> bool {
+      if (!big_enough || pairs > 20 || (size_t)n_cols * 8 + 1024 > (size_t)max_smem) return false;
       h->fused_pairs = (int)(((pairs + 3) / 4) * 4);
       h->fused_ctas = h->n_sm;
       h->fused_rows_per_cta = (n_rows + h->fused_ctas - 1) / h->fused_ctas;
@@ -934,6 +1186,24 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       h->fused_ctas = (int)((n_rows + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
       if ((size_t)h->fused_ctas > h->gpart_rows) h->gpart_rows = (size_t)h->fused_ctas;
       if ((size_t)h->fused_ctas > sq_rows) sq_rows = (size_t)h->fused_ctas;
+      return true;
+    };
+    if (off) {
+      // two-pass kernels
+    } else if (env_tma) {
+      try_tma(atoi(env_tma));
+    } else if (env_cluster) {
+      try_cluster(atoi(env_cluster));
+    } else if (env_fused) {
+      try_single();
+    } else if (n_cols <= 6144) {
+      try_single();
+    } else if (n_cols <= 8192) {
+      if (!try_tma(2)) try_single();
+    } else if (n_cols <= 16384) {
+      try_cluster(2);
+    } else {
+      if (!try_tma(4)) try_cluster(2);
     }
   }
   cudaError_t e = cudaSuccess;
