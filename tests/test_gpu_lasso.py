@@ -144,3 +144,51 @@ def test_large_a_properties(gpu):
     assert F[-1] < 1e-3 * F[0]
     x = np.asarray(res.x)
     assert np.all(np.abs(x[:32]) > 1.0) and np.max(np.abs(x[32:])) < 0.05
+
+
+@pytest.mark.parametrize("env,shape,passes", [
+    ({"ZF_LASSO_FUSED": "0"}, (700, 1030), 2),            # two-pass kernels
+    ({}, (700, 2050), 1),                                  # single-CTA fused (default policy)
+    ({"ZF_LASSO_CLUSTER": "2"}, (701, 3000), 1),           # 2-CTA cluster, L2 re-read, odd rows
+    ({"ZF_LASSO_CLUSTER": "2", "ZF_LASSO_THREADS": "1024"}, (1200, 9000), 1),
+    ({"ZF_LASSO_TMA": "2"}, (900, 2000), 1),               # TMA ring, cluster 2
+    ({"ZF_LASSO_TMA": "4"}, (1000, 5002), 1),              # TMA ring, cluster 4, ragged slices
+    ({"ZF_LASSO_TMA": "2", "ZF_LASSO_TMA_STAGES": "3", "ZF_LASSO_TMA_PIPE": "1"}, (911, 2000), 1),
+])
+def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
+    """Each form of the A^T(A v - b) pass (csrc/zf_lasso.cu) forced through its environment
+    switch: gradient / f against a torch fp64 reference, and a FISTA solve that must agree
+    with the two-pass kernels' solve (same nit, x to 1e-9)."""
+    import torch
+    from zfista_b200.lasso import DenseLasso
+
+    for k in ("ZF_LASSO_FUSED", "ZF_LASSO_CLUSTER", "ZF_LASSO_THREADS", "ZF_LASSO_TMA",
+              "ZF_LASSO_TMA_STAGES", "ZF_LASSO_TMA_PIPE"):
+        monkeypatch.delenv(k, raising=False)
+    rows, cols = shape
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    A = torch.randn(rows, cols, dtype=torch.float64, device="cuda", generator=g)
+    w = torch.zeros(cols, dtype=torch.float64, device="cuda")
+    w[:12] = 1.0
+    b = A @ w + 0.01 * torch.randn(rows, dtype=torch.float64, device="cuda", generator=g)
+    monkeypatch.setenv("ZF_LASSO_FUSED", "0")
+    two_pass = DenseLasso(A, b, 0.02, scale=1 / (2 * rows))
+    assert two_pass.hbm_passes_per_gradient() == 2
+    monkeypatch.delenv("ZF_LASSO_FUSED")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    prob = DenseLasso(A, b, 0.02, scale=1 / (2 * rows))
+    assert prob.hbm_passes_per_gradient() == passes
+    x = torch.randn(cols, dtype=torch.float64, device="cuda", generator=g)
+    grad, f = prob.gradient(x)
+    r = A @ x - b
+    torch.testing.assert_close(grad, (A.T @ r) / rows, rtol=1e-12, atol=1e-13)
+    torch.testing.assert_close(f[0], (r @ r) / (2 * rows), rtol=1e-13, atol=0)
+    opts = dict(nesterov=True, max_iter=40)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = prob.minimize_proximal_gradient(np.zeros(cols), **opts)
+        c = two_pass.minimize_proximal_gradient(np.zeros(cols), **opts)
+    assert a.nit == c.nit and a.status == c.status
+    np.testing.assert_allclose(a.x, c.x, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(a.fun, c.fun, rtol=1e-11)
