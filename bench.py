@@ -268,6 +268,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...") goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     zbuild.build()
     L = _lib.lib()
@@ -705,7 +707,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--lasso-rows", type=int, default=65536)
     ap.add_argument("--lasso-cols", type=int, default=16384)
-    ap.add_argument("--lasso-iters", type=int, default=20)
+    ap.add_argument("--lasso-iters", type=int, default=50)
     ap.add_argument("--cameraman-iters", type=int, default=2000)
     args = ap.parse_args()
     try:

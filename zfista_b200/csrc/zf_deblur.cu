@@ -216,7 +216,6 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
   __shared__ double U[DB_UR][DB_UR + 1];
   __shared__ double V[DB_VR][DB_VR + 1];
   __shared__ double red[6][DB_THREADS / 32];
-  __shared__ int is_last;
   const int tid = threadIdx.x;
   const int tyo = (blockIdx.x / d.tiles_x) * T, txo = (blockIdx.x % d.tiles_x) * T;
   const long long q = (long long)d.h2 * d.w2;
@@ -402,19 +401,21 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
       B.fx_part[slot] = t[0];
       B.abs_part[slot] = t[1];
     }
+  }
+  // ticket + decision: only warp 0 stays for it, the other warps are done
+  if (decide && tid < 32) {
     int last = 0;
-    if (decide) {
+    if (tid == 0) {
       __threadfence();
       const unsigned int done = atomicAdd(&B.tickets[run], 1u);
       last = (done == (unsigned int)d.n_tiles - 1u);
       if (last) B.tickets[run] = 0u;
     }
-    is_last = last;
-  }
-  __syncthreads();
-  if (decide && is_last && tid < 32) {
-    __threadfence();
-    deblur_decide(d, c, B, run, tid, count != 0);
+    last = __shfl_sync(ZF_FULL_MASK, last, 0);
+    if (last) {
+      __threadfence();
+      deblur_decide(d, c, B, run, tid, count != 0);
+    }
   }
 }
 
