@@ -472,3 +472,26 @@ def test_option_coverage(gpu):
     small = prob.minimize_proximal_gradient_batched(Xb[1000:1040], nesterov=True, tol_internal=1e-11)
     np.testing.assert_array_equal(big.x[1000:1040], small.x)
     np.testing.assert_array_equal(big.nit[1000:1040], small.nit)
+
+
+def test_largest_benchmark_dimension_matches_oracle(gpu):
+    """JOS1 with n_features = 1000, the largest size in benchmarks/benchmark.py:418 (40 KB of
+    shared memory per start): same nit, x and F within 1e-8 of the CPU oracle."""
+    from oracle import zfista_oracle as zo
+    import zfista_b200.problems as zp
+
+    prob = zp.JOS1(n_features=1000)
+    spec = zo.make_spec("JOS1", n_features=1000)
+    rng = np.random.RandomState(12)
+    X0 = rng.uniform(-2, 4, size=(3, 1000))
+    opts = dict(nesterov=True, tol_internal=1e-11)
+    br = prob.minimize_proximal_gradient_batched(X0, **opts)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(2):
+            r = zo.minimize_proximal_gradient(spec, X0[i], **opts)
+            assert br.nit[i] == r["nit"]
+            _rel_close(br.x[i], r["x"])
+            _rel_close(br.fun[i], r["fun"])
+    with pytest.raises(Exception, match="shared memory"):
+        zp.JOS1(n_features=20000).minimize_proximal_gradient_batched(np.zeros((1, 20000)))
