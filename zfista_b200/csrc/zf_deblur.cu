@@ -19,6 +19,7 @@
 // coefficient loads and the gradient store stays in shared memory.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -68,7 +69,8 @@ struct DeblurBufs {
   DeblurRun* runs;
   unsigned int* tickets;                    // [run]
   double *allerrs, *allfuns;
-  unsigned int* n_active;
+  unsigned int* n_active;                   // [group]
+  int run0, group;                          // this launch covers runs run0 .. run0 + gridDim.y - 1
 };
 
 __constant__ double c_kernel[81];
@@ -173,7 +175,7 @@ __device__ void deblur_decide(const DeblurDims& d, const DeblurCtl& c, const Deb
     }
   }
   B.runs[run] = st;
-  if (count && st.phase != DP_DONE && st.phase != DP_FINAL) atomicAdd(B.n_active, 1u);
+  if (count && st.phase != DP_DONE && st.phase != DP_FINAL) atomicAdd(B.n_active + B.group, 1u);
 }
 
 // MODE 0: gradient round.  U = W y on tile + 2R halo, V = R U - b on tile + R halo, R V on the
@@ -193,7 +195,7 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
   constexpr int OFF = HU - HV - R;                // U index of tap (0,0) of V position (0,0)
   constexpr int UR = T + 2 * HU, VR = T + 2 * HV;
   constexpr int K = 2 * R + 1;
-  const int run = blockIdx.y;
+  const int run = B.run0 + blockIdx.y;
   const DeblurRun st = B.runs[run];
   const double *xa, *xb;
   double mom = 0.0;
@@ -423,7 +425,7 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
 // stored y and g into the run's spare buffer + block partials.
 __global__ void __launch_bounds__(DB_THREADS)
 deblur_prox_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B) {
-  const int run = blockIdx.y;
+  const int run = B.run0 + blockIdx.y;
   const DeblurRun st = B.runs[run];
   if (st.phase != DP_RETRY) return;
   double* xn = B.X[st.nxt] + (long long)run * d.n;
@@ -460,7 +462,7 @@ deblur_prox_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B) {
 
 __global__ void __launch_bounds__(DB_THREADS)
 deblur_gather_kernel(DeblurDims d, DeblurBufs B, double* __restrict__ out) {
-  const int run = blockIdx.y;
+  const int run = B.run0 + blockIdx.y;
   const double* src = B.X[B.runs[run].res_buf] + (long long)run * d.n;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < d.n;
        j += (long long)gridDim.x * blockDim.x)
@@ -475,7 +477,9 @@ struct zf_deblur {
   zf::DeblurBufs B{};
   double l1 = 0.0;
   int max_runs = 0;
-  unsigned int* h_active = nullptr;   // pinned
+  unsigned int* h_active = nullptr;   // pinned, [group]
+  cudaStream_t st2[3] = {nullptr, nullptr, nullptr};   // further groups of runs (see deblur_run)
+  cudaEvent_t ev = nullptr;
   double* scratch = nullptr;          // max_runs x n: gathered results
   size_t trace_cap_alloc = 0;
   cudaStream_t st = nullptr;
@@ -493,27 +497,43 @@ namespace {
     if (_e != cudaSuccess) return zf::zf_fail_cuda(_e, #call); \
   } while (0)
 
+struct RunGroup {
+  cudaStream_t st;
+  int run0, n_runs, group;
+};
+
 template <int MODE>
-int launch_tile(zf_deblur* h, int n_runs, const zf::DeblurCtl& c, bool decide, bool count) {
-  dim3 grid((unsigned)h->d.n_tiles, (unsigned)n_runs);
+int launch_tile_g(zf_deblur* h, const RunGroup& g, const zf::DeblurCtl& c, bool decide, bool count) {
+  dim3 grid((unsigned)h->d.n_tiles, (unsigned)g.n_runs);
   const int dd = decide ? 1 : 0, cc = count ? 1 : 0;
+  zf::DeblurBufs B = h->B;
+  B.run0 = g.run0;
+  B.group = g.group;
   switch (h->d.R) {
-    case 1: zf::deblur_tile_kernel<1, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
-    case 2: zf::deblur_tile_kernel<2, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
-    case 3: zf::deblur_tile_kernel<3, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
-    default: zf::deblur_tile_kernel<4, MODE><<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B, dd, cc); break;
+    case 1: zf::deblur_tile_kernel<1, MODE><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
+    case 2: zf::deblur_tile_kernel<2, MODE><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
+    case 3: zf::deblur_tile_kernel<3, MODE><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
+    default: zf::deblur_tile_kernel<4, MODE><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
   }
   ZF_CUDA(cudaGetLastError());
   if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
 }
 
-int launch_prox(zf_deblur* h, int n_runs, const zf::DeblurCtl& c) {
-  dim3 grid((unsigned)h->d.prox_blocks, (unsigned)n_runs);
-  zf::deblur_prox_kernel<<<grid, zf::DB_THREADS, 0, h->st>>>(h->d, c, h->B);
+int launch_prox_g(zf_deblur* h, const RunGroup& g, const zf::DeblurCtl& c) {
+  dim3 grid((unsigned)h->d.prox_blocks, (unsigned)g.n_runs);
+  zf::DeblurBufs B = h->B;
+  B.run0 = g.run0;
+  B.group = g.group;
+  zf::deblur_prox_kernel<<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B);
   ZF_CUDA(cudaGetLastError());
   if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
+}
+
+template <int MODE>
+int launch_tile(zf_deblur* h, int n_runs, const zf::DeblurCtl& c, bool decide, bool count) {
+  return launch_tile_g<MODE>(h, RunGroup{h->st, 0, n_runs, 0}, c, decide, count);
 }
 
 int deblur_check_options(const zf_options* o) {
@@ -578,35 +598,54 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
   int rc = zero_partials(h, n_runs);
   if (rc != ZF_OK) return rc;
   ZF_CUDA(cudaStreamSynchronize(h->st));   // `init` must outlive the copy
-  // one round; `count`: the deciding kernel also counts the runs that remain active
-  auto round = [&](bool count) -> int {
+  // The runs are split into two groups that advance on two streams.  Runs are independent,
+  // and a round is one wave of CTAs whose phases (gather from L2, then two FP64 stencils) all
+  // CTAs go through in lockstep; two groups drift apart, so one group's gather overlaps the
+  // other's stencils.
+  int n_groups = (n_runs >= 4) ? 2 : 1;
+  if (const char* env = getenv("ZF_DEBLUR_GROUPS")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 4) n_groups = v < n_runs ? v : n_runs;
+  }
+  RunGroup groups[4];
+  for (int gi = 0, r0 = 0; gi < n_groups; ++gi) {
+    const int cnt = (n_runs - r0 + (n_groups - gi) - 1) / (n_groups - gi);
+    groups[gi] = RunGroup{gi == 0 ? h->st : h->st2[gi - 1], r0, cnt, gi};
+    r0 += cnt;
+  }
+  if (n_groups > 1) {
+    ZF_CUDA(cudaEventRecord(h->ev, h->st));
+    for (int gi = 1; gi < n_groups; ++gi) ZF_CUDA(cudaStreamWaitEvent(groups[gi].st, h->ev, 0));
+  }
+  // one round of a group; `count`: the deciding kernel also counts the runs that stay active
+  auto round = [&](const RunGroup& g, bool count) -> int {
     int r2;
-    if (count) ZF_CUDA(cudaMemsetAsync(h->B.n_active, 0, sizeof(unsigned int), h->st));
-    if (!c.need_F) return launch_tile<0>(h, n_runs, c, true, count);
-    if ((r2 = launch_tile<0>(h, n_runs, c, false, false)) != ZF_OK) return r2;
-    if (c.store_yg && (r2 = launch_prox(h, n_runs, c)) != ZF_OK) return r2;
-    return launch_tile<1>(h, n_runs, c, true, count);
+    if (count) ZF_CUDA(cudaMemsetAsync(h->B.n_active + g.group, 0, sizeof(unsigned int), g.st));
+    if (!c.need_F) return launch_tile_g<0>(h, g, c, true, count);
+    if ((r2 = launch_tile_g<0>(h, g, c, false, false)) != ZF_OK) return r2;
+    if (c.store_yg && (r2 = launch_prox_g(h, g, c)) != ZF_OK) return r2;
+    return launch_tile_g<1>(h, g, c, true, count);
   };
   // Chunks of rounds between polls (8, 16, 32, 64, 64, ...: short solves do not over-run much,
   // long ones poll rarely).  A chunk is captured once into a CUDA graph and replayed: every
   // kernel argument is constant during a solve (all state is in device memory).
   const int kernels_per_round = c.need_F ? (c.store_yg ? 3 : 2) : 1;
-  cudaGraphExec_t execs[4] = {nullptr, nullptr, nullptr, nullptr};
-  auto build_graph = [&](int chunk, cudaGraphExec_t* out) -> int {
+  cudaGraphExec_t execs[4][4] = {};
+  auto build_graph = [&](const RunGroup& g, int chunk, cudaGraphExec_t* out) -> int {
     cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    if (cudaStreamBeginCapture(g.st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
       return ZF_ERR_CUDA;
     }
     h->capturing = true;
     int r2 = ZF_OK;
-    for (int k = 0; k < chunk && r2 == ZF_OK; ++k) r2 = round(k == chunk - 1);
+    for (int k = 0; k < chunk && r2 == ZF_OK; ++k) r2 = round(g, k == chunk - 1);
     if (r2 == ZF_OK &&
-        cudaMemcpyAsync(h->h_active, h->B.n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost,
-                        h->st) != cudaSuccess)
+        cudaMemcpyAsync(h->h_active + g.group, h->B.n_active + g.group, sizeof(unsigned int),
+                        cudaMemcpyDeviceToHost, g.st) != cudaSuccess)
       r2 = ZF_ERR_CUDA;
     h->capturing = false;
-    cudaError_t e = cudaStreamEndCapture(h->st, &graph);
+    cudaError_t e = cudaStreamEndCapture(g.st, &graph);
     if (r2 != ZF_OK || e != cudaSuccess || !graph) {
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError();
@@ -619,22 +658,35 @@ int deblur_run(zf_deblur* h, const zf_options* opt, int n_runs, const double* h_
   };
   int chunk = 8, slot = 0;
   bool use_graph = true;
+  bool active[4] = {n_groups > 0, n_groups > 1, n_groups > 2, n_groups > 3};
   rc = ZF_OK;
-  while (true) {
-    if (use_graph && !execs[slot] && build_graph(chunk, &execs[slot]) != ZF_OK) use_graph = false;
-    if (use_graph) {
-      if (cudaGraphLaunch(execs[slot], h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "cudaGraphLaunch failed"); break; }
-      zf::zf_count_launch((int64_t)kernels_per_round * chunk);
-    } else {
-      for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = round(k == chunk - 1);
-      if (rc != ZF_OK) break;
-      if (cudaMemcpyAsync(h->h_active, h->B.n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "memcpy failed"); break; }
+  while (rc == ZF_OK && (active[0] || active[1] || active[2] || active[3])) {
+    for (int gi = 0; gi < n_groups && rc == ZF_OK; ++gi) {
+      if (!active[gi]) continue;
+      const RunGroup& g = groups[gi];
+      if (use_graph && !execs[gi][slot] && build_graph(g, chunk, &execs[gi][slot]) != ZF_OK)
+        use_graph = false;
+      if (use_graph) {
+        if (cudaGraphLaunch(execs[gi][slot], g.st) != cudaSuccess) rc = zf::zf_fail(ZF_ERR_CUDA, "cudaGraphLaunch failed");
+        else zf::zf_count_launch((int64_t)kernels_per_round * chunk);
+      } else {
+        for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = round(g, k == chunk - 1);
+        if (rc == ZF_OK &&
+            cudaMemcpyAsync(h->h_active + gi, h->B.n_active + gi, sizeof(unsigned int),
+                            cudaMemcpyDeviceToHost, g.st) != cudaSuccess)
+          rc = zf::zf_fail(ZF_ERR_CUDA, "memcpy failed");
+      }
     }
-    if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = zf::zf_fail(ZF_ERR_CUDA, "stream sync failed"); break; }
-    if (*h->h_active == 0) break;
+    for (int gi = 0; gi < n_groups && rc == ZF_OK; ++gi) {
+      if (!active[gi]) continue;
+      if (cudaStreamSynchronize(groups[gi].st) != cudaSuccess) rc = zf::zf_fail(ZF_ERR_CUDA, "stream sync failed");
+      else if (h->h_active[gi] == 0) active[gi] = false;
+    }
     if (chunk < 64) { chunk *= 2; ++slot; }
   }
-  for (auto& ex : execs) if (ex) cudaGraphExecDestroy(ex);
+  for (auto& row : execs)
+    for (auto& ex : row)
+      if (ex) cudaGraphExecDestroy(ex);
   if (rc != ZF_OK) return rc;
   if (!c.need_F) {   // res.fun = F(x): one evaluation of the result buffer
     c.finalize = 1;
@@ -692,8 +744,11 @@ extern "C" int zf_deblur_create(zf_deblur** out, int32_t height, int32_t width,
   alloc((void**)&B.psum, sizeof(zf::DeblurSums) * (size_t)max_runs * d.prox_blocks);
   alloc((void**)&B.runs, sizeof(zf::DeblurRun) * (size_t)max_runs);
   alloc((void**)&B.tickets, sizeof(unsigned int) * (size_t)max_runs);
-  alloc((void**)&B.n_active, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_active, sizeof(unsigned int));
+  alloc((void**)&B.n_active, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_active, 4 * sizeof(unsigned int));
+  for (int k = 0; k < 3; ++k)
+    if (e == cudaSuccess) e = cudaStreamCreate(&h->st2[k]);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(bimg, h_observed, sizeof(double) * (size_t)d.n, cudaMemcpyHostToDevice, h->st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
@@ -716,6 +771,9 @@ extern "C" void zf_deblur_destroy(zf_deblur* h) {
   cudaFree(B.allerrs); cudaFree(B.allfuns);
   if (h->h_active) cudaFreeHost(h->h_active);
   if (h->own_st) cudaStreamDestroy(h->own_st);
+  for (int k = 0; k < 3; ++k)
+    if (h->st2[k]) cudaStreamDestroy(h->st2[k]);
+  if (h->ev) cudaEventDestroy(h->ev);
   delete h;
 }
 
