@@ -268,8 +268,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...") goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed
+        # to stdout at NCCL_DEBUG=VERSION, which this image sets) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     zbuild.build()
     L = _lib.lib()
