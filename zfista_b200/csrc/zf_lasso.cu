@@ -4,8 +4,12 @@
 // closures of tests/test_proximal_gradient.py:49-63 at sizes where A >> L2).
 //
 // Per FISTA iteration the device does
-//   r = A y - b                      lasso_residual_kernel   (one pass over A)
-//   q = A^T r                        lasso_atr_kernel        (one pass over A)
+//   q = A^T (A y - b), sum r^2       ONE pass over A with a fused kernel chosen per shape
+//                                    (lasso_fused_kernel: single CTA, L2 re-read;
+//                                     lasso_fused_cluster_kernel: 2-CTA cluster + DSMEM;
+//                                     lasso_fused_tma_kernel: TMA ring, row pair stays in smem)
+//                                    or two passes where a row is too wide for them:
+//                                    lasso_residual_kernel (r = A y - b), lasso_atr_kernel (A^T r)
 //   x = soft(y - lr*2*scale*q, lr*l1) + the four sums the line search / stop test need
 //                                    lasso_prox_kernel       (n_cols work)
 //   [line search]  ||A x - b||^2     lasso_residual_kernel   (one pass per trial)
