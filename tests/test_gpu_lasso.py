@@ -192,3 +192,25 @@ def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     assert a.nit == c.nit and a.status == c.status
     np.testing.assert_allclose(a.x, c.x, rtol=0, atol=1e-9)
     np.testing.assert_allclose(a.fun, c.fun, rtol=1e-11)
+
+
+def test_reference_lasso_zero_and_return_all(gpu):
+    """tests/test_proximal_gradient.py:43-68 (A = 0, b = 0: the minimiser is x = 0) and
+    :221-243 (return_all fields), through both single-objective device paths."""
+    import zfista_b200.problems as zp
+    from zfista_b200 import minimize_proximal_gradient
+    from zfista_b200.lasso import DenseLasso
+
+    A = np.zeros((3, 1))
+    b = np.zeros(3)
+    x0 = np.array([0.5488135039273248])
+    for prob in (zp.LeastSquaresL1(A, b, 0.1, scale=1 / 6), DenseLasso(A, b, 0.1, scale=1 / 6)):
+        res = minimize_proximal_gradient(prob.f, prob.g, prob.jac_f, prob.prox_wsum_g, x0)
+        res_nesterov = minimize_proximal_gradient(prob.f, prob.g, prob.jac_f, prob.prox_wsum_g, x0,
+                                                  nesterov=True)
+        np.testing.assert_array_almost_equal(res.x, [0], decimal=3)
+        np.testing.assert_array_almost_equal(res_nesterov.x, [0], decimal=3)
+        res = minimize_proximal_gradient(prob.f, prob.g, prob.jac_f, prob.prox_wsum_g, x0,
+                                         return_all=True)
+        assert "allvecs" in res and "allerrs" in res and "allfuns" in res
+        assert len(res.allerrs) == res.nit and len(res.allfuns) == res.nit + 1
