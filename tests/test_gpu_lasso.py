@@ -153,7 +153,8 @@ def test_large_a_properties(gpu):
     ({"ZF_LASSO_CLUSTER": "2", "ZF_LASSO_THREADS": "1024"}, (1200, 9000), 1),
     ({"ZF_LASSO_TMA": "2"}, (900, 2000), 1),               # TMA ring, cluster 2
     ({"ZF_LASSO_TMA": "4"}, (1000, 5002), 1),              # TMA ring, cluster 4, ragged slices
-    ({"ZF_LASSO_TMA": "2", "ZF_LASSO_TMA_STAGES": "3", "ZF_LASSO_TMA_PIPE": "1"}, (911, 2000), 1),
+    ({"ZF_LASSO_TMA": "2", "ZF_LASSO_TMA_ROWS": "3"}, (911, 2000), 1),   # 3 rows per stage, ragged
+    ({"ZF_LASSO_TMA": "4", "ZF_LASSO_TMA_ROWS": "4"}, (1001, 3000), 1),  # 4 rows per stage
 ])
 def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     """Each form of the A^T(A v - b) pass (csrc/zf_lasso.cu) forced through its environment
@@ -163,7 +164,7 @@ def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     from zfista_b200.lasso import DenseLasso
 
     for k in ("ZF_LASSO_FUSED", "ZF_LASSO_CLUSTER", "ZF_LASSO_THREADS", "ZF_LASSO_TMA",
-              "ZF_LASSO_TMA_STAGES", "ZF_LASSO_TMA_PIPE"):
+              "ZF_LASSO_TMA_ROWS"):
         monkeypatch.delenv(k, raising=False)
     rows, cols = shape
     g = torch.Generator(device="cuda").manual_seed(rows + cols)

@@ -499,11 +499,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 constexpr int TMA_THREADS = 512;
 
-// NS: stages of the ring; PIPE: form the dot products of pair k+1 between the cluster barrier's
-// arrive and wait of pair k (needs NS >= 3 to keep a full pair in flight meanwhile)
+// Two rows per stage, hand-specialised (measured 5-10 % faster than the generic kernel below
+// instantiated at R = 2).  PIPE (dot products of pair k+1 between the cluster barrier's arrive
+// and wait of pair k) was measured slower and is instantiated off.
 template <int PAIRS, int NS, bool PIPE>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ b,
+lasso_fused_tma_pair_kernel(const double* __restrict__ A, const double* __restrict__ b,
                        const double* __restrict__ v, long long n_rows, long long n_cols,
                        long long rows_per_cluster, long long pairs_per_cta,
                        double* __restrict__ gpart, double* __restrict__ sq_part) {
@@ -616,6 +617,136 @@ lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ 
     if (tid == 0 && my_pairs > 0 && k + NS < n_pairs) issue(k + NS);
     if (PIPE) { acc[0] = nacc[0]; acc[1] = nacc[1]; }
     else if (k + 1 < n_pairs) dots(k + 1, acc);
+  }
+  double* out = gpart + cid * n_cols;
+#pragma unroll
+  for (int u = 0; u < PAIRS; ++u) {
+    const long long p = tid + (long long)u * TMA_THREADS;
+    if (p < my_pairs) reinterpret_cast<double2*>(out)[p_lo + p] = q[u];
+  }
+  if (tid == 0 && crank == 0) sq_part[cid] = ss;
+  cluster.sync();
+}
+
+// R: rows per stage (one cluster barrier per R rows); NS: stages of the ring.
+template <int PAIRS, int NS, int R>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ b,
+                       const double* __restrict__ v, long long n_rows, long long n_cols,
+                       long long rows_per_cluster, long long pairs_per_cta,
+                       double* __restrict__ gpart, double* __restrict__ sq_part) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+  const long long cid = blockIdx.x / csize;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ double red[TMA_THREADS / 32][R];
+  __shared__ double xch[2][R][8];                    // [parity][row][cluster rank]
+  __shared__ __align__(8) unsigned long long full[NS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n2 = n_cols >> 1;
+  const long long p_lo = (long long)crank * pairs_per_cta;
+  const long long p_hi = (p_lo + pairs_per_cta < n2) ? p_lo + pairs_per_cta : n2;
+  const long long my_pairs = p_hi > p_lo ? p_hi - p_lo : 0;
+  const unsigned slice_bytes = (unsigned)(my_pairs * 16);
+  const size_t slice_stride = (size_t)pairs_per_cta * 16;        // bytes reserved per row slice
+  double2* vsm = reinterpret_cast<double2*>(dyn);
+  unsigned char* ring = dyn + slice_stride;                      // NS stages x R row slices
+  for (long long p = tid; p < my_pairs; p += TMA_THREADS)
+    vsm[p] = __ldg(reinterpret_cast<const double2*>(v) + p_lo + p);
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long i0 = cid * rows_per_cluster;
+  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
+  const long long n_groups = (i1 > i0) ? (i1 - i0 + R - 1) / R : 0;
+  auto issue = [&](long long k) {        // elected thread: stream row group k into stage k % NS
+    const int s = (int)(k % NS);
+    const long long i = i0 + (long long)R * k;
+    unsigned char* dst = ring + (size_t)s * R * slice_stride;
+    mbar_expect_tx(&full[s], R * slice_bytes);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = (i + r < i1) ? i + r : i;          // rows past the end: a duplicate,
+      tma_load_1d(dst + (size_t)r * slice_stride,               // its residual is forced to 0
+                  A + row * n_cols + 2 * p_lo, slice_bytes, &full[s]);
+    }
+  };
+  if (tid == 0 && my_pairs > 0)
+    for (long long k = 0; k < NS && k < n_groups; ++k) issue(k);
+  double2 q[PAIRS];
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) q[k] = make_double2(0.0, 0.0);
+  double ss = 0.0;
+  int parity = 0;
+  for (long long k = 0; k < n_groups; ++k) {
+    const int s = (int)(k % NS);
+    const long long i = i0 + (long long)R * k;
+    const double2* rowp[R];               // the R row slices of this stage
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      rowp[r] = reinterpret_cast<const double2*>(ring + ((size_t)s * R + r) * slice_stride);
+    if (my_pairs > 0) mbar_wait(&full[s], (unsigned)((k / NS) & 1));
+    // ---- phase 1: partial dot products of the R rows over this CTA's columns
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const long long p = tid + (long long)u * TMA_THREADS;
+      if (p < my_pairs) {
+        const double2 vv = vsm[p];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double2 x = rowp[r][p];
+          acc[r] += x.x * vv.x + x.y * vv.y;
+        }
+      }
+    }
+    warp_sum_k<R>(acc);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) red[warp][r] = acc[r];
+    }
+    __syncthreads();
+    if (tid < csize) {
+      double* remote = cluster.map_shared_rank(&xch[0][0][0], tid);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < TMA_THREADS / 32; ++w) t += red[w][r];
+        remote[(parity * R + r) * 8 + crank] = t;
+      }
+    }
+    cluster.sync();
+    double res[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double t = 0.0;
+      for (int c = 0; c < csize; ++c) t += xch[parity][r][c];
+      res[r] = (i + r < i1) ? t - b[i + r] : 0.0;
+      ss += res[r] * res[r];
+    }
+    parity ^= 1;
+    // ---- phase 2: rank-1 updates from the same shared-memory stage
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const long long p = tid + (long long)u * TMA_THREADS;
+      if (p < my_pairs) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double2 x = rowp[r][p];
+          q[u].x += res[r] * x.x;
+          q[u].y += res[r] * x.y;
+        }
+      }
+    }
+    __syncthreads();                      // every thread is done with stage s
+    if (tid == 0 && my_pairs > 0 && k + NS < n_groups) issue(k + NS);
   }
   double* out = gpart + cid * n_cols;
 #pragma unroll
@@ -775,8 +906,7 @@ struct zf_lasso {
   int fused_cluster = 1;              // CTAs per cluster (1: single-CTA kernel)
   int fused_threads = 512;            // threads per CTA of the cluster form
   bool fused_tma = false;             // TMA / shared-memory-resident form
-  int tma_stages = 2;
-  bool tma_pipe = false;
+  int tma_rows = 2;                   // rows per TMA stage (one cluster barrier per stage)
   long long fused_pairs_per_cta = 0;  // column pairs per CTA (cluster form)
   size_t gpart_rows = 0;
   // solver state (host scalars)
@@ -861,12 +991,15 @@ int launch_fused_cluster_t(zf_lasso* h, const double* v) {
   return ZF_OK;
 }
 
-template <int PAIRS, int NS, bool PIPE>
+template <int PAIRS, int R>
 int launch_fused_tma_t(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
-  auto k = zf::lasso_fused_tma_kernel<PAIRS, NS, PIPE>;
-  const size_t smem = (size_t)h->fused_pairs_per_cta * 16 * (1 + 2 * NS);
+  constexpr int NS = 2;
+  void (*k)(const double*, const double*, const double*, long long, long long, long long,
+            long long, double*, double*);
+  if (R == 2) k = zf::lasso_fused_tma_pair_kernel<PAIRS, NS, false>;
+  else k = zf::lasso_fused_tma_kernel<PAIRS, NS, (R == 2 ? 3 : R)>;
+  const size_t smem = (size_t)h->fused_pairs_per_cta * 16 * (1 + R * NS);
   ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (h->fused_cluster > 8) ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)h->fused_ctas);
   cfg.blockDim = dim3(zf::TMA_THREADS);
@@ -890,25 +1023,25 @@ int launch_fused_tma_t(zf_lasso* h, const double* v, bool query_only, int* max_c
   return ZF_OK;
 }
 
-template <int NS, bool PIPE>
-int launch_fused_tma_p(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+template <int R>
+int launch_fused_tma_r(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
   switch (h->fused_pairs) {
-    case 1: return launch_fused_tma_t<1, NS, PIPE>(h, v, query_only, max_clusters);
-    case 2: return launch_fused_tma_t<2, NS, PIPE>(h, v, query_only, max_clusters);
-    case 3: return launch_fused_tma_t<3, NS, PIPE>(h, v, query_only, max_clusters);
-    case 4: return launch_fused_tma_t<4, NS, PIPE>(h, v, query_only, max_clusters);
-    case 5: return launch_fused_tma_t<5, NS, PIPE>(h, v, query_only, max_clusters);
-    case 6: return launch_fused_tma_t<6, NS, PIPE>(h, v, query_only, max_clusters);
-    default: return launch_fused_tma_t<8, NS, PIPE>(h, v, query_only, max_clusters);
+    case 1: return launch_fused_tma_t<1, R>(h, v, query_only, max_clusters);
+    case 2: return launch_fused_tma_t<2, R>(h, v, query_only, max_clusters);
+    case 3: return launch_fused_tma_t<3, R>(h, v, query_only, max_clusters);
+    case 4: return launch_fused_tma_t<4, R>(h, v, query_only, max_clusters);
+    case 5: return launch_fused_tma_t<5, R>(h, v, query_only, max_clusters);
+    case 6: return launch_fused_tma_t<6, R>(h, v, query_only, max_clusters);
+    default: return launch_fused_tma_t<8, R>(h, v, query_only, max_clusters);
   }
 }
 
 int launch_fused_tma(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
-  if (h->tma_stages == 3)
-    return h->tma_pipe ? launch_fused_tma_p<3, true>(h, v, query_only, max_clusters)
-                       : launch_fused_tma_p<3, false>(h, v, query_only, max_clusters);
-  return h->tma_pipe ? launch_fused_tma_p<2, true>(h, v, query_only, max_clusters)
-                     : launch_fused_tma_p<2, false>(h, v, query_only, max_clusters);
+  switch (h->tma_rows) {
+    case 4: return launch_fused_tma_r<4>(h, v, query_only, max_clusters);
+    case 3: return launch_fused_tma_r<3>(h, v, query_only, max_clusters);
+    default: return launch_fused_tma_r<2>(h, v, query_only, max_clusters);
+  }
 }
 
 // gradient pass at v: leaves the A^T r partials in gpart (n_gpart_rows x n_cols) and the
@@ -1116,12 +1249,13 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   if (vb > zf::VEC_MAX_BLOCKS) vb = zf::VEC_MAX_BLOCKS;
   h->vec_blocks = (int)vb;
   // ---- which kernels compute A^T(A v - b) for this shape.  Measured on B200 (DESIGN.md 3.3,
-  // fraction of the one-pass HBM bound): single-CTA fused 0.62 at 8192 columns; 2-CTA cluster
-  // with L2 re-read 0.77 at 16384, 0.69 at 12000, 0.64 at 20000; TMA / shared-memory-resident
-  // form 0.73 at 8192 (cluster 2) and 0.72 at 20000 (cluster 4) but 0.66 at 16384; two-pass
-  // kernels 0.53 everywhere.  Environment overrides for experiments:
+  // fraction of the one-pass HBM bound): single-CTA fused 0.83 at 4096 columns, 0.52 at 6000;
+  // TMA / shared-memory-resident form 0.72 at 6000 and 0.76 at 8192 (cluster 2, 4 / 3 rows per
+  // stage), 0.67-0.72 at 20000 (cluster 4) but 0.69 at 16384; 2-CTA cluster with L2 re-read
+  // 0.77 at 16384, 0.70 at 12000, 0.65 at 20000; two-pass kernels 0.53 everywhere.
+  // Environment overrides for experiments:
   //   ZF_LASSO_FUSED=0 (two-pass), ZF_LASSO_CLUSTER=2|4, ZF_LASSO_THREADS=512|1024,
-  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_STAGES=2|3, ZF_LASSO_TMA_PIPE=0|1.
+  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4.
   h->gpart_rows = (size_t)h->n_rowblocks;
   size_t sq_rows = (size_t)h->res_blocks;
   {
@@ -1134,9 +1268,9 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
     const char* env_cluster = getenv("ZF_LASSO_CLUSTER");
     const char* env_tma = getenv("ZF_LASSO_TMA");
     const bool off = env_fused && env_fused[0] == '0';
-    auto finish_cluster_grid = [&](int cluster, int n_clusters) {
+    auto finish_cluster_grid = [&](int cluster, int n_clusters, int row_multiple) {
       h->fused_rows_per_cta = (n_rows + n_clusters - 1) / n_clusters;      // rows per cluster
-      if (h->fused_rows_per_cta % 2) h->fused_rows_per_cta += 1;
+      while (h->fused_rows_per_cta % row_multiple) h->fused_rows_per_cta += 1;
       const int used = (int)((n_rows + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
       h->fused_ctas = used * cluster;
       if ((size_t)used > h->gpart_rows) h->gpart_rows = (size_t)used;
@@ -1146,11 +1280,13 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       if (!(c == 2 || c == 4 || c == 8) || !big_enough) return false;
       const long long ppc = (n2 + c - 1) / c;
       const long long ppt = (ppc + zf::TMA_THREADS - 1) / zf::TMA_THREADS;
-      h->tma_stages = 2;
-      h->tma_pipe = false;
-      if (const char* e2 = getenv("ZF_LASSO_TMA_STAGES")) h->tma_stages = atoi(e2) == 3 ? 3 : 2;
-      if (const char* e3 = getenv("ZF_LASSO_TMA_PIPE")) h->tma_pipe = atoi(e3) != 0;
-      const size_t smem = (size_t)ppc * 16 * (1 + 2 * h->tma_stages);
+      // rows per stage: as many as fit (v slice + 2 stages x R row slices in shared memory),
+      // up to 4 -- one block reduction + one cluster barrier is paid per stage
+      int R = 4;
+      if (const char* e2 = getenv("ZF_LASSO_TMA_ROWS")) { R = atoi(e2); if (R < 2 || R > 4) R = 2; }
+      while (R > 2 && (size_t)ppc * 16 * (1 + 2 * R) + 2048 > (size_t)max_smem) --R;
+      h->tma_rows = R;
+      const size_t smem = (size_t)ppc * 16 * (1 + 2 * R);
       if (ppt > 8 || smem + 2048 > (size_t)max_smem) return false;
       h->fused_tma = true;
       h->fused_cluster = c;
@@ -1162,7 +1298,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       int active = 0;
       if (launch_fused_tma(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
         n_clusters = active;              // only clusters that can be co-resident: one wave
-      finish_cluster_grid(c, n_clusters);
+      finish_cluster_grid(c, n_clusters, h->tma_rows);
       return true;
     };
     auto try_cluster = [&](int c) -> bool {
@@ -1178,7 +1314,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       h->fused_threads = threads;
       h->fused_pairs_per_cta = ppc;
       h->fused_pairs = threads == 1024 ? (int)ppt : (int)(((ppt + 1) / 2) * 2);
-      finish_cluster_grid(c, h->n_sm / c);
+      finish_cluster_grid(c, h->n_sm / c, 2);
       return true;
     };
     auto try_single = [&]() -> bool {
@@ -1200,7 +1336,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       try_cluster(atoi(env_cluster));
     } else if (env_fused) {
       try_single();
-    } else if (n_cols <= 6144) {
+    } else if (n_cols <= 4608) {
       try_single();
     } else if (n_cols <= 8192) {
       if (!try_tma(2)) try_single();
