@@ -17,8 +17,8 @@
 
 namespace zf {
 
-__device__ __forceinline__ size_t warp_smem_doubles(int n, int m, int n_rows) {
-  return (size_t)(3 + m) * n + n_rows;
+__host__ __device__ __forceinline__ size_t warp_smem_doubles(int n, int m, int n_rows) {
+  return (size_t)(3 + m) * n + n_rows + (size_t)(n + 7) / 8;     // + n pattern bytes
 }
 
 template <int M>
@@ -72,11 +72,13 @@ __device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const
         out.w[1] = 1.0 - xf;
         out.fun = -fmin;
       }
+      primal_from_weights<M>(P, c, lr, out.w, c.xn);
     } else {
-      out.fun = dual_newton<M>(P, c, d, out.w, 60, &nf);
+      bool x_ready = false;
+      out.fun = dual_newton<M>(P, c, d, out.w, 60, &nf, &x_ready);
+      if (!x_ready) primal_from_weights<M>(P, c, lr, out.w, c.xn);
     }
     out.n_dual = nf;
-    primal_from_weights<M>(P, c, lr, out.w, c.xn);
   }
 }
 
@@ -100,6 +102,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
   c.xn = base + 2 * (size_t)n;
   c.J = base + 3 * (size_t)n;
   c.scratch = base + (size_t)(3 + M) * n;
+  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
 
   using F = Fn<KIND, M>;
   const long long total_warps = (long long)gridDim.x * warps_per_block;
@@ -264,6 +267,7 @@ subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* _
   c.lane = lane; c.n = n;
   c.y = base; c.xp = base + n; c.xn = base + 2 * (size_t)n; c.J = base + 3 * (size_t)n;
   c.scratch = base + (size_t)(3 + M) * n;
+  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
   using F = Fn<KIND, M>;
   const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
   if (s >= n_items) return;
@@ -311,6 +315,7 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
   c.lane = lane; c.n = n;
   c.y = base; c.xp = base + n; c.xn = base + 2 * (size_t)n; c.J = base + 3 * (size_t)n;
   c.scratch = base + (size_t)(3 + M) * n;
+  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
   using F = Fn<KIND, M>;
   const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
   if (s >= n_items) return;
@@ -370,7 +375,7 @@ template <int KIND, int M>
 static int launch_t(const LaunchArgs& L) {
   const int n = L.P.n_features;
   const int n_rows = (KIND == ZF_LSQ_L1) ? L.P.n_rows : 0;
-  const size_t per_warp = ((size_t)(3 + M) * n + n_rows) * sizeof(double);
+  const size_t per_warp = warp_smem_doubles(n, M, n_rows) * sizeof(double);
   const size_t smem_cap = 200 * 1024;
   if (per_warp > smem_cap) {
     return zf_fail(ZF_ERR_UNSUPPORTED,

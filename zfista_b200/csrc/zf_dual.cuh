@@ -191,6 +191,41 @@ __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualDa
 //   max_{w' in simplex}  (G + Qm w) . w' - 1/2 w'^T Qm w'
 // is then solved exactly in registers by enumerating the 2^M - 1 faces.
 // ------------------------------------------------------------------------------------
+// Which linear piece of the prox chain a coordinate is on: 0 if pinned at a kink / bound
+// (alpha = 0), else 1 | the side of every shift it lies on.  The dual is one quadratic wherever
+// these codes do not change.
+template <int M>
+__device__ __forceinline__ unsigned char piece_code(double alpha, const double (&eps)[M]) {
+  if (alpha == 0.0) return 0;
+  unsigned code = 1u;
+#pragma unroll
+  for (int i = 0; i < M; ++i) code |= (eps[i] > 0.0 ? 1u : 0u) << (i + 1);
+  return (unsigned char)code;
+}
+
+// x = prox_wsum_g(lr * w, y - lr * w @ J) into `out`, and whether every coordinate is on the
+// same piece as at the last full dual evaluation (c.pat)
+template <int M>
+__device__ bool primal_probe(const zf_problem& P, const WarpCtx& c, double lr,
+                             const double (&w)[M], double* out) {
+  double wt[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) wt[i] = lr * w[i];
+  int same = 1;
+#pragma unroll 1
+  for (int j = c.lane; j < c.n; j += 32) {
+    double wj = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + j];
+    const double v = c.y[j] - lr * wj;
+    double alpha, eps[M];
+    out[j] = prox_elem<M, true>(P, j, v, wt, alpha, eps);
+    same &= (piece_code<M>(alpha, eps) == c.pat[j]);
+  }
+  __syncwarp();
+  return __all_sync(ZF_FULL_MASK, same) != 0;
+}
+
 template <int M>
 struct DualPoint {
   double D;
@@ -233,6 +268,7 @@ __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<
       double alpha, eps[M];
       const double p = prox_elem<M, true>(P, j, v, wt, alpha, eps);
       const double keep = live ? 1.0 : 0.0;
+      if (live) c.pat[j] = piece_code<M>(alpha, eps);
       double mcol[M];
 #pragma unroll
       for (int i = 0; i < M; ++i) {
@@ -433,7 +469,7 @@ __device__ void simplex_qp(const double (&Q)[M][M], const double (&G)[M],
 // the iteration stops (oracle/dual_model.py:simplex_newton is the CPU statement).
 template <int M>
 __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
-                              double (&w)[M], int max_iter, int* nfev) {
+                              double (&w)[M], int max_iter, int* nfev, bool* x_ready) {
   // One evaluation site and one QP site (code size: see zf_common.cuh): the loop body is
   // "evaluate the point under test, then either accept it and take the next Newton step from
   // it, or halve the step".
@@ -484,6 +520,18 @@ __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualD
 #pragma unroll
       for (int i = 0; i < M; ++i) w[i] = wn[i];
       cur.D += pred;
+      break;
+    }
+    // The dual is one quadratic as long as no coordinate changes piece.  If the primal point
+    // of the Newton candidate lies on the same pieces as the point just evaluated, the model
+    // is exact there: the candidate is the maximiser, D(candidate) = D + pred, and evaluating
+    // it (plus the QP that would return it unchanged) is only a confirmation -- skip both.
+    // The probe is the primal recovery the caller needs anyway, so it costs nothing extra.
+    if (primal_probe<M>(P, c, d.lr, wn, c.xn)) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) w[i] = wn[i];
+      cur.D += pred;
+      *x_ready = true;
       break;
     }
     step = 1.0;
