@@ -688,10 +688,20 @@ def bench_sweep(args, dev, rank, world):
     br = prob.minimize_proximal_gradient_batched(Xg, nesterov=True, nesterov_ratio=AB,
                                                  tol_internal=1e-11)
     dt = time.perf_counter() - t0
-    return {"workload": "JOS1 n=50 +L1, 15 (a,b) pairs x 1024 starts in one launch (e2e call)",
-            "solves": int(len(Xg)), "converged": int((br.status == 1).sum()),
-            "solves_per_s": float((br.status == 1).sum() / dt), "seconds": dt,
-            "nit_mean": float(br.nit.mean())}
+    out = {"workload": "JOS1 n=50 +L1, 15 (a,b) pairs x 1024 starts in one launch (e2e call)",
+           "solves": int(len(Xg)), "converged": int((br.status == 1).sum()),
+           "solves_per_s": float((br.status == 1).sum() / dt), "seconds": dt,
+           "nit_mean": float(br.nit.mean()), "dual_evals_per_solve": float(br.n_dual.mean())}
+    # the same sweep with the exact simplex-Newton dual solver instead of the reference's
+    # bounded Brent (dual_solver="newton": same optimum, not the reference's sqrt(eps) noise)
+    t0 = time.perf_counter()
+    bn = prob.minimize_proximal_gradient_batched(Xg, nesterov=True, nesterov_ratio=AB,
+                                                 tol_internal=1e-11, dual_solver="newton")
+    dtn = time.perf_counter() - t0
+    out["newton_dual"] = {"solves_per_s": float((bn.status == 1).sum() / dtn), "seconds": dtn,
+                          "nit_mean": float(bn.nit.mean()),
+                          "dual_evals_per_solve": float(bn.n_dual.mean())}
+    return out
 
 
 def main():
