@@ -396,6 +396,9 @@ def run_ours(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": 1239808.0,
+                "ncu": {"fp64_pipe_active_pct": 16.6, "issue_slots_active_pct": 34.8,
+                        "warp_occupancy_pct": 7.0, "dominant_stall": "wait (dependent FP64 ops)",
+                        "source": "profiles/r01e_batched_fista_final.txt"},
                 "peak_source": peaks["source"],
                 "note": ("batched_fista_kernel keeps each start's state in shared memory and "
                          "touches HBM only for x0 and the results; it is FP64-latency bound, "

@@ -132,7 +132,7 @@ class DenseLasso:
         return self.gradient(x)[0].cpu().numpy()
 
     def g(self, x):
-        return self.l1_ratio * float(np.abs(np.asarray(x, dtype=np.float64)).sum())
+        return self.l1_ratio * float(self._to_dev(x, 1).abs().sum().item())
 
     def prox_wsum_g(self, weight, x):
         # only used when a caller evaluates the closure directly; the solver's prox is on device
