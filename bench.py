@@ -237,7 +237,7 @@ def run_reference_arm(args):
         "gpu_launches": 0, "nit_mean": float(np.mean(nits)) if nits else None,
         "steps_timed": len(times),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -268,10 +268,6 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed
-        # to stdout at NCCL_DEBUG=VERSION, which this image sets) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     zbuild.build()
     L = _lib.lib()
@@ -427,7 +423,7 @@ def run_ours(args):
                     also[name] = {"error": repr(e)}
         if rank == 0:
             line["also"] = also
-            print(json.dumps(line), flush=True)
+            emit(line)
     del keep
     if world > 1:
         dist.destroy_process_group()
@@ -708,6 +704,30 @@ def bench_sweep(args, dev, rank, world):
     return out
 
 
+_JSON_FD = None
+
+
+def capture_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write to file descriptor 1 on
+    their own (NCCL prints "NCCL version ..." at communicator creation whatever NCCL_DEBUG
+    says).  Everything written to fd 1 from here on goes to stderr; emit() writes the JSON
+    line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -726,6 +746,7 @@ def main():
     ap.add_argument("--lasso-iters", type=int, default=50)
     ap.add_argument("--cameraman-iters", type=int, default=2000)
     args = ap.parse_args()
+    capture_stdout()
     try:
         if args.impl == "reference":
             return run_reference_arm(args)
