@@ -10,10 +10,12 @@ box with the repo snapshot.
 from __future__ import annotations
 
 import argparse
+import fcntl
 import hashlib
 import os
 import subprocess
 import sys
+import tempfile
 from concurrent.futures import ThreadPoolExecutor
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -22,12 +24,15 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libzfista_b200.so")
 
-NVCC_FLAGS = [
+# flags that define the build (hashed into the fingerprint); the include paths are added at
+# compile time only: the repo is mounted at different absolute paths here and on the GPU box,
+# and a path in the fingerprint would force a rebuild there on every run
+NVCC_BASE_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC",
-    "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
 ]
+NVCC_FLAGS = NVCC_BASE_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
 def _nvcc() -> str:
@@ -49,20 +54,40 @@ def _fingerprint() -> str:
                 with open(os.path.join(d, f), "rb") as fh:
                     h.update(f.encode())
                     h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_BASE_FLAGS).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(BUILD_DIR, exist_ok=True)
+def _up_to_date(fp: str) -> bool:
     stamp = os.path.join(BUILD_DIR, "fingerprint.txt")
+    if not (os.path.exists(LIB_PATH) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as fh:
+        return fh.read().strip() == fp
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Build (if the sources changed) and return the library path.  Safe to call from several
+    processes at once (one rank per GPU under torchrun): an exclusive file lock lets one of
+    them build while the others wait, and the library is moved into place atomically so that
+    nobody can ever map a half-written file."""
+    os.makedirs(BUILD_DIR, exist_ok=True)
     fp = _fingerprint()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
-        with open(stamp) as fh:
-            if fh.read().strip() == fp:
+    if not force and _up_to_date(fp):
+        return LIB_PATH
+    with open(os.path.join(BUILD_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(fp):      # another process built it meanwhile
                 return LIB_PATH
+            return _build_locked(fp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(fp: str, verbose: bool) -> str:
+    stamp = os.path.join(BUILD_DIR, "fingerprint.txt")
     nvcc = _nvcc()
-    objs = []
 
     def compile_one(src):
         obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
@@ -79,10 +104,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    fd, tmp = tempfile.mkstemp(prefix=".libzfista_b200.", suffix=".so.tmp", dir=PKG_DIR)
+    os.close(fd)
+    try:
+        r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True,
+                           text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.chmod(tmp, 0o755)
+        os.replace(tmp, LIB_PATH)          # atomic: readers see the old or the new file
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
     with open(stamp, "w") as fh:
         fh.write(fp)
     return LIB_PATH
