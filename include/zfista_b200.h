@@ -177,6 +177,42 @@ int zf_lasso_passes(zf_lasso* h);
 /* one gradient pass only (bench / roofline): grad = 2*scale*A^T(Ax-b), returns f */
 int zf_lasso_gradient_device(zf_lasso* h, const double* d_x, double* d_grad, double* d_f);
 
+/* ---- (c'') many LASSO runs sharing one A: FP64 tensor-core DGEMM passes ----------------
+ * replaces the joblib fan-out of minimize_proximal_gradient(f, g, jac_f, prox_wsum_g, x0_k,
+ * nesterov_ratio=(a_k, b_k)) over runs k = 0..n_runs-1 that share the dense A of
+ * tests/test_proximal_gradient.py:49-63 (examples/PGM_experiment_with_various_a_b.ipynb run(),
+ * examples/cameraman.ipynb): run k minimises scale*||A x - b_k||^2 + l1*||x||_1.
+ * n_runs <= 32; b is one vector (b_is_batched = 0) or n_runs x n_rows; x0 one vector or
+ * n_runs x n_cols; ab n_runs x 2 on the host or NULL (options.nesterov_a/b for every run).
+ * One gradient of ALL runs = two passes over A (R = A V - B, G = A^T R) on the FP64 tensor
+ * cores, i.e. 2/n_runs HBM passes per run.  n_cols must be even and A 16-byte aligned
+ * (ZF_ERR_UNSUPPORTED otherwise).  Outputs: x (n_runs x n_cols, device), fun / nit / status /
+ * lr / err (n_runs, host), allerrs (n_runs x cap), allfuns (n_runs x (cap+1)) on the host.
+ * The split form mirrors zf_lasso_begin/grad/step/finish; zf_lasso_multi_partial() is
+ * [A^T R | sum r^2] of every run, the buffer a row-sharded run all-reduces.            */
+typedef struct zf_lasso_multi zf_lasso_multi;
+
+int zf_lasso_multi_create(zf_lasso_multi** out, const double* d_A, int64_t n_rows,
+                          int64_t n_cols, const double* d_b, int32_t b_is_batched,
+                          int32_t n_runs, double scale, double l1, void* cuda_stream);
+void zf_lasso_multi_destroy(zf_lasso_multi* h);
+int zf_lasso_multi_solve(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                         int32_t x0_is_batched, const double* h_ab, double* d_x, double* h_fun,
+                         int64_t* h_nit, int32_t* h_status, double* h_lr, double* h_err,
+                         double* h_allerrs, double* h_allfuns);
+int zf_lasso_multi_begin(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                         int32_t x0_is_batched, const double* h_ab);
+int zf_lasso_multi_grad(zf_lasso_multi* h, int which /*0: gradients at y, 1: f at the candidates*/);
+double* zf_lasso_multi_partial(zf_lasso_multi* h, int64_t* n_values);
+int zf_lasso_multi_step(zf_lasso_multi* h, int32_t* h_next);
+int zf_lasso_multi_finish(zf_lasso_multi* h, double* d_x, double* h_fun, int64_t* h_nit,
+                          int32_t* h_status, double* h_lr, double* h_err);
+/* the closures at n_runs points: grad (n_runs x n_cols) = 2*scale*A^T(A x_k - b_k), f (n_runs) */
+int zf_lasso_multi_gradient_device(zf_lasso_multi* h, const double* d_X, double* d_grad,
+                                   double* d_f);
+/* one DGEMM pass alone (bench / roofline): which = 0  R = A X - B,  1  A^T R of the last R */
+int zf_lasso_multi_pass_device(zf_lasso_multi* h, const double* d_X, int which);
+
 /* ---- (c') cameraman-style deblurring:  ||R W x - b||^2 + l1*||x||_1 ----------------
  * replaces minimize_proximal_gradient(f, g, jac_f, prox_wsum_g, x0, ...) with the closures of
  * examples/cameraman.ipynb ("Objective function" cell): R = correlate2d(., kernel,

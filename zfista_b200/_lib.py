@@ -138,6 +138,28 @@ def _bind_lasso(L):
     L.zf_lasso_gradient_device.restype = C.c_int
     L.zf_lasso_passes.argtypes = [C.c_void_p]
     L.zf_lasso_passes.restype = C.c_int
+    # many runs sharing one A (FP64 tensor-core passes)
+    V, I32, I64, D = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.zf_lasso_multi_create.argtypes = [C.POINTER(V), V, I64, I64, V, I32, I32, D, D, V]
+    L.zf_lasso_multi_create.restype = C.c_int
+    L.zf_lasso_multi_destroy.argtypes = [V]
+    L.zf_lasso_multi_destroy.restype = None
+    L.zf_lasso_multi_solve.argtypes = [V, C.POINTER(ZfOptions), V, I32, V, V, V, V, V, V, V, V, V]
+    L.zf_lasso_multi_solve.restype = C.c_int
+    L.zf_lasso_multi_begin.argtypes = [V, C.POINTER(ZfOptions), V, I32, V]
+    L.zf_lasso_multi_begin.restype = C.c_int
+    L.zf_lasso_multi_grad.argtypes = [V, C.c_int]
+    L.zf_lasso_multi_grad.restype = C.c_int
+    L.zf_lasso_multi_partial.argtypes = [V, c_int64_p]
+    L.zf_lasso_multi_partial.restype = V
+    L.zf_lasso_multi_step.argtypes = [V, c_int32_p]
+    L.zf_lasso_multi_step.restype = C.c_int
+    L.zf_lasso_multi_finish.argtypes = [V, V, V, V, V, V, V]
+    L.zf_lasso_multi_finish.restype = C.c_int
+    L.zf_lasso_multi_gradient_device.argtypes = [V, V, V, V]
+    L.zf_lasso_multi_gradient_device.restype = C.c_int
+    L.zf_lasso_multi_pass_device.argtypes = [V, V, C.c_int]
+    L.zf_lasso_multi_pass_device.restype = C.c_int
     # deblurring handle API
     L.zf_deblur_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_void_p]

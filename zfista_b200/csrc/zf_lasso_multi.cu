@@ -1,0 +1,1122 @@
+// Dense LASSO with MANY runs sharing one A (BASELINE north_star (c): "dense A uses FP64
+// tensor-core DGEMM only when many right-hand sides share A").
+//
+//   run k:  minimise  scale*||A x - b_k||^2 + l1*||x||_1   from x0_k with momentum (a_k, b_k)
+//
+// The reference would call minimize_proximal_gradient once per run (joblib fan-out over
+// (a, b) pairs / starting points / observations, examples/PGM_experiment_with_various_a_b.ipynb
+// and examples/cameraman.ipynb) with the dense closures of tests/test_proximal_gradient.py:49-63,
+// so every run streams A through the CPU caches twice per iteration.  Here the K <= 32 runs of a
+// call advance in lockstep and one gradient evaluation of ALL runs is two skinny DGEMMs
+//
+//   pass 1   R = A  V - B      (n_rows x K)    V = [y_1 .. y_K]
+//   pass 2   G = A^T R         (n_cols x K)
+//
+// each of which reads A from HBM exactly once, whatever K is: the HBM cost per run drops from
+// one (fused) pass to 2/K passes.  Both passes are hand-written for sm_100a:
+//   * a producer warp streams 64x64 tiles of A (and the matching slice of V or R) into a ring
+//     of shared-memory stages with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx);
+//   * eight consumer warps feed the FP64 tensor cores (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4)
+//     straight from shared memory; row pitches are padded so that every 16-byte fragment load
+//     is bank-conflict free (pass 1: pitch = 64 B mod 128, pass 2: 2*pitch = 32 B mod 128);
+//   * stages are handed back through a second set of mbarriers, so the copy of tile k+NS
+//     overlaps the tensor-core work on tile k.
+// Runs are independent (own step size, momentum, line search, stop test): the host keeps the
+// reference's scalar logic per run (proximal_gradient.py:474-555) and a finished run simply
+// stops being updated, so each run's iterates are what a solo solve produces.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "zf_common.cuh"
+#include "zf_host.h"
+
+namespace zf {
+namespace multi {
+
+constexpr int MAX_RUNS = 32;
+constexpr int TILE = 64;        // rows and columns of one A stage
+constexpr int CONSUMERS = 8;    // tensor-core warps
+constexpr int THREADS = (CONSUMERS + 1) * 32;
+
+struct VecPtrs { const double* v[MAX_RUNS]; };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void consumer_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS * 32) : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64 tensor core.  Lane l = 4g + q holds
+// A[g][q], B[q][g] and D[g][2q], D[g][2q+1].
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NT>
+struct Cfg {
+  static constexpr int KP = 8 * NT;               // runs, padded to whole n-tiles
+  static constexpr int NS = (NT <= 2) ? 4 : 3;    // ring stages
+  // pass 1: A tile pitch 72 doubles (576 B = 64 mod 128), V slice the same
+  static constexpr int P1_A = 72, P1_V = 72;
+  static constexpr int P1_STAGE = TILE * P1_A + KP * P1_V;
+  static constexpr size_t P1_SMEM = sizeof(double) * (size_t)(NS * P1_STAGE + KP * TILE) +
+                                    sizeof(unsigned long long) * 2 * NS;
+  // pass 2: A tile pitch 66 doubles (2*528 B = 32 mod 128), R slice pitch 72
+  static constexpr int P2_A = 66, P2_R = 72;
+  static constexpr int P2_STAGE = TILE * P2_A + KP * P2_R;
+  static constexpr size_t P2_SMEM = sizeof(double) * (size_t)(NS * P2_STAGE + 2 * KP * TILE) +
+                                    sizeof(unsigned long long) * 2 * NS;
+};
+
+// ---------------------------------------------------------------------------------------
+// pass 1:  R[k][i] = sum_j A[i][j] * V_k[j] - b_k[i],  block partials of sum_i R[k][i]^2
+// Persistent CTAs over 64-row blocks; the ring streams the block's 64-column tiles.  Consumer
+// warp w owns columns 8w..8w+7 of every tile (two k-steps of the m8n8k4 shape, taken from one
+// 16-byte load: a lane's .x feeds the even column, .y the odd one, in A and V alike) for all
+// eight 8-row m-tiles and all NT run tiles; the eight partial products are added through
+// shared memory once per row block, in warp order (fixed summation order).
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(THREADS, 1)
+multi_residual_kernel(const double* __restrict__ A, long long n_rows, long long n_cols,
+                      VecPtrs V, const double* __restrict__ b, long long b_stride,
+                      double* __restrict__ R, long long pitch_r, double* __restrict__ sq_part) {
+  using C_ = Cfg<NT>;
+  constexpr int KP = C_::KP, NS = C_::NS, PA = C_::P1_A, PV = C_::P1_V, STAGE = C_::P1_STAGE;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* red = stages + NS * STAGE;                         // [KP][TILE]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(red + KP * TILE);
+  unsigned long long* empty = full + NS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long n_rb = (n_rows + TILE - 1) / TILE;
+  const int n_ch = (int)((n_cols + TILE - 1) / TILE);
+  const int tail_cols = (int)(n_cols - (long long)(n_ch - 1) * TILE);    // 1..64, even
+
+  if (warp == CONSUMERS) {
+    // ------------------------------------------------------------------ producer warp
+    long long it = 0;
+    for (long long rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+      const long long row0 = rb * TILE;
+      const int rows_valid = (int)((n_rows - row0 < TILE) ? n_rows - row0 : TILE);
+      for (int c = 0; c < n_ch; ++c, ++it) {
+        const int s = (int)(it % NS);
+        const long long u = it / NS;
+        if (it >= NS) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));
+        const unsigned bytes = (unsigned)((c == n_ch - 1 ? tail_cols : TILE) * 8);
+        if (lane == 0) mbar_expect_tx(&full[s], (unsigned)(rows_valid + KP) * bytes);
+        __syncwarp();
+        double* sa = stages + (size_t)s * STAGE;
+        double* sv = sa + TILE * PA;
+        const double* src = A + row0 * n_cols + (long long)c * TILE;
+        for (int r = lane; r < rows_valid; r += 32)
+          tma_load_1d(sa + r * PA, src + (long long)r * n_cols, bytes, &full[s]);
+        if (lane < KP) tma_load_1d(sv + lane * PV, V.v[lane] + (long long)c * TILE, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumer warps
+  const int g = lane >> 2, q = lane & 3;
+  const int col = warp * 8 + 2 * q;            // this lane's column pair inside a tile
+  double ssacc[2 * NT];
+#pragma unroll
+  for (int i = 0; i < 2 * NT; ++i) ssacc[i] = 0.0;
+  long long it = 0;
+  for (long long rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+    const long long row0 = rb * TILE;
+    double acc[8][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int c = 0; c < n_ch; ++c, ++it) {
+      const int s = (int)(it % NS);
+      mbar_wait(&full[s], (unsigned)((it / NS) & 1));
+      const double* sa = stages + (size_t)s * STAGE + col;
+      const double* sv = stages + (size_t)s * STAGE + TILE * PA + col;
+      // columns past n_cols in the last tile were not copied: they must contribute 0
+      const bool dead = (c == n_ch - 1) && (col >= tail_cols);
+      double2 vb[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        vb[nt] = *reinterpret_cast<const double2*>(sv + (8 * nt + g) * PV);
+        if (dead) vb[nt] = make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) {
+        double2 a = *reinterpret_cast<const double2*>(sa + (8 * mt + g) * PA);
+        if (dead) a = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          dmma(acc[mt][nt][0], acc[mt][nt][1], a.x, vb[nt].x);
+          dmma(acc[mt][nt][0], acc[mt][nt][1], a.y, vb[nt].y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // add the eight warps' partial products in warp order: red[run][row]
+#pragma unroll 1
+    for (int w = 0; w < CONSUMERS; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int idx = (8 * nt + 2 * q + e) * TILE + 8 * mt + g;
+              red[idx] = (w == 0) ? acc[mt][nt][e] : red[idx] + acc[mt][nt][e];
+            }
+      }
+      consumer_barrier();
+    }
+    {
+      const int row = tid & (TILE - 1);
+      const long long grow = row0 + row;
+      if (grow < n_rows) {
+#pragma unroll
+        for (int i = 0; i < 2 * NT; ++i) {
+          const int k = (tid >> 6) + 4 * i;
+          const double val = red[k * TILE + row] - b[(long long)k * b_stride + grow];
+          R[(long long)k * pitch_r + grow] = val;
+          ssacc[i] += val * val;
+        }
+      }
+    }
+    consumer_barrier();                          // red is free for the next row block
+  }
+  // sum r^2 per run: rows live in two warps per run quarter (tid >> 6), fixed order
+#pragma unroll
+  for (int i = 0; i < 2 * NT; ++i) ssacc[i] = warp_sum(ssacc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 2 * NT; ++i) red[warp * 2 * NT + i] = ssacc[i];
+  }
+  consumer_barrier();
+  if (tid < KP) {
+    const int j = tid & 3, i = tid >> 2;         // run = j + 4 i, held by warps 2j and 2j+1
+    sq_part[(long long)blockIdx.x * KP + tid] =
+        red[(2 * j) * 2 * NT + i] + red[(2 * j + 1) * 2 * NT + i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 2:  gpart[split][k][j] = sum_{i in split} A[i][j] * R[k][i]
+// Work item = (64-column slab, row split); persistent CTAs take items round-robin.  The ring
+// streams 64-row tiles of the slab and the matching 64 residuals of every run.  A^T is the
+// tensor-core "A" operand: consumer warp w = (cg = w & 3, kh = w >> 2) owns columns
+// 16cg..16cg+15 (even columns = one m-tile, odd columns = the other, from one 16-byte load)
+// and rows 32kh..32kh+31 of the tile; the two row halves are added through shared memory.
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(THREADS, 1)
+multi_atr_kernel(const double* __restrict__ A, long long n_rows, long long n_cols,
+                 const double* __restrict__ R, long long pitch_r, long long rows_per_split,
+                 int n_splits, double* __restrict__ gpart, long long pitch_c) {
+  using C_ = Cfg<NT>;
+  constexpr int KP = C_::KP, NS = C_::NS, PA = C_::P2_A, PR = C_::P2_R, STAGE = C_::P2_STAGE;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* red = stages + NS * STAGE;                         // [2][KP][TILE]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(red + 2 * KP * TILE);
+  unsigned long long* empty = full + NS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long n_slabs = (n_cols + TILE - 1) / TILE;
+  const long long n_items = n_slabs * n_splits;
+
+  if (warp == CONSUMERS) {
+    long long it = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const long long slab = item % n_slabs, split = item / n_slabs;
+      const long long col0 = slab * TILE;
+      const unsigned bytes_a = (unsigned)(((n_cols - col0 < TILE) ? n_cols - col0 : TILE) * 8);
+      const long long r_lo = split * rows_per_split;
+      const long long r_hi = (r_lo + rows_per_split < n_rows) ? r_lo + rows_per_split : n_rows;
+      for (long long rc = r_lo; rc < r_hi; rc += TILE, ++it) {
+        const int s = (int)(it % NS);
+        const long long u = it / NS;
+        if (it >= NS) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));
+        const int valid = (int)((r_hi - rc < TILE) ? r_hi - rc : TILE);
+        const unsigned bytes_r = (unsigned)(((valid + 1) & ~1) * 8);   // R rows are padded to even
+        if (lane == 0)
+          mbar_expect_tx(&full[s], (unsigned)valid * bytes_a + (unsigned)KP * bytes_r);
+        __syncwarp();
+        double* sa = stages + (size_t)s * STAGE;
+        double* sr = sa + TILE * PA;
+        const double* src = A + rc * n_cols + col0;
+        for (int r = lane; r < valid; r += 32)
+          tma_load_1d(sa + r * PA, src + (long long)r * n_cols, bytes_a, &full[s]);
+        if (lane < KP) tma_load_1d(sr + lane * PR, R + (long long)lane * pitch_r + rc, bytes_r, &full[s]);
+      }
+    }
+    return;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  const int cg = warp & 3, kh = warp >> 2;
+  long long it = 0;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const long long slab = item % n_slabs, split = item / n_slabs;
+    const long long col0 = slab * TILE;
+    const int seg = (int)((n_cols - col0 < TILE) ? n_cols - col0 : TILE);
+    const long long r_lo = split * rows_per_split;
+    const long long r_hi = (r_lo + rows_per_split < n_rows) ? r_lo + rows_per_split : n_rows;
+    double acc[2][NT][2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[e][nt][0] = acc[e][nt][1] = 0.0;
+    for (long long rc = r_lo; rc < r_hi; rc += TILE, ++it) {
+      const int s = (int)(it % NS);
+      mbar_wait(&full[s], (unsigned)((it / NS) & 1));
+      const int valid = (int)((r_hi - rc < TILE) ? r_hi - rc : TILE);
+      const double* sa = stages + (size_t)s * STAGE + 16 * cg + 2 * g;
+      const double* sr = stages + (size_t)s * STAGE + TILE * PA + g * PR;
+#pragma unroll
+      for (int sp = 0; sp < 4; ++sp) {
+        const int rbase = 32 * kh + 8 * sp + 2 * q;     // this lane's row pair (k index)
+        double2 a0 = *reinterpret_cast<const double2*>(sa + rbase * PA);
+        double2 a1 = *reinterpret_cast<const double2*>(sa + (rbase + 1) * PA);
+        double2 rv[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          rv[nt] = *reinterpret_cast<const double2*>(sr + 8 * nt * PR + rbase);
+        if (valid < TILE) {                              // rows past the split: contribute 0
+          if (rbase >= valid) {
+            a0 = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) rv[nt].x = 0.0;
+          }
+          if (rbase + 1 >= valid) {
+            a1 = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) rv[nt].y = 0.0;
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          dmma(acc[0][nt][0], acc[0][nt][1], a0.x, rv[nt].x);
+          dmma(acc[1][nt][0], acc[1][nt][1], a0.y, rv[nt].x);
+          dmma(acc[0][nt][0], acc[0][nt][1], a1.x, rv[nt].y);
+          dmma(acc[1][nt][0], acc[1][nt][1], a1.y, rv[nt].y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // red[kh][run][col] ; then (kh = 0) + (kh = 1), coalesced store of the slab's partial
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          red[(kh * KP + 8 * nt + 2 * q + j) * TILE + 16 * cg + 2 * g + e] = acc[e][nt][j];
+    consumer_barrier();
+    for (int e = tid; e < KP * TILE; e += CONSUMERS * 32) {
+      const int k = e >> 6, cc = e & (TILE - 1);
+      if (cc < seg)
+        gpart[((long long)split * KP + k) * pitch_c + col0 + cc] = red[e] + red[KP * TILE + e];
+    }
+    consumer_barrier();
+  }
+}
+
+// partial[k][j] = sum_split gpart[split][k][j] (fixed order); ss[k] = sum_blk sq_part[blk][k]
+// `partial` = [KP][pitch_c] followed by ss[KP]: the one buffer a row-sharded run all-reduces.
+__global__ void __launch_bounds__(256)
+multi_collect_kernel(const double* __restrict__ gpart, int n_splits, const double* __restrict__ sq_part,
+                     int n_sq, int kp, long long pitch_c, long long n_cols,
+                     double* __restrict__ partial) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (gpart && j < n_cols) {
+    double s = 0.0;
+    for (int sp = 0; sp < n_splits; ++sp) s += gpart[((long long)sp * kp + k) * pitch_c + j];
+    partial[(long long)k * pitch_c + j] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int bl = 0; bl < n_sq; ++bl) s += sq_part[(long long)bl * kp + k];
+    partial[(long long)kp * pitch_c + k] = s;
+  }
+}
+
+constexpr int VEC_THREADS = 256;
+constexpr int VEC_BLOCKS = 64;     // per run
+
+struct StepSums { double gd, dd, abs1, maxd; };
+
+struct StepArgs {
+  double lr[MAX_RUNS];       // prox: step size;  momentum: (t_k - 1) / t_{k+1}
+  unsigned mask;             // runs this launch touches
+  unsigned cur;              // bit k set: run k's previous iterate is in buffer 1
+};
+
+// per run k in `mask`:  x_new = soft(y - lr*g, lr*l1) with g = src[k]*two_scale
+// (tests/test_proximal_gradient.py:55-63), g stored to g_out (first trial of an iteration), and
+//   gd = g.(x-y), dd = ||x-y||^2, abs1 = ||x||_1, maxd = max|x-y|
+// abs_only: only abs1 of the previous iterate (g(x0) at start-up).
+__global__ void __launch_bounds__(VEC_THREADS)
+multi_prox_kernel(StepArgs a, const double* __restrict__ Y, double* __restrict__ buf0,
+                  double* __restrict__ buf1, long long pitch_c, const double* __restrict__ src,
+                  double two_scale, double l1, long long n, double* __restrict__ g_out,
+                  StepSums* __restrict__ block_sums, unsigned int* __restrict__ counter,
+                  StepSums* __restrict__ out, int abs_only) {
+  const int k = blockIdx.y;
+  if (!((a.mask >> k) & 1u)) return;
+  __shared__ StepSums sh[VEC_THREADS / 32];
+  __shared__ bool is_last;
+  const bool prev_in_1 = (a.cur >> k) & 1u;
+  const double* xp = (prev_in_1 ? buf1 : buf0) + (long long)k * pitch_c;
+  double* xn = (prev_in_1 ? buf0 : buf1) + (long long)k * pitch_c;
+  const double* y = Y + (long long)k * pitch_c;
+  const double* gs = src + (long long)k * pitch_c;
+  double* go = g_out ? g_out + (long long)k * pitch_c : nullptr;
+  const double lr = a.lr[k], thresh = lr * l1;
+  StepSums s{0.0, 0.0, 0.0, 0.0};
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    if (abs_only) {
+      s.abs1 += fabs(xp[j]);
+    } else {
+      const double gj = gs[j] * two_scale;
+      const double yj = y[j];
+      const double xj = soft_threshold(yj - lr * gj, thresh);
+      const double d = xj - yj;
+      xn[j] = xj;
+      if (go) go[j] = gj;
+      s.gd += gj * d;
+      s.dd += d * d;
+      s.abs1 += fabs(xj);
+      s.maxd = fmax(s.maxd, fabs(d));
+    }
+  }
+  s.gd = warp_sum(s.gd);
+  s.dd = warp_sum(s.dd);
+  s.abs1 = warp_sum(s.abs1);
+  s.maxd = warp_max(s.maxd);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    StepSums t = sh[0];
+    for (int w = 1; w < VEC_THREADS / 32; ++w) {
+      t.gd += sh[w].gd; t.dd += sh[w].dd; t.abs1 += sh[w].abs1; t.maxd = fmax(t.maxd, sh[w].maxd);
+    }
+    block_sums[(long long)k * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    const unsigned int done = atomicAdd(&counter[k], 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    const StepSums* bs = block_sums + (long long)k * gridDim.x;
+    StepSums t = bs[0];
+    for (unsigned int i = 1; i < gridDim.x; ++i) {
+      const StepSums u = bs[i];
+      t.gd += u.gd; t.dd += u.dd; t.abs1 += u.abs1; t.maxd = fmax(t.maxd, u.maxd);
+    }
+    out[k] = t;
+    counter[k] = 0u;
+  }
+}
+
+// per run k in `mask`:  y = x_new + mom*(x_new - x_prev)   (proximal_gradient.py:534)
+__global__ void __launch_bounds__(VEC_THREADS)
+multi_momentum_kernel(StepArgs a, const double* __restrict__ buf0, const double* __restrict__ buf1,
+                      long long pitch_c, long long n, double* __restrict__ Y) {
+  const int k = blockIdx.y;
+  if (!((a.mask >> k) & 1u)) return;
+  const bool prev_in_1 = (a.cur >> k) & 1u;
+  const double* xp = (prev_in_1 ? buf1 : buf0) + (long long)k * pitch_c;
+  const double* xn = (prev_in_1 ? buf0 : buf1) + (long long)k * pitch_c;
+  double* y = Y + (long long)k * pitch_c;
+  const double mom = a.lr[k];
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double xj = xn[j];
+    y[j] = xj + mom * (xj - xp[j]);
+  }
+}
+
+// grad[k][j] = partial[k][j] * 2*scale ; f[k] = ||r_k||^2 * scale   (bench / closures)
+__global__ void __launch_bounds__(VEC_THREADS)
+multi_scale_kernel(const double* __restrict__ partial, int kp, long long pitch_c, long long n,
+                   double two_scale, double scale, double* __restrict__ grad,
+                   double* __restrict__ f_out) {
+  const int k = blockIdx.y;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x)
+    grad[(long long)k * n + j] = partial[(long long)k * pitch_c + j] * two_scale;
+  if (f_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double nrm = sqrt(partial[(long long)kp * pitch_c + k]);
+    f_out[k] = nrm * nrm * scale;
+  }
+}
+
+}  // namespace multi
+}  // namespace zf
+
+// =======================================================================================
+// handle
+// =======================================================================================
+namespace {
+enum MultiPhase { MP_IDLE = 0, MP_INIT, MP_GRAD, MP_FNEW, MP_FINAL, MP_DONE };
+
+struct RunState {
+  double lr = 1.0, t_prev = 1.0, F_prev = 0.0, F_x = 0.0, f_y = 0.0, sub_fun = 0.0, err = 0.0;
+  double a = 0.0, b = 0.25;
+  long long nit = 0;
+  int status = 0, bt = 0;
+  bool F_known = false, result_is_prev = false;
+  zf::multi::StepSums sums{};
+};
+}  // namespace
+
+struct zf_lasso_multi {
+  const double* A = nullptr;
+  long long n_rows = 0, n_cols = 0, pitch_c = 0, pitch_r = 0;
+  int n_runs = 0, nt = 1, kp = 8;
+  double scale = 1.0, l1 = 0.0;
+  cudaStream_t st = 0;
+  int n_sm = 148, grid = 148, n_splits = 1;
+  long long rows_per_split = 0;
+  bool b_batched = false;
+  // device workspace
+  double* vecs = nullptr;      // 4 * kp * pitch_c : buf0, buf1, Y, G
+  double *buf0 = nullptr, *buf1 = nullptr, *Y = nullptr, *G = nullptr;
+  double* zeros = nullptr;     // pitch_c (vector of the padding runs)
+  double* bcopy = nullptr;     // kp * pitch_r (batched b) or pitch_r
+  double* R = nullptr;         // kp * pitch_r
+  double* gpart = nullptr;     // n_splits * kp * pitch_c
+  double* sq_part = nullptr;   // grid * kp
+  double* partial = nullptr;   // kp * pitch_c + kp
+  zf::multi::StepSums* block_sums = nullptr;   // kp * VEC_BLOCKS
+  zf::multi::StepSums* d_sums = nullptr;       // kp
+  unsigned int* counter = nullptr;             // kp
+  double* h_pin = nullptr;                     // pinned: StepSums[kp] | ss[kp]
+  // solver state
+  zf_options opt{};
+  int phase = MP_IDLE;
+  bool need_F = false;
+  unsigned active = 0, trial = 0, accepted = 0, cur = 0;
+  RunState run[zf::multi::MAX_RUNS];
+  double* h_allerrs = nullptr;
+  double* h_allfuns = nullptr;
+};
+
+namespace {
+
+#define ZF_CUDA(call)                                          \
+  do {                                                         \
+    cudaError_t _e = (call);                                   \
+    if (_e != cudaSuccess) return zf::zf_fail_cuda(_e, #call); \
+  } while (0)
+
+using zf::multi::Cfg;
+using zf::multi::StepArgs;
+using zf::multi::StepSums;
+using zf::multi::VecPtrs;
+
+template <int NT>
+int launch_residual_t(zf_lasso_multi* h, const VecPtrs& v) {
+  auto k = zf::multi::multi_residual_kernel<NT>;
+  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)Cfg<NT>::P1_SMEM));
+  k<<<h->grid, zf::multi::THREADS, Cfg<NT>::P1_SMEM, h->st>>>(
+      h->A, h->n_rows, h->n_cols, v, h->bcopy, h->b_batched ? h->pitch_r : 0, h->R, h->pitch_r,
+      h->sq_part);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int launch_residual(zf_lasso_multi* h, const VecPtrs& v) {
+  switch (h->nt) {
+    case 1: return launch_residual_t<1>(h, v);
+    case 2: return launch_residual_t<2>(h, v);
+    case 3: return launch_residual_t<3>(h, v);
+    default: return launch_residual_t<4>(h, v);
+  }
+}
+
+template <int NT>
+int launch_atr_t(zf_lasso_multi* h) {
+  auto k = zf::multi::multi_atr_kernel<NT>;
+  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)Cfg<NT>::P2_SMEM));
+  k<<<h->grid, zf::multi::THREADS, Cfg<NT>::P2_SMEM, h->st>>>(
+      h->A, h->n_rows, h->n_cols, h->R, h->pitch_r, h->rows_per_split, h->n_splits, h->gpart,
+      h->pitch_c);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int launch_atr(zf_lasso_multi* h) {
+  switch (h->nt) {
+    case 1: return launch_atr_t<1>(h);
+    case 2: return launch_atr_t<2>(h);
+    case 3: return launch_atr_t<3>(h);
+    default: return launch_atr_t<4>(h);
+  }
+}
+
+int launch_collect(zf_lasso_multi* h, bool with_gradient) {
+  dim3 grid(with_gradient ? (unsigned)((h->n_cols + 255) / 256) : 1u, (unsigned)h->kp);
+  zf::multi::multi_collect_kernel<<<grid, 256, 0, h->st>>>(
+      with_gradient ? h->gpart : nullptr, h->n_splits, h->sq_part, h->grid, h->kp, h->pitch_c,
+      h->n_cols, h->partial);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+// vectors pass 1 multiplies: which = 0 -> y_k, 1 -> the candidate x_new_k
+VecPtrs vec_ptrs(const zf_lasso_multi* h, int which) {
+  VecPtrs v;
+  for (int k = 0; k < zf::multi::MAX_RUNS; ++k) {
+    if (k >= h->n_runs) {
+      v.v[k] = h->zeros;
+    } else if (which == 0) {
+      v.v[k] = h->Y + (long long)k * h->pitch_c;
+    } else {
+      const bool prev_in_1 = (h->cur >> k) & 1u;
+      v.v[k] = (prev_in_1 ? h->buf0 : h->buf1) + (long long)k * h->pitch_c;
+    }
+  }
+  return v;
+}
+
+int gradient_pass(zf_lasso_multi* h, const VecPtrs& v) {
+  int rc = launch_residual(h, v);
+  if (rc != ZF_OK) return rc;
+  rc = launch_atr(h);
+  if (rc != ZF_OK) return rc;
+  return launch_collect(h, true);
+}
+
+// prox (or |x0|_1) for the runs in `mask`; their sums and every run's ss land in h_pin
+int run_prox(zf_lasso_multi* h, unsigned mask, bool first_trial, bool abs_only) {
+  StepArgs a{};
+  for (int k = 0; k < h->n_runs; ++k) a.lr[k] = h->run[k].lr;
+  a.mask = mask;
+  a.cur = h->cur;
+  dim3 grid(zf::multi::VEC_BLOCKS, (unsigned)h->n_runs);
+  zf::multi::multi_prox_kernel<<<grid, zf::multi::VEC_THREADS, 0, h->st>>>(
+      a, h->Y, h->buf0, h->buf1, h->pitch_c, first_trial ? h->partial : h->G,
+      first_trial ? 2.0 * h->scale : 1.0, h->l1, h->n_cols, first_trial ? h->G : nullptr,
+      h->block_sums, h->counter, h->d_sums, abs_only ? 1 : 0);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int fetch(zf_lasso_multi* h, bool sums, unsigned sums_mask) {
+  if (sums)
+    ZF_CUDA(cudaMemcpyAsync(h->h_pin, h->d_sums, sizeof(StepSums) * h->kp,
+                            cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->h_pin + 4 * h->kp, h->partial + (long long)h->kp * h->pitch_c,
+                          sizeof(double) * h->kp, cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  if (sums)
+    for (int k = 0; k < h->n_runs; ++k)
+      if ((sums_mask >> k) & 1u) std::memcpy(&h->run[k].sums, h->h_pin + 4 * k, sizeof(StepSums));
+  return ZF_OK;
+}
+
+inline double ss_of(const zf_lasso_multi* h, int k) { return h->h_pin[4 * h->kp + k]; }
+
+// f = np.linalg.norm(A @ x - b) ** 2 * scale   (test_proximal_gradient.py:50)
+inline double f_from_ss(const zf_lasso_multi* h, double ss) {
+  const double nrm = std::sqrt(ss);
+  return nrm * nrm * h->scale;
+}
+
+// proximal_gradient.py:149-155 for one objective
+inline double subproblem_fun(const zf_lasso_multi* h, const RunState& r) {
+  const double nrm = std::sqrt(r.sums.dd);
+  double fun = r.sums.gd + h->l1 * r.sums.abs1 + nrm * nrm / 2.0 / r.lr;
+  if (!h->opt.deprecated) fun += r.f_y - r.F_prev;
+  return fun;
+}
+
+// every run of this round has an accepted candidate (or failed): stop tests, momentum, next
+// iterates (proximal_gradient.py:510-538), run by run
+int advance(zf_lasso_multi* h, int* next) {
+  StepArgs m{};
+  unsigned adv = 0;
+  const int cap = h->opt.trace_capacity;
+  for (int k = 0; k < h->n_runs; ++k) {
+    if (!((h->accepted >> k) & 1u)) continue;
+    RunState& r = h->run[k];
+    r.err = r.sums.maxd;
+    if (cap > 0 && r.nit <= cap) {
+      if (h->h_allerrs) h->h_allerrs[(long long)k * cap + r.nit - 1] = r.err;
+      if (h->h_allfuns && r.F_known) h->h_allfuns[(long long)k * (cap + 1) + r.nit] = r.F_x;
+    }
+    const bool converged = r.err < h->opt.tol;
+    if (converged || r.nit >= h->opt.max_iter) {
+      r.status = converged ? 1 : 0;
+      h->active &= ~(1u << k);
+      continue;
+    }
+    double mom = 0.0;
+    if (h->opt.nesterov) {
+      const double t = r.t_prev;
+      const double t_new = std::sqrt(t * t - r.a * t + r.b) + 0.5;
+      mom = (t - 1.0) / t_new;
+      r.t_prev = t_new;
+    }
+    m.lr[k] = mom;
+    adv |= 1u << k;
+    r.F_prev = r.F_x;
+    r.nit += 1;
+  }
+  h->accepted = 0;
+  if (adv) {
+    m.mask = adv;
+    m.cur = h->cur;
+    dim3 grid(zf::multi::VEC_BLOCKS, (unsigned)h->n_runs);
+    zf::multi::multi_momentum_kernel<<<grid, zf::multi::VEC_THREADS, 0, h->st>>>(
+        m, h->buf0, h->buf1, h->pitch_c, h->n_cols, h->Y);
+    ZF_CUDA(cudaGetLastError());
+    zf::zf_count_launch();
+    h->cur ^= adv;       // the candidate becomes the previous iterate of the runs that go on
+  }
+  if (h->active) {
+    h->phase = MP_GRAD;
+    *next = 0;
+    return ZF_OK;
+  }
+  bool all_known = true;
+  for (int k = 0; k < h->n_runs; ++k)
+    if (!h->run[k].F_known && !h->run[k].result_is_prev) all_known = false;
+  if (all_known) {
+    h->phase = MP_DONE;
+    *next = 2;
+  } else {
+    h->phase = MP_FINAL;   // one more residual pass for res.fun = F(x) of every run
+    *next = 1;
+  }
+  return ZF_OK;
+}
+
+int check_options(const zf_options* o) {
+  if (!o) return zf::zf_fail(ZF_ERR_INVALID, "options is NULL");
+  if (!(o->lr > 0.0)) return zf::zf_fail(ZF_ERR_INVALID, "lr must be > 0");
+  if (o->max_iter < 1) return zf::zf_fail(ZF_ERR_INVALID, "max_iter must be >= 1");
+  if (o->max_backtrack_iter < 1) return zf::zf_fail(ZF_ERR_INVALID, "max_backtrack_iter must be >= 1");
+  if (!(o->decay_rate > 0.0 && o->decay_rate <= 1.0))
+    return zf::zf_fail(ZF_ERR_INVALID, "decay_rate must be in (0, 1]");
+  if (o->trace_capacity < 0) return zf::zf_fail(ZF_ERR_INVALID, "trace_capacity must be >= 0");
+  return ZF_OK;
+}
+
+int begin_impl(zf_lasso_multi* h, const zf_options* opt, const double* d_x0, int x0_is_batched,
+               const double* h_ab, double* h_allerrs, double* h_allfuns) {
+  if (!h || !d_x0) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int rc = check_options(opt);
+  if (rc != ZF_OK) return rc;
+  h->opt = *opt;
+  h->h_allerrs = h_allerrs;
+  h->h_allfuns = h_allfuns;
+  h->need_F = (opt->decay_rate != 1.0) || (opt->trace_capacity > 0 && h_allfuns != nullptr);
+  h->active = (h->n_runs == 32) ? 0xffffffffu : ((1u << h->n_runs) - 1u);
+  h->trial = h->accepted = h->cur = 0;
+  for (int k = 0; k < h->n_runs; ++k) {
+    RunState& r = h->run[k];
+    r = RunState();
+    r.lr = opt->lr;
+    r.a = h_ab ? h_ab[2 * k] : opt->nesterov_a;
+    r.b = h_ab ? h_ab[2 * k + 1] : opt->nesterov_b;
+    r.err = INFINITY;
+    const double* src = d_x0 + (x0_is_batched ? (long long)k * h->n_cols : 0);
+    const size_t nb = sizeof(double) * (size_t)h->n_cols;
+    const long long off = (long long)k * h->pitch_c;
+    ZF_CUDA(cudaMemcpyAsync(h->buf0 + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->buf1 + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->Y + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+  }
+  // F(x0): residual norms (all-reduced by the caller if the rows are sharded)
+  rc = launch_residual(h, vec_ptrs(h, 0));
+  if (rc != ZF_OK) return rc;
+  rc = launch_collect(h, false);
+  if (rc != ZF_OK) return rc;
+  h->phase = MP_INIT;
+  return ZF_OK;
+}
+
+}  // namespace
+
+extern "C" int zf_lasso_multi_create(zf_lasso_multi** out, const double* d_A, int64_t n_rows,
+                                     int64_t n_cols, const double* d_b, int32_t b_is_batched,
+                                     int32_t n_runs, double scale, double l1,
+                                     void* cuda_stream) {
+  if (!out || !d_A || !d_b) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  if (n_rows < 1 || n_cols < 1) return zf::zf_fail(ZF_ERR_INVALID, "n_rows and n_cols must be >= 1");
+  if (n_runs < 1 || n_runs > zf::multi::MAX_RUNS)
+    return zf::zf_fail(ZF_ERR_INVALID, "n_runs must be in 1..%d", zf::multi::MAX_RUNS);
+  if ((n_cols & 1) || (reinterpret_cast<uintptr_t>(d_A) & 15u))
+    return zf::zf_fail(ZF_ERR_UNSUPPORTED,
+                       "the shared-A path streams rows with 16-byte bulk copies: n_cols must be "
+                       "even and A 16-byte aligned");
+  int rc = zf::zf_require_device();
+  if (rc != ZF_OK) return rc;
+  zf_lasso_multi* h = new (std::nothrow) zf_lasso_multi();
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "out of host memory");
+  h->A = d_A;
+  h->n_rows = n_rows;
+  h->n_cols = n_cols;
+  h->n_runs = n_runs;
+  h->nt = (n_runs + 7) / 8;
+  h->kp = 8 * h->nt;
+  h->scale = scale;
+  h->l1 = l1;
+  h->st = (cudaStream_t)cuda_stream;
+  h->b_batched = b_is_batched != 0;
+  h->pitch_c = n_cols;                       // even
+  h->pitch_r = (n_rows + 1) & ~1LL;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
+  h->grid = h->n_sm;
+  const long long n_slabs = (n_cols + zf::multi::TILE - 1) / zf::multi::TILE;
+  const long long n_rowtiles = (n_rows + zf::multi::TILE - 1) / zf::multi::TILE;
+  long long splits = (16LL * h->grid + n_slabs - 1) / n_slabs;     // >= 16 items per CTA
+  if (splits > n_rowtiles) splits = n_rowtiles;
+  if (splits < 1) splits = 1;
+  h->rows_per_split = ((n_rowtiles + splits - 1) / splits) * zf::multi::TILE;
+  h->n_splits = (int)((n_rows + h->rows_per_split - 1) / h->rows_per_split);
+  auto fail = [&](int code) {
+    zf_lasso_multi_destroy(h);
+    return code;
+  };
+#define ZF_TRY(call)                                                      \
+  do {                                                                    \
+    cudaError_t _e = (call);                                              \
+    if (_e != cudaSuccess) return fail(zf::zf_fail_cuda(_e, #call));      \
+  } while (0)
+  const size_t vec_b = sizeof(double) * (size_t)h->kp * (size_t)h->pitch_c;
+  const size_t r_b = sizeof(double) * (size_t)h->kp * (size_t)h->pitch_r;
+  ZF_TRY(cudaMalloc(&h->vecs, 4 * vec_b));
+  ZF_TRY(cudaMemsetAsync(h->vecs, 0, 4 * vec_b, h->st));
+  h->buf0 = h->vecs;
+  h->buf1 = h->buf0 + (size_t)h->kp * h->pitch_c;
+  h->Y = h->buf1 + (size_t)h->kp * h->pitch_c;
+  h->G = h->Y + (size_t)h->kp * h->pitch_c;
+  ZF_TRY(cudaMalloc(&h->zeros, sizeof(double) * (size_t)h->pitch_c));
+  ZF_TRY(cudaMemsetAsync(h->zeros, 0, sizeof(double) * (size_t)h->pitch_c, h->st));
+  const size_t b_b = h->b_batched ? r_b : sizeof(double) * (size_t)h->pitch_r;
+  ZF_TRY(cudaMalloc(&h->bcopy, b_b));
+  ZF_TRY(cudaMemsetAsync(h->bcopy, 0, b_b, h->st));
+  if (h->b_batched)
+    ZF_TRY(cudaMemcpy2DAsync(h->bcopy, sizeof(double) * h->pitch_r, d_b, sizeof(double) * n_rows,
+                             sizeof(double) * n_rows, n_runs, cudaMemcpyDeviceToDevice, h->st));
+  else
+    ZF_TRY(cudaMemcpyAsync(h->bcopy, d_b, sizeof(double) * n_rows, cudaMemcpyDeviceToDevice, h->st));
+  ZF_TRY(cudaMalloc(&h->R, r_b));
+  ZF_TRY(cudaMemsetAsync(h->R, 0, r_b, h->st));
+  ZF_TRY(cudaMalloc(&h->gpart, vec_b * (size_t)h->n_splits));
+  ZF_TRY(cudaMalloc(&h->sq_part, sizeof(double) * (size_t)h->grid * h->kp));
+  ZF_TRY(cudaMalloc(&h->partial, vec_b + sizeof(double) * h->kp));
+  ZF_TRY(cudaMemsetAsync(h->partial, 0, vec_b + sizeof(double) * h->kp, h->st));
+  ZF_TRY(cudaMalloc(&h->block_sums, sizeof(StepSums) * (size_t)h->kp * zf::multi::VEC_BLOCKS));
+  ZF_TRY(cudaMalloc(&h->d_sums, sizeof(StepSums) * h->kp));
+  ZF_TRY(cudaMemsetAsync(h->d_sums, 0, sizeof(StepSums) * h->kp, h->st));
+  ZF_TRY(cudaMalloc(&h->counter, sizeof(unsigned int) * h->kp));
+  ZF_TRY(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * h->kp, h->st));
+  ZF_TRY(cudaMallocHost(&h->h_pin, sizeof(double) * 5 * h->kp));
+  ZF_TRY(cudaStreamSynchronize(h->st));
+#undef ZF_TRY
+  *out = h;
+  return ZF_OK;
+}
+
+extern "C" void zf_lasso_multi_destroy(zf_lasso_multi* h) {
+  if (!h) return;
+  cudaFree(h->vecs);
+  cudaFree(h->zeros);
+  cudaFree(h->bcopy);
+  cudaFree(h->R);
+  cudaFree(h->gpart);
+  cudaFree(h->sq_part);
+  cudaFree(h->partial);
+  cudaFree(h->block_sums);
+  cudaFree(h->d_sums);
+  cudaFree(h->counter);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  delete h;
+}
+
+extern "C" int zf_lasso_multi_begin(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                                    int32_t x0_is_batched, const double* h_ab) {
+  return begin_impl(h, opt, d_x0, x0_is_batched, h_ab, nullptr, nullptr);
+}
+
+extern "C" int zf_lasso_multi_grad(zf_lasso_multi* h, int which) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (which == 0) {
+    if (h->phase != MP_GRAD) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_grad(0) out of order");
+    return gradient_pass(h, vec_ptrs(h, 0));
+  }
+  if (which == 1) {
+    if (h->phase != MP_FNEW && h->phase != MP_FINAL)
+      return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_grad(1) out of order");
+    int rc = launch_residual(h, vec_ptrs(h, 1));
+    if (rc != ZF_OK) return rc;
+    return launch_collect(h, false);
+  }
+  return zf::zf_fail(ZF_ERR_INVALID, "which must be 0 or 1");
+}
+
+extern "C" double* zf_lasso_multi_partial(zf_lasso_multi* h, int64_t* n_values) {
+  if (!h) return nullptr;
+  if (n_values) *n_values = (int64_t)h->kp * h->pitch_c + h->kp;
+  return h->partial;
+}
+
+extern "C" int zf_lasso_multi_step(zf_lasso_multi* h, int32_t* h_next) {
+  if (!h || !h_next) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int next = 2;
+  int rc = ZF_OK;
+  const int cap = h->opt.trace_capacity;
+  switch (h->phase) {
+    case MP_INIT: {
+      // F(x0) = f(x0) + g(x0)   (proximal_gradient.py:466, 279)
+      rc = run_prox(h, h->active, false, true);
+      if (rc != ZF_OK) return rc;
+      rc = fetch(h, true, h->active);
+      if (rc != ZF_OK) return rc;
+      for (int k = 0; k < h->n_runs; ++k) {
+        RunState& r = h->run[k];
+        r.F_prev = f_from_ss(h, ss_of(h, k)) + h->l1 * r.sums.abs1;
+        r.F_x = r.F_prev;
+        if (cap > 0 && h->h_allfuns) h->h_allfuns[(long long)k * (cap + 1)] = r.F_prev;
+        r.nit = 1;
+      }
+      h->phase = MP_GRAD;
+      next = 0;
+      break;
+    }
+    case MP_GRAD: {
+      h->trial = h->active;
+      rc = run_prox(h, h->trial, true, false);
+      if (rc != ZF_OK) return rc;
+      rc = fetch(h, true, h->trial);
+      if (rc != ZF_OK) return rc;
+      for (int k = 0; k < h->n_runs; ++k) {
+        if (!((h->trial >> k) & 1u)) continue;
+        RunState& r = h->run[k];
+        r.bt = 0;
+        r.f_y = f_from_ss(h, ss_of(h, k));
+        r.sub_fun = subproblem_fun(h, r);
+        r.F_known = false;
+      }
+      if (h->need_F) {
+        h->phase = MP_FNEW;
+        next = 1;
+      } else {
+        h->accepted = h->trial;
+        h->trial = 0;
+        rc = advance(h, &next);
+      }
+      break;
+    }
+    case MP_FNEW: {
+      rc = fetch(h, false, 0);
+      if (rc != ZF_OK) return rc;
+      for (int k = 0; k < h->n_runs; ++k) {
+        if (!((h->trial >> k) & 1u)) continue;
+        RunState& r = h->run[k];
+        const double f_x = f_from_ss(h, ss_of(h, k));
+        r.F_x = f_x + h->l1 * r.sums.abs1;
+        r.F_known = true;
+        bool ok;
+        if (h->opt.decay_rate == 1.0) ok = true;                      // proximal_gradient.py:298
+        else if (h->opt.deprecated) ok = (f_x - r.f_y <= r.sub_fun + h->opt.tol_internal);
+        else ok = (r.F_x - r.F_prev <= r.sub_fun + h->opt.tol_internal);
+        if (ok) {
+          h->trial &= ~(1u << k);
+          h->accepted |= 1u << k;
+          continue;
+        }
+        r.lr *= h->opt.decay_rate;
+        r.bt += 1;
+        if (r.bt >= h->opt.max_backtrack_iter) {
+          // RuntimeError("Backtracking failed ...") -> x = x_prev, nit - 1 (493-509)
+          r.result_is_prev = true;
+          r.F_x = r.F_prev;
+          r.nit -= 1;
+          r.status = -1;
+          h->trial &= ~(1u << k);
+          h->active &= ~(1u << k);
+        }
+      }
+      if (h->trial) {
+        // same gradients, smaller steps: redo the prox of the rejected runs from the stored g
+        rc = run_prox(h, h->trial, false, false);
+        if (rc != ZF_OK) return rc;
+        rc = fetch(h, true, h->trial);
+        if (rc != ZF_OK) return rc;
+        for (int k = 0; k < h->n_runs; ++k)
+          if ((h->trial >> k) & 1u) h->run[k].sub_fun = subproblem_fun(h, h->run[k]);
+        h->phase = MP_FNEW;
+        next = 1;
+      } else {
+        rc = advance(h, &next);
+      }
+      break;
+    }
+    case MP_FINAL: {
+      rc = fetch(h, false, 0);
+      if (rc != ZF_OK) return rc;
+      for (int k = 0; k < h->n_runs; ++k) {
+        RunState& r = h->run[k];
+        if (r.F_known || r.result_is_prev) continue;
+        r.F_x = f_from_ss(h, ss_of(h, k)) + h->l1 * r.sums.abs1;
+        r.F_known = true;
+      }
+      h->phase = MP_DONE;
+      next = 2;
+      break;
+    }
+    case MP_DONE:
+      next = 2;
+      break;
+    default:
+      return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_step called before zf_lasso_multi_begin");
+  }
+  if (rc != ZF_OK) return rc;
+  *h_next = next;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_multi_finish(zf_lasso_multi* h, double* d_x, double* h_fun, int64_t* h_nit,
+                                     int32_t* h_status, double* h_lr, double* h_err) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (h->phase != MP_DONE)
+    return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_finish before the solve ended");
+  for (int k = 0; k < h->n_runs; ++k) {
+    const RunState& r = h->run[k];
+    if (d_x) {
+      // a run that ended normally keeps its result in the candidate buffer; after a failed
+      // line search the result is the previous iterate
+      const bool prev_in_1 = (h->cur >> k) & 1u;
+      const double* prev = (prev_in_1 ? h->buf1 : h->buf0) + (long long)k * h->pitch_c;
+      const double* cand = (prev_in_1 ? h->buf0 : h->buf1) + (long long)k * h->pitch_c;
+      ZF_CUDA(cudaMemcpyAsync(d_x + (long long)k * h->n_cols, r.result_is_prev ? prev : cand,
+                              sizeof(double) * (size_t)h->n_cols, cudaMemcpyDeviceToDevice, h->st));
+    }
+    if (h_fun) h_fun[k] = r.F_x;
+    if (h_nit) h_nit[k] = r.nit;
+    if (h_status) h_status[k] = r.status;
+    if (h_lr) h_lr[k] = r.lr;
+    if (h_err) h_err[k] = r.err;
+  }
+  if (d_x) ZF_CUDA(cudaStreamSynchronize(h->st));
+  h->phase = MP_IDLE;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_multi_solve(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                                    int32_t x0_is_batched, const double* h_ab, double* d_x,
+                                    double* h_fun, int64_t* h_nit, int32_t* h_status,
+                                    double* h_lr, double* h_err, double* h_allerrs,
+                                    double* h_allfuns) {
+  int rc = begin_impl(h, opt, d_x0, x0_is_batched, h_ab, h_allerrs, h_allfuns);
+  if (rc != ZF_OK) return rc;
+  int32_t next = 0;
+  rc = zf_lasso_multi_step(h, &next);
+  while (rc == ZF_OK && next != 2) {
+    rc = zf_lasso_multi_grad(h, next);
+    if (rc != ZF_OK) break;
+    rc = zf_lasso_multi_step(h, &next);
+  }
+  if (rc != ZF_OK) {
+    h->phase = MP_IDLE;
+    return rc;
+  }
+  return zf_lasso_multi_finish(h, d_x, h_fun, h_nit, h_status, h_lr, h_err);
+}
+
+extern "C" int zf_lasso_multi_gradient_device(zf_lasso_multi* h, const double* d_X,
+                                              double* d_grad, double* d_f) {
+  if (!h || !d_X || !d_grad) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  if (reinterpret_cast<uintptr_t>(d_X) & 15u)
+    return zf::zf_fail(ZF_ERR_INVALID, "X must be 16-byte aligned");
+  VecPtrs v;
+  for (int k = 0; k < zf::multi::MAX_RUNS; ++k)
+    v.v[k] = (k < h->n_runs) ? d_X + (long long)k * h->n_cols : h->zeros;
+  int rc = gradient_pass(h, v);
+  if (rc != ZF_OK) return rc;
+  dim3 grid(zf::multi::VEC_BLOCKS, (unsigned)h->n_runs);
+  zf::multi::multi_scale_kernel<<<grid, zf::multi::VEC_THREADS, 0, h->st>>>(
+      h->partial, h->kp, h->pitch_c, h->n_cols, 2.0 * h->scale, h->scale, d_grad, d_f);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_multi_pass_device(zf_lasso_multi* h, const double* d_X, int which) {
+  // one pass alone (bench / roofline): which = 0 residual DGEMM of X, 1 the A^T R DGEMM of the
+  // residuals the last pass-0 left in the workspace
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (which == 0) {
+    if (!d_X) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+    VecPtrs v;
+    for (int k = 0; k < zf::multi::MAX_RUNS; ++k)
+      v.v[k] = (k < h->n_runs) ? d_X + (long long)k * h->n_cols : h->zeros;
+    return launch_residual(h, v);
+  }
+  return launch_atr(h);
+}

@@ -225,3 +225,189 @@ class DenseLasso:
         res.update(x0=x0, tol=tol, tol_internal=tol_internal, nesterov=nesterov,
                    nesterov_ratio=nesterov_ratio)
         return res
+
+
+class DenseLassoMulti:
+    """``n_runs`` LASSO runs that share one dense ``A``:  run k minimises
+    ``scale*||A x - b_k||^2 + l1_ratio*||x||_1`` from ``x0_k`` with momentum ``(a_k, b_k)``.
+
+    This is the reference's joblib fan-out of ``minimize_proximal_gradient`` over (a, b)
+    pairs / starting points / observations (examples/PGM_experiment_with_various_a_b.ipynb
+    ``run()``, examples/cameraman.ipynb) for the dense closures of
+    tests/test_proximal_gradient.py:49-63.  All runs advance in lockstep and one gradient of
+    every run is two FP64 tensor-core DGEMM passes over ``A`` (csrc/zf_lasso_multi.cu), so ``A``
+    crosses HBM ``2/n_runs`` times per run and iteration instead of once.
+
+    Parameters
+    ----------
+    A : (n_rows, n_cols) float64, n_cols even; numpy array or CUDA tensor.  With
+        ``process_group`` set this is the calling rank's block of rows.
+    b : (n_rows,) shared by all runs, or (n_runs, n_rows).
+    n_runs : 1..32.
+    """
+
+    n_objectives = 1
+    MAX_RUNS = 32
+
+    def __init__(self, A, b, l1_ratio: float, n_runs: int, scale: float = 1.0, device=None,
+                 process_group=None, distributed: bool = False):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("DenseLassoMulti needs a CUDA device (zfista_b200 has no CPU fallback)")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.n_runs = int(n_runs)
+        if not 1 <= self.n_runs <= self.MAX_RUNS:
+            raise ValueError(f"n_runs must be in 1..{self.MAX_RUNS}")
+        self.A = DenseLasso._to_dev(self, A, 2)
+        bt = b if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+        self.b = DenseLasso._to_dev(self, bt, bt.ndim if not isinstance(bt, torch.Tensor) else bt.dim())
+        self.n_rows, self.n_features = int(self.A.shape[0]), int(self.A.shape[1])
+        self.b_batched = self.b.dim() == 2
+        if self.b.shape[-1] != self.n_rows or (self.b_batched and self.b.shape[0] != self.n_runs):
+            raise ValueError("b must have shape (n_rows,) or (n_runs, n_rows)")
+        self.l1_ratio = float(l1_ratio)
+        self.scale = float(scale)
+        self.group = process_group
+        self.distributed = bool(distributed or process_group is not None)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self._stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().zf_lasso_multi_create(
+                C.byref(self._h), C.c_void_p(self.A.data_ptr()), self.n_rows, self.n_features,
+                C.c_void_p(self.b.data_ptr()), int(self.b_batched), self.n_runs, self.scale,
+                self.l1_ratio, C.c_void_p(self._stream)))
+        n = C.c_int64()
+        ptr = _lib.lib().zf_lasso_multi_partial(self._h, C.byref(n))
+        self._partial = torch.as_tensor(_DevView(int(ptr), int(n.value)), device=self.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.lib().zf_lasso_multi_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def _allreduce(self):
+        if self.distributed:
+            import torch.distributed as dist
+
+            dist.all_reduce(self._partial, group=self.group)
+
+    def _x_batch(self, x):
+        """(tensor, is_batched): one vector shared by all runs or (n_runs, n_features)."""
+        torch = _torch()
+        nd = x.dim() if isinstance(x, torch.Tensor) else np.asarray(x).ndim
+        xd = DenseLasso._to_dev(self, x, nd)
+        if tuple(xd.shape) not in ((self.n_features,), (self.n_runs, self.n_features)):
+            raise ValueError("x must have shape (n_features,) or (n_runs, n_features)")
+        return xd, xd.dim() == 2
+
+    def gradient(self, X):
+        """(grad f_k(x_k), f_k(x_k)) for every run as device tensors (n_runs, n_features) and
+        (n_runs,): the two DGEMM passes."""
+        torch = _torch()
+        if self.distributed:
+            raise NotImplementedError("gradient() is the single-GPU convenience entry")
+        xd, batched = self._x_batch(X)
+        if not batched:
+            xd = xd.expand(self.n_runs, -1).contiguous()
+        grad = torch.empty(self.n_runs, self.n_features, dtype=torch.float64, device=self.device)
+        fval = torch.empty(self.n_runs, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().zf_lasso_multi_gradient_device(
+            self._h, C.c_void_p(xd.data_ptr()), C.c_void_p(grad.data_ptr()),
+            C.c_void_p(fval.data_ptr())))
+        return grad, fval
+
+    def minimize_proximal_gradient_batched(self, x0, nesterov_ratios=None, lr=1, tol=1e-5,
+                                           tol_internal=1e-12, max_iter=1000000,
+                                           max_backtrack_iter=100, decay_rate=0.5,
+                                           nesterov=False, nesterov_ratio=(0, 0.25),
+                                           return_all=False, deprecated=False,
+                                           trace_capacity=None, return_device=False):
+        """One run per row of ``nesterov_ratios`` (``(n_runs, 2)``; default: ``nesterov_ratio``
+        for every run); ``x0`` is one vector or ``(n_runs, n_features)``.  Keyword arguments
+        and the fields of each returned OptimizeResult are the reference's
+        (proximal_gradient.py:311-555); ``allvecs`` is not recorded."""
+        from .proximal_gradient import _make_options, _message
+
+        torch = _torch()
+        if deprecated:
+            warn("Using the deprecated option is not mathematically proven to converge. "
+                 "Please consider using the recommended condition instead.", stacklevel=2)
+        t0 = time.time()
+        K, n = self.n_runs, self.n_features
+        if nesterov_ratios is None:
+            ab = np.tile(np.asarray(nesterov_ratio, dtype=np.float64), (K, 1))
+        else:
+            ab = np.ascontiguousarray(np.asarray(nesterov_ratios, dtype=np.float64).reshape(-1, 2))
+            if len(ab) != K:
+                raise ValueError(f"nesterov_ratios must have {K} rows")
+        x0d, batched = self._x_batch(x0)
+        cap = 0
+        if return_all:
+            cap = int(trace_capacity) if trace_capacity is not None else int(min(max_iter, 1 << 16))
+        L = _lib.lib()
+        while True:
+            opts = _make_options(lr, tol, tol_internal, max_iter, 100000, max_backtrack_iter,
+                                 False, decay_rate, nesterov, nesterov_ratio, deprecated,
+                                 "reference", cap)
+            xd = torch.empty(K, n, dtype=torch.float64, device=self.device)
+            fun, lrs, err = np.empty(K), np.empty(K), np.empty(K)
+            nit, status = np.zeros(K, dtype=np.int64), np.zeros(K, dtype=np.int32)
+            allerrs = np.zeros((K, cap)) if cap else None
+            allfuns = np.zeros((K, cap + 1)) if cap else None
+            p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+            with torch.cuda.device(self.device):
+                if not self.distributed:
+                    _lib.check(L.zf_lasso_multi_solve(
+                        self._h, C.byref(opts), C.c_void_p(x0d.data_ptr()), int(batched), p(ab),
+                        C.c_void_p(xd.data_ptr()), p(fun), p(nit), p(status), p(lrs), p(err),
+                        p(allerrs), p(allfuns)))
+                else:
+                    if cap:
+                        raise NotImplementedError("return_all is not available on the row-sharded path")
+                    from .distributed import run_split_lasso
+
+                    h = self._h
+
+                    class _Ops:
+                        def begin(self_):
+                            _lib.check(L.zf_lasso_multi_begin(h, C.byref(opts),
+                                                              C.c_void_p(x0d.data_ptr()),
+                                                              int(batched), p(ab)))
+
+                        def grad(self_, which):
+                            _lib.check(L.zf_lasso_multi_grad(h, int(which)))
+
+                        def step(self_):
+                            nxt = C.c_int32(0)
+                            _lib.check(L.zf_lasso_multi_step(h, C.byref(nxt)))
+                            return nxt.value
+
+                        def finish(self_):
+                            _lib.check(L.zf_lasso_multi_finish(h, C.c_void_p(xd.data_ptr()), p(fun),
+                                                               p(nit), p(status), p(lrs), p(err)))
+
+                    run_split_lasso(_Ops(), self._allreduce)
+            if cap and int(nit.max()) > cap and trace_capacity is None:
+                cap = int(nit.max())
+                continue
+            break
+        elapsed = time.time() - t0
+        xh = None if return_device else xd.cpu().numpy()
+        out = []
+        for k in range(K):
+            st, it = int(status[k]), int(nit[k])
+            res = OptimizeResult(
+                x=xd[k] if return_device else xh[k], fun=float(fun[k]), nit=it, success=st == 1,
+                status=st, message=_message(st), time=elapsed, lr=float(lrs[k]),
+                err=float(err[k]), nesterov_ratio=(float(ab[k, 0]), float(ab[k, 1])),
+                allvecs=None, allfuns=None, allerrs=None)
+            if return_all:
+                res.allerrs = list(allerrs[k, :it])
+                res.allfuns = list(allfuns[k, :it + 1])
+            out.append(res)
+        return out
