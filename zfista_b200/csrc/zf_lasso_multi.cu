@@ -14,16 +14,23 @@
 //
 // each of which reads A from HBM exactly once, whatever K is: the HBM cost per run drops from
 // one (fused) pass to 2/K passes.  Both passes are hand-written for sm_100a:
-//   * a producer warp streams 64x64 tiles of A (and the matching slice of V or R) into a ring
-//     of shared-memory stages with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx);
+//   * a producer thread streams 64x64 tiles of A (and the matching slice of V or R) into a ring
+//     of shared-memory stages with 2-D tensor-map TMA copies (cp.async.bulk.tensor.2d +
+//     mbarrier complete_tx; four 64-row x 128-byte boxes per tile, SWIZZLE_128B; out-of-range
+//     rows / columns arrive as zeros).  The first version issued one 512-byte 1-D bulk copy
+//     per tile row and ran at 0.3 of the HBM roofline whatever K was: ~60 cycles per copy
+//     instruction, 80 of them per stage;
 //   * eight consumer warps feed the FP64 tensor cores (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4)
-//     straight from shared memory; row pitches are padded so that every 16-byte fragment load
-//     is bank-conflict free (pass 1: pitch = 64 B mod 128, pass 2: 2*pitch = 32 B mod 128);
+//     straight from shared memory; with the 128-byte swizzle (and the rows of an m- / n-tile
+//     taken in the order 0,5,2,7,4,1,6,3) every 16-byte fragment load is bank-conflict free
+//     in both passes;
 //   * stages are handed back through a second set of mbarriers, so the copy of tile k+NS
 //     overlaps the tensor-core work on tile k.
 // Runs are independent (own step size, momentum, line search, stop test): the host keeps the
 // reference's scalar logic per run (proximal_gradient.py:474-555) and a finished run simply
 // stops being updated, so each run's iterates are what a solo solve produces.
+#include <cuda.h>
+
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -39,8 +46,6 @@ constexpr int TILE = 64;        // rows and columns of one A stage
 constexpr int CONSUMERS = 8;    // tensor-core warps
 constexpr int THREADS = (CONSUMERS + 1) * 32;
 
-struct VecPtrs { const double* v[MAX_RUNS]; };
-
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
 }
@@ -54,11 +59,14 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes,
+// one box of a 2-D tensor map: c0 = coordinate along the contiguous dimension, c1 = row
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
                                             unsigned long long* bar) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1),
+        "r"(smem_u32(bar)) : "memory");
 }
 // bounded wait: a protocol bug must trap, not hang the GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
@@ -82,21 +90,34 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
       : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+constexpr int BOXC = 16;        // doubles per box row: 128 bytes, the swizzle span
+constexpr int NBOX = TILE / BOXC;
+
 template <int NT>
 struct Cfg {
   static constexpr int KP = 8 * NT;               // runs, padded to whole n-tiles
-  static constexpr int NS = (NT <= 2) ? 4 : 3;    // ring stages
-  // pass 1: A tile pitch 72 doubles (576 B = 64 mod 128), V slice the same
-  static constexpr int P1_A = 72, P1_V = 72;
-  static constexpr int P1_STAGE = TILE * P1_A + KP * P1_V;
-  static constexpr size_t P1_SMEM = sizeof(double) * (size_t)(NS * P1_STAGE + KP * TILE) +
-                                    sizeof(unsigned long long) * 2 * NS;
-  // pass 2: A tile pitch 66 doubles (2*528 B = 32 mod 128), R slice pitch 72
-  static constexpr int P2_A = 66, P2_R = 72;
-  static constexpr int P2_STAGE = TILE * P2_A + KP * P2_R;
-  static constexpr size_t P2_SMEM = sizeof(double) * (size_t)(NS * P2_STAGE + 2 * KP * TILE) +
-                                    sizeof(unsigned long long) * 2 * NS;
+  // one stage = A tile (4 boxes of 64 rows x 128 B) + vector slice (4 boxes of KP rows x 128 B)
+  static constexpr int BOX_A = TILE * BOXC;       // doubles
+  static constexpr int BOX_V = KP * BOXC;
+  static constexpr int STAGE = NBOX * (BOX_A + BOX_V);
+  static constexpr int NS1 = 4;
+  static constexpr int NS2 = (NT <= 3) ? 4 : 3;
+  static constexpr size_t P1_SMEM = 1024 + sizeof(double) * (size_t)(NS1 * STAGE + KP * TILE) +
+                                    sizeof(unsigned long long) * 2 * NS1;
+  static constexpr size_t P2_SMEM = 1024 + sizeof(double) * (size_t)(NS2 * STAGE + 2 * KP * TILE) +
+                                    sizeof(unsigned long long) * 2 * NS2;
 };
+
+// the swizzle pattern repeats every 1024 bytes: boxes must start on that boundary
+__device__ __forceinline__ double* align_1024(unsigned char* raw) {
+  const unsigned a = smem_u32(raw);
+  return reinterpret_cast<double*>(raw + ((1024u - (a & 1023u)) & 1023u));
+}
+// Row order inside an 8-row m- / n-tile: tensor-core row g reads physical row g ^ 4*(g & 1)
+// (0,5,2,7,4,1,6,3).  Under SWIZZLE_128B the 16-byte chunk c of physical row r sits at chunk
+// c ^ (r & 7); a quarter warp (g = 2j, 2j+1; q = 0..3) then touches chunks whose bit 2
+// differs between its two rows, i.e. all 32 banks once.
+__device__ __forceinline__ int tile_row(int g) { return g ^ ((g & 1) << 2); }
 
 // ---------------------------------------------------------------------------------------
 // pass 1:  R[k][i] = sum_j A[i][j] * V_k[j] - b_k[i],  block partials of sum_i R[k][i]^2
@@ -108,13 +129,14 @@ struct Cfg {
 // ---------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(THREADS, 1)
-multi_residual_kernel(const double* __restrict__ A, long long n_rows, long long n_cols,
-                      VecPtrs V, const double* __restrict__ b, long long b_stride,
-                      double* __restrict__ R, long long pitch_r, double* __restrict__ sq_part) {
+multi_residual_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmV,
+                      long long n_rows, long long n_cols, const double* __restrict__ b,
+                      long long b_stride, double* __restrict__ R, long long pitch_r,
+                      double* __restrict__ sq_part) {
   using C_ = Cfg<NT>;
-  constexpr int KP = C_::KP, NS = C_::NS, PA = C_::P1_A, PV = C_::P1_V, STAGE = C_::P1_STAGE;
+  constexpr int KP = C_::KP, NS = C_::NS1, BOX_A = C_::BOX_A, BOX_V = C_::BOX_V, STAGE = C_::STAGE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* stages = align_1024(smem_raw);
   double* red = stages + NS * STAGE;                         // [KP][TILE]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(red + KP * TILE);
   unsigned long long* empty = full + NS;
@@ -129,34 +151,37 @@ multi_residual_kernel(const double* __restrict__ A, long long n_rows, long long 
   __syncthreads();
   const long long n_rb = (n_rows + TILE - 1) / TILE;
   const int n_ch = (int)((n_cols + TILE - 1) / TILE);
-  const int tail_cols = (int)(n_cols - (long long)(n_ch - 1) * TILE);    // 1..64, even
+  const int tail_cols = (int)(n_cols - (long long)(n_ch - 1) * TILE);    // 2..64, even
 
   if (warp == CONSUMERS) {
-    // ------------------------------------------------------------------ producer warp
+    // ------------------------------------------------------------------ producer thread
+    if (lane != 0) return;
     long long it = 0;
     for (long long rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
-      const long long row0 = rb * TILE;
-      const int rows_valid = (int)((n_rows - row0 < TILE) ? n_rows - row0 : TILE);
+      const int row0 = (int)(rb * TILE);
       for (int c = 0; c < n_ch; ++c, ++it) {
         const int s = (int)(it % NS);
-        const long long u = it / NS;
-        if (it >= NS) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));
-        const unsigned bytes = (unsigned)((c == n_ch - 1 ? tail_cols : TILE) * 8);
-        if (lane == 0) mbar_expect_tx(&full[s], (unsigned)(rows_valid + KP) * bytes);
-        __syncwarp();
+        if (it >= NS) mbar_wait(&empty[s], (unsigned)((it / NS - 1) & 1));
+        // boxes wholly past n_cols are not fetched (their lanes multiply zeros, see `dead`)
+        const int nbox = (c == n_ch - 1) ? (tail_cols + BOXC - 1) / BOXC : NBOX;
+        mbar_expect_tx(&full[s], (unsigned)(nbox * (BOX_A + BOX_V) * sizeof(double)));
         double* sa = stages + (size_t)s * STAGE;
-        double* sv = sa + TILE * PA;
-        const double* src = A + row0 * n_cols + (long long)c * TILE;
-        for (int r = lane; r < rows_valid; r += 32)
-          tma_load_1d(sa + r * PA, src + (long long)r * n_cols, bytes, &full[s]);
-        if (lane < KP) tma_load_1d(sv + lane * PV, V.v[lane] + (long long)c * TILE, bytes, &full[s]);
+        double* sv = sa + NBOX * BOX_A;
+        for (int bx = 0; bx < nbox; ++bx) {
+          tma_load_2d(sa + bx * BOX_A, &tmA, c * TILE + bx * BOXC, row0, &full[s]);
+          tma_load_2d(sv + bx * BOX_V, &tmV, c * TILE + bx * BOXC, 0, &full[s]);
+        }
       }
     }
     return;
   }
   // -------------------------------------------------------------------- consumer warps
   const int g = lane >> 2, q = lane & 3;
+  const int rho = tile_row(g);
   const int col = warp * 8 + 2 * q;            // this lane's column pair inside a tile
+  const int chunk = 4 * (warp & 1) + q;        // its 16-byte chunk inside the box row
+  const int a_off = (warp >> 1) * BOX_A + rho * BOXC + ((chunk ^ rho) << 1);
+  const int v_off = NBOX * BOX_A + (warp >> 1) * BOX_V + rho * BOXC + ((chunk ^ rho) << 1);
   double ssacc[2 * NT];
 #pragma unroll
   for (int i = 0; i < 2 * NT; ++i) ssacc[i] = 0.0;
@@ -171,19 +196,20 @@ multi_residual_kernel(const double* __restrict__ A, long long n_rows, long long 
     for (int c = 0; c < n_ch; ++c, ++it) {
       const int s = (int)(it % NS);
       mbar_wait(&full[s], (unsigned)((it / NS) & 1));
-      const double* sa = stages + (size_t)s * STAGE + col;
-      const double* sv = stages + (size_t)s * STAGE + TILE * PA + col;
-      // columns past n_cols in the last tile were not copied: they must contribute 0
+      const double* sa = stages + (size_t)s * STAGE + a_off;
+      const double* sv = stages + (size_t)s * STAGE + v_off;
+      // columns past n_cols in the last tile must contribute 0 (TMA zero-fills a partial box,
+      // a box wholly out of range is skipped and its stage memory is stale)
       const bool dead = (c == n_ch - 1) && (col >= tail_cols);
       double2 vb[NT];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        vb[nt] = *reinterpret_cast<const double2*>(sv + (8 * nt + g) * PV);
+        vb[nt] = *reinterpret_cast<const double2*>(sv + nt * 8 * BOXC);
         if (dead) vb[nt] = make_double2(0.0, 0.0);
       }
 #pragma unroll
       for (int mt = 0; mt < 8; ++mt) {
-        double2 a = *reinterpret_cast<const double2*>(sa + (8 * mt + g) * PA);
+        double2 a = *reinterpret_cast<const double2*>(sa + mt * 8 * BOXC);
         if (dead) a = make_double2(0.0, 0.0);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
@@ -204,7 +230,7 @@ multi_residual_kernel(const double* __restrict__ A, long long n_rows, long long 
           for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int idx = (8 * nt + 2 * q + e) * TILE + 8 * mt + g;
+              const int idx = (8 * nt + tile_row(2 * q + e)) * TILE + 8 * mt + rho;
               red[idx] = (w == 0) ? acc[mt][nt][e] : red[idx] + acc[mt][nt][e];
             }
       }
@@ -250,13 +276,13 @@ multi_residual_kernel(const double* __restrict__ A, long long n_rows, long long 
 // ---------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(THREADS, 1)
-multi_atr_kernel(const double* __restrict__ A, long long n_rows, long long n_cols,
-                 const double* __restrict__ R, long long pitch_r, long long rows_per_split,
-                 int n_splits, double* __restrict__ gpart, long long pitch_c) {
+multi_atr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR,
+                 long long n_rows, long long n_cols, long long rows_per_split, int n_splits,
+                 double* __restrict__ gpart, long long pitch_c) {
   using C_ = Cfg<NT>;
-  constexpr int KP = C_::KP, NS = C_::NS, PA = C_::P2_A, PR = C_::P2_R, STAGE = C_::P2_STAGE;
+  constexpr int KP = C_::KP, NS = C_::NS2, BOX_A = C_::BOX_A, BOX_R = C_::BOX_V, STAGE = C_::STAGE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* stages = align_1024(smem_raw);
   double* red = stages + NS * STAGE;                         // [2][KP][TILE]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(red + 2 * KP * TILE);
   unsigned long long* empty = full + NS;
@@ -273,33 +299,33 @@ multi_atr_kernel(const double* __restrict__ A, long long n_rows, long long n_col
   const long long n_items = n_slabs * n_splits;
 
   if (warp == CONSUMERS) {
+    if (lane != 0) return;
     long long it = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const long long slab = item % n_slabs, split = item / n_slabs;
-      const long long col0 = slab * TILE;
-      const unsigned bytes_a = (unsigned)(((n_cols - col0 < TILE) ? n_cols - col0 : TILE) * 8);
+      const int col0 = (int)(slab * TILE);
+      const int seg = (int)((n_cols - col0 < TILE) ? n_cols - col0 : TILE);
+      const int nbox_a = (seg + BOXC - 1) / BOXC;    // columns past n_cols are never stored
       const long long r_lo = split * rows_per_split;
       const long long r_hi = (r_lo + rows_per_split < n_rows) ? r_lo + rows_per_split : n_rows;
       for (long long rc = r_lo; rc < r_hi; rc += TILE, ++it) {
         const int s = (int)(it % NS);
-        const long long u = it / NS;
-        if (it >= NS) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));
+        if (it >= NS) mbar_wait(&empty[s], (unsigned)((it / NS - 1) & 1));
         const int valid = (int)((r_hi - rc < TILE) ? r_hi - rc : TILE);
-        const unsigned bytes_r = (unsigned)(((valid + 1) & ~1) * 8);   // R rows are padded to even
-        if (lane == 0)
-          mbar_expect_tx(&full[s], (unsigned)valid * bytes_a + (unsigned)KP * bytes_r);
-        __syncwarp();
+        const int nbox_r = (valid + BOXC - 1) / BOXC;
+        mbar_expect_tx(&full[s], (unsigned)((nbox_a * BOX_A + nbox_r * BOX_R) * sizeof(double)));
         double* sa = stages + (size_t)s * STAGE;
-        double* sr = sa + TILE * PA;
-        const double* src = A + rc * n_cols + col0;
-        for (int r = lane; r < valid; r += 32)
-          tma_load_1d(sa + r * PA, src + (long long)r * n_cols, bytes_a, &full[s]);
-        if (lane < KP) tma_load_1d(sr + lane * PR, R + (long long)lane * pitch_r + rc, bytes_r, &full[s]);
+        double* sr = sa + NBOX * BOX_A;
+        for (int bx = 0; bx < nbox_a; ++bx)
+          tma_load_2d(sa + bx * BOX_A, &tmA, col0 + bx * BOXC, (int)rc, &full[s]);
+        for (int bx = 0; bx < nbox_r; ++bx)
+          tma_load_2d(sr + bx * BOX_R, &tmR, (int)rc + bx * BOXC, 0, &full[s]);
       }
     }
     return;
   }
   const int g = lane >> 2, q = lane & 3;
+  const int rho = tile_row(g);
   const int cg = warp & 3, kh = warp >> 2;
   long long it = 0;
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -317,17 +343,21 @@ multi_atr_kernel(const double* __restrict__ A, long long n_rows, long long n_col
       const int s = (int)(it % NS);
       mbar_wait(&full[s], (unsigned)((it / NS) & 1));
       const int valid = (int)((r_hi - rc < TILE) ? r_hi - rc : TILE);
-      const double* sa = stages + (size_t)s * STAGE + 16 * cg + 2 * g;
-      const double* sr = stages + (size_t)s * STAGE + TILE * PA + g * PR;
+      const double* sa = stages + (size_t)s * STAGE + cg * BOX_A;
+      const double* sr = stages + (size_t)s * STAGE + NBOX * BOX_A + rho * BOXC;
 #pragma unroll
       for (int sp = 0; sp < 4; ++sp) {
         const int rbase = 32 * kh + 8 * sp + 2 * q;     // this lane's row pair (k index)
-        double2 a0 = *reinterpret_cast<const double2*>(sa + rbase * PA);
-        double2 a1 = *reinterpret_cast<const double2*>(sa + (rbase + 1) * PA);
+        // rows rbase, rbase+1 of the tile: (row & 7) = 2q, 2q+1
+        double2 a0 = *reinterpret_cast<const double2*>(sa + rbase * BOXC + ((g ^ (2 * q)) << 1));
+        double2 a1 = *reinterpret_cast<const double2*>(sa + (rbase + 1) * BOXC +
+                                                       ((g ^ (2 * q + 1)) << 1));
+        const int chunk = 4 * (sp & 1) + q;              // residual pair inside its 16-row box
+        const double* srb = sr + (2 * kh + (sp >> 1)) * BOX_R + ((chunk ^ rho) << 1);
         double2 rv[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
-          rv[nt] = *reinterpret_cast<const double2*>(sr + 8 * nt * PR + rbase);
+          rv[nt] = *reinterpret_cast<const double2*>(srb + nt * 8 * BOXC);
         if (valid < TILE) {                              // rows past the split: contribute 0
           if (rbase >= valid) {
             a0 = make_double2(0.0, 0.0);
@@ -358,7 +388,7 @@ multi_atr_kernel(const double* __restrict__ A, long long n_rows, long long n_col
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          red[(kh * KP + 8 * nt + 2 * q + j) * TILE + 16 * cg + 2 * g + e] = acc[e][nt][j];
+          red[(kh * KP + 8 * nt + tile_row(2 * q + j)) * TILE + 16 * cg + 2 * g + e] = acc[e][nt][j];
     consumer_barrier();
     for (int e = tid; e < KP * TILE; e += CONSUMERS * 32) {
       const int k = e >> 6, cc = e & (TILE - 1);
@@ -397,7 +427,6 @@ struct StepSums { double gd, dd, abs1, maxd; };
 struct StepArgs {
   double lr[MAX_RUNS];       // prox: step size;  momentum: (t_k - 1) / t_{k+1}
   unsigned mask;             // runs this launch touches
-  unsigned cur;              // bit k set: run k's previous iterate is in buffer 1
 };
 
 // per run k in `mask`:  x_new = soft(y - lr*g, lr*l1) with g = src[k]*two_scale
@@ -405,8 +434,8 @@ struct StepArgs {
 //   gd = g.(x-y), dd = ||x-y||^2, abs1 = ||x||_1, maxd = max|x-y|
 // abs_only: only abs1 of the previous iterate (g(x0) at start-up).
 __global__ void __launch_bounds__(VEC_THREADS)
-multi_prox_kernel(StepArgs a, const double* __restrict__ Y, double* __restrict__ buf0,
-                  double* __restrict__ buf1, long long pitch_c, const double* __restrict__ src,
+multi_prox_kernel(StepArgs a, const double* __restrict__ Y, const double* __restrict__ Xp,
+                  double* __restrict__ Xn, long long pitch_c, const double* __restrict__ src,
                   double two_scale, double l1, long long n, double* __restrict__ g_out,
                   StepSums* __restrict__ block_sums, unsigned int* __restrict__ counter,
                   StepSums* __restrict__ out, int abs_only) {
@@ -414,9 +443,8 @@ multi_prox_kernel(StepArgs a, const double* __restrict__ Y, double* __restrict__
   if (!((a.mask >> k) & 1u)) return;
   __shared__ StepSums sh[VEC_THREADS / 32];
   __shared__ bool is_last;
-  const bool prev_in_1 = (a.cur >> k) & 1u;
-  const double* xp = (prev_in_1 ? buf1 : buf0) + (long long)k * pitch_c;
-  double* xn = (prev_in_1 ? buf0 : buf1) + (long long)k * pitch_c;
+  const double* xp = Xp + (long long)k * pitch_c;
+  double* xn = Xn + (long long)k * pitch_c;
   const double* y = Y + (long long)k * pitch_c;
   const double* gs = src + (long long)k * pitch_c;
   double* go = g_out ? g_out + (long long)k * pitch_c : nullptr;
@@ -470,21 +498,23 @@ multi_prox_kernel(StepArgs a, const double* __restrict__ Y, double* __restrict__
   }
 }
 
-// per run k in `mask`:  y = x_new + mom*(x_new - x_prev)   (proximal_gradient.py:534)
+// per run k in `mask`:  y = x_new + mom*(x_new - x_prev), then x_prev = x_new
+// (proximal_gradient.py:534-538).  The iterates of all runs stay in the fixed arrays Xp / Xn / Y
+// (one tensor map each); a run that is not in `mask` (finished, failed) keeps all three.
 __global__ void __launch_bounds__(VEC_THREADS)
-multi_momentum_kernel(StepArgs a, const double* __restrict__ buf0, const double* __restrict__ buf1,
+multi_momentum_kernel(StepArgs a, double* __restrict__ Xp, const double* __restrict__ Xn,
                       long long pitch_c, long long n, double* __restrict__ Y) {
   const int k = blockIdx.y;
   if (!((a.mask >> k) & 1u)) return;
-  const bool prev_in_1 = (a.cur >> k) & 1u;
-  const double* xp = (prev_in_1 ? buf1 : buf0) + (long long)k * pitch_c;
-  const double* xn = (prev_in_1 ? buf0 : buf1) + (long long)k * pitch_c;
+  double* xp = Xp + (long long)k * pitch_c;
+  const double* xn = Xn + (long long)k * pitch_c;
   double* y = Y + (long long)k * pitch_c;
   const double mom = a.lr[k];
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
     const double xj = xn[j];
     y[j] = xj + mom * (xj - xp[j]);
+    xp[j] = xj;
   }
 }
 
@@ -532,9 +562,9 @@ struct zf_lasso_multi {
   long long rows_per_split = 0;
   bool b_batched = false;
   // device workspace
-  double* vecs = nullptr;      // 4 * kp * pitch_c : buf0, buf1, Y, G
-  double *buf0 = nullptr, *buf1 = nullptr, *Y = nullptr, *G = nullptr;
-  double* zeros = nullptr;     // pitch_c (vector of the padding runs)
+  double* vecs = nullptr;      // 4 * kp * pitch_c : Xp, Xn, Y, G (rows of padding runs stay 0)
+  double *Xp = nullptr, *Xn = nullptr, *Y = nullptr, *G = nullptr;
+  CUtensorMap tmA, tmY, tmXn, tmR;   // SWIZZLE_128B boxes of 16 doubles x (64 | kp) rows
   double* bcopy = nullptr;     // kp * pitch_r (batched b) or pitch_r
   double* R = nullptr;         // kp * pitch_r
   double* gpart = nullptr;     // n_splits * kp * pitch_c
@@ -548,7 +578,7 @@ struct zf_lasso_multi {
   zf_options opt{};
   int phase = MP_IDLE;
   bool need_F = false;
-  unsigned active = 0, trial = 0, accepted = 0, cur = 0;
+  unsigned active = 0, trial = 0, accepted = 0;
   RunState run[zf::multi::MAX_RUNS];
   double* h_allerrs = nullptr;
   double* h_allfuns = nullptr;
@@ -565,27 +595,27 @@ namespace {
 using zf::multi::Cfg;
 using zf::multi::StepArgs;
 using zf::multi::StepSums;
-using zf::multi::VecPtrs;
 
+// which = 0: the vectors are the y_k, 1: the candidates x_new_k
 template <int NT>
-int launch_residual_t(zf_lasso_multi* h, const VecPtrs& v) {
+int launch_residual_t(zf_lasso_multi* h, int which) {
   auto k = zf::multi::multi_residual_kernel<NT>;
   ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)Cfg<NT>::P1_SMEM));
   k<<<h->grid, zf::multi::THREADS, Cfg<NT>::P1_SMEM, h->st>>>(
-      h->A, h->n_rows, h->n_cols, v, h->bcopy, h->b_batched ? h->pitch_r : 0, h->R, h->pitch_r,
-      h->sq_part);
+      h->tmA, which == 0 ? h->tmY : h->tmXn, h->n_rows, h->n_cols, h->bcopy,
+      h->b_batched ? h->pitch_r : 0, h->R, h->pitch_r, h->sq_part);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
 }
 
-int launch_residual(zf_lasso_multi* h, const VecPtrs& v) {
+int launch_residual(zf_lasso_multi* h, int which) {
   switch (h->nt) {
-    case 1: return launch_residual_t<1>(h, v);
-    case 2: return launch_residual_t<2>(h, v);
-    case 3: return launch_residual_t<3>(h, v);
-    default: return launch_residual_t<4>(h, v);
+    case 1: return launch_residual_t<1>(h, which);
+    case 2: return launch_residual_t<2>(h, which);
+    case 3: return launch_residual_t<3>(h, which);
+    default: return launch_residual_t<4>(h, which);
   }
 }
 
@@ -595,8 +625,7 @@ int launch_atr_t(zf_lasso_multi* h) {
   ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)Cfg<NT>::P2_SMEM));
   k<<<h->grid, zf::multi::THREADS, Cfg<NT>::P2_SMEM, h->st>>>(
-      h->A, h->n_rows, h->n_cols, h->R, h->pitch_r, h->rows_per_split, h->n_splits, h->gpart,
-      h->pitch_c);
+      h->tmA, h->tmR, h->n_rows, h->n_cols, h->rows_per_split, h->n_splits, h->gpart, h->pitch_c);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -621,24 +650,8 @@ int launch_collect(zf_lasso_multi* h, bool with_gradient) {
   return ZF_OK;
 }
 
-// vectors pass 1 multiplies: which = 0 -> y_k, 1 -> the candidate x_new_k
-VecPtrs vec_ptrs(const zf_lasso_multi* h, int which) {
-  VecPtrs v;
-  for (int k = 0; k < zf::multi::MAX_RUNS; ++k) {
-    if (k >= h->n_runs) {
-      v.v[k] = h->zeros;
-    } else if (which == 0) {
-      v.v[k] = h->Y + (long long)k * h->pitch_c;
-    } else {
-      const bool prev_in_1 = (h->cur >> k) & 1u;
-      v.v[k] = (prev_in_1 ? h->buf0 : h->buf1) + (long long)k * h->pitch_c;
-    }
-  }
-  return v;
-}
-
-int gradient_pass(zf_lasso_multi* h, const VecPtrs& v) {
-  int rc = launch_residual(h, v);
+int gradient_pass(zf_lasso_multi* h) {
+  int rc = launch_residual(h, 0);
   if (rc != ZF_OK) return rc;
   rc = launch_atr(h);
   if (rc != ZF_OK) return rc;
@@ -650,10 +663,9 @@ int run_prox(zf_lasso_multi* h, unsigned mask, bool first_trial, bool abs_only) 
   StepArgs a{};
   for (int k = 0; k < h->n_runs; ++k) a.lr[k] = h->run[k].lr;
   a.mask = mask;
-  a.cur = h->cur;
   dim3 grid(zf::multi::VEC_BLOCKS, (unsigned)h->n_runs);
   zf::multi::multi_prox_kernel<<<grid, zf::multi::VEC_THREADS, 0, h->st>>>(
-      a, h->Y, h->buf0, h->buf1, h->pitch_c, first_trial ? h->partial : h->G,
+      a, h->Y, h->Xp, h->Xn, h->pitch_c, first_trial ? h->partial : h->G,
       first_trial ? 2.0 * h->scale : 1.0, h->l1, h->n_cols, first_trial ? h->G : nullptr,
       h->block_sums, h->counter, h->d_sums, abs_only ? 1 : 0);
   ZF_CUDA(cudaGetLastError());
@@ -725,13 +737,11 @@ int advance(zf_lasso_multi* h, int* next) {
   h->accepted = 0;
   if (adv) {
     m.mask = adv;
-    m.cur = h->cur;
     dim3 grid(zf::multi::VEC_BLOCKS, (unsigned)h->n_runs);
     zf::multi::multi_momentum_kernel<<<grid, zf::multi::VEC_THREADS, 0, h->st>>>(
-        m, h->buf0, h->buf1, h->pitch_c, h->n_cols, h->Y);
+        m, h->Xp, h->Xn, h->pitch_c, h->n_cols, h->Y);
     ZF_CUDA(cudaGetLastError());
     zf::zf_count_launch();
-    h->cur ^= adv;       // the candidate becomes the previous iterate of the runs that go on
   }
   if (h->active) {
     h->phase = MP_GRAD;
@@ -748,6 +758,37 @@ int advance(zf_lasso_multi* h, int* next) {
     h->phase = MP_FINAL;   // one more residual pass for res.fun = F(x) of every run
     *next = 1;
   }
+  return ZF_OK;
+}
+
+// 2-D fp64 tensor map over a row-major array: boxes of 16 doubles (128 B, SWIZZLE_128B) x box_rows
+// rows; elements outside [0, inner) x [0, outer) read as 0.  cuTensorMapEncodeTiled is taken from
+// the driver through the runtime (no link-time dependency on libcuda).
+int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
+             int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                               const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ZF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess)
+      return zf::zf_fail(ZF_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {pitch * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)zf::multi::BOXC, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return zf::zf_fail(ZF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return ZF_OK;
 }
 
@@ -772,7 +813,7 @@ int begin_impl(zf_lasso_multi* h, const zf_options* opt, const double* d_x0, int
   h->h_allfuns = h_allfuns;
   h->need_F = (opt->decay_rate != 1.0) || (opt->trace_capacity > 0 && h_allfuns != nullptr);
   h->active = (h->n_runs == 32) ? 0xffffffffu : ((1u << h->n_runs) - 1u);
-  h->trial = h->accepted = h->cur = 0;
+  h->trial = h->accepted = 0;
   for (int k = 0; k < h->n_runs; ++k) {
     RunState& r = h->run[k];
     r = RunState();
@@ -783,12 +824,12 @@ int begin_impl(zf_lasso_multi* h, const zf_options* opt, const double* d_x0, int
     const double* src = d_x0 + (x0_is_batched ? (long long)k * h->n_cols : 0);
     const size_t nb = sizeof(double) * (size_t)h->n_cols;
     const long long off = (long long)k * h->pitch_c;
-    ZF_CUDA(cudaMemcpyAsync(h->buf0 + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
-    ZF_CUDA(cudaMemcpyAsync(h->buf1 + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->Xp + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->Xn + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
     ZF_CUDA(cudaMemcpyAsync(h->Y + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
   }
   // F(x0): residual norms (all-reduced by the caller if the rows are sharded)
-  rc = launch_residual(h, vec_ptrs(h, 0));
+  rc = launch_residual(h, 0);
   if (rc != ZF_OK) return rc;
   rc = launch_collect(h, false);
   if (rc != ZF_OK) return rc;
@@ -850,12 +891,10 @@ extern "C" int zf_lasso_multi_create(zf_lasso_multi** out, const double* d_A, in
   const size_t r_b = sizeof(double) * (size_t)h->kp * (size_t)h->pitch_r;
   ZF_TRY(cudaMalloc(&h->vecs, 4 * vec_b));
   ZF_TRY(cudaMemsetAsync(h->vecs, 0, 4 * vec_b, h->st));
-  h->buf0 = h->vecs;
-  h->buf1 = h->buf0 + (size_t)h->kp * h->pitch_c;
-  h->Y = h->buf1 + (size_t)h->kp * h->pitch_c;
+  h->Xp = h->vecs;
+  h->Xn = h->Xp + (size_t)h->kp * h->pitch_c;
+  h->Y = h->Xn + (size_t)h->kp * h->pitch_c;
   h->G = h->Y + (size_t)h->kp * h->pitch_c;
-  ZF_TRY(cudaMalloc(&h->zeros, sizeof(double) * (size_t)h->pitch_c));
-  ZF_TRY(cudaMemsetAsync(h->zeros, 0, sizeof(double) * (size_t)h->pitch_c, h->st));
   const size_t b_b = h->b_batched ? r_b : sizeof(double) * (size_t)h->pitch_r;
   ZF_TRY(cudaMalloc(&h->bcopy, b_b));
   ZF_TRY(cudaMemsetAsync(h->bcopy, 0, b_b, h->st));
@@ -878,6 +917,11 @@ extern "C" int zf_lasso_multi_create(zf_lasso_multi** out, const double* d_A, in
   ZF_TRY(cudaMallocHost(&h->h_pin, sizeof(double) * 5 * h->kp));
   ZF_TRY(cudaStreamSynchronize(h->st));
 #undef ZF_TRY
+  rc = make_map(&h->tmA, d_A, (uint64_t)n_cols, (uint64_t)n_rows, (uint64_t)n_cols, zf::multi::TILE);
+  if (rc == ZF_OK) rc = make_map(&h->tmY, h->Y, (uint64_t)n_cols, (uint64_t)h->kp, (uint64_t)h->pitch_c, h->kp);
+  if (rc == ZF_OK) rc = make_map(&h->tmXn, h->Xn, (uint64_t)n_cols, (uint64_t)h->kp, (uint64_t)h->pitch_c, h->kp);
+  if (rc == ZF_OK) rc = make_map(&h->tmR, h->R, (uint64_t)n_rows, (uint64_t)h->kp, (uint64_t)h->pitch_r, h->kp);
+  if (rc != ZF_OK) return fail(rc);
   *out = h;
   return ZF_OK;
 }
@@ -885,7 +929,6 @@ extern "C" int zf_lasso_multi_create(zf_lasso_multi** out, const double* d_A, in
 extern "C" void zf_lasso_multi_destroy(zf_lasso_multi* h) {
   if (!h) return;
   cudaFree(h->vecs);
-  cudaFree(h->zeros);
   cudaFree(h->bcopy);
   cudaFree(h->R);
   cudaFree(h->gpart);
@@ -907,12 +950,12 @@ extern "C" int zf_lasso_multi_grad(zf_lasso_multi* h, int which) {
   if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
   if (which == 0) {
     if (h->phase != MP_GRAD) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_grad(0) out of order");
-    return gradient_pass(h, vec_ptrs(h, 0));
+    return gradient_pass(h);
   }
   if (which == 1) {
     if (h->phase != MP_FNEW && h->phase != MP_FINAL)
       return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_grad(1) out of order");
-    int rc = launch_residual(h, vec_ptrs(h, 1));
+    int rc = launch_residual(h, 1);
     if (rc != ZF_OK) return rc;
     return launch_collect(h, false);
   }
@@ -1051,9 +1094,8 @@ extern "C" int zf_lasso_multi_finish(zf_lasso_multi* h, double* d_x, double* h_f
     if (d_x) {
       // a run that ended normally keeps its result in the candidate buffer; after a failed
       // line search the result is the previous iterate
-      const bool prev_in_1 = (h->cur >> k) & 1u;
-      const double* prev = (prev_in_1 ? h->buf1 : h->buf0) + (long long)k * h->pitch_c;
-      const double* cand = (prev_in_1 ? h->buf0 : h->buf1) + (long long)k * h->pitch_c;
+      const double* prev = h->Xp + (long long)k * h->pitch_c;
+      const double* cand = h->Xn + (long long)k * h->pitch_c;
       ZF_CUDA(cudaMemcpyAsync(d_x + (long long)k * h->n_cols, r.result_is_prev ? prev : cand,
                               sizeof(double) * (size_t)h->n_cols, cudaMemcpyDeviceToDevice, h->st));
     }
@@ -1089,15 +1131,22 @@ extern "C" int zf_lasso_multi_solve(zf_lasso_multi* h, const zf_options* opt, co
   return zf_lasso_multi_finish(h, d_x, h_fun, h_nit, h_status, h_lr, h_err);
 }
 
+// the closure entries evaluate at caller-supplied points: they go through the y_k array (the
+// array the vector tensor map covers), so they are only legal between solves
+static int load_points(zf_lasso_multi* h, const double* d_X) {
+  if (h->phase != MP_IDLE && h->phase != MP_DONE)
+    return zf::zf_fail(ZF_ERR_INVALID, "closure evaluation in the middle of a solve");
+  ZF_CUDA(cudaMemcpyAsync(h->Y, d_X, sizeof(double) * (size_t)h->n_runs * (size_t)h->n_cols,
+                          cudaMemcpyDeviceToDevice, h->st));
+  return ZF_OK;
+}
+
 extern "C" int zf_lasso_multi_gradient_device(zf_lasso_multi* h, const double* d_X,
                                               double* d_grad, double* d_f) {
   if (!h || !d_X || !d_grad) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
-  if (reinterpret_cast<uintptr_t>(d_X) & 15u)
-    return zf::zf_fail(ZF_ERR_INVALID, "X must be 16-byte aligned");
-  VecPtrs v;
-  for (int k = 0; k < zf::multi::MAX_RUNS; ++k)
-    v.v[k] = (k < h->n_runs) ? d_X + (long long)k * h->n_cols : h->zeros;
-  int rc = gradient_pass(h, v);
+  int rc = load_points(h, d_X);
+  if (rc != ZF_OK) return rc;
+  rc = gradient_pass(h);
   if (rc != ZF_OK) return rc;
   dim3 grid(zf::multi::VEC_BLOCKS, (unsigned)h->n_runs);
   zf::multi::multi_scale_kernel<<<grid, zf::multi::VEC_THREADS, 0, h->st>>>(
@@ -1113,10 +1162,9 @@ extern "C" int zf_lasso_multi_pass_device(zf_lasso_multi* h, const double* d_X, 
   if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
   if (which == 0) {
     if (!d_X) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
-    VecPtrs v;
-    for (int k = 0; k < zf::multi::MAX_RUNS; ++k)
-      v.v[k] = (k < h->n_runs) ? d_X + (long long)k * h->n_cols : h->zeros;
-    return launch_residual(h, v);
+    const int rc = load_points(h, d_X);
+    if (rc != ZF_OK) return rc;
+    return launch_residual(h, 0);
   }
   return launch_atr(h);
 }
