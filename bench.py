@@ -415,7 +415,8 @@ def run_ours(args):
     if rank == 0 or world > 1:
         also = {}
         if not args.no_extras:
-            for name, fn in (("lasso", bench_lasso), ("cameraman", bench_cameraman),
+            for name, fn in (("lasso", bench_lasso), ("lasso_multi", bench_lasso_multi),
+                             ("cameraman", bench_cameraman),
                              ("ab_sweep", bench_sweep), ("batch_scaling", bench_batch_scaling)):
                 try:
                     also[name] = fn(args, dev, rank, world)
@@ -439,6 +440,103 @@ def _measured_peaks():
     return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
+_LASSO_DATA = {}
+
+
+def _lasso_data(rows, cols, dev, rank):
+    """Synthetic dense A (rows x cols fp64, this rank's row shard) and b = A w; built once and
+    shared by the single-run and the multi-run LASSO extras."""
+    import torch
+
+    key = (rows, cols, str(dev), rank)
+    if key not in _LASSO_DATA:
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        A = torch.empty(rows, cols, dtype=torch.float64, device=dev)
+        chunk = max(1, (64 << 20) // (cols * 8))
+        for r0 in range(0, rows, chunk):
+            r1 = min(rows, r0 + chunk)
+            A[r0:r1] = torch.randn(r1 - r0, cols, dtype=torch.float64, device=dev, generator=g)
+        w = torch.zeros(cols, dtype=torch.float64, device=dev)
+        w[:64] = 1.0
+        _LASSO_DATA.clear()
+        _LASSO_DATA[key] = (A, A @ w)
+    return _LASSO_DATA[key]
+
+
+def bench_lasso_multi(args, dev, rank, world):
+    """Many LASSO runs sharing one A (north_star (c): FP64 tensor-core DGEMM when many
+    right-hand sides share A): `--lasso-runs` FISTA runs with different momentum (a, b) over the
+    same A as `also.lasso`.  One gradient of all runs = 2 DGEMM passes over A on the FP64 tensor
+    cores (csrc/zf_lasso_multi.cu).  Reports the roofline of each pass (CUDA events on the
+    launching stream, L2 flushed between launches) and FISTA run-iterations/s."""
+    import ctypes as C
+    import warnings
+
+    import torch
+    import torch.distributed as dist
+
+    from zfista_b200 import _lib
+    from zfista_b200.lasso import DenseLassoMulti
+
+    rows, cols, K = args.lasso_rows, args.lasso_cols, args.lasso_runs
+    A, b = _lasso_data(rows, cols, dev, rank)
+    prob = DenseLassoMulti(A, b, 1e-3, K, scale=1.0 / (2 * rows * world), distributed=world > 1)
+    grid = [AB_GRID[k % len(AB_GRID)] for k in range(K)]
+    X = torch.zeros(K, cols, dtype=torch.float64, device=dev)
+    a_bytes = rows * cols * 8
+    out = {"A": f"{rows}x{cols} fp64 per GPU ({a_bytes / 2**30:.1f} GiB, > L2)", "runs": K}
+    stream = torch.cuda.current_stream()
+    if world == 1:
+        L = _lib.lib()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        peaks = _measured_peaks()
+        prob.gradient(X)
+        torch.cuda.synchronize()
+        # algorithmic bytes of one pass: A once + the K vectors in and out
+        alg = a_bytes + K * (rows + cols) * 8
+        flops = 2.0 * rows * cols * K
+        for which, name in ((0, "pass1_residual"), (1, "pass2_atr")):
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                _lib.check(L.zf_lasso_multi_pass_device(prob._h, C.c_void_p(X.data_ptr()), which))
+                e1.record(stream)
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sum(ts) / len(ts)
+            ach = alg / (ms / 1e3) / 1e9
+            out[name] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"], "ms_per_launch": ms,
+                         "fp64_tensor_tflops": flops / (ms / 1e3) / 1e12,
+                         "peak_source": peaks["source"]}
+        del flush
+        ms2 = out["pass1_residual"]["ms_per_launch"] + out["pass2_atr"]["ms_per_launch"]
+        out["ms_per_gradient_of_all_runs"] = ms2
+        out["ms_per_gradient_per_run"] = ms2 / K
+    iters = args.lasso_iters
+    kw = dict(lr=0.5, decay_rate=1, nesterov=True, tol=0.0, return_device=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        prob.minimize_proximal_gradient_batched(X, grid, max_iter=3, **kw)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = prob.minimize_proximal_gradient_batched(X, grid, max_iter=iters, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    n_it = sum(r.nit for r in res)
+    out["fista_run_iters_per_s"] = n_it / tt.item()
+    out["fista_iters_per_run"] = res[0].nit
+    out["global_rows"] = rows * world
+    return out
+
+
 def bench_lasso(args, dev, rank, world):
     """Dense LASSO gradient pass (the HBM-bound kernels): A rows x cols fp64 per GPU, rows
     sharded over ranks (weak: every rank holds `rows` rows), A^T r all-reduced over NCCL.
@@ -450,15 +548,7 @@ def bench_lasso(args, dev, rank, world):
     from zfista_b200.lasso import DenseLasso
 
     rows, cols = args.lasso_rows, args.lasso_cols
-    g = torch.Generator(device=dev).manual_seed(7 + rank)
-    A = torch.empty(rows, cols, dtype=torch.float64, device=dev)
-    chunk = max(1, (64 << 20) // (cols * 8))
-    for r0 in range(0, rows, chunk):
-        r1 = min(rows, r0 + chunk)
-        A[r0:r1] = torch.randn(r1 - r0, cols, dtype=torch.float64, device=dev, generator=g)
-    w = torch.zeros(cols, dtype=torch.float64, device=dev)
-    w[:64] = 1.0
-    b = A @ w
+    A, b = _lasso_data(rows, cols, dev, rank)
     prob = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows * world),
                       distributed=world > 1)
     x = torch.zeros(cols, dtype=torch.float64, device=dev)
@@ -744,6 +834,8 @@ def main():
     ap.add_argument("--lasso-rows", type=int, default=65536)
     ap.add_argument("--lasso-cols", type=int, default=16384)
     ap.add_argument("--lasso-iters", type=int, default=50)
+    ap.add_argument("--lasso-runs", type=int, default=16,
+                    help="runs sharing A in also.lasso_multi (1..32)")
     ap.add_argument("--cameraman-iters", type=int, default=2000)
     args = ap.parse_args()
     capture_stdout()

@@ -17,6 +17,10 @@ KEYS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "launch__occupancy_limit_warps", "sm__maximum_warps_per_active_cycle_pct",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",

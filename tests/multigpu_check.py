@@ -4,7 +4,9 @@
         --master-port 29511 tests/multigpu_check.py
 
 Checks, with NCCL: (1) the row-sharded DenseLasso gives the single-GPU result and the CPU
-oracle's; (2) starts sharded over ranks (no collective) give the single-GPU batch result."""
+oracle's; (2) starts sharded over ranks (no collective) give the single-GPU batch result;
+(3) the row-sharded shared-A multi-run path (DenseLassoMulti, [A^T R | sum r^2] of every run
+all-reduced) gives, run by run, the oracle's result."""
 import os
 import sys
 import warnings
@@ -21,7 +23,7 @@ def main():
 
     from oracle import zfista_oracle as zo
     from zfista_b200 import distributed as zd
-    from zfista_b200.lasso import DenseLasso
+    from zfista_b200.lasso import DenseLasso, DenseLassoMulti
     import zfista_b200.problems as zp
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -54,6 +56,18 @@ def main():
         dist.all_gather_object(xs, r_sh.x)
         for other in xs[1:]:
             np.testing.assert_array_equal(other, xs[0])
+    grid = [(0.0, 0.25), (0.5, 1 / 16), (0.25, 17 / 128), (0.0, 0.0), (0.75, 0.25)]
+    X0m = np.random.RandomState(5).standard_normal((len(grid), n_cols)) * 0.1
+    msh = DenseLassoMulti(A[lo:hi], b[lo:hi], l1, len(grid), scale=scale, distributed=True)
+    for opts in (dict(nesterov=True), dict(nesterov=True, lr=0.2, decay_rate=1)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = msh.minimize_proximal_gradient_batched(X0m, grid, **opts)
+            for k, ab in enumerate(grid):
+                ref = zo.minimize_proximal_gradient(spec, X0m[k], nesterov_ratio=ab, **opts)
+                assert got[k].nit == ref["nit"], (k, got[k].nit, ref["nit"])
+                np.testing.assert_allclose(got[k].x, ref["x"], rtol=1e-8, atol=1e-9)
+                np.testing.assert_allclose(got[k].fun, ref["fun"], rtol=1e-9)
     prob = zp.JOS1(n_features=20)
     X0 = np.random.RandomState(3).uniform(-2, 4, size=(101, 20))
     full = zd.minimize_proximal_gradient_sharded(prob, X0, nesterov=True, tol_internal=1e-11)

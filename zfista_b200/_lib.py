@@ -61,6 +61,10 @@ EXPORTED_SYMBOLS = [
     "zf_lasso_create", "zf_lasso_destroy", "zf_lasso_solve", "zf_lasso_begin",
     "zf_lasso_grad", "zf_lasso_partial", "zf_lasso_step", "zf_lasso_finish",
     "zf_lasso_gradient_device", "zf_lasso_passes",
+    "zf_lasso_multi_create", "zf_lasso_multi_destroy", "zf_lasso_multi_solve",
+    "zf_lasso_multi_begin", "zf_lasso_multi_grad", "zf_lasso_multi_partial",
+    "zf_lasso_multi_step", "zf_lasso_multi_finish", "zf_lasso_multi_gradient_device",
+    "zf_lasso_multi_pass_device",
     "zf_deblur_create", "zf_deblur_destroy", "zf_deblur_solve_host", "zf_deblur_solve_device",
     "zf_deblur_eval_host",
 ]
