@@ -155,6 +155,12 @@ def test_large_a_properties(gpu):
     ({"ZF_LASSO_TMA": "4"}, (1000, 5002), 1),              # TMA ring, cluster 4, ragged slices
     ({"ZF_LASSO_TMA": "2", "ZF_LASSO_TMA_ROWS": "3"}, (911, 2000), 1),   # 3 rows per stage, ragged
     ({"ZF_LASSO_TMA": "4", "ZF_LASSO_TMA_ROWS": "4"}, (1001, 3000), 1),  # 4 rows per stage
+    ({"ZF_LASSO_RING": "1"}, (903, 2050), 1),              # chunk ring, no cluster, 2 chunks (ragged)
+    ({"ZF_LASSO_RING": "1"}, (700, 10240), 1),             # 5 full chunks per row
+    ({"ZF_LASSO_RING": "2"}, (1001, 5002), 1),             # cluster 2, ragged slices and chunks
+    ({"ZF_LASSO_RING": "2"}, (640, 20000), 1),             # BASELINE configs[3] row width
+    ({"ZF_LASSO_RING": "4"}, (1300, 8200), 1),             # cluster 4: few rows per cluster
+    ({"ZF_LASSO_RING": "2"}, (640, 6), 1),                 # one short chunk, slices of 2 and 1 pairs
 ])
 def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     """Each form of the A^T(A v - b) pass (csrc/zf_lasso.cu) forced through its environment
@@ -164,7 +170,7 @@ def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     from zfista_b200.lasso import DenseLasso
 
     for k in ("ZF_LASSO_FUSED", "ZF_LASSO_CLUSTER", "ZF_LASSO_THREADS", "ZF_LASSO_TMA",
-              "ZF_LASSO_TMA_ROWS"):
+              "ZF_LASSO_TMA_ROWS", "ZF_LASSO_RING"):
         monkeypatch.delenv(k, raising=False)
     rows, cols = shape
     g = torch.Generator(device="cuda").manual_seed(rows + cols)

@@ -758,6 +758,274 @@ lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ 
   cluster.sync();
 }
 
+// ------------------------------------------------------------------------------------
+// Fused one-pass gradient, warp-specialised chunk ring (round-1 final form).
+// The TMA kernels above pay one block reduction + one cluster barrier per stage in the
+// critical path of every thread, and with 4-CTA clusters only 132 of the 148 SMs can be
+// co-resident.  Here the roles are split and nothing waits for a barrier it does not need:
+//   * producer warp: streams each row of the CTA's column slice as 16 KB
+//     chunks (1-D bulk TMA) into a ring of RING_SLOTS chunks -- rows simply follow each other
+//     through the ring, a slot is refilled as soon as the update warps release it, so HBM
+//     requests never pause;
+//   * dot warps (8): keep their part of v in REGISTERS, form the partial dot product of a row
+//     chunk by chunk as the chunks land; one warp per row (round-robin, the others move on)
+//     adds the warp partials and posts the CTA's part to every CTA of the cluster with
+//     st.async (remote shared-memory store that completes on the remote `ready` mbarrier);
+//   * update warps (8): wait for the row's `ready` mbarrier, sum the parts in rank order
+//     (rank 0's part carries -b_i), and apply the rank-1 update q += r * row from the
+//     SAME shared-memory chunks (q in registers), releasing each chunk to the producer.
+// The dot warps run up to a ring ahead of the update warps, so the cluster exchange latency
+// is off the critical path.  Partial-dot slots and `ready` barriers are indexed by row modulo
+// RING_NR >= 2 * (rows a ring can hold) + 2, which is what makes reuse race-free: a peer can
+// post row n + RING_NR only after this CTA's update warps have consumed row n.
+// Cluster size 1 (n_cols <= 10240), 2 (<= 20480: all 148 SMs) or 4.
+// ------------------------------------------------------------------------------------
+constexpr int RING_GROUP = 256;                    // threads of the dot / update group
+constexpr int RING_WARPS = RING_GROUP / 32;
+constexpr int RING_THREADS = 2 * RING_GROUP + 64;  // 8 dot + 8 update warps, producer, exchange warp
+constexpr int RING_CH_PAIRS = 1024;                // double2 per chunk: 2048 columns, 16 KB
+constexpr int RING_SLOTS = 12;
+constexpr int RING_NR = 2 * RING_SLOTS + 2;
+constexpr int RING_U = RING_CH_PAIRS / RING_GROUP; // double2 per thread and chunk
+
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_local(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+// 8-byte store into a (possibly remote) CTA of the cluster that completes on THAT CTA's
+// mbarrier (async proxy, like a TMA write): the reader only needs a CTA-scope wait.  The first
+// version used st.shared::cluster + mbarrier.arrive.release.cluster and a
+// try_wait.acquire.cluster spin on the reader: every spin iteration compiled to CCTL.IVALL (an
+// L1 invalidate) and the kernel ran at 0.43 of the roofline (22 % of the stall samples).
+__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_bar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+      ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+
+// timing experiment (ZF_LASSO_RING_DBG=1): clock64 stamps of rows 64..127 of CTA 0:
+// [0] first chunk issued, [1] dot warps saw the last chunk, [2] part posted, [3] update warps saw
+// `ready`, [4] last chunk released
+__device__ long long zf_ring_dbg[8][64];
+__device__ long long zf_ring_dbg2[8][64];
+#define RING_STAMP(k, row) \
+  do { if (dbg && blockIdx.x == 0 && (row) >= 64 && (row) < 128) zf_ring_dbg[k][(row) - 64] = clock64(); } while (0)
+
+template <int NCH>
+__global__ void __maxnreg__(96)
+lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__ b,
+                        const double* __restrict__ v, long long n_rows, long long n_cols,
+                        long long rows_per_cluster, long long pairs_per_cta,
+                        double* __restrict__ gpart, double* __restrict__ sq_part, int xmode,
+                        int dbg) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+  const long long cid = blockIdx.x / csize;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ double xslot[RING_NR][4];                 // [row mod NR][cluster rank]
+  __shared__ double dpart[RING_NR][RING_WARPS];        // [row mod NR][dot warp]
+  __shared__ __align__(8) unsigned long long full[RING_SLOTS];
+  __shared__ __align__(8) unsigned long long empty[RING_SLOTS];
+  __shared__ __align__(8) unsigned long long ready[RING_NR];   // the row's residual parts are here
+  __shared__ __align__(8) unsigned long long dbar[RING_NR];    // the row's 8 warp partials are here
+  double2* ring = reinterpret_cast<double2*>(dyn);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n2 = n_cols >> 1;
+  const long long p_lo = (long long)crank * pairs_per_cta;
+  const long long p_hi = (p_lo + pairs_per_cta < n2) ? p_lo + pairs_per_cta : n2;
+  const int my_pairs = (int)(p_hi > p_lo ? p_hi - p_lo : 0);
+  const int nch = (my_pairs + RING_CH_PAIRS - 1) / RING_CH_PAIRS;      // <= NCH
+  if (tid == 0) {
+    for (int s = 0; s < RING_SLOTS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], RING_WARPS);
+    }
+    for (int s = 0; s < RING_NR; ++s) {
+      mbar_init(&ready[s], xmode == 1 ? (unsigned)csize : 1u);
+      mbar_init(&dbar[s], RING_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster.sync();                                      // every CTA's barriers exist
+  const long long i0 = cid * rows_per_cluster;
+  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
+  const long long my_rows = i1 > i0 ? i1 - i0 : 0;
+
+  if (warp == 2 * RING_WARPS) {
+    // ---------------------------------------------------------------- producer
+    // A dedicated warp: one 16 KB bulk copy occupies the issuing thread for ~600 cycles (measured
+    // with clock64 stamps when a lane of an update warp issued them between its own work: the
+    // update warps, and with them the whole ring, ran at the producer's pace -- 0.55 of the
+    // roofline).  Five warps on one scheduler limit the kernel to 96 registers per thread.
+    if (lane == 0) {
+      int psl = 0, pc = 0;
+      unsigned pph = 1;                                  // parity of the slot's previous release
+      long long prow = 0;
+      const long long total = my_rows * nch;
+      for (long long jp = 0; jp < total; ++jp) {
+        if (jp >= RING_SLOTS) mbar_wait(&empty[psl], pph);
+        const int cp = (my_pairs - pc * RING_CH_PAIRS < RING_CH_PAIRS) ? my_pairs - pc * RING_CH_PAIRS
+                                                                       : RING_CH_PAIRS;
+        if (pc == 0) RING_STAMP(0, prow);
+        mbar_expect_tx(&full[psl], (unsigned)cp * 16u);
+        tma_load_1d(ring + (size_t)psl * RING_CH_PAIRS,
+                    A + (i0 + prow) * n_cols + 2 * (p_lo + (long long)pc * RING_CH_PAIRS),
+                    (unsigned)cp * 16u, &full[psl]);
+        if (++pc == nch) { pc = 0; ++prow; }
+        if (++psl == RING_SLOTS) { psl = 0; pph ^= 1u; }
+      }
+    }
+  } else if (warp < RING_WARPS) {
+    // ---------------------------------------------------------------- dot warps
+    double2 vreg[NCH][RING_U];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int u = 0; u < RING_U; ++u) {
+        const int p = c * RING_CH_PAIRS + u * RING_GROUP + tid;
+        vreg[c][u] = (p < my_pairs) ? __ldg(reinterpret_cast<const double2*>(v) + p_lo + p)
+                                    : make_double2(0.0, 0.0);
+      }
+    const unsigned xs_base = smem_u32(&xslot[0][0]);
+    const unsigned rd_base = smem_u32(&ready[0]);
+    int s = 0, sl = 0;
+    unsigned ph = 0;                          // phase parities of ring slot / row slot
+    for (long long n = 0; n < my_rows; ++n) {
+      double accu[RING_U];                  // independent chains: a warp handles every chunk, its
+#pragma unroll                              // per-chunk latency is what bounds the dot warps
+      for (int u = 0; u < RING_U; ++u) accu[u] = 0.0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c < nch) {
+          mbar_wait(&full[s], ph);
+          const double2* ch = ring + (size_t)s * RING_CH_PAIRS;
+          const int cp = my_pairs - c * RING_CH_PAIRS;           // valid pairs (may exceed a chunk)
+#pragma unroll
+          for (int u = 0; u < RING_U; ++u) {
+            const int p = u * RING_GROUP + tid;
+            if (p < cp) {                                        // stale shared memory past the copy
+              const double2 x = ch[p];
+              accu[u] += x.x * vreg[c][u].x + x.y * vreg[c][u].y;
+            }
+          }
+          if (++s == RING_SLOTS) { s = 0; ph ^= 1u; }
+        }
+      }
+      if (tid == 0) RING_STAMP(1, n);
+      if (dbg && lane == 0 && blockIdx.x == 0 && n >= 64 && n < 128) zf_ring_dbg2[warp][n - 64] = clock64();
+      double acc = (accu[0] + accu[1]) + (accu[2] + accu[3]);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        dpart[sl][warp] = acc;
+        mbar_arrive_local(&dbar[sl]);
+      }
+      if (++sl == RING_NR) { sl = 0; }
+    }
+  } else if (warp == 2 * RING_WARPS + 1) {
+    // ---------------------------------------------------------------- exchange warp
+    // adds the 8 warp partials of a row and posts the CTA's part to every CTA of the cluster.
+    // (When the dot warps took turns at this, each turn cost a warp ~3500 cycles of waiting for
+    // the other seven, and it needed seven rows to catch up: the slowest dot warp was always
+    // ~3000 cycles behind, and so was every row's residual.)
+    const unsigned xs_base = smem_u32(&xslot[0][0]);
+    const unsigned rd_base = smem_u32(&ready[0]);
+    int sl = 0;
+    unsigned rph = 0;
+    for (long long n = 0; n < my_rows; ++n) {
+      double bi = 0.0;
+      if (crank == 0) bi = __ldg(b + i0 + n);          // rank 0 folds -b_i into its part
+      if (lane == 0 && xmode != 1) mbar_expect_tx(&ready[sl], 8u * (unsigned)csize);
+      mbar_wait(&dbar[sl], rph);
+      if (lane == 0) RING_STAMP(6, n);
+      if (lane < csize) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < RING_WARPS; ++w) t += dpart[sl][w];
+        t -= bi;
+        const unsigned ra = mapa_u32(xs_base + (unsigned)((sl * 4 + crank) * 8), (unsigned)lane);
+        const unsigned rb = mapa_u32(rd_base + (unsigned)(sl * 8), (unsigned)lane);
+        if (xmode == 1) {
+          asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(t) : "memory");
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rb)
+                       : "memory");
+        } else {
+          st_async_f64(ra, t, rb);
+        }
+        if (lane == 0) RING_STAMP(2, n);
+      }
+      if (++sl == RING_NR) { sl = 0; rph ^= 1u; }
+    }
+  } else {
+    // ---------------------------------------------------------------- update warps
+    const int ut = tid - RING_GROUP;
+    double2 q[NCH][RING_U];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int u = 0; u < RING_U; ++u) q[c][u] = make_double2(0.0, 0.0);
+    double ss = 0.0;
+    int s = 0, sl = 0;
+    unsigned ph = 0, rph = 0;
+    for (long long n = 0; n < my_rows; ++n) {
+      double r = 0.0;
+      {
+        mbar_wait(&ready[sl], rph);
+        if (ut == 0) RING_STAMP(3, n);
+        if (xmode == 1) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        for (int c = 0; c < csize; ++c) r += xslot[sl][c];
+      }
+      ss += r * r;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c < nch) {
+          mbar_wait(&full[s], ph);                               // complete long ago: visibility
+          const double2* ch = ring + (size_t)s * RING_CH_PAIRS;
+          const int cp = my_pairs - c * RING_CH_PAIRS;
+#pragma unroll
+          for (int u = 0; u < RING_U; ++u) {
+            const int p = u * RING_GROUP + ut;
+            if (p < cp) {
+              const double2 x = ch[p];
+              q[c][u].x += r * x.x;
+              q[c][u].y += r * x.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(&empty[s]);
+          if (ut == 0 && c == nch - 1) RING_STAMP(4, n);
+          if (++s == RING_SLOTS) { s = 0; ph ^= 1u; }
+        }
+      }
+      if (++sl == RING_NR) { sl = 0; rph ^= 1u; }
+    }
+    double2* out = reinterpret_cast<double2*>(gpart + cid * n_cols) + p_lo;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int u = 0; u < RING_U; ++u) {
+        const int p = c * RING_CH_PAIRS + u * RING_GROUP + ut;
+        if (p < my_pairs) out[p] = q[c][u];
+      }
+    if (ut == 0 && crank == 0) sq_part[cid] = ss;
+  }
+  cluster.sync();          // no CTA leaves while a peer may still post into its shared memory
+}
+
 // partial[j] = sum_rb gpart[rb][j] (fixed order);  partial[n_cols] = sum_blk sq_part[blk]
 __global__ void __launch_bounds__(256)
 lasso_collect_kernel(const double* __restrict__ gpart, int n_rowblocks,
@@ -905,6 +1173,7 @@ struct zf_lasso {
   long long fused_rows_per_cta = 0;
   int fused_cluster = 1;              // CTAs per cluster (1: single-CTA kernel)
   int fused_threads = 512;            // threads per CTA of the cluster form
+  bool fused_ring = false;            // warp-specialised chunk ring (lasso_fused_ring_kernel)
   bool fused_tma = false;             // TMA / shared-memory-resident form
   int tma_rows = 2;                   // rows per TMA stage (one cluster barrier per stage)
   long long fused_pairs_per_cta = 0;  // column pairs per CTA (cluster form)
@@ -1044,9 +1313,70 @@ int launch_fused_tma(zf_lasso* h, const double* v, bool query_only, int* max_clu
   }
 }
 
+template <int NCH>
+int launch_fused_ring_t(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+  auto k = zf::lasso_fused_ring_kernel<NCH>;
+  const size_t smem = (size_t)zf::RING_SLOTS * zf::RING_CH_PAIRS * 16;
+  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)h->fused_ctas);
+  cfg.blockDim = dim3(zf::RING_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)h->fused_cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (query_only) {
+    ZF_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, k, &cfg));
+    return ZF_OK;
+  }
+  static const int xmode = getenv("ZF_LASSO_RING_X") ? atoi(getenv("ZF_LASSO_RING_X")) : 0;
+  static const int dbg = getenv("ZF_LASSO_RING_DBG") ? 1 : 0;
+  ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, h->fused_rows_per_cta,
+                             h->fused_pairs_per_cta, h->gpart, h->sq_part, xmode, dbg));
+  zf::zf_count_launch();
+  if (dbg) {
+    long long st[8][64], st2[8][64];
+    ZF_CUDA(cudaStreamSynchronize(h->st));
+    ZF_CUDA(cudaMemcpyFromSymbol(st, zf::zf_ring_dbg, sizeof(st)));
+    ZF_CUDA(cudaMemcpyFromSymbol(st2, zf::zf_ring_dbg2, sizeof(st2)));
+    for (int r = 16; r < 24; ++r) {
+      fprintf(stderr, "[ring dbg2] row %3d dot done per warp:", 64 + r);
+      for (int w = 0; w < 8; ++w) fprintf(stderr, " %6lld", st2[w][r] - st[0][r]);
+      fprintf(stderr, "\n");
+    }
+    for (int r = 0; r < 64; r += 4)
+      fprintf(stderr, "[ring dbg] row %3d: issue 0  warp0 dot done %6lld  tail warp summed %6lld  all warps in %6lld  posted %6lld  ready %6lld  released %6lld | next issue %6lld\n",
+              64 + r, st[1][r] - st[0][r], st[5][r] - st[0][r], st[6][r] - st[0][r],
+              st[2][r] - st[0][r], st[3][r] - st[0][r], st[4][r] - st[0][r],
+              st[0][r + 1] - st[0][r]);
+  }
+  return ZF_OK;
+}
+
+int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+  switch (h->fused_pairs) {          // chunks per row slice
+    case 1: return launch_fused_ring_t<1>(h, v, query_only, max_clusters);
+    case 2: return launch_fused_ring_t<2>(h, v, query_only, max_clusters);
+    case 3: return launch_fused_ring_t<3>(h, v, query_only, max_clusters);
+    case 4: return launch_fused_ring_t<4>(h, v, query_only, max_clusters);
+    default: return launch_fused_ring_t<5>(h, v, query_only, max_clusters);
+  }
+}
+
 // gradient pass at v: leaves the A^T r partials in gpart (n_gpart_rows x n_cols) and the
 // sum r^2 partials in sq_part (n_sq), by the fused kernel when it applies
 int launch_gradient_pass(zf_lasso* h, const double* v, int* n_gpart_rows, int* n_sq) {
+  if (h->fused_pairs > 0 && h->fused_ring) {
+    const int rc = launch_fused_ring(h, v, false, nullptr);
+    *n_gpart_rows = h->fused_ctas / h->fused_cluster;
+    *n_sq = h->fused_ctas / h->fused_cluster;
+    return rc;
+  }
   if (h->fused_pairs > 0 && h->fused_tma) {
     const int rc = launch_fused_tma(h, v, false, nullptr);
     *n_gpart_rows = h->fused_ctas / h->fused_cluster;
@@ -1255,7 +1585,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   // 0.77 at 16384, 0.70 at 12000, 0.65 at 20000; two-pass kernels 0.53 everywhere.
   // Environment overrides for experiments:
   //   ZF_LASSO_FUSED=0 (two-pass), ZF_LASSO_CLUSTER=2|4, ZF_LASSO_THREADS=512|1024,
-  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4.
+  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4, ZF_LASSO_RING=1|2|4.
   h->gpart_rows = (size_t)h->n_rowblocks;
   size_t sq_rows = (size_t)h->res_blocks;
   {
@@ -1301,6 +1631,25 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       finish_cluster_grid(c, n_clusters, h->tma_rows);
       return true;
     };
+    auto try_ring = [&](int c) -> bool {
+      if (c < 1 || c > 4 || !big_enough || n2 < c) return false;
+      const long long ppc = (n2 + c - 1) / c;
+      const long long nchunks = (ppc + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
+      if (nchunks > 5 || (size_t)zf::RING_SLOTS * zf::RING_CH_PAIRS * 16 + 4096 > (size_t)max_smem)
+        return false;
+      h->fused_ring = true;
+      h->fused_cluster = c;
+      h->fused_pairs_per_cta = ppc;
+      h->fused_pairs = (int)nchunks;
+      int n_clusters = h->n_sm / c;
+      h->fused_ctas = n_clusters * c;
+      h->fused_rows_per_cta = 1;
+      int active = 0;
+      if (launch_fused_ring(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
+        n_clusters = active;
+      finish_cluster_grid(c, n_clusters, 1);
+      return true;
+    };
     auto try_cluster = [&](int c) -> bool {
       if (!(c == 2 || c == 4) || !big_enough) return false;
       const long long ppc = (n2 + c - 1) / c;
@@ -1328,8 +1677,11 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       if ((size_t)h->fused_ctas > sq_rows) sq_rows = (size_t)h->fused_ctas;
       return true;
     };
+    const char* env_ring = getenv("ZF_LASSO_RING");
     if (off) {
       // two-pass kernels
+    } else if (env_ring) {
+      try_ring(atoi(env_ring));
     } else if (env_tma) {
       try_tma(atoi(env_tma));
     } else if (env_cluster) {
