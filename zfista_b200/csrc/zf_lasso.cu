@@ -778,15 +778,20 @@ lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ 
 // is off the critical path.  Partial-dot slots and `ready` barriers are indexed by row modulo
 // RING_NR >= 2 * (rows a ring can hold) + 2, which is what makes reuse race-free: a peer can
 // post row n + RING_NR only after this CTA's update warps have consumed row n.
-// Cluster size 1 (n_cols <= 10240), 2 (<= 20480: all 148 SMs) or 4.
+// Cluster size 1, 2, 4 or 8: a row slice of at most 4 chunks (8192 columns) per CTA keeps three
+// rows in the ring; with 5 chunks (2.4 rows) the kernel drops to 0.64.
 // ------------------------------------------------------------------------------------
 constexpr int RING_GROUP = 256;                    // threads of the dot / update group
 constexpr int RING_WARPS = RING_GROUP / 32;
 constexpr int RING_THREADS = 2 * RING_GROUP + 64;  // 8 dot + 8 update warps, producer, exchange warp
+// (five warps on a scheduler cap the kernel at 96 registers per thread.  Moving registers from
+// the two service warps to the others with setmaxnreg -- 20 warps, 104 / 120 registers for the
+// dot / update warps -- was measured and is not used: 0.93 instead of 0.98 at 16384 columns.)
 constexpr int RING_CH_PAIRS = 1024;                // double2 per chunk: 2048 columns, 16 KB
 constexpr int RING_SLOTS = 12;
 constexpr int RING_NR = 2 * RING_SLOTS + 2;
 constexpr int RING_U = RING_CH_PAIRS / RING_GROUP; // double2 per thread and chunk
+constexpr int RING_MAX_CLUSTER = 8;
 
 __device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
   unsigned r;
@@ -837,7 +842,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
   const int csize = (int)cluster.num_blocks();
   const long long cid = blockIdx.x / csize;
   extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ double xslot[RING_NR][4];                 // [row mod NR][cluster rank]
+  __shared__ double xslot[RING_NR][RING_MAX_CLUSTER];  // [row mod NR][cluster rank]
   __shared__ double dpart[RING_NR][RING_WARPS];        // [row mod NR][dot warp]
   __shared__ __align__(8) unsigned long long full[RING_SLOTS];
   __shared__ __align__(8) unsigned long long empty[RING_SLOTS];
@@ -901,10 +906,8 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
         vreg[c][u] = (p < my_pairs) ? __ldg(reinterpret_cast<const double2*>(v) + p_lo + p)
                                     : make_double2(0.0, 0.0);
       }
-    const unsigned xs_base = smem_u32(&xslot[0][0]);
-    const unsigned rd_base = smem_u32(&ready[0]);
     int s = 0, sl = 0;
-    unsigned ph = 0;                          // phase parities of ring slot / row slot
+    unsigned ph = 0;                          // phase parity of the ring slot
     for (long long n = 0; n < my_rows; ++n) {
       double accu[RING_U];                  // independent chains: a warp handles every chunk, its
 #pragma unroll                              // per-chunk latency is what bounds the dot warps
@@ -957,7 +960,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
 #pragma unroll
         for (int w = 0; w < RING_WARPS; ++w) t += dpart[sl][w];
         t -= bi;
-        const unsigned ra = mapa_u32(xs_base + (unsigned)((sl * 4 + crank) * 8), (unsigned)lane);
+        const unsigned ra = mapa_u32(xs_base + (unsigned)((sl * RING_MAX_CLUSTER + crank) * 8), (unsigned)lane);
         const unsigned rb = mapa_u32(rd_base + (unsigned)(sl * 8), (unsigned)lane);
         if (xmode == 1) {
           asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(t) : "memory");
@@ -970,7 +973,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
       }
       if (++sl == RING_NR) { sl = 0; rph ^= 1u; }
     }
-  } else {
+  } else if (warp < 2 * RING_WARPS) {
     // ---------------------------------------------------------------- update warps
     const int ut = tid - RING_GROUP;
     double2 q[NCH][RING_U];
@@ -1579,13 +1582,16 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   if (vb > zf::VEC_MAX_BLOCKS) vb = zf::VEC_MAX_BLOCKS;
   h->vec_blocks = (int)vb;
   // ---- which kernels compute A^T(A v - b) for this shape.  Measured on B200 (DESIGN.md 3.3,
-  // fraction of the one-pass HBM bound): single-CTA fused 0.83 at 4096 columns, 0.52 at 6000;
+  // fraction of the one-pass HBM bound).  Warp-specialised chunk ring: 0.89 at 4096 columns,
+  // 0.97-0.99 at 6000-8192 (no cluster), 0.95-0.98 at 12000-16384 (cluster 2), 0.82 at 30000
+  // (cluster 4: 132 of 148 SMs).  The older forms, kept behind the overrides and as fall-backs:
+  // single-CTA fused 0.83 at 4096 columns, 0.52 at 6000;
   // TMA / shared-memory-resident form 0.72 at 6000 and 0.76 at 8192 (cluster 2, 4 / 3 rows per
   // stage), 0.67-0.72 at 20000 (cluster 4) but 0.69 at 16384; 2-CTA cluster with L2 re-read
   // 0.77 at 16384, 0.70 at 12000, 0.65 at 20000; two-pass kernels 0.53 everywhere.
   // Environment overrides for experiments:
   //   ZF_LASSO_FUSED=0 (two-pass), ZF_LASSO_CLUSTER=2|4, ZF_LASSO_THREADS=512|1024,
-  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4, ZF_LASSO_RING=1|2|4.
+  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4, ZF_LASSO_RING=1|2|4|8.
   h->gpart_rows = (size_t)h->n_rowblocks;
   size_t sq_rows = (size_t)h->res_blocks;
   {
@@ -1632,7 +1638,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       return true;
     };
     auto try_ring = [&](int c) -> bool {
-      if (c < 1 || c > 4 || !big_enough || n2 < c) return false;
+      if (!(c == 1 || c == 2 || c == 4 || c == 8) || !big_enough || n2 < c) return false;
       const long long ppc = (n2 + c - 1) / c;
       const long long nchunks = (ppc + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
       if (nchunks > 5 || (size_t)zf::RING_SLOTS * zf::RING_CH_PAIRS * 16 + 4096 > (size_t)max_smem)
@@ -1688,14 +1694,16 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       try_cluster(atoi(env_cluster));
     } else if (env_fused) {
       try_single();
-    } else if (n_cols <= 4608) {
+    } else if (n_cols < 4096) {
       try_single();
-    } else if (n_cols <= 8192) {
-      if (!try_tma(2)) try_single();
-    } else if (n_cols <= 16384) {
-      try_cluster(2);
     } else {
-      if (!try_tma(4)) try_cluster(2);
+      // chunk ring: the smallest cluster whose row slice is at most 4 chunks (8192 columns)
+      const int c = n_cols <= 8192 ? 1 : n_cols <= 16384 ? 2 : n_cols <= 32768 ? 4 : 8;
+      if (!try_ring(c) && !try_ring(8)) {
+        if (n_cols <= 8192) { if (!try_tma(2)) try_single(); }
+        else if (n_cols <= 16384) try_cluster(2);
+        else if (!try_tma(4)) try_cluster(2);
+      }
     }
   }
   cudaError_t e = cudaSuccess;
