@@ -581,7 +581,7 @@ def bench_lasso(args, dev, rank, world):
         if os.path.exists(tp):        # ncu-measured DRAM bytes / |A| per kernel form
             with open(tp) as fh:
                 tj = json.load(fh)
-            keys = (["lasso_fused_cluster_kernel"] if passes == 1
+            keys = (["lasso_fused_ring_kernel"] if passes == 1
                     else ["lasso_residual_kernel", "lasso_atr_kernel"])
             traffic = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"])
                           / tj[k]["algorithmic_bytes"] for k in keys) * a_bytes
