@@ -417,7 +417,8 @@ def run_ours(args):
         if not args.no_extras:
             for name, fn in (("lasso", bench_lasso), ("lasso_multi", bench_lasso_multi),
                              ("cameraman", bench_cameraman),
-                             ("ab_sweep", bench_sweep), ("batch_scaling", bench_batch_scaling)):
+                             ("ab_sweep", bench_sweep), ("batch_scaling", bench_batch_scaling),
+                             ("lasso_configs3", bench_lasso_configs3)):
                 try:
                     also[name] = fn(args, dev, rank, world)
                 except Exception as e:  # extras must never lose the headline line
@@ -534,6 +535,74 @@ def bench_lasso_multi(args, dev, rank, world):
     out["fista_run_iters_per_s"] = n_it / tt.item()
     out["fista_iters_per_run"] = res[0].nit
     out["global_rows"] = rows * world
+    return out
+
+
+def bench_lasso_configs3(args, dev, rank, world):
+    """BASELINE configs[3]: dense LASSO A 200000 x 20000 fp64 (29.8 GiB), rows sharded over the
+    ranks (strong scaling: 200000 / world rows per GPU), A^T r all-reduced over NCCL.  Single-run
+    path (one-pass fused gradient) and 16 runs sharing A (two FP64 tensor-core passes)."""
+    import warnings
+
+    import torch
+    import torch.distributed as dist
+
+    from zfista_b200.lasso import DenseLasso, DenseLassoMulti
+
+    _LASSO_DATA.clear()                      # free the 8 GiB matrix of the other extras
+    torch.cuda.empty_cache()
+    rows_total, cols, K = 200000, 20000, 16
+    rows = rows_total // world
+    free, _ = torch.cuda.mem_get_info()
+    if free < rows * cols * 8 * 1.15:
+        return {"skipped": f"needs {rows * cols * 8 / 2**30:.1f} GiB of free HBM"}
+    A, b = _lasso_data(rows, cols, dev, rank)
+    peaks = _measured_peaks()
+    a_bytes = rows * cols * 8
+    out = {"A": f"{rows_total}x{cols} fp64, {rows} rows per GPU ({a_bytes / 2**30:.1f} GiB per GPU)"}
+    x = torch.zeros(cols, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    single = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows_total), distributed=world > 1)
+    multi = DenseLassoMulti(A, b, 1e-3, K, scale=1.0 / (2 * rows_total), distributed=world > 1)
+    if world == 1:
+        X = torch.zeros(K, cols, dtype=torch.float64, device=dev)
+        for name, fn, n_pass in (("single_run_gradient", lambda: single.gradient(x), 1),
+                                 ("multi_run_gradient", lambda: multi.gradient(X), 2)):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            ach = n_pass * a_bytes / (ms / 1e3) / 1e9
+            out[name] = {"bound": "hbm", "ms": ms, "algorithmic_passes_over_A": n_pass,
+                         "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"]}
+        out["multi_run_gradient"]["runs"] = K
+        out["multi_run_gradient"]["ms_per_run"] = out["multi_run_gradient"]["ms"] / K
+    kw = dict(lr=0.5, decay_rate=1, nesterov=True, tol=0.0, return_device=True)
+    grid = [AB_GRID[k % len(AB_GRID)] for k in range(K)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, run in (("single", lambda n: [single.minimize_proximal_gradient(x, max_iter=n, **kw)]),
+                          ("multi", lambda n: multi.minimize_proximal_gradient_batched(x, grid, max_iter=n, **kw))):
+            run(2)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = run(10)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            out[f"{name}_fista_run_iters_per_s"] = sum(r.nit for r in res) / tt.item()
+    del single, multi
+    _LASSO_DATA.clear()
+    torch.cuda.empty_cache()
     return out
 
 

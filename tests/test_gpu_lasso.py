@@ -221,3 +221,53 @@ def test_reference_lasso_zero_and_return_all(gpu):
                                          return_all=True)
         assert "allvecs" in res and "allerrs" in res and "allfuns" in res
         assert len(res.allerrs) == res.nit and len(res.allfuns) == res.nit + 1
+
+
+def test_baseline_configs3_full_size(gpu):
+    """BASELINE configs[3] at its full size on one GPU: A 200000 x 20000 fp64 (29.8 GiB).  No CPU
+    pass over A is possible in test time, so the checks are (a) an independent fp64 evaluation
+    of the same gradient / f by cuBLAS (torch mv) on the same device buffer, (b) affinity in x,
+    (c) the single-run chunk-ring kernel (4-CTA clusters at this width) against the multi-run
+    tensor-core passes, (d) a few FISTA iterations that must agree between the two paths."""
+    import torch
+    from zfista_b200.lasso import DenseLasso, DenseLassoMulti
+
+    n_rows, n_cols = 200000, 20000
+    free, _ = torch.cuda.mem_get_info()
+    if free < (n_rows * n_cols * 8) * 1.15:
+        pytest.skip("needs ~35 GB of free HBM")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.empty(n_rows, n_cols, dtype=torch.float64, device="cuda")
+    for r0 in range(0, n_rows, 4000):
+        A[r0:r0 + 4000] = torch.randn(4000, n_cols, dtype=torch.float64, device="cuda", generator=g)
+    w = torch.zeros(n_cols, dtype=torch.float64, device="cuda")
+    w[:50] = 2.0
+    b = A @ w + 0.1 * torch.randn(n_rows, dtype=torch.float64, device="cuda", generator=g)
+    scale = 1 / (2 * n_rows)
+    prob = DenseLasso(A, b, l1_ratio=1e-3, scale=scale)
+    assert prob.hbm_passes_per_gradient() == 1
+    x1 = torch.randn(n_cols, dtype=torch.float64, device="cuda", generator=g)
+    x2 = torch.randn(n_cols, dtype=torch.float64, device="cuda", generator=g)
+    zero = torch.zeros_like(x1)
+    (j1, f1), (j2, _), (j0, _), (j12, _) = (prob.gradient(v) for v in (x1, x2, zero, x1 + x2))
+    r1 = torch.mv(A, x1) - b
+    torch.testing.assert_close(j1, torch.mv(A.T, r1) * (2 * scale), rtol=1e-11, atol=1e-11)
+    torch.testing.assert_close(f1[0], (r1 @ r1) * scale, rtol=1e-12, atol=0)
+    torch.testing.assert_close(j12 + j0, j1 + j2, rtol=1e-11, atol=1e-11)
+    multi = DenseLassoMulti(A, b, 1e-3, 3, scale=scale)
+    G, F = multi.gradient(torch.stack([x1, x2, zero]))
+    torch.testing.assert_close(G[0], j1, rtol=1e-11, atol=1e-11)
+    torch.testing.assert_close(G[1], j2, rtol=1e-11, atol=1e-11)
+    torch.testing.assert_close(G[2], j0, rtol=1e-11, atol=1e-11)
+    torch.testing.assert_close(F[0], f1[0], rtol=1e-12, atol=0)
+    opts = dict(lr=0.4, decay_rate=1, nesterov=True, max_iter=6, tol=0.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = prob.minimize_proximal_gradient(zero, **opts)
+        m = multi.minimize_proximal_gradient_batched(zero, [(0, 0.25), (0.5, 1 / 16), (0, 0.25)], **opts)
+    assert a.nit == m[0].nit == 6
+    np.testing.assert_allclose(m[0].x, a.x, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(m[2].x, m[0].x, rtol=0, atol=0)      # same run twice: bit-identical
+    np.testing.assert_allclose(m[0].fun, a.fun, rtol=1e-11)
+    del A
+    torch.cuda.empty_cache()
