@@ -835,7 +835,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
                         const double* __restrict__ v, long long n_rows, long long n_cols,
                         long long rows_per_cluster, long long pairs_per_cta,
                         double* __restrict__ gpart, double* __restrict__ sq_part, int xmode,
-                        int dbg) {
+                        int dbg, long long row_begin, long long row_end, int part_base) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -867,8 +867,9 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cluster.sync();                                      // every CTA's barriers exist
-  const long long i0 = cid * rows_per_cluster;
-  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
+  // this launch covers rows [row_begin, row_end) and writes partial rows part_base + cid
+  const long long i0 = row_begin + cid * rows_per_cluster;
+  const long long i1 = (i0 + rows_per_cluster < row_end) ? i0 + rows_per_cluster : row_end;
   const long long my_rows = i1 > i0 ? i1 - i0 : 0;
 
   if (warp == 2 * RING_WARPS) {
@@ -1016,7 +1017,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
       }
       if (++sl == RING_NR) { sl = 0; rph ^= 1u; }
     }
-    double2* out = reinterpret_cast<double2*>(gpart + cid * n_cols) + p_lo;
+    double2* out = reinterpret_cast<double2*>(gpart + (part_base + cid) * n_cols) + p_lo;
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -1024,7 +1025,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
         const int p = c * RING_CH_PAIRS + u * RING_GROUP + ut;
         if (p < my_pairs) out[p] = q[c][u];
       }
-    if (ut == 0 && crank == 0) sq_part[cid] = ss;
+    if (ut == 0 && crank == 0) sq_part[part_base + cid] = ss;
   }
   cluster.sync();          // no CTA leaves while a peer may still post into its shared memory
 }
@@ -1177,6 +1178,12 @@ struct zf_lasso {
   int fused_cluster = 1;              // CTAs per cluster (1: single-CTA kernel)
   int fused_threads = 512;            // threads per CTA of the cluster form
   bool fused_ring = false;            // warp-specialised chunk ring (lasso_fused_ring_kernel)
+  // second, concurrent ring launch on the SMs the first one cannot use (4-CTA clusters fit on
+  // 132 of 148 SMs): 2-CTA clusters over the last rows, on its own stream
+  int ring2_ctas = 0, ring2_nch = 0, ring1_clusters = 0;
+  long long ring2_row0 = 0, ring2_rows_per_cluster = 0, ring2_pairs_per_cta = 0;
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fused_tma = false;             // TMA / shared-memory-resident form
   int tma_rows = 2;                   // rows per TMA stage (one cluster barrier per stage)
   long long fused_pairs_per_cta = 0;  // column pairs per CTA (cluster form)
@@ -1316,19 +1323,27 @@ int launch_fused_tma(zf_lasso* h, const double* v, bool query_only, int* max_clu
   }
 }
 
+struct RingLaunch {
+  int ctas, cluster;
+  long long rows_per_cluster, pairs_per_cta, row_begin, row_end;
+  int part_base;
+  cudaStream_t stream;
+};
+
 template <int NCH>
-int launch_fused_ring_t(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+int launch_fused_ring_t(zf_lasso* h, const double* v, const RingLaunch& L, bool query_only,
+                        int* max_clusters) {
   auto k = zf::lasso_fused_ring_kernel<NCH>;
   const size_t smem = (size_t)zf::RING_SLOTS * zf::RING_CH_PAIRS * 16;
   ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)h->fused_ctas);
+  cfg.gridDim = dim3((unsigned)L.ctas);
   cfg.blockDim = dim3(zf::RING_THREADS);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->st;
+  cfg.stream = L.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)h->fused_cluster;
+  attr[0].val.clusterDim.x = (unsigned)L.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -1339,12 +1354,13 @@ int launch_fused_ring_t(zf_lasso* h, const double* v, bool query_only, int* max_
   }
   static const int xmode = getenv("ZF_LASSO_RING_X") ? atoi(getenv("ZF_LASSO_RING_X")) : 0;
   static const int dbg = getenv("ZF_LASSO_RING_DBG") ? 1 : 0;
-  ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, h->fused_rows_per_cta,
-                             h->fused_pairs_per_cta, h->gpart, h->sq_part, xmode, dbg));
+  ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, L.rows_per_cluster,
+                             L.pairs_per_cta, h->gpart, h->sq_part, xmode, dbg, L.row_begin,
+                             L.row_end, L.part_base));
   zf::zf_count_launch();
-  if (dbg) {
+  if (dbg && L.part_base == 0) {
     long long st[8][64], st2[8][64];
-    ZF_CUDA(cudaStreamSynchronize(h->st));
+    ZF_CUDA(cudaStreamSynchronize(L.stream));
     ZF_CUDA(cudaMemcpyFromSymbol(st, zf::zf_ring_dbg, sizeof(st)));
     ZF_CUDA(cudaMemcpyFromSymbol(st2, zf::zf_ring_dbg2, sizeof(st2)));
     for (int r = 16; r < 24; ++r) {
@@ -1353,22 +1369,42 @@ int launch_fused_ring_t(zf_lasso* h, const double* v, bool query_only, int* max_
       fprintf(stderr, "\n");
     }
     for (int r = 0; r < 64; r += 4)
-      fprintf(stderr, "[ring dbg] row %3d: issue 0  warp0 dot done %6lld  tail warp summed %6lld  all warps in %6lld  posted %6lld  ready %6lld  released %6lld | next issue %6lld\n",
-              64 + r, st[1][r] - st[0][r], st[5][r] - st[0][r], st[6][r] - st[0][r],
-              st[2][r] - st[0][r], st[3][r] - st[0][r], st[4][r] - st[0][r],
-              st[0][r + 1] - st[0][r]);
+      fprintf(stderr, "[ring dbg] row %3d: issue 0  warp0 dot done %6lld  all warps in %6lld  posted %6lld  ready %6lld  released %6lld | next issue %6lld\n",
+              64 + r, st[1][r] - st[0][r], st[6][r] - st[0][r], st[2][r] - st[0][r],
+              st[3][r] - st[0][r], st[4][r] - st[0][r], st[0][r + 1] - st[0][r]);
   }
   return ZF_OK;
 }
 
-int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
-  switch (h->fused_pairs) {          // chunks per row slice
-    case 1: return launch_fused_ring_t<1>(h, v, query_only, max_clusters);
-    case 2: return launch_fused_ring_t<2>(h, v, query_only, max_clusters);
-    case 3: return launch_fused_ring_t<3>(h, v, query_only, max_clusters);
-    case 4: return launch_fused_ring_t<4>(h, v, query_only, max_clusters);
-    default: return launch_fused_ring_t<5>(h, v, query_only, max_clusters);
+int launch_fused_ring_n(zf_lasso* h, const double* v, int nch, const RingLaunch& L, bool query_only,
+                        int* max_clusters) {
+  switch (nch) {                     // chunks per row slice
+    case 1: return launch_fused_ring_t<1>(h, v, L, query_only, max_clusters);
+    case 2: return launch_fused_ring_t<2>(h, v, L, query_only, max_clusters);
+    case 3: return launch_fused_ring_t<3>(h, v, L, query_only, max_clusters);
+    case 4: return launch_fused_ring_t<4>(h, v, L, query_only, max_clusters);
+    default: return launch_fused_ring_t<5>(h, v, L, query_only, max_clusters);
   }
+}
+
+int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
+  RingLaunch L1{h->fused_ctas, h->fused_cluster, h->fused_rows_per_cta, h->fused_pairs_per_cta, 0,
+                h->ring2_ctas > 0 ? h->ring2_row0 : h->n_rows, 0, h->st};
+  if (query_only || h->ring2_ctas == 0)
+    return launch_fused_ring_n(h, v, h->fused_pairs, L1, query_only, max_clusters);
+  // fork: the wide launch first (it takes every SM a 4-CTA cluster fits on), then the 2-CTA
+  // launch for the SMs it left idle; join on the handle's stream
+  ZF_CUDA(cudaEventRecord(h->ev_fork, h->st));
+  ZF_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+  int rc = launch_fused_ring_n(h, v, h->fused_pairs, L1, false, nullptr);
+  if (rc != ZF_OK) return rc;
+  RingLaunch L2{h->ring2_ctas, 2, h->ring2_rows_per_cluster, h->ring2_pairs_per_cta, h->ring2_row0,
+                h->n_rows, h->ring1_clusters, h->st2};
+  rc = launch_fused_ring_n(h, v, h->ring2_nch, L2, false, nullptr);
+  if (rc != ZF_OK) return rc;
+  ZF_CUDA(cudaEventRecord(h->ev_join, h->st2));
+  ZF_CUDA(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+  return ZF_OK;
 }
 
 // gradient pass at v: leaves the A^T r partials in gpart (n_gpart_rows x n_cols) and the
@@ -1376,8 +1412,8 @@ int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_cl
 int launch_gradient_pass(zf_lasso* h, const double* v, int* n_gpart_rows, int* n_sq) {
   if (h->fused_pairs > 0 && h->fused_ring) {
     const int rc = launch_fused_ring(h, v, false, nullptr);
-    *n_gpart_rows = h->fused_ctas / h->fused_cluster;
-    *n_sq = h->fused_ctas / h->fused_cluster;
+    *n_gpart_rows = h->fused_ctas / h->fused_cluster + h->ring2_ctas / 2;
+    *n_sq = *n_gpart_rows;
     return rc;
   }
   if (h->fused_pairs > 0 && h->fused_tma) {
@@ -1591,7 +1627,8 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   // 0.77 at 16384, 0.70 at 12000, 0.65 at 20000; two-pass kernels 0.53 everywhere.
   // Environment overrides for experiments:
   //   ZF_LASSO_FUSED=0 (two-pass), ZF_LASSO_CLUSTER=2|4, ZF_LASSO_THREADS=512|1024,
-  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4, ZF_LASSO_RING=1|2|4|8.
+  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4, ZF_LASSO_RING=1|2|4|8,
+  //   ZF_LASSO_RING_SPLIT=0 (no second launch on the idle SMs) | .NN (its per-SM rate).
   h->gpart_rows = (size_t)h->n_rowblocks;
   size_t sq_rows = (size_t)h->res_blocks;
   {
@@ -1653,7 +1690,41 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       int active = 0;
       if (launch_fused_ring(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
         n_clusters = active;
-      finish_cluster_grid(c, n_clusters, 1);
+      // 4-CTA clusters leave SMs idle (33 clusters = 132 of 148 SMs on B200).  When a 2-CTA
+      // cluster can still hold the row slice (<= 5 chunks), a second launch of 2-CTA clusters
+      // takes the last rows on those SMs, concurrently, on its own stream.  Measured per-SM
+      // rates: 0.82 (4-CTA, 3 chunks per row) against 0.64 (2-CTA, 5 chunks).
+      const int idle = h->n_sm - n_clusters * c;
+      const long long ppc2 = (n2 + 1) / 2;
+      const long long nch2 = (ppc2 + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
+      const char* env_split = getenv("ZF_LASSO_RING_SPLIT");
+      if (c == 4 && idle >= 2 && nch2 <= 5 && !(env_split && env_split[0] == '0')) {
+        const int clusters2 = idle / 2;
+        double rate2 = 0.60;       // 0.5: 0.787, 0.58-0.64: 0.795, 0.7: 0.728 (second launch too long)
+        if (env_split && atof(env_split) > 0.0) rate2 = atof(env_split);      // experiment knob
+        const double w1 = 0.82 * n_clusters * c, w2 = rate2 * clusters2 * 2;
+        long long rows2 = (long long)((double)n_rows * w2 / (w1 + w2));
+        if (rows2 >= clusters2 && cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess) {
+          h->ring2_row0 = n_rows - rows2;
+          h->ring2_rows_per_cluster = (rows2 + clusters2 - 1) / clusters2;
+          h->ring2_ctas = 2 * (int)((rows2 + h->ring2_rows_per_cluster - 1) / h->ring2_rows_per_cluster);
+          h->ring2_pairs_per_cta = ppc2;
+          h->ring2_nch = (int)nch2;
+        }
+      }
+      {
+        // rows of the first launch over its clusters
+        const long long rows1 = h->ring2_ctas > 0 ? h->ring2_row0 : n_rows;
+        h->fused_rows_per_cta = (rows1 + n_clusters - 1) / n_clusters;
+        const int used = (int)((rows1 + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
+        h->fused_ctas = used * c;
+        h->ring1_clusters = used;
+        const size_t parts = (size_t)used + (size_t)(h->ring2_ctas / 2);
+        if (parts > h->gpart_rows) h->gpart_rows = parts;
+        if (parts > sq_rows) sq_rows = parts;
+      }
       return true;
     };
     auto try_cluster = [&](int c) -> bool {
@@ -1743,6 +1814,9 @@ extern "C" void zf_lasso_destroy(zf_lasso* h) {
   cudaFree(h->d_sums);
   cudaFree(h->counter);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->st2) cudaStreamDestroy(h->st2);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
