@@ -1180,7 +1180,7 @@ struct zf_lasso {
   bool fused_ring = false;            // warp-specialised chunk ring (lasso_fused_ring_kernel)
   // second, concurrent ring launch on the SMs the first one cannot use (4-CTA clusters fit on
   // 132 of 148 SMs): 2-CTA clusters over the last rows, on its own stream
-  int ring2_ctas = 0, ring2_nch = 0, ring1_clusters = 0;
+  int ring2_ctas = 0, ring2_nch = 0, ring2_cluster = 2, ring1_clusters = 0;
   long long ring2_row0 = 0, ring2_rows_per_cluster = 0, ring2_pairs_per_cta = 0;
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1398,7 +1398,7 @@ int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_cl
   ZF_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
   int rc = launch_fused_ring_n(h, v, h->fused_pairs, L1, false, nullptr);
   if (rc != ZF_OK) return rc;
-  RingLaunch L2{h->ring2_ctas, 2, h->ring2_rows_per_cluster, h->ring2_pairs_per_cta, h->ring2_row0,
+  RingLaunch L2{h->ring2_ctas, h->ring2_cluster, h->ring2_rows_per_cluster, h->ring2_pairs_per_cta, h->ring2_row0,
                 h->n_rows, h->ring1_clusters, h->st2};
   rc = launch_fused_ring_n(h, v, h->ring2_nch, L2, false, nullptr);
   if (rc != ZF_OK) return rc;
@@ -1412,7 +1412,7 @@ int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_cl
 int launch_gradient_pass(zf_lasso* h, const double* v, int* n_gpart_rows, int* n_sq) {
   if (h->fused_pairs > 0 && h->fused_ring) {
     const int rc = launch_fused_ring(h, v, false, nullptr);
-    *n_gpart_rows = h->fused_ctas / h->fused_cluster + h->ring2_ctas / 2;
+    *n_gpart_rows = h->fused_ctas / h->fused_cluster + h->ring2_ctas / h->ring2_cluster;
     *n_sq = *n_gpart_rows;
     return rc;
   }
@@ -1695,21 +1695,25 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       // takes the last rows on those SMs, concurrently, on its own stream.  Measured per-SM
       // rates: 0.82 (4-CTA, 3 chunks per row) against 0.64 (2-CTA, 5 chunks).
       const int idle = h->n_sm - n_clusters * c;
-      const long long ppc2 = (n2 + 1) / 2;
+      const int c2 = c / 2;                                  // cluster size of the second launch
+      const long long ppc2 = c2 > 0 ? (n2 + c2 - 1) / c2 : n2;
       const long long nch2 = (ppc2 + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
       const char* env_split = getenv("ZF_LASSO_RING_SPLIT");
-      if (c == 4 && idle >= 2 && nch2 <= 5 && !(env_split && env_split[0] == '0')) {
-        const int clusters2 = idle / 2;
+      // (8-CTA clusters + a 4-CTA second launch was measured: the 4-CTA clusters do not fit on the
+      // idle SMs and run afterwards, 0.38 instead of 0.59 at 36000 columns -- only c == 4 splits)
+      if (c == 4 && idle >= c2 && nch2 <= 5 && !(env_split && env_split[0] == '0')) {
+        const int clusters2 = idle / c2;
         double rate2 = 0.60;       // 0.5: 0.787, 0.58-0.64: 0.795, 0.7: 0.728 (second launch too long)
         if (env_split && atof(env_split) > 0.0) rate2 = atof(env_split);      // experiment knob
-        const double w1 = 0.82 * n_clusters * c, w2 = rate2 * clusters2 * 2;
+        const double w1 = 0.82 * n_clusters * c, w2 = rate2 * clusters2 * c2;
         long long rows2 = (long long)((double)n_rows * w2 / (w1 + w2));
         if (rows2 >= clusters2 && cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess) {
           h->ring2_row0 = n_rows - rows2;
           h->ring2_rows_per_cluster = (rows2 + clusters2 - 1) / clusters2;
-          h->ring2_ctas = 2 * (int)((rows2 + h->ring2_rows_per_cluster - 1) / h->ring2_rows_per_cluster);
+          h->ring2_cluster = c2;
+          h->ring2_ctas = c2 * (int)((rows2 + h->ring2_rows_per_cluster - 1) / h->ring2_rows_per_cluster);
           h->ring2_pairs_per_cta = ppc2;
           h->ring2_nch = (int)nch2;
         }
@@ -1721,7 +1725,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
         const int used = (int)((rows1 + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
         h->fused_ctas = used * c;
         h->ring1_clusters = used;
-        const size_t parts = (size_t)used + (size_t)(h->ring2_ctas / 2);
+        const size_t parts = (size_t)used + (size_t)(h->ring2_ctas / h->ring2_cluster);
         if (parts > h->gpart_rows) h->gpart_rows = parts;
         if (parts > sq_rows) sq_rows = parts;
       }
