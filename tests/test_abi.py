@@ -120,3 +120,33 @@ def test_no_cpu_fallback_without_a_device(built_lib):
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         DenseLasso(np.eye(3), np.ones(3), 0.1)
+
+
+def test_shared_a_entry_points_validate_and_refuse_without_a_device(built_lib):
+    """zf_lasso_multi_*: argument validation happens before any device work, and on a box
+    without a GPU creation fails with ZF_ERR_CUDA (no compute call is made here)."""
+    from zfista_b200 import _lib
+    from zfista_b200.lasso import DenseLassoMulti
+
+    L = _lib.lib()
+    h = C.c_void_p()
+    fake = C.c_void_p(0x1000)          # never dereferenced: validation comes first
+
+    def create(rows, cols, runs, ptr=fake):
+        return L.zf_lasso_multi_create(C.byref(h), ptr, rows, cols, fake, 0, runs, 1.0, 0.1, None)
+
+    assert create(4, 4, 2, None) == -1 and b"NULL" in L.zf_last_error()
+    assert create(0, 4, 2) == -1
+    assert create(4, 4, 0) == -1 and create(4, 4, 33) == -1
+    assert create(4, 3, 2) == -3 and b"even" in L.zf_last_error()            # odd n_cols
+    assert create(4, 4, 2, C.c_void_p(0x1008)) == -3                          # misaligned A
+    assert L.zf_lasso_multi_step(None, None) == -1
+    assert L.zf_lasso_multi_grad(None, 0) == -1
+    assert L.zf_lasso_multi_finish(None, None, None, None, None, None, None) == -1
+    assert L.zf_lasso_multi_partial(None, None) is None
+    L.zf_lasso_multi_destroy(None)                                             # no-op
+    if L.zf_device_count() > 0:
+        pytest.skip("a GPU is visible: the no-device half does not apply")
+    assert create(4, 4, 2) == -2 and b"no CPU fallback" in L.zf_last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DenseLassoMulti(np.eye(4), np.ones(4), 0.1, 2)
