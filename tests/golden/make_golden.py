@@ -255,6 +255,47 @@ def gen_lasso_cases(only, overwrite):
     np.savez(path, **save)
 
 
+def gen_lasso_sweep_cases(only, overwrite):
+    """Many runs sharing one A: the dense LASSO of build_dataset() solved by the UNMODIFIED
+    reference once per (a, b) pair of the momentum grid (the joblib fan-out of
+    examples/PGM_experiment_with_various_a_b.ipynb run()), from per-run starting points, with
+    and without the line search.  Parity target of the lockstep device path
+    (csrc/zf_lasso_multi.cu)."""
+    from zfista import minimize_proximal_gradient
+
+    path = os.path.join(HERE, "lasso_ab_sweep.npz")
+    if only and only not in "lasso_ab_sweep":
+        return
+    if os.path.exists(path) and not overwrite:
+        return
+    warnings.simplefilter("ignore")
+    grid = [(0.0, 0.0), (0.0, 1 / 8), (0.0, 1 / 4), (1 / 6, 1 / 144), (1 / 6, 37 / 288),
+            (1 / 6, 1 / 4), (1 / 4, 1 / 64), (1 / 4, 17 / 128), (1 / 4, 1 / 4), (1 / 2, 1 / 16),
+            (1 / 2, 5 / 32), (1 / 2, 1 / 4), (3 / 4, 9 / 64), (3 / 4, 25 / 128), (3 / 4, 1 / 4)]
+    rs = np.random.RandomState(0)
+    w = rs.randn(200)
+    w[10:] = 0.0
+    X = rs.randn(50, 200)
+    y = X @ w
+    X0 = np.random.RandomState(1).randn(len(grid), 200) * 0.1
+    L = 2 * (1 / (2 * 50)) * np.linalg.norm(X, 2) ** 2
+    save = {"A": X, "b": y, "X0": X0, "grid": np.array(grid), "L": np.array(L),
+            "l1": np.array(0.1), "scale": np.array(1 / 100)}
+    f, g, jac_f, prox = _lasso_closures(X, y, 0.1, 1 / 100)
+    for tag, opts in {"bt": dict(), "fixed": dict(lr=1 / L, decay_rate=1)}.items():
+        xs, funs, nits = [], [], []
+        for k, ab in enumerate(grid):
+            r = minimize_proximal_gradient(f, g, jac_f, prox, X0[k], nesterov=True,
+                                           nesterov_ratio=ab, max_iter=20000, **opts)
+            xs.append(np.asarray(r.x))
+            funs.append(float(r.fun))
+            nits.append(r.nit)
+        save[f"{tag}_x"], save[f"{tag}_fun"], save[f"{tag}_nit"] = (np.array(xs), np.array(funs),
+                                                                  np.array(nits))
+        print(f"[golden] lasso (a, b) sweep {tag}: nit={nits}", flush=True)
+    np.savez(path, **save)
+
+
 def gen_deblur_cases(only, overwrite):
     """Cameraman-notebook workload at small sizes: the UNMODIFIED reference solver
     (zfista.minimize_proximal_gradient) driven by the notebook's closures as restated in
@@ -393,6 +434,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     gen_problem_eval_cases(a.only, a.overwrite)
     gen_lasso_cases(a.only, a.overwrite)
+    gen_lasso_sweep_cases(a.only, a.overwrite)
     gen_deblur_cases(a.only, a.overwrite)
     gen_subproblem_cases(a.only, a.overwrite)
     gen_problem_cases(a.only, a.jobs, a.overwrite)

@@ -135,10 +135,32 @@ def test_runs_match_single_run_path(gpu):
         _close(res[k].fun, d["ds_bt_fista_fun"])
 
 
+def test_ab_sweep_matches_the_reference_fixture(gpu):
+    """tests/golden/lasso_ab_sweep.npz holds what the UNMODIFIED reference returns for the 15
+    (a, b) pairs of the momentum grid on one shared A (one solve per pair, per-run x0), with the
+    line search and with a fixed step.  One lockstep call must give every run's nit exactly and
+    x, F within 1e-8."""
+    from zfista_b200.lasso import DenseLassoMulti
+
+    d = helpers.load("lasso_ab_sweep")
+    grid = [(float(a), float(b)) for a, b in d["grid"]]
+    prob = DenseLassoMulti(d["A"], d["b"], float(d["l1"]), len(grid), scale=float(d["scale"]))
+    L = float(d["L"])
+    for tag, opts in {"bt": dict(), "fixed": dict(lr=1 / L, decay_rate=1)}.items():
+        res = prob.minimize_proximal_gradient_batched(d["X0"], grid, nesterov=True,
+                                                      max_iter=20000, **opts)
+        assert [r.nit for r in res] == [int(v) for v in d[f"{tag}_nit"]], tag
+        assert all(r.success for r in res)
+        for k, r in enumerate(res):
+            _close(r.x, d[f"{tag}_x"][k])
+            _close(r.fun, d[f"{tag}_fun"][k])
+
+
 def test_failure_and_max_iter_are_per_run(gpu):
-    """One run whose line search cannot succeed (huge A scale in its own b? no: huge lr and 2
-    trials) must not disturb the others: here every run fails / hits max_iter identically to
-    a solo solve."""
+    """Status handling is per run: with a huge initial step and only 2 trials every run fails
+    its line search (x = x0, nit = 0, status -1) exactly as a solo solve does; max_iter is hit
+    per run; a run that starts at its fixed point stops after one iteration while the others
+    go on."""
     from zfista_b200.lasso import DenseLassoMulti
 
     rng = np.random.RandomState(1)

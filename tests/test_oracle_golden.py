@@ -213,6 +213,24 @@ def test_lasso_single_objective_matches_reference():
         np.testing.assert_array_equal(np.array(r["allerrs"]), d[f"ds_{tag}_allerrs"])
 
 
+def test_lasso_ab_sweep_matches_reference():
+    """The (a, b) momentum sweep over one shared A (fixture made by the unmodified reference,
+    one solve per pair): the oracle reproduces every run bit for bit -- the parity anchor of
+    the lockstep multi-run device path (tests/test_gpu_lasso_multi.py)."""
+    d = helpers.load("lasso_ab_sweep")
+    spec = zo.make_least_squares_l1(d["A"], d["b"], float(d["l1"]), scale=float(d["scale"]))
+    L = float(d["L"])
+    for tag, opts in {"bt": dict(), "fixed": dict(lr=1 / L, decay_rate=1)}.items():
+        for k, ab in enumerate(d["grid"]):
+            r = zo.minimize_proximal_gradient(spec, d["X0"][k], nesterov=True,
+                                              nesterov_ratio=(float(ab[0]), float(ab[1])),
+                                              max_iter=20000, **opts)
+            assert r["nit"] == int(d[f"{tag}_nit"][k]), (tag, k)
+            np.testing.assert_array_equal(r["x"], d[f"{tag}_x"][k])
+            assert float(r["fun"]) == float(d[f"{tag}_fun"][k])
+    assert np.allclose(d["grid"], helpers.AB_GRID)
+
+
 def test_reference_is_rounding_sensitive_on_l1_cases():
     """Evidence for the parity tiers of DESIGN.md: with zero noise the restated Brent route
     reproduces the reference bit for bit; with ONE ulp of relative noise on the dual value
