@@ -5,9 +5,11 @@
 //
 // Per FISTA iteration the device does
 //   q = A^T (A y - b), sum r^2       ONE pass over A with a fused kernel chosen per shape
-//                                    (lasso_fused_kernel: single CTA, L2 re-read;
-//                                     lasso_fused_cluster_kernel: 2-CTA cluster + DSMEM;
-//                                     lasso_fused_tma_kernel: TMA ring, row pair stays in smem)
+//                                    (lasso_fused_ring_kernel: warp-specialised TMA chunk
+//                                     ring, the default from 4096 columns up;
+//                                     lasso_fused_kernel: single CTA, L2 re-read, below that;
+//                                     lasso_fused_cluster_kernel / lasso_fused_tma_kernel:
+//                                     earlier cluster forms, kept behind ZF_LASSO_* switches)
 //                                    or two passes where a row is too wide for them:
 //                                    lasso_residual_kernel (r = A y - b), lasso_atr_kernel (A^T r)
 //   x = soft(y - lr*2*scale*q, lr*l1) + the four sums the line search / stop test need
