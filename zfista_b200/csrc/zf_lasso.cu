@@ -849,7 +849,7 @@ __global__ void __maxnreg__(96)
 lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__ b,
                         const double* __restrict__ v, long long n_rows, long long n_cols,
                         long long rows_per_cluster, long long pairs_per_cta,
-                        double* __restrict__ gpart, double* __restrict__ sq_part, int xmode,
+                        double* __restrict__ gpart, double* __restrict__ sq_part,
                         int dbg, long long row_begin, long long row_end, int part_base) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -876,7 +876,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
       mbar_init(&empty[s], RING_WARPS);
     }
     for (int s = 0; s < RING_NR; ++s) {
-      mbar_init(&ready[s], xmode == 1 ? (unsigned)csize : 1u);
+      mbar_init(&ready[s], 1u);
       mbar_init(&dbar[s], RING_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -968,7 +968,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
     for (long long n = 0; n < my_rows; ++n) {
       double bi = 0.0;
       if (crank == 0) bi = __ldg(b + i0 + n);          // rank 0 folds -b_i into its part
-      if (lane == 0 && xmode != 1) mbar_expect_tx(&ready[sl], 8u * (unsigned)csize);
+      if (lane == 0) mbar_expect_tx(&ready[sl], 8u * (unsigned)csize);
       mbar_wait(&dbar[sl], rph);
       if (lane == 0) RING_STAMP(6, n);
       if (lane < csize) {
@@ -978,13 +978,7 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
         t -= bi;
         const unsigned ra = mapa_u32(xs_base + (unsigned)((sl * RING_MAX_CLUSTER + crank) * 8), (unsigned)lane);
         const unsigned rb = mapa_u32(rd_base + (unsigned)(sl * 8), (unsigned)lane);
-        if (xmode == 1) {
-          asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(t) : "memory");
-          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rb)
-                       : "memory");
-        } else {
-          st_async_f64(ra, t, rb);
-        }
+        st_async_f64(ra, t, rb);
         if (lane == 0) RING_STAMP(2, n);
       }
       if (++sl == RING_NR) { sl = 0; rph ^= 1u; }
@@ -1005,7 +999,6 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
       {
         mbar_wait(&ready[sl], rph);
         if (ut == 0) RING_STAMP(3, n);
-        if (xmode == 1) asm volatile("fence.acq_rel.cluster;" ::: "memory");
         for (int c = 0; c < csize; ++c) r += xslot[sl][c];
       }
       ss += r * r;
@@ -1367,10 +1360,9 @@ int launch_fused_ring_t(zf_lasso* h, const double* v, const RingLaunch& L, bool 
     ZF_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, k, &cfg));
     return ZF_OK;
   }
-  static const int xmode = getenv("ZF_LASSO_RING_X") ? atoi(getenv("ZF_LASSO_RING_X")) : 0;
   static const int dbg = (ZF_RING_DEBUG && getenv("ZF_LASSO_RING_DBG")) ? 1 : 0;
   ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, L.rows_per_cluster,
-                             L.pairs_per_cta, h->gpart, h->sq_part, xmode, dbg, L.row_begin,
+                             L.pairs_per_cta, h->gpart, h->sq_part, dbg, L.row_begin,
                              L.row_end, L.part_base));
   zf::zf_count_launch();
   if (dbg && L.part_base == 0) {
