@@ -790,7 +790,7 @@ constexpr int RING_THREADS = 2 * RING_GROUP + 64;  // 8 dot + 8 update warps, pr
 // the two service warps to the others with setmaxnreg -- 20 warps, 104 / 120 registers for the
 // dot / update warps -- was measured and is not used: 0.93 instead of 0.98 at 16384 columns.)
 constexpr int RING_CH_PAIRS = 1024;                // double2 per chunk: 2048 columns, 16 KB
-constexpr int RING_SLOTS = 12;
+constexpr int RING_SLOTS = 13;                    // 208 KB ring + 4 KB static: the most that fits in 227 KB
 constexpr int RING_NR = 2 * RING_SLOTS + 2;
 constexpr int RING_U = RING_CH_PAIRS / RING_GROUP; // double2 per thread and chunk
 constexpr int RING_MAX_CLUSTER = 8;
