@@ -157,70 +157,121 @@ def simplex_qp(Q, G, w_cur):
     (Q PSD, m <= 4) by face enumeration; singular faces are skipped (their optimum
     lies on a sub-face).  Everything is expressed in the step d: the gradient G is
     O(1) while Q w can be ~1e12 (FDS, n = 100), so forming G + Q w first would wipe
-    out the low bits of G that decide the optimum."""
+    out the low bits of G that decide the optimum.
+
+    Faces are visited in the device's order (zf_dual.cuh:QpFaces): support masks from the
+    whole simplex (2^m - 1) down to 1, and if the maximiser over the whole simplex's affine
+    hull is feasible it is the global maximiser and the sub-faces are not visited."""
     m = G.shape[0]
-    best_w, best_val = None, -np.inf
-    scale = max(np.trace(Q), 1e-300)
-    for k in range(1, m + 1):
-        for S in itertools.combinations(range(m), k):
-            S = list(S)
-            w = np.zeros(m)
-            e0 = np.zeros(m)
-            e0[S[0]] = 1.0
-            if k == 1:
-                w = e0
-            else:
-                u = Q @ (e0 - w_cur)
-                R = np.empty((k - 1, k - 1))
-                rhs = np.empty(k - 1)
-                s0 = S[0]
-                for a in range(k - 1):
-                    ia = S[a + 1]
-                    rhs[a] = (G[ia] - u[ia]) - (G[s0] - u[s0])
-                    for b in range(k - 1):
-                        ib = S[b + 1]
-                        R[a, b] = Q[ia, ib] - Q[ia, s0] - Q[s0, ib] + Q[s0, s0]
-                # LDL^T without pivoting; a pivot at rounding level = singular face
-                A = R.copy()
-                ok = True
-                for kk in range(k - 1):
-                    if not (A[kk, kk] > 1e-13 * scale):
-                        ok = False
-                        break
-                    for r in range(kk + 1, k - 1):
-                        fct = A[r, kk] / A[kk, kk]
-                        A[r, kk + 1:] -= fct * A[kk, kk + 1:]
-                        rhs[r] -= fct * rhs[kk]
-                if not ok:
-                    continue
-                z = np.zeros(k - 1)
-                for kk in range(k - 2, -1, -1):
-                    z[kk] = (rhs[kk] - A[kk, kk + 1:] @ z[kk + 1:]) / A[kk, kk]
-                if (z < 0).any() or 1.0 - z.sum() < 0:
-                    continue
-                w[S[1:]] = z
-                w[s0] = 1.0 - z.sum()
-            d = w - w_cur
-            val = G @ d - 0.5 * d @ Q @ d
-            if val > best_val:
-                best_val, best_w = val, w
+    best_w, best_val = w_cur.copy(), -np.inf
+    scale = np.trace(Q)
+    for mask in range((1 << m) - 1, 0, -1):
+        S = [b for b in range(m) if mask & (1 << b)]
+        k = len(S)
+        w = np.zeros(m)
+        e0 = np.zeros(m)
+        s0 = S[0]
+        e0[s0] = 1.0
+        if k == 1:
+            w = e0
+        else:
+            u = Q @ (e0 - w_cur)
+            R = np.empty((k - 1, k - 1))
+            rhs = np.empty(k - 1)
+            for a in range(k - 1):
+                ia = S[a + 1]
+                rhs[a] = (G[ia] - u[ia]) - (G[s0] - u[s0])
+                for b in range(k - 1):
+                    ib = S[b + 1]
+                    R[a, b] = Q[ia, ib] - Q[ia, s0] - Q[s0, ib] + Q[s0, s0]
+            # LDL^T without pivoting; a pivot at rounding level = singular face
+            A = R.copy()
+            ok = True
+            for kk in range(k - 1):
+                if not (A[kk, kk] > 1e-13 * scale):
+                    ok = False
+                    break
+                inv = 1.0 / A[kk, kk]
+                for r in range(kk + 1, k - 1):
+                    fct = A[r, kk] * inv
+                    A[r, kk + 1:] -= fct * A[kk, kk + 1:]
+                    rhs[r] -= fct * rhs[kk]
+            if not ok:
+                continue
+            z = np.zeros(k - 1)
+            for kk in range(k - 2, -1, -1):
+                z[kk] = (rhs[kk] - A[kk, kk + 1:] @ z[kk + 1:]) / A[kk, kk]
+            if (z < 0).any() or 1.0 - z.sum() < 0:
+                continue
+            w[S[1:]] = z
+            w[s0] = 1.0 - z.sum()
+        d = w - w_cur
+        val = sum(d[i] * (G[i] - 0.5 * (Q[i] @ d)) for i in range(m))
+        if val > best_val:
+            best_val, best_w = val, w
+        if mask == (1 << m) - 1 and best_val > -np.inf:
+            break
     return best_w
 
 
-def simplex_newton(y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun, w0=None,
-                   max_iter=60):
-    """Maximise the dual over the simplex.  Returns (w, D(w), p(w), iterations).
+def piece_codes(alpha, eps):
+    """Per coordinate: which linear piece of the prox chain it is on -- 0 if pinned at a kink or
+    a bound (alpha = 0), else 1 | the side of every shift it lies on (zf_dual.cuh:piece_code)."""
+    code = np.ones(alpha.shape[0], dtype=np.int64)
+    for i in range(eps.shape[0]):
+        code |= (eps[i] > 0).astype(np.int64) << (i + 1)
+    return np.where(alpha == 0.0, 0, code)
 
-    Each step solves the QP of the current quadratic piece exactly.  When the
-    model-predicted gain of a step is below the rounding level of D the step is
-    taken on trust and the iteration stops (a Newton step is accurate far below
-    what a comparison of D values can resolve)."""
+
+def simplex_newton(y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun, w0=None,
+                   max_iter=60, shortcut=True, info=None):
+    """Maximise the dual over the simplex.  Returns (w, D(w), p(w), dual evaluations).
+
+    Statement, step for step, of zf_dual.cuh:dual_newton.  Each step solves the QP of the
+    current quadratic piece exactly.  When the model-predicted gain of a step is below the
+    rounding level of D the step is taken on trust and the iteration stops (a Newton step is
+    accurate far below what a comparison of D values can resolve).  ``shortcut``: the dual is
+    ONE quadratic while no coordinate changes its piece of the prox chain, so if the primal
+    point of the Newton candidate lies on the same pieces as the point just evaluated the
+    candidate IS the maximiser and D(candidate) = D + pred; the confirming evaluation is
+    skipped and the primal point of the probe is returned."""
     m = J.shape[0]
+    has_l1 = l1_ratios is not None
+    lam = l1_ratios if has_l1 else np.zeros(m)
+    sh = l1_shifts if has_l1 else np.zeros(m)
     w = np.ones(m) / m if w0 is None else np.array(w0, dtype=np.float64)
     args = (y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun)
-    D, G, Q, p = dual_eval(w, *args)
-    it = 0
-    for it in range(1, max_iter + 1):
+
+    def full(wq):
+        Dq, Gq, Qq, pq = dual_eval(wq, *args)
+        vq = y - lr * (wq @ J)
+        _, al, ep = prox_chain(vq, lr * wq * lam, sh, lower, upper, has_l1)
+        return Dq, Gq, Qq, piece_codes(al, ep)
+
+    wt = w.copy()
+    d = np.zeros(m)
+    step, evals, it, bt, first = 1.0, 0, 0, 0, True
+    D = G = Q = pat = None
+    x_ready = None
+    while True:
+        Dt, Gt, Qt, patt = full(wt)
+        evals += 1
+        if first or Dt >= D:
+            first = False
+            w, D, G, Q, pat = wt.copy(), Dt, Gt, Qt, patt
+        else:
+            # the device overwrites the stored piece codes at every full evaluation, also at a
+            # rejected trial point
+            pat = patt
+            step *= 0.5
+            bt += 1
+            if bt >= 30:
+                break
+            wt = w + step * d
+            continue
+        it += 1
+        if it > max_iter:
+            break
         wn = simplex_qp(Q, G, w)
         d = wn - w
         if np.max(np.abs(d)) == 0.0:
@@ -230,17 +281,19 @@ def simplex_newton(y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun, w0=No
             w = wn
             D = D + pred
             break
-        step = 1.0
-        accepted = False
-        for _ in range(30):
-            wt = wn if step == 1.0 else w + step * d
-            Dt, Gt, Qt, pt = dual_eval(wt, *args)
-            if Dt >= D:
-                accepted = True
+        if shortcut:
+            vn = y - lr * (wn @ J)
+            pn, al, ep = prox_chain(vn, lr * wn * lam, sh, lower, upper, has_l1)
+            if np.array_equal(piece_codes(al, ep), pat):
+                w = wn
+                D = D + pred
+                x_ready = pn
                 break
-            step *= 0.5
-        if not accepted:
-            break
-        w, D, G, Q = wt, Dt, Gt, Qt
-    _, _, _, p = dual_eval(w, *args)
-    return w, D, p, it
+        step, bt = 1.0, 0
+        wt = wn.copy()
+    if x_ready is None:
+        v = y - lr * (w @ J)
+        x_ready, _, _ = prox_chain(v, lr * w * lam, sh, lower, upper, has_l1)
+    if info is not None:
+        info["evals"] = evals
+    return w, D, x_ready, evals

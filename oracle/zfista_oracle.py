@@ -401,7 +401,32 @@ def solve_subproblem_device_model(spec, lr, x_prev, y, w_init, tol=1e-12, max_it
         lam, sh = np.full(m, spec.l1), np.zeros(m)
     else:
         lam, sh = spec.l1_ratios, spec.l1_shifts
-    weight, D, p, its = dm.simplex_newton(y, Jy, lr, c, lam, sh, spec.lower, spec.upper,
-                                          lambda q: g(spec, q), w0=w_init)
-    x = prox_wsum_g(spec, lr * weight, y - lr * weight @ Jy)
-    return x, D, weight, its
+    weight, D, p, evals = dm.simplex_newton(y, Jy, lr, c, lam, sh, spec.lower, spec.upper,
+                                            lambda q: g(spec, q), w0=w_init)
+    return p, D, weight, evals
+
+
+class DeviceModel:
+    """``subproblem=DeviceModel()`` -- the CPU statement of what ONE start of
+    batched_fista_kernel (zf_batched.cu) does around its inner solver: like
+    :func:`solve_subproblem_device_model`, plus the one piece of state the kernel carries from
+    subproblem to subproblem: the simplex Newton solver always continues from the previous
+    subproblem's weights (``wwarm`` in zf_batched.cu; the reference's ``warm_start`` option only
+    matters for the Brent route, which has no initial guess).  One instance per solve.
+    ``newton_for_two`` = the kernel's ``dual_solver="newton"`` for two objectives."""
+
+    def __init__(self, newton_for_two=False):
+        self.newton_for_two = newton_for_two
+        self.w = None
+        self.dual_evals = 0
+
+    def __call__(self, spec, lr, x_prev, y, w_init, tol=1e-12, max_iter=1000, deprecated=False):
+        m = spec.n_objectives
+        newton = m >= 3 or (m == 2 and self.newton_for_two)
+        w0 = self.w if (newton and self.w is not None) else w_init
+        x, fun, weight, evals = solve_subproblem_device_model(
+            spec, lr, x_prev, y, w0, tol, max_iter, deprecated, self.newton_for_two)
+        if newton:
+            self.w = weight
+        self.dual_evals += evals
+        return x, fun, weight, evals
