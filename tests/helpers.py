@@ -161,3 +161,49 @@ def oracle_noise_envelope(spec, X0, x_ref, fun_ref, nit_ref, opts, n_starts=4, s
                                           / np.maximum(1.0, np.abs(fun_ref[i])))))
                 dnit = max(dnit, abs(int(r["nit"]) - int(nit_ref[i])))
     return dict(dx=dx, dF=dF, dnit=dnit)
+
+
+# ---------------------------------------------------------------------------------------
+# m >= 3: converged fixtures of the unmodified reference (tests/golden/make_golden_converged.py)
+# and the CPU statement of the device algorithm (oracle DeviceModel)
+# ---------------------------------------------------------------------------------------
+def converged_cases():
+    return sorted(os.path.basename(p)[:-4]
+                  for p in glob.glob(os.path.join(GOLDEN, "converged", "*__*.npz")))
+
+
+def load_converged(name):
+    return np.load(os.path.join(GOLDEN, "converged", name + ".npz"), allow_pickle=False)
+
+
+def converged_trace(d, i):
+    """(allerrs, allfuns) of start i of a converged fixture (ragged traces, stored flat)."""
+    o = d["trace_offsets"]
+    return d["allerrs"][o[i]:o[i + 1]], d["allfuns"][o[i] + i:o[i + 1] + i + 1]
+
+
+def device_model_solve(spec, x0, opts, newton_for_two=False):
+    import warnings
+
+    from oracle import zfista_oracle as zo
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return zo.minimize_proximal_gradient(
+            spec, x0, subproblem=zo.DeviceModel(newton_for_two=newton_for_two), **opts)
+
+
+def device_model_envelope(spec, x0, opts, ref=None, seeds=(0, 1, 2, 3)):
+    """How far the CPU statement of the device algorithm moves when x0 is perturbed by ONE ulp
+    (a different summation order -- numpy pairwise on the CPU, lane-strided + butterfly on the
+    GPU -- is a perturbation of at least that size at every operation).  Returns the unperturbed
+    result and dict(dnit, dx, dF) = the largest deviation over the seeds."""
+    r = device_model_solve(spec, x0, opts) if ref is None else ref
+    dnit, dx, dF = 0, 0.0, 0.0
+    for s in seeds:
+        sg = np.sign(np.random.RandomState(s).uniform(-1, 1, x0.shape[0]))
+        rp = device_model_solve(spec, x0 * (1 + 1.1e-16 * sg), opts)
+        dnit = max(dnit, abs(int(rp["nit"]) - int(r["nit"])))
+        dx = max(dx, float(np.max(np.abs(rp["x"] - r["x"]))))
+        dF = max(dF, float(np.max(np.abs(rp["fun"] - r["fun"]) / np.maximum(1.0, np.abs(r["fun"])))))
+    return r, dict(dnit=dnit, dx=dx, dF=dF)

@@ -1,0 +1,179 @@
+"""GPU parity tests of the m >= 3 path (batched kernel + simplex-Newton dual, DESIGN.md 4 tier 3).
+
+The reference's inner solver for three or more objectives is scipy trust-constr
+(proximal_gradient.py:193-202), which cannot be reproduced step by step and reaches the dual
+optimum only to ~1e-6.  The parity chain is therefore
+
+  reference (trust-constr)  <->  oracle DeviceModel  <->  CUDA kernel
+        trust-constr accuracy          north_star tolerance (same nit, 1e-8)
+
+* DeviceModel (oracle/zfista_oracle.py) is the CPU statement of exactly what the kernel does
+  (exact simplex Newton dual, warm start across subproblems, exact-model shortcut).  The kernel
+  must agree with it at north_star's tolerance: the same iteration count per start, x and F
+  within 1e-8 relative -- tested to convergence on FDS (n = 10, +L1, +box, (a, b) grid), TRIDIA
+  (+L1), LinearFunctionRank1 (4 objectives) and the headline FDS n = 100 + L1.
+* DeviceModel and the kernel are compared with CONVERGED runs of the unmodified reference
+  (tests/golden/converged/, default max_iter_internal) at trust-constr's accuracy, with the
+  measured margins stated in the assertions.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+REL = 1e-8
+
+
+def _l1(n, m):
+    return dict(l1_ratios=(np.arange(m) + 1) / n, l1_shifts=np.arange(m))
+
+
+def _rel_close(a, b, rel=REL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.max(np.abs(b)), 1.0)
+    np.testing.assert_allclose(a, b, rtol=rel, atol=rel * scale)
+
+
+STRICT_CASES = {
+    "FDS_n10": ("FDS", dict(n_features=10), -2, 2),
+    "FDS_n10_l1": ("FDS", dict(n_features=10, **_l1(10, 3)), -2, 2),
+    "FDS_n10_box": ("FDS", dict(n_features=10, bounds=(0, np.inf)), 0, 2),
+    "FDS_n20_l1": ("FDS", dict(n_features=20, **_l1(20, 3)), -2, 2),
+    "TRIDIA": ("TRIDIA", dict(), -1, 1),
+    "TRIDIA_l1": ("TRIDIA", _l1(3, 3), -1, 1),
+    "LFR1_n30": ("LinearFunctionRank1", dict(n_features=30), -1, 1),
+    "LFR1_n10_m3_l1": ("LinearFunctionRank1", dict(n_features=10, n_objectives=3, **_l1(10, 3)),
+                       -1, 1),
+}
+ALGOS = {"ista": dict(nesterov=False), "fista": dict(nesterov=True),
+         "fista_ab7": dict(nesterov=True, nesterov_ratio=helpers.AB_GRID[7]),
+         "fista_ab13": dict(nesterov=True, nesterov_ratio=helpers.AB_GRID[13]),
+         "fista_dep": dict(nesterov=True, deprecated=True)}
+
+
+@pytest.mark.parametrize("algo", ["ista", "fista", "fista_ab7", "fista_ab13", "fista_dep"])
+@pytest.mark.parametrize("pname", sorted(STRICT_CASES))
+def test_kernel_matches_device_model(gpu, pname, algo):
+    """Full solves to convergence, 8 fresh starts: the same nit per start, x, F and the whole F
+    trace within 1e-8 relative of the CPU statement of the same algorithm."""
+    cls, kw, lo, hi = STRICT_CASES[pname]
+    if algo.startswith("fista_") and not pname.startswith("FDS_n10"):
+        pytest.skip("momentum grid / deprecated variants run on the FDS n = 10 cases")
+    prob = helpers.device_problem(cls, kw)
+    spec = helpers.oracle_spec(cls, kw)
+    rng = np.random.RandomState(3000 + sum(map(ord, pname + algo)))
+    X0 = rng.uniform(lo, hi, size=(8, prob.n_features))
+    opts = dict(tol_internal=1e-11, max_iter=100000, **ALGOS[algo])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        br = prob.minimize_proximal_gradient_batched(X0, return_all=True, **opts)
+    for i in range(len(X0)):
+        r = helpers.device_model_solve(spec, X0[i], dict(opts, return_all=True))
+        assert int(br.status[i]) == r["status"] == 1, (i, br.status[i], r["status"])
+        assert int(br.nit[i]) == r["nit"], (i, int(br.nit[i]), r["nit"])
+        _rel_close(br.x[i], r["x"])
+        _rel_close(br.fun[i], r["fun"])
+        _rel_close(br.allfuns[i, :r["nit"] + 1], np.array(r["allfuns"]))
+        _rel_close(br.allerrs[i, :r["nit"]], np.array(r["allerrs"]), rel=1e-6)
+
+
+def test_momentum_grid_fds_one_launch(gpu):
+    """FDS (a, b) sweep (configs[4]): one launch with a per-start (a, b) table gives, bit for bit,
+    what one launch per pair gives."""
+    cls, kw, lo, hi = STRICT_CASES["FDS_n10_l1"]
+    prob = helpers.device_problem(cls, kw)
+    rng = np.random.RandomState(5)
+    X0 = rng.uniform(lo, hi, size=(6, 10))
+    grid = np.array(helpers.AB_GRID)
+    X0g = np.repeat(X0, len(grid), axis=0)
+    ABg = np.tile(grid, (len(X0), 1))
+    allin = prob.minimize_proximal_gradient_batched(X0g, nesterov=True, nesterov_ratio=ABg,
+                                                    tol_internal=1e-11)
+    assert np.all(allin.status == 1)
+    for gi in (0, 4, 7, 13, 14):
+        one = prob.minimize_proximal_gradient_batched(X0, nesterov=True,
+                                                      nesterov_ratio=tuple(grid[gi]),
+                                                      tol_internal=1e-11)
+        sel = np.arange(len(X0)) * len(grid) + gi
+        np.testing.assert_array_equal(allin.nit[sel], one.nit)
+        np.testing.assert_array_equal(allin.x[sel], one.x)
+
+
+@pytest.mark.parametrize("algo,n_starts", [("fista", 16), ("ista", 6)])
+def test_headline_fds_n100_l1_matches_device_model(gpu, algo, n_starts):
+    """BASELINE configs[2], FDS n = 100 with the L1 term, to convergence.
+
+    On this problem the objective values are ~1e7 while the dual gradient is O(1): the term
+    f(y) - F(x^{k-1}) of the subproblem carries an absolute rounding error of ~1e-9, and a ONE-ulp
+    perturbation of x0 moves the CPU model's own final x by 1e-9 .. 1e-3 depending on the start
+    (helpers.device_model_envelope).  So: every start must agree with the model within the
+    model's own 1-ulp envelope (3x the largest deviation over 4 seeds, iteration count included);
+    starts on which the model is stable (same nit under perturbation, envelope < 1e-9) must in
+    addition meet north_star's tolerance as is: the same nit, x and F within 1e-8 relative."""
+    n = 100
+    kw = dict(n_features=n, **_l1(n, 3))
+    prob = helpers.device_problem("FDS", kw)
+    spec = helpers.oracle_spec("FDS", kw)
+    X0 = np.random.RandomState(2000 + sum(map(ord, "FDS")) + n).uniform(-2, 2, size=(n_starts, n))
+    opts = dict(tol_internal=1e-11, max_iter=3000, nesterov=(algo == "fista"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        br = prob.minimize_proximal_gradient_batched(X0, **opts)
+    stable = same_nit = 0
+    margins = []
+    for i in range(n_starts):
+        r, env = helpers.device_model_envelope(spec, X0[i], opts)
+        scale = max(1.0, float(np.max(np.abs(r["x"]))))
+        dx = float(np.max(np.abs(br.x[i] - r["x"])))
+        dF = float(np.max(np.abs(br.fun[i] - r["fun"]) / np.maximum(1.0, np.abs(r["fun"]))))
+        dnit = abs(int(br.nit[i]) - r["nit"])
+        same_nit += dnit == 0
+        margins.append((i, dnit, dx, dF, env["dnit"], env["dx"], env["dF"]))
+        assert int(br.status[i]) == r["status"]
+        assert dnit <= 3 * env["dnit"], margins[-1]
+        assert dx <= max(REL * scale, 3 * env["dx"]), margins[-1]
+        assert dF <= max(REL, 3 * env["dF"]), margins[-1]
+        if env["dnit"] == 0 and env["dx"] < 1e-9 * scale:
+            stable += 1
+            assert dnit == 0, margins[-1]
+            assert dx <= REL * scale and dF <= REL, margins[-1]
+    print("start, |dnit|, dx, dF (GPU vs model) | model 1-ulp envelope dnit, dx, dF")
+    for m in margins:
+        print("  %2d %d %.2e %.2e | %d %.2e %.2e" % m)
+    # measured on B200 (round 2): FISTA 15/16 same nit, 10/16 stable; ISTA 5/6 same nit
+    assert same_nit >= 0.8 * n_starts, margins
+    assert stable >= 0.4 * n_starts, margins
+
+
+@pytest.mark.parametrize("case", helpers.converged_cases())
+def test_kernel_vs_converged_reference(gpu, case):
+    """Against CONVERGED solves of the unmodified reference (trust-constr with its default
+    max_iter_internal = 100000; tests/golden/make_golden_converged.py).  trust-constr returns the
+    dual weights to ~1e-6, so two runs that both converge follow slightly different paths along
+    the Pareto set.  Measured (CPU model == kernel to 1e-12 on these cases, see
+    test_kernel_matches_device_model): final F within 3.6e-3 relative on every start, the
+    first 10 iterations of F within 1.7e-2, the iteration count identical on 32 % of the starts
+    (25 of 78) and within a factor 2.5 on all.  The bounds asserted are those numbers
+    with a small margin."""
+    d = helpers.load_converged(case)
+    cls, kw, opts = str(d["problem"]), helpers.case_kwargs(d), helpers.case_options(d)
+    prob = helpers.device_problem(cls, kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        br = prob.minimize_proximal_gradient_batched(d["x0"], return_all=True, **opts)
+    ok = d["success"].astype(bool)
+    # the exact dual never breaks the line search; the reference sometimes does (TRIDIA FISTA)
+    assert np.all(br.status == 1)
+    for i in np.flatnonzero(ok):
+        ref_nit = int(d["nit"][i])
+        _, F_ref = helpers.converged_trace(d, i)
+        scale = np.maximum(1.0, np.abs(d["fun"][i]))
+        assert np.max(np.abs(br.fun[i] - d["fun"][i]) / scale) < 5e-3, (i, br.fun[i], d["fun"][i])
+        k = min(10, ref_nit, int(br.nit[i]))
+        head = np.abs(br.allfuns[i, :k + 1] - F_ref[:k + 1]) / np.maximum(1.0, np.abs(F_ref[:k + 1]))
+        assert head.max() < 2e-2, (i, head.max())
+        ratio = int(br.nit[i]) / max(1, ref_nit)
+        assert 1 / 3.5 <= ratio <= 3.5, (i, int(br.nit[i]), ref_nit)

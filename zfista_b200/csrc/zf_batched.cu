@@ -1,419 +1,12 @@
-// Batched FISTA / ISTA: the whole minimize_proximal_gradient loop
-// (proximal_gradient.py:474-555) on device, one warp per starting point.
-//
-// Per outer iteration a warp does, without leaving the SM:
-//   f(y), jac_f(y)                     -> registers / shared memory
-//   backtracking on lr                 (proximal_gradient.py:279-308)
-//     dual solve of the subproblem     (zf_dual.cuh)
-//     x = prox(...), F(x) = f(x)+g(x)
-//   stopping test  max|x - y| < tol
-//   t_{k+1}(a, b), extrapolation y = x + (t_k - 1)/t_{k+1} (x - x_prev)
-// State (y, x_prev, x, J rows) lives in the warp's slice of shared memory.
+// Batched FISTA / ISTA: host-side dispatch and the C ABI of the batched entry points.  The
+// kernels (the whole minimize_proximal_gradient loop, proximal_gradient.py:474-555, on device,
+// one warp per starting point) are in zf_batched_kernels.cuh.
 #include <cstdio>
 #include <mutex>
 
-#include "zf_dual.cuh"
-#include "zf_host.h"
+#include "zf_batched_kernels.cuh"
 
 namespace zf {
-
-__host__ __device__ __forceinline__ size_t warp_smem_doubles(int n, int m, int n_rows) {
-  return (size_t)(3 + m) * n + n_rows + (size_t)(n + 7) / 8;     // + n pattern bytes
-}
-
-template <int M>
-struct SubproblemOut {
-  double fun;       // primal subproblem value (= D(w*), res.fun of _solve_subproblem)
-  double w[M];
-  int n_dual;
-};
-
-// _solve_subproblem (proximal_gradient.py:35-209) given f(y), J(y) already in ctx.
-// Writes x into c.xn.
-template <int KIND, int M>
-__device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const WarpCtx& c,
-                                 double lr, const double (&fy)[M], const double (&Fprev)[M],
-                                 bool deprecated, SubproblemOut<M>& out) {
-  if constexpr (M == 1) {
-    // x = prox(lr, y - lr * jac); fun = jac.(x - y) + g(x) + ||x - y||^2 / 2 / lr (+ f_y - F_prev)
-    double wt[1] = {lr};
-    double s[2] = {0.0, 0.0};
-#pragma unroll 1
-    for (int j = c.lane; j < c.n; j += 32) {
-      const double yj = c.y[j];
-      const double gj = c.J[j];
-      double alpha, eps[1];
-      const double p = prox_elem<1, false>(P, j, yj - lr * gj, wt, alpha, eps);
-      c.xn[j] = p;
-      s[0] += gj * (p - yj);
-      s[1] += (p - yj) * (p - yj);
-    }
-    __syncwarp();
-    warp_sum_k<2>(s);
-    double gx[1];
-    g_eval<1>(P, c, c.xn, gx);
-    double fun = s[0] + gx[0] + norm_sq_like_numpy(s[1]) / 2.0 / lr;
-    if (!deprecated) fun += fy[0] - Fprev[0];
-    out.fun = fun;
-    out.w[0] = 1.0;
-    out.n_dual = 1;
-  } else {
-    DualData<M> d;
-    d.lr = lr;
-    d.use_c = !deprecated;
-#pragma unroll
-    for (int i = 0; i < M; ++i) d.c[i] = fy[i] - Fprev[i];
-    int nf = 0;
-    if (M == 2 && O.dual_solver == 0) {
-      if constexpr (M == 2) {
-        double fmin;
-        const double xf = dual_brent(P, c, d, O.tol_internal, O.max_iter_internal, &fmin, &nf);
-        out.w[0] = xf;
-        out.w[1] = 1.0 - xf;
-        out.fun = -fmin;
-      }
-      primal_from_weights<M>(P, c, lr, out.w, c.xn);
-    } else {
-      bool x_ready = false;
-      out.fun = dual_newton<M>(P, c, d, out.w, 60, &nf, &x_ready);
-      if (!x_ready) primal_from_weights<M>(P, c, lr, out.w, c.xn);
-    }
-    out.n_dual = nf;
-  }
-}
-
-template <int KIND, int M>
-__global__ void __launch_bounds__(128)
-batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const double* __restrict__ x0,
-                     const double* __restrict__ ab, zf_result R) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp_in_block = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const int n = P.n_features;
-  const int n_rows = (KIND == ZF_LSQ_L1) ? P.n_rows : 0;
-  double* base = smem + (size_t)warp_in_block * warp_smem_doubles(n, M, n_rows);
-
-  WarpCtx c;
-  c.lane = lane;
-  c.n = n;
-  c.y = base;
-  c.xp = base + n;
-  c.xn = base + 2 * (size_t)n;
-  c.J = base + 3 * (size_t)n;
-  c.scratch = base + (size_t)(3 + M) * n;
-  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
-
-  using F = Fn<KIND, M>;
-  const long long total_warps = (long long)gridDim.x * warps_per_block;
-  for (long long s = (long long)blockIdx.x * warps_per_block + warp_in_block; s < n_starts;
-       s += total_warps) {
-    const double* xs = x0 + s * n;
-    const int cap = O.trace_capacity;
-#pragma unroll 1
-    for (int j = lane; j < n; j += 32) {
-      const double v = xs[j];
-      c.y[j] = v;
-      c.xp[j] = v;
-      c.xn[j] = v;
-      if (cap > 0 && R.allvecs) R.allvecs[(s * (cap + 1)) * n + j] = v;
-    }
-    __syncwarp();
-    const double na = ab ? ab[2 * s] : O.nesterov_a;
-    const double nb = ab ? ab[2 * s + 1] : O.nesterov_b;
-    double lr = O.lr;
-    double t_prev = 1.0;
-    double Fprev[M], Fx[M], fx[M], fy[M], gx[M];
-    F::f(P, c, c.xp, fx);
-    g_eval<M>(P, c, c.xp, gx);
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      Fprev[i] = fx[i] + gx[i];
-      Fx[i] = Fprev[i];
-    }
-    if (cap > 0 && R.allfuns && lane == 0) {
-#pragma unroll
-      for (int i = 0; i < M; ++i) R.allfuns[(s * (cap + 1)) * M + i] = Fprev[i];
-    }
-    long long nfev = 1, ndual = 0;
-    double wwarm[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) wwarm[i] = 1.0 / (double)M;
-
-    int status = 0;          // max_iter reached unless set otherwise
-    long long nit = 0;
-    double err = CUDART_INF;
-    bool failed = false;
-    for (long long it = 1; it <= O.max_iter; ++it) {
-      nit = it;
-      F::f_jac(P, c, c.y, c.J, fy);
-      __syncwarp();
-      ++nfev;
-      // ---- backtracking line search ----
-      bool found = false;
-      SubproblemOut<M> sub;
-      for (int bt = 0; bt < O.max_backtrack_iter; ++bt) {
-#pragma unroll
-        for (int i = 0; i < M; ++i) sub.w[i] = wwarm[i];
-        solve_subproblem<KIND, M>(P, O, c, lr, fy, Fprev, O.deprecated != 0, sub);
-        ndual += sub.n_dual;
-        F::f(P, c, c.xn, fx);
-        g_eval<M>(P, c, c.xn, gx);
-        ++nfev;
-#pragma unroll
-        for (int i = 0; i < M; ++i) Fx[i] = fx[i] + gx[i];
-        // The reference passes w0 = 1/m to its inner solver unless warm_start is set.  The
-        // simplex Newton solver converges to the same (exact) maximiser from any start, so it
-        // always continues from the previous subproblem's weights: near convergence that is
-        // one or two dual evaluations instead of three or four.
-        if (O.warm_start || !(M == 2 && O.dual_solver == 0)) {
-#pragma unroll
-          for (int i = 0; i < M; ++i) wwarm[i] = sub.w[i];
-        }
-        if (O.decay_rate == 1.0) { found = true; break; }
-        bool ok = true;
-        if (O.deprecated) {
-#pragma unroll
-          for (int i = 0; i < M; ++i) ok = ok && (fx[i] - fy[i] <= sub.fun + O.tol_internal);
-        } else {
-#pragma unroll
-          for (int i = 0; i < M; ++i) ok = ok && (Fx[i] - Fprev[i] <= sub.fun + O.tol_internal);
-        }
-        if (ok) { found = true; break; }
-        lr *= O.decay_rate;
-      }
-      if (!found) {
-        // RuntimeError("Backtracking failed...") -> x = x_prev, nit - 1 (proximal_gradient.py:493-509)
-        failed = true;
-        nit = it - 1;
-        break;
-      }
-      double e = 0.0;
-#pragma unroll 1
-      for (int j = lane; j < n; j += 32) e = fmax(e, fabs(c.xn[j] - c.y[j]));
-      err = warp_max(e);
-      if (cap > 0 && it <= cap) {
-        if (R.allerrs && lane == 0) R.allerrs[s * cap + (it - 1)] = err;
-        if (R.allfuns && lane == 0) {
-#pragma unroll
-          for (int i = 0; i < M; ++i) R.allfuns[(s * (cap + 1) + it) * M + i] = Fx[i];
-        }
-        if (R.allvecs) {
-#pragma unroll 1
-          for (int j = lane; j < n; j += 32) R.allvecs[(s * (cap + 1) + it) * n + j] = c.xn[j];
-        }
-      }
-      if (err < O.tol) { status = 1; break; }
-      if (it == O.max_iter) break;   // keep x = x^k as the reference's for/else does
-      // ---- momentum and extrapolation (proximal_gradient.py:530-538) ----
-      if (O.nesterov) {
-        const double t_new = sqrt(t_prev * t_prev - na * t_prev + nb) + 0.5;
-        const double mom = (t_prev - 1.0) / t_new;
-#pragma unroll 1
-        for (int j = lane; j < n; j += 32) {
-          const double xj = c.xn[j];
-          c.y[j] = xj + mom * (xj - c.xp[j]);
-        }
-        t_prev = t_new;
-        double* tmp = c.xp; c.xp = c.xn; c.xn = tmp;
-      } else {
-        // y = x_prev = x^k
-#pragma unroll 1
-        for (int j = lane; j < n; j += 32) c.y[j] = c.xn[j];
-        double* tmp = c.xp; c.xp = c.xn; c.xn = tmp;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < M; ++i) Fprev[i] = Fx[i];
-    }
-    // ---- results ----
-    const double* xres = failed ? c.xp : c.xn;
-    if (failed) {
-      status = -1;
-#pragma unroll
-      for (int i = 0; i < M; ++i) Fx[i] = Fprev[i];
-    }
-#pragma unroll 1
-    for (int j = lane; j < n; j += 32) R.x[s * n + j] = xres[j];
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < M; ++i) R.fun[s * M + i] = Fx[i];
-      R.nit[s] = nit;
-      R.status[s] = status;
-      if (R.lr) R.lr[s] = lr;
-      if (R.nfev) R.nfev[s] = nfev;
-      if (R.n_dual) R.n_dual[s] = ndual;
-      if (R.err) R.err[s] = err;
-    }
-    __syncwarp();
-  }
-}
-
-// One subproblem per warp: _solve_subproblem(f, g, jac_f, prox, lr, xk_old, yk, w0)
-template <int KIND, int M>
-__global__ void __launch_bounds__(128)
-subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* __restrict__ Y,
-                  const double* __restrict__ Xold, const double* __restrict__ LR,
-                  const int* __restrict__ dep, double* __restrict__ X, double* __restrict__ FUN,
-                  double* __restrict__ W) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp_in_block = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const int n = P.n_features;
-  const int n_rows = (KIND == ZF_LSQ_L1) ? P.n_rows : 0;
-  double* base = smem + (size_t)warp_in_block * warp_smem_doubles(n, M, n_rows);
-  WarpCtx c;
-  c.lane = lane; c.n = n;
-  c.y = base; c.xp = base + n; c.xn = base + 2 * (size_t)n; c.J = base + 3 * (size_t)n;
-  c.scratch = base + (size_t)(3 + M) * n;
-  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
-  using F = Fn<KIND, M>;
-  const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
-  if (s >= n_items) return;
-#pragma unroll 1
-  for (int j = lane; j < n; j += 32) {
-    c.y[j] = Y[s * n + j];
-    c.xp[j] = Xold[s * n + j];
-  }
-  __syncwarp();
-  double fy[M], fp[M], gp[M], Fprev[M];
-  F::f(P, c, c.xp, fp);
-  g_eval<M>(P, c, c.xp, gp);
-#pragma unroll
-  for (int i = 0; i < M; ++i) Fprev[i] = fp[i] + gp[i];
-  F::f_jac(P, c, c.y, c.J, fy);
-  __syncwarp();
-  SubproblemOut<M> sub;
-#pragma unroll
-  for (int i = 0; i < M; ++i) sub.w[i] = 1.0 / (double)M;
-  const bool deprecated = dep ? (dep[s] != 0) : (O.deprecated != 0);
-  solve_subproblem<KIND, M>(P, O, c, LR[s], fy, Fprev, deprecated, sub);
-#pragma unroll 1
-  for (int j = lane; j < n; j += 32) X[s * n + j] = c.xn[j];
-  if (lane == 0) {
-    FUN[s] = sub.fun;
-#pragma unroll
-    for (int i = 0; i < M; ++i) W[s * M + i] = sub.w[i];
-  }
-}
-
-// Problem.f / g / jac_f / prox_wsum_g at a batch of points (one warp per point).
-template <int KIND, int M>
-__global__ void __launch_bounds__(128)
-problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ Xin,
-                    const double* __restrict__ Win, double* __restrict__ fo,
-                    double* __restrict__ go, double* __restrict__ jo, double* __restrict__ po) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp_in_block = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const int n = P.n_features;
-  const int n_rows = (KIND == ZF_LSQ_L1) ? P.n_rows : 0;
-  double* base = smem + (size_t)warp_in_block * warp_smem_doubles(n, M, n_rows);
-  WarpCtx c;
-  c.lane = lane; c.n = n;
-  c.y = base; c.xp = base + n; c.xn = base + 2 * (size_t)n; c.J = base + 3 * (size_t)n;
-  c.scratch = base + (size_t)(3 + M) * n;
-  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
-  using F = Fn<KIND, M>;
-  const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
-  if (s >= n_items) return;
-#pragma unroll 1
-  for (int j = lane; j < n; j += 32) c.y[j] = Xin[s * n + j];
-  __syncwarp();
-  double fy[M], gy[M];
-  F::f_jac(P, c, c.y, c.J, fy);
-  __syncwarp();
-  g_eval<M>(P, c, c.y, gy);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      if (fo) fo[s * M + i] = fy[i];
-      if (go) go[s * M + i] = gy[i];
-    }
-  }
-  if (jo) {
-#pragma unroll 1
-    for (int j = lane; j < n; j += 32) {
-#pragma unroll
-      for (int i = 0; i < M; ++i) jo[(s * M + i) * n + j] = c.J[i * n + j];
-    }
-  }
-  if (po && Win) {
-    double wt[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) wt[i] = Win[s * M + i];
-#pragma unroll 1
-    for (int j = lane; j < n; j += 32) {
-      double alpha, eps[M];
-      po[s * n + j] = prox_elem<M, false>(P, j, c.y[j], wt, alpha, eps);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// host-side dispatch
-// ---------------------------------------------------------------------------------------
-enum class Op { Solve, Subproblem, Eval };
-
-struct LaunchArgs {
-  Op op;
-  zf_problem P;
-  zf_options O;
-  long long n_items;
-  const double* a0;   // x0 | Y | X
-  const double* a1;   // ab | Xold | W
-  const double* a2;   // - | LR | -
-  const int* i0;      // - | dep | -
-  zf_result R;        // Solve outputs
-  double* o0; double* o1; double* o2; double* o3;  // Subproblem: X, FUN, W ; Eval: f, g, jac, prox
-  cudaStream_t stream;
-};
-
-template <int KIND, int M>
-static int launch_t(const LaunchArgs& L) {
-  const int n = L.P.n_features;
-  const int n_rows = (KIND == ZF_LSQ_L1) ? L.P.n_rows : 0;
-  const size_t per_warp = warp_smem_doubles(n, M, n_rows) * sizeof(double);
-  const size_t smem_cap = 200 * 1024;
-  if (per_warp > smem_cap) {
-    return zf_fail(ZF_ERR_UNSUPPORTED,
-                   "n_features=%d needs %zu B of shared memory per start (limit %zu); "
-                   "use the large-n LASSO path for single-objective problems",
-                   n, per_warp, smem_cap);
-  }
-  // Few starts: one warp per block so the warps spread over all SMs / schedulers.
-  int wpb = (L.n_items <= 148LL * 16) ? 1 : 4;
-  while (wpb > 1 && per_warp * wpb > smem_cap) wpb >>= 1;
-  const size_t smem = per_warp * wpb;
-  long long blocks = (L.n_items + wpb - 1) / wpb;
-  if (L.op == Op::Solve && blocks > 148LL * 64) blocks = 148LL * 64;  // grid-stride beyond
-  if (blocks < 1) blocks = 1;
-  cudaError_t e;
-  if (L.op == Op::Solve) {
-    auto k = batched_fista_kernel<KIND, M>;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return zf_fail_cuda(e, "cudaFuncSetAttribute");
-    k<<<(unsigned)blocks, wpb * 32, smem, L.stream>>>(L.P, L.O, L.n_items, L.a0, L.a1, L.R);
-  } else if (L.op == Op::Subproblem) {
-    auto k = subproblem_kernel<KIND, M>;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return zf_fail_cuda(e, "cudaFuncSetAttribute");
-    k<<<(unsigned)blocks, wpb * 32, smem, L.stream>>>(L.P, L.O, L.n_items, L.a0, L.a1, L.a2, L.i0,
-                                                     L.o0, L.o1, L.o2);
-  } else {
-    auto k = problem_eval_kernel<KIND, M>;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return zf_fail_cuda(e, "cudaFuncSetAttribute");
-    k<<<(unsigned)blocks, wpb * 32, smem, L.stream>>>(L.P, L.n_items, L.a0, L.a1, L.o0, L.o1, L.o2,
-                                                     L.o3);
-  }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return zf_fail_cuda(e, "kernel launch");
-  zf_count_launch();
-  return ZF_OK;
-}
 
 static int validate_problem(const zf_problem& P) {
   if (P.n_features < 1) return zf_fail(ZF_ERR_INVALID, "n_features must be >= 1");
@@ -448,26 +41,47 @@ static int validate_problem(const zf_problem& P) {
   return ZF_OK;
 }
 
+// launch_t<KIND, M, L1> is instantiated in the zf_batched_inst_*.cu files (one translation unit
+// per group of problem classes, so that the build compiles them in parallel)
+#define ZF_DECL(K, M_, L) extern template int launch_t<K, M_, L>(const LaunchArgs&);
+ZF_DECL(ZF_JOS1, 2, false) ZF_DECL(ZF_JOS1, 2, true)
+ZF_DECL(ZF_SD, 2, false)
+ZF_DECL(ZF_FDS, 3, false) ZF_DECL(ZF_FDS, 3, true)
+ZF_DECL(ZF_ZDT1, 2, false)
+ZF_DECL(ZF_TOI4, 2, false) ZF_DECL(ZF_TOI4, 2, true)
+ZF_DECL(ZF_TRIDIA, 3, false) ZF_DECL(ZF_TRIDIA, 3, true)
+ZF_DECL(ZF_LFR1, 1, false) ZF_DECL(ZF_LFR1, 1, true)
+ZF_DECL(ZF_LFR1, 2, false) ZF_DECL(ZF_LFR1, 2, true)
+ZF_DECL(ZF_LFR1, 3, false) ZF_DECL(ZF_LFR1, 3, true)
+ZF_DECL(ZF_LFR1, 4, false) ZF_DECL(ZF_LFR1, 4, true)
+ZF_DECL(ZF_LSQ_L1, 1, false) ZF_DECL(ZF_LSQ_L1, 2, false) ZF_DECL(ZF_LSQ_L1, 3, false)
+#undef ZF_DECL
+
+template <int KIND, int M>
+static int launch_l1(const LaunchArgs& L) {
+  return L.P.has_l1 ? launch_t<KIND, M, true>(L) : launch_t<KIND, M, false>(L);
+}
+
 int zf_launch(const LaunchArgs& L) {
   int rc = validate_problem(L.P);
   if (rc != ZF_OK) return rc;
   const int m = L.P.n_objectives;
   switch (L.P.kind) {
-    case ZF_JOS1: return launch_t<ZF_JOS1, 2>(L);
-    case ZF_SD: return launch_t<ZF_SD, 2>(L);
-    case ZF_FDS: return launch_t<ZF_FDS, 3>(L);
-    case ZF_ZDT1: return launch_t<ZF_ZDT1, 2>(L);
-    case ZF_TOI4: return launch_t<ZF_TOI4, 2>(L);
-    case ZF_TRIDIA: return launch_t<ZF_TRIDIA, 3>(L);
+    case ZF_JOS1: return launch_l1<ZF_JOS1, 2>(L);
+    case ZF_SD: return launch_t<ZF_SD, 2, false>(L);         // SD / ZDT1 take no l1 arguments
+    case ZF_FDS: return launch_l1<ZF_FDS, 3>(L);
+    case ZF_ZDT1: return launch_t<ZF_ZDT1, 2, false>(L);
+    case ZF_TOI4: return launch_l1<ZF_TOI4, 2>(L);
+    case ZF_TRIDIA: return launch_l1<ZF_TRIDIA, 3>(L);
     case ZF_LFR1:
-      if (m == 1) return launch_t<ZF_LFR1, 1>(L);
-      if (m == 2) return launch_t<ZF_LFR1, 2>(L);
-      if (m == 3) return launch_t<ZF_LFR1, 3>(L);
-      return launch_t<ZF_LFR1, 4>(L);
+      if (m == 1) return launch_l1<ZF_LFR1, 1>(L);
+      if (m == 2) return launch_l1<ZF_LFR1, 2>(L);
+      if (m == 3) return launch_l1<ZF_LFR1, 3>(L);
+      return launch_l1<ZF_LFR1, 4>(L);
     case ZF_LSQ_L1:
-      if (m == 1) return launch_t<ZF_LSQ_L1, 1>(L);
-      if (m == 2) return launch_t<ZF_LSQ_L1, 2>(L);
-      return launch_t<ZF_LSQ_L1, 3>(L);
+      if (m == 1) return launch_t<ZF_LSQ_L1, 1, false>(L);
+      if (m == 2) return launch_t<ZF_LSQ_L1, 2, false>(L);
+      return launch_t<ZF_LSQ_L1, 3, false>(L);
   }
   return zf_fail(ZF_ERR_INVALID, "unknown problem kind %d", L.P.kind);
 }

@@ -13,9 +13,6 @@
 #pragma once
 #include "zf_problems.cuh"
 
-#ifndef ZF_DUAL_UNROLL
-#define ZF_DUAL_UNROLL 1
-#endif
 #ifndef ZF_QP_BRANCHFREE
 #define ZF_QP_BRANCHFREE 0
 #endif
@@ -29,10 +26,25 @@ struct DualData {
   bool use_c;         // !deprecated
 };
 
+// what the dual sweeps read of one coordinate: the Jacobian column and y_j
+template <int M>
+struct CoordIn {
+  double J[M];
+  double y;
+};
+template <int M>
+__device__ __forceinline__ CoordIn<M> load_coord(const WarpCtx& c, int jc) {
+  CoordIn<M> in;
+#pragma unroll
+  for (int i = 0; i < M; ++i) in.J[i] = c.J[i * c.n + jc];
+  in.y = c.y[jc];
+  return in;
+}
+
 // ------------------------------------------------------------------------------------
 // -D(w) exactly as _dual_minimized_fun_jac (proximal_gradient.py:161-177) forms it.
 // ------------------------------------------------------------------------------------
-template <int M>
+template <int KIND, int M, bool L1>
 __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
                                  const double (&w)[M]) {
   double wt[M];
@@ -42,31 +54,31 @@ __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const Du
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
-  const bool lsq = (P.kind == ZF_LSQ_L1);
-#pragma unroll 1
-  for (int j = c.lane; j < c.n; j += 32) {
+  constexpr bool lsq = (KIND == ZF_LSQ_L1);
+  sweep(c.n, c.lane, [&](int j, bool live) {
+    const int jc = live ? j : 0;
     double wj = 0.0;
 #pragma unroll
-    for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + j];
-    const double v = c.y[j] - d.lr * wj;
+    for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + jc];
+    const double v = c.y[jc] - d.lr * wj;
     double alpha, eps[M];
-    const double p = prox_elem<M, false>(P, j, v, wt, alpha, eps);
+    const double p = prox_elem<KIND, M, L1, false>(P, jc, v, wt, alpha, eps);
     if (lsq) {
-      s[0] += fabs(p);
-    } else if (P.has_l1) {
+      s[0] += msk(live, fabs(p));
+    } else if (L1) {
 #pragma unroll
-      for (int i = 0; i < M; ++i) s[i] += fabs(p - P.l1_shifts[i]);
+      for (int i = 0; i < M; ++i) s[i] += msk(live, fabs(p - P.l1_shifts[i]));
     }
-    s[M] += (p - v) * (p - v);
-    s[M + 1] += wj * wj;
-  }
+    s[M] += msk(live, p - v) * (p - v);
+    s[M + 1] += msk(live, wj) * wj;
+  });
   warp_sum_k<NS>(s);
   double wg = 0.0;
   if (lsq) {
     const double gl = P.l1 * s[0];
 #pragma unroll
     for (int i = 0; i < M; ++i) wg += w[i] * gl;
-  } else if (P.has_l1) {
+  } else if (L1) {
 #pragma unroll
     for (int i = 0; i < M; ++i) wg += w[i] * (P.l1_ratios[i] * s[i]);
   }
@@ -82,21 +94,25 @@ __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const Du
 }
 
 // x = prox_wsum_g(lr * w, y - lr * w @ J)   (proximal_gradient.py:206)
-template <int M>
+template <int KIND, int M, bool L1>
 __device__ void primal_from_weights(const zf_problem& P, const WarpCtx& c, double lr,
                                     const double (&w)[M], double* out) {
   double wt[M];
 #pragma unroll
   for (int i = 0; i < M; ++i) wt[i] = lr * w[i];
-#pragma unroll 1
-  for (int j = c.lane; j < c.n; j += 32) {
-    double wj = 0.0;
+  sweep3<CoordIn<M>, double>(
+      c.n, c.lane, [&](int j, bool live) { return load_coord<M>(c, live ? j : 0); },
+      [&](const CoordIn<M>& in, int j, bool live) {
+        double wj = 0.0;
 #pragma unroll
-    for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + j];
-    const double v = c.y[j] - lr * wj;
-    double alpha, eps[M];
-    out[j] = prox_elem<M, false>(P, j, v, wt, alpha, eps);
-  }
+        for (int i = 0; i < M; ++i) wj += w[i] * in.J[i];
+        const double v = in.y - lr * wj;
+        double alpha, eps[M];
+        return prox_elem<KIND, M, L1, false>(P, live ? j : 0, v, wt, alpha, eps);
+      },
+      [&](int j, bool live, double p) {
+        if (live) out[j] = p;
+      });
   __syncwarp();
 }
 
@@ -111,6 +127,7 @@ __device__ __forceinline__ double sgn_plus(double v) {
   return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : (v == 0.0 ? 1.0 : v));
 }
 
+template <int KIND, bool L1>
 __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualData<2>& d,
                              double xatol, int maxfun, double* fmin, int* nfev) {
   const double sqrt_eps = sqrt(2.2e-16);
@@ -121,7 +138,7 @@ __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualDa
   double rat = 0.0, e = 0.0;
   double x = xf;
   double w2[2] = {x, 1.0 - x};
-  double fx = neg_dual_value<2>(P, c, d, w2);
+  double fx = neg_dual_value<KIND, 2, L1>(P, c, d, w2);
   int num = 1;
   double fu = CUDART_INF;
   double ffulc = fx, fnfc = fx;
@@ -157,7 +174,7 @@ __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualDa
     x = xf + sgn_plus(rat) * fmax(fabs(rat), tol1);
     w2[0] = x;
     w2[1] = 1.0 - x;
-    fu = neg_dual_value<2>(P, c, d, w2);
+    fu = neg_dual_value<KIND, 2, L1>(P, c, d, w2);
     num += 1;
     if (fu <= fx) {
       if (x >= xf) a = xf; else b = xf;
@@ -205,23 +222,33 @@ __device__ __forceinline__ unsigned char piece_code(double alpha, const double (
 
 // x = prox_wsum_g(lr * w, y - lr * w @ J) into `out`, and whether every coordinate is on the
 // same piece as at the last full dual evaluation (c.pat)
-template <int M>
+template <int KIND, int M, bool L1>
 __device__ bool primal_probe(const zf_problem& P, const WarpCtx& c, double lr,
                              const double (&w)[M], double* out) {
   double wt[M];
 #pragma unroll
   for (int i = 0; i < M; ++i) wt[i] = lr * w[i];
   int same = 1;
-#pragma unroll 1
-  for (int j = c.lane; j < c.n; j += 32) {
-    double wj = 0.0;
+  struct In { CoordIn<M> c; unsigned char pat; };
+  sweep3<In, double>(
+      c.n, c.lane,
+      [&](int j, bool live) {
+        const int jc = live ? j : 0;
+        return In{load_coord<M>(c, jc), c.pat[jc]};
+      },
+      [&](const In& in, int j, bool live) {
+        double wj = 0.0;
 #pragma unroll
-    for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + j];
-    const double v = c.y[j] - lr * wj;
-    double alpha, eps[M];
-    out[j] = prox_elem<M, true>(P, j, v, wt, alpha, eps);
-    same &= (piece_code<M>(alpha, eps) == c.pat[j]);
-  }
+        for (int i = 0; i < M; ++i) wj += w[i] * in.c.J[i];
+        const double v = in.c.y - lr * wj;
+        double alpha, eps[M];
+        const double p = prox_elem<KIND, M, L1, true>(P, live ? j : 0, v, wt, alpha, eps);
+        same &= live ? (int)(piece_code<M>(alpha, eps) == in.pat) : 1;
+        return p;
+      },
+      [&](int j, bool live, double p) {
+        if (live) out[j] = p;
+      });
   __syncwarp();
   return __all_sync(ZF_FULL_MASK, same) != 0;
 }
@@ -233,7 +260,7 @@ struct DualPoint {
   double Q[M][M];
 };
 
-template <int M>
+template <int KIND, int M, bool L1>
 __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
                           const double (&w)[M], DualPoint<M>& out) {
   double wt[M];
@@ -244,58 +271,55 @@ __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<
   double s[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) s[k] = 0.0;
-  const bool lsq = (P.kind == ZF_LSQ_L1);
-  // Two coordinates per trip: the prox chain of one coordinate is a long dependent sequence
-  // and the kernel is latency bound, so the second, independent chain is almost free.  The
-  // out-of-range slot works on coordinate 0 and contributes exact zeros, which keeps every
-  // partial sum bit-identical to the one-coordinate-per-trip order.
-#pragma unroll 1
-  for (int j0 = c.lane; j0 < c.n; j0 += 32 * ZF_DUAL_UNROLL) {
+  constexpr bool lsq = (KIND == ZF_LSQ_L1);
+  double lam[M], shift[M];
 #pragma unroll
-    for (int u = 0; u < ZF_DUAL_UNROLL; ++u) {
-      const int jr = j0 + 32 * u;
-      const bool live = jr < c.n;
-      const int j = live ? jr : 0;
-      double Jc[M];
-      double wj = 0.0;
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        Jc[i] = c.J[i * c.n + j];
-        wj += w[i] * Jc[i];
-      }
-      const double yj = c.y[j];
-      const double v = yj - d.lr * wj;
-      double alpha, eps[M];
-      const double p = prox_elem<M, true>(P, j, v, wt, alpha, eps);
-      const double keep = live ? 1.0 : 0.0;
-      if (live) c.pat[j] = piece_code<M>(alpha, eps);
-      double mcol[M];
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        double lam = 0.0, shift = 0.0;
-        if (lsq) lam = P.l1;
-        else if (P.has_l1) { lam = P.l1_ratios[i]; shift = P.l1_shifts[i]; }
-        s[i] += keep * fabs(p - shift);
-        s[M + i] += keep * (Jc[i] * (p - yj));
-        mcol[i] = (keep * alpha) * (Jc[i] + lam * eps[i]);
-      }
-      s[2 * M] += keep * ((p - v) * (p - v));
-      s[2 * M + 1] += keep * (wj * wj);
-      int k = 2 * M + 2;
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-#pragma unroll
-        for (int l = i; l < M; ++l) s[k++] += mcol[i] * mcol[l];
-      }
-    }
+  for (int i = 0; i < M; ++i) {
+    lam[i] = 0.0;
+    shift[i] = 0.0;
+    if (lsq) lam[i] = P.l1;
+    else if (L1) { lam[i] = P.l1_ratios[i]; shift[i] = P.l1_shifts[i]; }
   }
+  sweep3<CoordIn<M>, unsigned char>(
+      c.n, c.lane, [&](int j, bool live) { return load_coord<M>(c, live ? j : 0); },
+      [&](const CoordIn<M>& in, int j, bool live) {
+        double wj = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) wj += w[i] * in.J[i];
+        const double yj = in.y;
+        const double v = yj - d.lr * wj;
+        double alpha, eps[M];
+        const double p = prox_elem<KIND, M, L1, true>(P, live ? j : 0, v, wt, alpha, eps);
+        // a dead slot contributes exact zeros: its alpha, p - y, p - v and w.J are masked
+        const double am = msk(live, alpha);
+        const double dy = msk(live, p - yj);
+        double mcol[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+          s[i] += msk(live, fabs(p - shift[i]));
+          s[M + i] += in.J[i] * dy;
+          mcol[i] = am * (in.J[i] + lam[i] * eps[i]);
+        }
+        s[2 * M] += msk(live, p - v) * (p - v);
+        s[2 * M + 1] += msk(live, wj) * wj;
+        int k = 2 * M + 2;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+#pragma unroll
+          for (int l = i; l < M; ++l) s[k++] += mcol[i] * mcol[l];
+        }
+        return piece_code<M>(alpha, eps);
+      },
+      [&](int j, bool live, unsigned char code) {
+        if (live) c.pat[j] = code;
+      });
   warp_sum_k<NS>(s);
   double Dv = s[2 * M] / 2.0 / d.lr - d.lr / 2.0 * s[2 * M + 1];
 #pragma unroll
   for (int i = 0; i < M; ++i) {
     double gi = 0.0;
     if (lsq) gi = P.l1 * s[i];
-    else if (P.has_l1) gi = P.l1_ratios[i] * s[i];
+    else if (L1) gi = P.l1_ratios[i] * s[i];
     const double ci = d.use_c ? d.c[i] : 0.0;
     out.G[i] = gi + s[M + i] + ci;
     Dv += w[i] * (gi + ci);
@@ -467,9 +491,13 @@ __device__ void simplex_qp(const double (&Q)[M][M], const double (&G)[M],
 // Each step solves the QP of the current quadratic piece exactly.  When the model's
 // predicted gain drops below the rounding level of D the step is taken on trust and
 // the iteration stops (oracle/dual_model.py:simplex_newton is the CPU statement).
-template <int M>
+// `probe(wn)` must write x = prox_wsum_g(lr * wn, y - lr * wn @ J) to c.xn and return whether
+// every coordinate is on the piece stored in c.pat (primal_probe, or the batched kernel's fused
+// sweep that also evaluates F(x) and max|x - y| while it is there).
+template <int KIND, int M, bool L1, class Probe>
 __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
-                              double (&w)[M], int max_iter, int* nfev, bool* x_ready) {
+                              double (&w)[M], int max_iter, int* nfev, bool* x_ready,
+                              Probe&& probe) {
   // One evaluation site and one QP site (code size: see zf_common.cuh): the loop body is
   // "evaluate the point under test, then either accept it and take the next Newton step from
   // it, or halve the step".
@@ -481,7 +509,7 @@ __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualD
   int evals = 0, it = 0, bt = 0;
   bool first = true;
   for (;;) {
-    dual_full<M>(P, c, d, wt, pt);
+    dual_full<KIND, M, L1>(P, c, d, wt, pt);
     ++evals;
     if (first || pt.D >= cur.D) {
       first = false;
@@ -527,7 +555,7 @@ __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualD
     // is exact there: the candidate is the maximiser, D(candidate) = D + pred, and evaluating
     // it (plus the QP that would return it unchanged) is only a confirmation -- skip both.
     // The probe is the primal recovery the caller needs anyway, so it costs nothing extra.
-    if (primal_probe<M>(P, c, d.lr, wn, c.xn)) {
+    if (probe(wn)) {
 #pragma unroll
       for (int i = 0; i < M; ++i) w[i] = wn[i];
       cur.D += pred;
