@@ -187,20 +187,21 @@ def simplex_qp(Q, G, w_cur):
             # LDL^T without pivoting; a pivot at rounding level = singular face
             A = R.copy()
             ok = True
+            inv = np.zeros(k - 1)
             for kk in range(k - 1):
                 if not (A[kk, kk] > 1e-13 * scale):
                     ok = False
                     break
-                inv = 1.0 / A[kk, kk]
+                inv[kk] = 1.0 / A[kk, kk]
                 for r in range(kk + 1, k - 1):
-                    fct = A[r, kk] * inv
+                    fct = A[r, kk] * inv[kk]
                     A[r, kk + 1:] -= fct * A[kk, kk + 1:]
                     rhs[r] -= fct * rhs[kk]
             if not ok:
                 continue
             z = np.zeros(k - 1)
             for kk in range(k - 2, -1, -1):
-                z[kk] = (rhs[kk] - A[kk, kk + 1:] @ z[kk + 1:]) / A[kk, kk]
+                z[kk] = (rhs[kk] - A[kk, kk + 1:] @ z[kk + 1:]) * inv[kk]   # as zf_dual.cuh:qp_face
             if (z < 0).any() or 1.0 - z.sum() < 0:
                 continue
             w[S[1:]] = z

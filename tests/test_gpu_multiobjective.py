@@ -41,7 +41,6 @@ STRICT_CASES = {
     "FDS_n10": ("FDS", dict(n_features=10), -2, 2),
     "FDS_n10_l1": ("FDS", dict(n_features=10, **_l1(10, 3)), -2, 2),
     "FDS_n10_box": ("FDS", dict(n_features=10, bounds=(0, np.inf)), 0, 2),
-    "FDS_n20_l1": ("FDS", dict(n_features=20, **_l1(20, 3)), -2, 2),
     "TRIDIA": ("TRIDIA", dict(), -1, 1),
     "TRIDIA_l1": ("TRIDIA", _l1(3, 3), -1, 1),
     "LFR1_n30": ("LinearFunctionRank1", dict(n_features=30), -1, 1),
@@ -102,18 +101,19 @@ def test_momentum_grid_fds_one_launch(gpu):
         np.testing.assert_array_equal(allin.x[sel], one.x)
 
 
-@pytest.mark.parametrize("algo,n_starts", [("fista", 16), ("ista", 6)])
-def test_headline_fds_n100_l1_matches_device_model(gpu, algo, n_starts):
-    """BASELINE configs[2], FDS n = 100 with the L1 term, to convergence.
+@pytest.mark.parametrize("n,algo,n_starts", [(100, "fista", 16), (100, "ista", 6),
+                                             (20, "fista", 8)])
+def test_large_fds_l1_matches_device_model(gpu, n, algo, n_starts):
+    """BASELINE configs[2], FDS n = 100 with the L1 term (and n = 20, benchmark.py:417), to
+    convergence.
 
     On this problem the objective values are ~1e7 while the dual gradient is O(1): the term
     f(y) - F(x^{k-1}) of the subproblem carries an absolute rounding error of ~1e-9, and a ONE-ulp
     perturbation of x0 moves the CPU model's own final x by 1e-9 .. 1e-3 depending on the start
-    (helpers.device_model_envelope).  So: every start must agree with the model within the
+    (helpers.device_model_envelope; n = 20: up to ~1e-7).  So: every start must agree with the model within the
     model's own 1-ulp envelope (3x the largest deviation over 4 seeds, iteration count included);
     starts on which the model is stable (same nit under perturbation, envelope < 1e-9) must in
     addition meet north_star's tolerance as is: the same nit, x and F within 1e-8 relative."""
-    n = 100
     kw = dict(n_features=n, **_l1(n, 3))
     prob = helpers.device_problem("FDS", kw)
     spec = helpers.oracle_spec("FDS", kw)
@@ -143,7 +143,7 @@ def test_headline_fds_n100_l1_matches_device_model(gpu, algo, n_starts):
     print("start, |dnit|, dx, dF (GPU vs model) | model 1-ulp envelope dnit, dx, dF")
     for m in margins:
         print("  %2d %d %.2e %.2e | %d %.2e %.2e" % m)
-    # measured on B200 (round 2): FISTA 15/16 same nit, 10/16 stable; ISTA 5/6 same nit
+    # measured on B200 (round 2), n = 100: FISTA 15/16 same nit, 10/16 stable; ISTA 5/6 same nit
     assert same_nit >= 0.8 * n_starts, margins
     assert stable >= 0.4 * n_starts, margins
 

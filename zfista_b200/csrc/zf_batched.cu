@@ -36,30 +36,38 @@ static int validate_problem(const zf_problem& P) {
       break;
     default: return zf_fail(ZF_ERR_INVALID, "unknown problem kind %d", P.kind);
   }
+  if ((P.kind == ZF_SD || P.kind == ZF_ZDT1) && (!P.has_bounds || P.has_l1))
+    return zf_fail(ZF_ERR_INVALID, "SD / ZDT1 are defined with bounds (1e-6, inf) and without "
+                                   "l1 terms (problems.py:238-245, 365-366)");
   if (P.has_bounds && P.bounds_are_arrays && (!P.lower_v || !P.upper_v))
     return zf_fail(ZF_ERR_INVALID, "array bounds requested but lower_v/upper_v missing");
   return ZF_OK;
 }
 
-// launch_t<KIND, M, L1> is instantiated in the zf_batched_inst_*.cu files (one translation unit
-// per group of problem classes, so that the build compiles them in parallel)
-#define ZF_DECL(K, M_, L) extern template int launch_t<K, M_, L>(const LaunchArgs&);
-ZF_DECL(ZF_JOS1, 2, false) ZF_DECL(ZF_JOS1, 2, true)
-ZF_DECL(ZF_SD, 2, false)
-ZF_DECL(ZF_FDS, 3, false) ZF_DECL(ZF_FDS, 3, true)
-ZF_DECL(ZF_ZDT1, 2, false)
-ZF_DECL(ZF_TOI4, 2, false) ZF_DECL(ZF_TOI4, 2, true)
-ZF_DECL(ZF_TRIDIA, 3, false) ZF_DECL(ZF_TRIDIA, 3, true)
-ZF_DECL(ZF_LFR1, 1, false) ZF_DECL(ZF_LFR1, 1, true)
-ZF_DECL(ZF_LFR1, 2, false) ZF_DECL(ZF_LFR1, 2, true)
-ZF_DECL(ZF_LFR1, 3, false) ZF_DECL(ZF_LFR1, 3, true)
-ZF_DECL(ZF_LFR1, 4, false) ZF_DECL(ZF_LFR1, 4, true)
-ZF_DECL(ZF_LSQ_L1, 1, false) ZF_DECL(ZF_LSQ_L1, 2, false) ZF_DECL(ZF_LSQ_L1, 3, false)
+// launch_t<KIND, M, GF> is instantiated in the zf_batched_inst_*.cu files (one translation unit
+// per group of problem classes, so that the build compiles them in parallel).  GF = which parts
+// g has (ZF_G_L1 | ZF_G_BOX).
+#define ZF_DECL(K, M_, G) extern template int launch_t<K, M_, G>(const LaunchArgs&);
+#define ZF_DECL4(K, M_) ZF_DECL(K, M_, 0) ZF_DECL(K, M_, 1) ZF_DECL(K, M_, 2) ZF_DECL(K, M_, 3)
+ZF_DECL4(ZF_JOS1, 2)
+ZF_DECL(ZF_SD, 2, ZF_G_BOX)
+ZF_DECL4(ZF_FDS, 3)
+ZF_DECL(ZF_ZDT1, 2, ZF_G_BOX)
+ZF_DECL4(ZF_TOI4, 2)
+ZF_DECL4(ZF_TRIDIA, 3)
+ZF_DECL4(ZF_LFR1, 1) ZF_DECL4(ZF_LFR1, 2) ZF_DECL4(ZF_LFR1, 3) ZF_DECL4(ZF_LFR1, 4)
+ZF_DECL(ZF_LSQ_L1, 1, 0) ZF_DECL(ZF_LSQ_L1, 2, 0) ZF_DECL(ZF_LSQ_L1, 3, 0)
+#undef ZF_DECL4
 #undef ZF_DECL
 
 template <int KIND, int M>
-static int launch_l1(const LaunchArgs& L) {
-  return L.P.has_l1 ? launch_t<KIND, M, true>(L) : launch_t<KIND, M, false>(L);
+static int launch_g(const LaunchArgs& L) {
+  switch ((L.P.has_l1 ? ZF_G_L1 : 0) | (L.P.has_bounds ? ZF_G_BOX : 0)) {
+    case 0: return launch_t<KIND, M, 0>(L);
+    case 1: return launch_t<KIND, M, 1>(L);
+    case 2: return launch_t<KIND, M, 2>(L);
+    default: return launch_t<KIND, M, 3>(L);
+  }
 }
 
 int zf_launch(const LaunchArgs& L) {
@@ -67,21 +75,21 @@ int zf_launch(const LaunchArgs& L) {
   if (rc != ZF_OK) return rc;
   const int m = L.P.n_objectives;
   switch (L.P.kind) {
-    case ZF_JOS1: return launch_l1<ZF_JOS1, 2>(L);
-    case ZF_SD: return launch_t<ZF_SD, 2, false>(L);         // SD / ZDT1 take no l1 arguments
-    case ZF_FDS: return launch_l1<ZF_FDS, 3>(L);
-    case ZF_ZDT1: return launch_t<ZF_ZDT1, 2, false>(L);
-    case ZF_TOI4: return launch_l1<ZF_TOI4, 2>(L);
-    case ZF_TRIDIA: return launch_l1<ZF_TRIDIA, 3>(L);
+    case ZF_JOS1: return launch_g<ZF_JOS1, 2>(L);
+    case ZF_SD: return launch_t<ZF_SD, 2, ZF_G_BOX>(L);   // SD / ZDT1: box (1e-6, inf), no l1
+    case ZF_FDS: return launch_g<ZF_FDS, 3>(L);
+    case ZF_ZDT1: return launch_t<ZF_ZDT1, 2, ZF_G_BOX>(L);
+    case ZF_TOI4: return launch_g<ZF_TOI4, 2>(L);
+    case ZF_TRIDIA: return launch_g<ZF_TRIDIA, 3>(L);
     case ZF_LFR1:
-      if (m == 1) return launch_l1<ZF_LFR1, 1>(L);
-      if (m == 2) return launch_l1<ZF_LFR1, 2>(L);
-      if (m == 3) return launch_l1<ZF_LFR1, 3>(L);
-      return launch_l1<ZF_LFR1, 4>(L);
+      if (m == 1) return launch_g<ZF_LFR1, 1>(L);
+      if (m == 2) return launch_g<ZF_LFR1, 2>(L);
+      if (m == 3) return launch_g<ZF_LFR1, 3>(L);
+      return launch_g<ZF_LFR1, 4>(L);
     case ZF_LSQ_L1:
-      if (m == 1) return launch_t<ZF_LSQ_L1, 1, false>(L);
-      if (m == 2) return launch_t<ZF_LSQ_L1, 2, false>(L);
-      return launch_t<ZF_LSQ_L1, 3, false>(L);
+      if (m == 1) return launch_t<ZF_LSQ_L1, 1, 0>(L);
+      if (m == 2) return launch_t<ZF_LSQ_L1, 2, 0>(L);
+      return launch_t<ZF_LSQ_L1, 3, 0>(L);
   }
   return zf_fail(ZF_ERR_INVALID, "unknown problem kind %d", L.P.kind);
 }

@@ -2,7 +2,8 @@
 #include "zf_batched_kernels.cuh"
 
 namespace zf {
-template int launch_t<ZF_JOS1, 2, false>(const LaunchArgs&);
-template int launch_t<ZF_JOS1, 2, true>(const LaunchArgs&);
-template int launch_t<ZF_ZDT1, 2, false>(const LaunchArgs&);
+template int launch_t<ZF_JOS1, 2, 0>(const LaunchArgs&);
+template int launch_t<ZF_JOS1, 2, 1>(const LaunchArgs&);
+template int launch_t<ZF_JOS1, 2, 2>(const LaunchArgs&);
+template int launch_t<ZF_JOS1, 2, 3>(const LaunchArgs&);
 }  // namespace zf

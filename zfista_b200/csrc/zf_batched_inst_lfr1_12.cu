@@ -1,0 +1,13 @@
+// Explicit instantiations of the batched kernels (zf_batched_kernels.cuh): lfr1_12
+#include "zf_batched_kernels.cuh"
+
+namespace zf {
+template int launch_t<ZF_LFR1, 1, 0>(const LaunchArgs&);
+template int launch_t<ZF_LFR1, 1, 1>(const LaunchArgs&);
+template int launch_t<ZF_LFR1, 1, 2>(const LaunchArgs&);
+template int launch_t<ZF_LFR1, 1, 3>(const LaunchArgs&);
+template int launch_t<ZF_LFR1, 2, 0>(const LaunchArgs&);
+template int launch_t<ZF_LFR1, 2, 1>(const LaunchArgs&);
+template int launch_t<ZF_LFR1, 2, 2>(const LaunchArgs&);
+template int launch_t<ZF_LFR1, 2, 3>(const LaunchArgs&);
+}  // namespace zf

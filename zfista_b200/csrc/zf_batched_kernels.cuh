@@ -40,8 +40,9 @@ struct StepEval {
 
 // f, g and max|x - y| of the x in c.xn by separate passes (single-objective path)
 template <int KIND, int M>
-__device__ void F_eval_plain(const zf_problem& P, const WarpCtx& c, StepEval<M>& ev) {
-  f_eval<KIND, M>(P, c, c.xn, ev.fx);
+__device__ void F_eval_plain(const zf_problem& P, const WarpCtx& c,
+                             const typename Fn<KIND, M>::Consts& K, StepEval<M>& ev) {
+  f_eval<KIND, M>(P, c, K, c.xn, ev.fx);
   g_eval<KIND, M>(P, c, c.xn, ev.gx);
   double e = 0.0;
 #pragma unroll 1
@@ -57,15 +58,17 @@ __device__ void F_eval_plain(const zf_problem& P, const WarpCtx& c, StepEval<M>&
 // the prox chain stored at the last full dual evaluation (zf_dual.cuh:primal_probe).  Every sum
 // is accumulated over the same coordinates in the same order as the separate passes
 // (primal_probe, f, g_eval, the error loop) did: results are bit-identical to theirs.
-template <int KIND, int M, bool L1, bool PROBE>
-__device__ bool fused_primal_eval(const zf_problem& P, const WarpCtx& c, double lr,
+template <int KIND, int M, int GF, bool PROBE>
+__device__ bool fused_primal_eval(const zf_problem& P, const WarpCtx& c,
+                                  const typename Fn<KIND, M>::Consts& K, double lr,
                                   const double (&w)[M], StepEval<M>& ev) {
   using F = Fn<KIND, M>;
+  constexpr bool L1 = (GF & ZF_G_L1) != 0, BOX = (GF & ZF_G_BOX) != 0;
   bool same_piece = true;
   if constexpr (!F::kPointwise) {
-    if constexpr (PROBE) same_piece = primal_probe<KIND, M, L1>(P, c, lr, w, c.xn);
-    else primal_from_weights<KIND, M, L1>(P, c, lr, w, c.xn);
-    F_eval_plain<KIND, M>(P, c, ev);
+    if constexpr (PROBE) same_piece = primal_probe<KIND, M, GF>(P, c, lr, w, c.xn);
+    else primal_from_weights<KIND, M, GF>(P, c, lr, w, c.xn);
+    F_eval_plain<KIND, M>(P, c, K, ev);
   } else {
     double wt[M];
 #pragma unroll
@@ -101,15 +104,17 @@ __device__ bool fused_primal_eval(const zf_problem& P, const WarpCtx& c, double 
             const double yj = in.c.y;
             const double v = yj - lr * wj;
             double alpha, eps[M];
-            const double p = prox_elem<KIND, M, L1, PROBE>(P, jc, v, wt, alpha, eps);
+            const double p = prox_elem<KIND, M, GF, PROBE>(P, jc, v, wt, alpha, eps);
             if constexpr (PROBE) same &= live ? (int)(piece_code<M>(alpha, eps) == in.pat) : 1;
             double t[F::NT];
             F::template f_pre<FAST>(c, jc, p, t, rare);
             F::f_acc(live, t, sf);
             // (p is already clipped to the box, so g's +inf branch can only fire on NaN bounds;
             // the test is kept because Problem.g makes it, problems.py:101-106)
-            const bool out_of_box = (p < lower_of(P, jc)) || (p > upper_of(P, jc));
-            bad |= (live && out_of_box) ? 1 : 0;
+            if constexpr (BOX) {
+              const bool out_of_box = (p < lower_of(P, jc)) || (p > upper_of(P, jc));
+              bad |= (live && out_of_box) ? 1 : 0;
+            }
             if constexpr (L1) {
 #pragma unroll
               for (int i = 0; i < M; ++i) sg[i] += msk(live, fabs(p - P.l1_shifts[i]));
@@ -140,8 +145,8 @@ __device__ bool fused_primal_eval(const zf_problem& P, const WarpCtx& c, double 
     }
     ev.err = warp_max(e);
     if constexpr (PROBE) same_piece = __all_sync(ZF_FULL_MASK, same) != 0;
-    F::f_finish(P, c, c.xn, sf, ev.fx);
-    const bool any_bad = P.has_bounds && __any_sync(ZF_FULL_MASK, bad);
+    F::f_finish(P, c, K, c.xn, sf, ev.fx);
+    const bool any_bad = BOX && __any_sync(ZF_FULL_MASK, bad);
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       double gi = 0.0;
@@ -156,9 +161,9 @@ __device__ bool fused_primal_eval(const zf_problem& P, const WarpCtx& c, double 
 
 // _solve_subproblem (proximal_gradient.py:35-209) given f(y), J(y) already in ctx.
 // Writes x into c.xn and, with EVAL, its F / error summary into ev.
-template <int KIND, int M, bool L1, bool EVAL>
+template <int KIND, int M, int GF, bool EVAL>
 __device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const WarpCtx& c,
-                                 double lr, const double (&fy)[M], const double (&Fprev)[M],
+                                 const typename Fn<KIND, M>::Consts& K, double lr, const double (&fy)[M], const double (&Fprev)[M],
                                  bool deprecated, SubproblemOut<M>& out, StepEval<M>& ev) {
   ev.valid = false;
   if constexpr (M == 1) {
@@ -170,7 +175,7 @@ __device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const
       const double yj = c.y[j];
       const double gj = c.J[j];
       double alpha, eps[1];
-      const double p = prox_elem<KIND, 1, L1, false>(P, j, yj - lr * gj, wt, alpha, eps);
+      const double p = prox_elem<KIND, 1, GF, false>(P, j, yj - lr * gj, wt, alpha, eps);
       c.xn[j] = p;
       s[0] += gj * (p - yj);
       s[1] += (p - yj) * (p - yj);
@@ -194,17 +199,17 @@ __device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const
     if (M == 2 && O.dual_solver == 0) {
       if constexpr (M == 2) {
         double fmin;
-        const double xf = dual_brent<KIND, L1>(P, c, d, O.tol_internal, O.max_iter_internal, &fmin, &nf);
+        const double xf = dual_brent<KIND, GF>(P, c, d, O.tol_internal, O.max_iter_internal, &fmin, &nf);
         out.w[0] = xf;
         out.w[1] = 1.0 - xf;
         out.fun = -fmin;
       }
     } else {
       bool x_ready = false;
-      out.fun = dual_newton<KIND, M, L1>(P, c, d, out.w, 60, &nf, &x_ready,
+      out.fun = dual_newton<KIND, M, GF>(P, c, d, out.w, 60, &nf, &x_ready,
                                          [&](const double (&wn)[M]) {
-        if constexpr (EVAL) return fused_primal_eval<KIND, M, L1, true>(P, c, lr, wn, ev);
-        else return primal_probe<KIND, M, L1>(P, c, lr, wn, c.xn);
+        if constexpr (EVAL) return fused_primal_eval<KIND, M, GF, true>(P, c, K, lr, wn, ev);
+        else return primal_probe<KIND, M, GF>(P, c, lr, wn, c.xn);
       });
       if (!x_ready) ev.valid = false;      // c.xn holds a rejected candidate's x
     }
@@ -213,17 +218,17 @@ __device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const
   if (!ev.valid) {
     if constexpr (EVAL) {
       if constexpr (M == 1) {
-        F_eval_plain<KIND, M>(P, c, ev);
+        F_eval_plain<KIND, M>(P, c, K, ev);
       } else {
-        fused_primal_eval<KIND, M, L1, false>(P, c, lr, out.w, ev);
+        fused_primal_eval<KIND, M, GF, false>(P, c, K, lr, out.w, ev);
       }
     } else if constexpr (M > 1) {
-      primal_from_weights<KIND, M, L1>(P, c, lr, out.w, c.xn);
+      primal_from_weights<KIND, M, GF>(P, c, lr, out.w, c.xn);
     }
   }
 }
 
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 __global__ void __launch_bounds__(128, 1)
 batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const double* __restrict__ x0,
                      const double* __restrict__ ab, zf_result R) {
@@ -246,6 +251,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
   c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
 
   using F = Fn<KIND, M>;
+  const typename F::Consts K = F::make_consts(c);
   const long long total_warps = (long long)gridDim.x * warps_per_block;
   for (long long s = (long long)blockIdx.x * warps_per_block + warp_in_block; s < n_starts;
        s += total_warps) {
@@ -265,7 +271,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
     double lr = O.lr;
     double t_prev = 1.0;
     double Fprev[M], Fx[M], fx[M], fy[M], gx[M];
-    f_eval<KIND, M>(P, c, c.xp, fx);
+    f_eval<KIND, M>(P, c, K, c.xp, fx);
     g_eval<KIND, M>(P, c, c.xp, gx);
 #pragma unroll
     for (int i = 0; i < M; ++i) {
@@ -292,9 +298,9 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
     for (long long it = 1; it <= O.max_iter; ++it) {
       nit = it;
       if constexpr (F::kFoldable) {
-        F::f_jac(P, c, YFold{c.y, c.xp, c.xn, mom, extrapolate}, c.J, fy);
+        F::f_jac(P, c, K, YFold{c.y, c.xp, c.xn, mom, extrapolate}, c.J, fy);
       } else {
-        F::f_jac(P, c, YPlain{c.y}, c.J, fy);
+        F::f_jac(P, c, K, YPlain{c.y}, c.J, fy);
       }
       __syncwarp();
       ++nfev;
@@ -305,7 +311,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
       for (int bt = 0; bt < O.max_backtrack_iter; ++bt) {
 #pragma unroll
         for (int i = 0; i < M; ++i) sub.w[i] = wwarm[i];
-        solve_subproblem<KIND, M, L1, true>(P, O, c, lr, fy, Fprev, O.deprecated != 0, sub, ev);
+        solve_subproblem<KIND, M, GF, true>(P, O, c, K, lr, fy, Fprev, O.deprecated != 0, sub, ev);
         ndual += sub.n_dual;
         ++nfev;
 #pragma unroll
@@ -402,7 +408,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
 }
 
 // One subproblem per warp: _solve_subproblem(f, g, jac_f, prox, lr, xk_old, yk, w0)
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 __global__ void __launch_bounds__(128)
 subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* __restrict__ Y,
                   const double* __restrict__ Xold, const double* __restrict__ LR,
@@ -430,18 +436,19 @@ subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* _
   }
   __syncwarp();
   double fy[M], fp[M], gp[M], Fprev[M];
-  f_eval<KIND, M>(P, c, c.xp, fp);
+  const typename F::Consts K = F::make_consts(c);
+  f_eval<KIND, M>(P, c, K, c.xp, fp);
   g_eval<KIND, M>(P, c, c.xp, gp);
 #pragma unroll
   for (int i = 0; i < M; ++i) Fprev[i] = fp[i] + gp[i];
-  F::f_jac(P, c, YPlain{c.y}, c.J, fy);
+  F::f_jac(P, c, K, YPlain{c.y}, c.J, fy);
   __syncwarp();
   SubproblemOut<M> sub;
   StepEval<M> ev;
 #pragma unroll
   for (int i = 0; i < M; ++i) sub.w[i] = 1.0 / (double)M;
   const bool deprecated = dep ? (dep[s] != 0) : (O.deprecated != 0);
-  solve_subproblem<KIND, M, L1, false>(P, O, c, LR[s], fy, Fprev, deprecated, sub, ev);
+  solve_subproblem<KIND, M, GF, false>(P, O, c, K, LR[s], fy, Fprev, deprecated, sub, ev);
 #pragma unroll 1
   for (int j = lane; j < n; j += 32) X[s * n + j] = c.xn[j];
   if (lane == 0) {
@@ -452,7 +459,7 @@ subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* _
 }
 
 // Problem.f / g / jac_f / prox_wsum_g at a batch of points (one warp per point).
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 __global__ void __launch_bounds__(128)
 problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ Xin,
                     const double* __restrict__ Win, double* __restrict__ fo,
@@ -476,7 +483,8 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
   for (int j = lane; j < n; j += 32) c.y[j] = Xin[s * n + j];
   __syncwarp();
   double fy[M], gy[M];
-  F::f_jac(P, c, YPlain{c.y}, c.J, fy);
+  const typename F::Consts K = F::make_consts(c);
+  F::f_jac(P, c, K, YPlain{c.y}, c.J, fy);
   __syncwarp();
   g_eval<KIND, M>(P, c, c.y, gy);
   if (lane == 0) {
@@ -500,7 +508,7 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
 #pragma unroll 1
     for (int j = lane; j < n; j += 32) {
       double alpha, eps[M];
-      po[s * n + j] = prox_elem<KIND, M, L1, false>(P, j, c.y[j], wt, alpha, eps);
+      po[s * n + j] = prox_elem<KIND, M, GF, false>(P, j, c.y[j], wt, alpha, eps);
     }
   }
 }
@@ -524,7 +532,7 @@ struct LaunchArgs {
   cudaStream_t stream;
 };
 
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 int launch_t(const LaunchArgs& L) {
   const int n = L.P.n_features;
   const int n_rows = (KIND == ZF_LSQ_L1) ? L.P.n_rows : 0;
@@ -545,18 +553,18 @@ int launch_t(const LaunchArgs& L) {
   if (blocks < 1) blocks = 1;
   cudaError_t e;
   if (L.op == Op::Solve) {
-    auto k = batched_fista_kernel<KIND, M, L1>;
+    auto k = batched_fista_kernel<KIND, M, GF>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return zf_fail_cuda(e, "cudaFuncSetAttribute");
     k<<<(unsigned)blocks, wpb * 32, smem, L.stream>>>(L.P, L.O, L.n_items, L.a0, L.a1, L.R);
   } else if (L.op == Op::Subproblem) {
-    auto k = subproblem_kernel<KIND, M, L1>;
+    auto k = subproblem_kernel<KIND, M, GF>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return zf_fail_cuda(e, "cudaFuncSetAttribute");
     k<<<(unsigned)blocks, wpb * 32, smem, L.stream>>>(L.P, L.O, L.n_items, L.a0, L.a1, L.a2, L.i0,
                                                      L.o0, L.o1, L.o2);
   } else {
-    auto k = problem_eval_kernel<KIND, M, L1>;
+    auto k = problem_eval_kernel<KIND, M, GF>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return zf_fail_cuda(e, "cudaFuncSetAttribute");
     k<<<(unsigned)blocks, wpb * 32, smem, L.stream>>>(L.P, L.n_items, L.a0, L.a1, L.o0, L.o1, L.o2,

@@ -44,12 +44,13 @@ __device__ __forceinline__ CoordIn<M> load_coord(const WarpCtx& c, int jc) {
 // ------------------------------------------------------------------------------------
 // -D(w) exactly as _dual_minimized_fun_jac (proximal_gradient.py:161-177) forms it.
 // ------------------------------------------------------------------------------------
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
                                  const double (&w)[M]) {
   double wt[M];
 #pragma unroll
   for (int i = 0; i < M; ++i) wt[i] = d.lr * w[i];
+  constexpr bool L1 = (GF & ZF_G_L1) != 0;
   constexpr int NS = M + 2;
   double s[NS];
 #pragma unroll
@@ -62,7 +63,7 @@ __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const Du
     for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + jc];
     const double v = c.y[jc] - d.lr * wj;
     double alpha, eps[M];
-    const double p = prox_elem<KIND, M, L1, false>(P, jc, v, wt, alpha, eps);
+    const double p = prox_elem<KIND, M, GF, false>(P, jc, v, wt, alpha, eps);
     if (lsq) {
       s[0] += msk(live, fabs(p));
     } else if (L1) {
@@ -94,7 +95,7 @@ __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const Du
 }
 
 // x = prox_wsum_g(lr * w, y - lr * w @ J)   (proximal_gradient.py:206)
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 __device__ void primal_from_weights(const zf_problem& P, const WarpCtx& c, double lr,
                                     const double (&w)[M], double* out) {
   double wt[M];
@@ -108,7 +109,7 @@ __device__ void primal_from_weights(const zf_problem& P, const WarpCtx& c, doubl
         for (int i = 0; i < M; ++i) wj += w[i] * in.J[i];
         const double v = in.y - lr * wj;
         double alpha, eps[M];
-        return prox_elem<KIND, M, L1, false>(P, live ? j : 0, v, wt, alpha, eps);
+        return prox_elem<KIND, M, GF, false>(P, live ? j : 0, v, wt, alpha, eps);
       },
       [&](int j, bool live, double p) {
         if (live) out[j] = p;
@@ -127,7 +128,7 @@ __device__ __forceinline__ double sgn_plus(double v) {
   return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : (v == 0.0 ? 1.0 : v));
 }
 
-template <int KIND, bool L1>
+template <int KIND, int GF>
 __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualData<2>& d,
                              double xatol, int maxfun, double* fmin, int* nfev) {
   const double sqrt_eps = sqrt(2.2e-16);
@@ -138,7 +139,7 @@ __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualDa
   double rat = 0.0, e = 0.0;
   double x = xf;
   double w2[2] = {x, 1.0 - x};
-  double fx = neg_dual_value<KIND, 2, L1>(P, c, d, w2);
+  double fx = neg_dual_value<KIND, 2, GF>(P, c, d, w2);
   int num = 1;
   double fu = CUDART_INF;
   double ffulc = fx, fnfc = fx;
@@ -174,7 +175,7 @@ __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualDa
     x = xf + sgn_plus(rat) * fmax(fabs(rat), tol1);
     w2[0] = x;
     w2[1] = 1.0 - x;
-    fu = neg_dual_value<KIND, 2, L1>(P, c, d, w2);
+    fu = neg_dual_value<KIND, 2, GF>(P, c, d, w2);
     num += 1;
     if (fu <= fx) {
       if (x >= xf) a = xf; else b = xf;
@@ -222,7 +223,7 @@ __device__ __forceinline__ unsigned char piece_code(double alpha, const double (
 
 // x = prox_wsum_g(lr * w, y - lr * w @ J) into `out`, and whether every coordinate is on the
 // same piece as at the last full dual evaluation (c.pat)
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 __device__ bool primal_probe(const zf_problem& P, const WarpCtx& c, double lr,
                              const double (&w)[M], double* out) {
   double wt[M];
@@ -242,7 +243,7 @@ __device__ bool primal_probe(const zf_problem& P, const WarpCtx& c, double lr,
         for (int i = 0; i < M; ++i) wj += w[i] * in.c.J[i];
         const double v = in.c.y - lr * wj;
         double alpha, eps[M];
-        const double p = prox_elem<KIND, M, L1, true>(P, live ? j : 0, v, wt, alpha, eps);
+        const double p = prox_elem<KIND, M, GF, true>(P, live ? j : 0, v, wt, alpha, eps);
         same &= live ? (int)(piece_code<M>(alpha, eps) == in.pat) : 1;
         return p;
       },
@@ -260,12 +261,13 @@ struct DualPoint {
   double Q[M][M];
 };
 
-template <int KIND, int M, bool L1>
+template <int KIND, int M, int GF>
 __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
                           const double (&w)[M], DualPoint<M>& out) {
   double wt[M];
 #pragma unroll
   for (int i = 0; i < M; ++i) wt[i] = d.lr * w[i];
+  constexpr bool L1 = (GF & ZF_G_L1) != 0;
   constexpr int NQ = M * (M + 1) / 2;
   constexpr int NS = 2 * M + 2 + NQ;   // |p - s_i| sums, J_i.(p-y), ||p-v||^2, ||wj||^2, Q
   double s[NS];
@@ -289,7 +291,7 @@ __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<
         const double yj = in.y;
         const double v = yj - d.lr * wj;
         double alpha, eps[M];
-        const double p = prox_elem<KIND, M, L1, true>(P, live ? j : 0, v, wt, alpha, eps);
+        const double p = prox_elem<KIND, M, GF, true>(P, live ? j : 0, v, wt, alpha, eps);
         // a dead slot contributes exact zeros: its alpha, p - y, p - v and w.J are masked
         const double am = msk(live, alpha);
         const double dy = msk(live, p - yj);
@@ -398,6 +400,7 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
     // branch free (a rejected face still runs to the end, its result is discarded): the
     // 2^M - 1 faces are independent, so straight-line code lets them overlap
     bool ok = true;
+    double inv_piv[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const double piv = A[k][k];
@@ -406,6 +409,7 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
       if (!ok) return;
 #endif
       const double inv = 1.0 / (ok ? piv : 1.0);
+      inv_piv[k] = inv;
 #pragma unroll
       for (int r = k + 1; r < R; ++r) {
         const double fct = A[r][k] * inv;
@@ -420,7 +424,7 @@ __device__ __forceinline__ void qp_face(const double (&Q)[M][M], const double (&
       double acc = rhs[k];
 #pragma unroll
       for (int cc = k + 1; cc < R; ++cc) acc -= A[k][cc] * z[cc];
-      z[k] = acc / (ok ? A[k][k] : 1.0);
+      z[k] = acc * inv_piv[k];     // the reciprocal of the pivot is already there
     }
     double zs = 0.0;
 #pragma unroll
@@ -494,7 +498,7 @@ __device__ void simplex_qp(const double (&Q)[M][M], const double (&G)[M],
 // `probe(wn)` must write x = prox_wsum_g(lr * wn, y - lr * wn @ J) to c.xn and return whether
 // every coordinate is on the piece stored in c.pat (primal_probe, or the batched kernel's fused
 // sweep that also evaluates F(x) and max|x - y| while it is there).
-template <int KIND, int M, bool L1, class Probe>
+template <int KIND, int M, int GF, class Probe>
 __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualData<M>& d,
                               double (&w)[M], int max_iter, int* nfev, bool* x_ready,
                               Probe&& probe) {
@@ -509,7 +513,7 @@ __device__ double dual_newton(const zf_problem& P, const WarpCtx& c, const DualD
   int evals = 0, it = 0, bt = 0;
   bool first = true;
   for (;;) {
-    dual_full<KIND, M, L1>(P, c, d, wt, pt);
+    dual_full<KIND, M, GF>(P, c, d, wt, pt);
     ++evals;
     if (first || pt.D >= cur.D) {
       first = false;

@@ -11,6 +11,9 @@
 
 namespace zf {
 
+// parts of g a kernel instantiation handles (template flag GF)
+constexpr int ZF_G_L1 = 1, ZF_G_BOX = 2;
+
 template <int KIND, int M>
 struct Fn;
 
@@ -52,6 +55,11 @@ template <>
 struct Fn<ZF_JOS1, 2> {
   static constexpr bool kPointwise = true, kFoldable = true;
   static constexpr int NF = 2, NT = 2;
+  // divisor shared by every coordinate and iteration: its reciprocal is refined once per start
+  struct Consts { Recip dn; };
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx& c) {
+    return Consts{make_recip((double)c.n)};
+  }
   template <bool FAST>
   __device__ __forceinline__ static void f_pre(const WarpCtx& c, int j, double xj,
                                                double (&t)[NT], int& rare) {
@@ -64,10 +72,10 @@ struct Fn<ZF_JOS1, 2> {
     s[1] += msk(live, t[1]) * t[1];
   }
   __device__ __forceinline__ static void f_finish(const zf_problem& P, const WarpCtx& c,
-                                                  const double* x, const double (&s)[NF],
+                                                  const Consts& K, const double* x, const double (&s)[NF],
                                                   double (&out)[2]) {
-    out[0] = norm_sq_like_numpy(s[0]) / (double)c.n;
-    out[1] = norm_sq_like_numpy(s[1]) / (double)c.n;
+    out[0] = div_exact(norm_sq_like_numpy(s[0]), K.dn);
+    out[1] = div_exact(norm_sq_like_numpy(s[1]), K.dn);
   }
   struct JacOut { double y, j0, j1; };
   template <bool FAST, class YL>
@@ -96,16 +104,16 @@ struct Fn<ZF_JOS1, 2> {
     return rare;
   }
   template <class YL>
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YL& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YL& Y,
+                               double* J,
                                double (&fy)[2]) {
     double s[NF] = {0.0, 0.0};
-    const Recip dnr = make_recip((double)c.n);
-    if (__any_sync(ZF_FULL_MASK, jac_sweep<true>(c, Y, J, s, dnr))) {
+    if (__any_sync(ZF_FULL_MASK, jac_sweep<true>(c, Y, J, s, K.dn))) {
       s[0] = s[1] = 0.0;
-      jac_sweep<false>(c, Y, J, s, dnr);
+      jac_sweep<false>(c, Y, J, s, K.dn);
     }
     warp_sum_k<NF>(s);
-    f_finish(P, c, nullptr, s, fy);
+    f_finish(P, c, K, nullptr, s, fy);
   }
 };
 
@@ -114,22 +122,25 @@ template <>
 struct Fn<ZF_SD, 2> {
   static constexpr bool kPointwise = true, kFoldable = false;
   static constexpr int NF = 1, NT = 1;
+  struct Consts {};
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx&) { return Consts{}; }
   template <bool FAST>
   __device__ __forceinline__ static void f_pre(const WarpCtx&, int, double, double (&)[NT], int&) {}
   __device__ __forceinline__ static void f_acc(bool, const double (&)[NT], double (&)[NF]) {}
   __device__ __forceinline__ static void f_finish(const zf_problem& P, const WarpCtx& c,
-                                                  const double* x, const double (&)[NF],
+                                                  const Consts& K, const double* x, const double (&)[NF],
                                                   double (&out)[2]) {
     const double r2 = sqrt(2.0);
     const double x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3];
     out[0] = 2.0 * x0 + r2 * x1 + r2 * x2 + x3;
     out[1] = 2.0 / x0 + 2.0 * r2 / x1 + 2.0 * r2 / x2 + 2.0 / x3;
   }
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YPlain& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YPlain& Y,
+                               double* J,
                                double (&fy)[2]) {
     const double* y = Y.y;
     double none[NF] = {0.0};
-    f_finish(P, c, y, none, fy);
+    f_finish(P, c, K, y, none, fy);
     const double r2 = sqrt(2.0);
     if (c.lane < 4) {
       const int j = c.lane;
@@ -147,6 +158,13 @@ template <>
 struct Fn<ZF_FDS, 3> {
   static constexpr bool kPointwise = true, kFoldable = true;
   static constexpr int NF = 4, NT = 5;
+  // divisors shared by every coordinate and iteration: reciprocals refined once per start
+  struct Consts { Recip dn, dn2, c3; double c1; };
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx& c) {
+    const double dn = (double)c.n;
+    return Consts{make_recip(dn), make_recip(dn * dn), make_recip(dn * (dn + 1.0)),
+                  4.0 / (dn * dn)};
+  }
   template <bool FAST>
   __device__ __forceinline__ static void f_pre(const WarpCtx& c, int j, double xj,
                                                double (&t)[NT], int& rare) {
@@ -166,19 +184,19 @@ struct Fn<ZF_FDS, 3> {
     s[2] += msk(live, t[2]) * t[2];
     s[3] += msk(live, t[3]) * t[4];
   }
-  __device__ __forceinline__ static void finish(const WarpCtx& c, const double (&s)[4],
-                                                double (&out)[3], double& e_mean) {
-    const double dn = (double)c.n;
-    e_mean = exp(s[1] / dn);
-    out[0] = s[0] / (dn * dn);
+  __device__ __forceinline__ static void finish(const WarpCtx& c, const Consts& K,
+                                                const double (&s)[4], double (&out)[3],
+                                                double& e_mean) {
+    e_mean = exp_exact(div_exact(s[1], K.dn));
+    out[0] = div_exact(s[0], K.dn2);
     out[1] = e_mean + norm_sq_like_numpy(s[2]);
-    out[2] = s[3] / (dn * (dn + 1.0));
+    out[2] = div_exact(s[3], K.c3);
   }
   __device__ __forceinline__ static void f_finish(const zf_problem& P, const WarpCtx& c,
-                                                  const double* x, const double (&s)[NF],
-                                                  double (&out)[3]) {
+                                                  const Consts& K, const double* x,
+                                                  const double (&s)[NF], double (&out)[3]) {
     double e;
-    finish(c, s, out, e);
+    finish(c, K, s, out, e);
   }
   struct JacOut { double y, j0, j2; };
   template <bool FAST, class YL>
@@ -215,21 +233,19 @@ struct Fn<ZF_FDS, 3> {
     return rare;
   }
   template <class YL>
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YL& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YL& Y,
+                               double* J,
                                double (&fy)[3]) {
     // one sweep: the moments of f and the Jacobian rows 1 and 3 share exp(-y_j); row 2 needs
     // exp(mean(y)), known only after the reduction, and is filled by a second (cheap) sweep
     double s[4] = {0.0, 0.0, 0.0, 0.0}, e;
-    const double dn = (double)c.n;
-    const double c1 = 4.0 / (dn * dn);
-    const Recip c3r = make_recip(dn * (dn + 1.0));
-    if (__any_sync(ZF_FULL_MASK, jac_sweep<true>(c, Y, J, s, c1, c3r))) {
+    if (__any_sync(ZF_FULL_MASK, jac_sweep<true>(c, Y, J, s, K.c1, K.c3))) {
       s[0] = s[1] = s[2] = s[3] = 0.0;
-      jac_sweep<false>(c, Y, J, s, c1, c3r);
+      jac_sweep<false>(c, Y, J, s, K.c1, K.c3);
     }
     warp_sum_k<4>(s);
-    finish(c, s, fy, e);
-    const double e_over_n = e / dn;
+    finish(c, K, s, fy, e);
+    const double e_over_n = div_exact(e, K.dn);
     const double* y = Y.y;        // a lane re-reads only coordinates it wrote itself
     sweep3<double, double>(
         c.n, c.lane, [&](int j, bool live) { return y[live ? j : 0]; },
@@ -245,6 +261,8 @@ template <>
 struct Fn<ZF_ZDT1, 2> {
   static constexpr bool kPointwise = true, kFoldable = true;
   static constexpr int NF = 1, NT = 1;
+  struct Consts {};
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx&) { return Consts{}; }
   template <bool FAST>
   __device__ __forceinline__ static void f_pre(const WarpCtx& c, int j, double xj,
                                                double (&t)[NT], int& rare) {
@@ -255,7 +273,7 @@ struct Fn<ZF_ZDT1, 2> {
     s[0] += msk(live, t[0]);
   }
   __device__ __forceinline__ static void f_finish(const zf_problem& P, const WarpCtx& c,
-                                                  const double* x, const double (&s)[NF],
+                                                  const Consts& K, const double* x, const double (&s)[NF],
                                                   double (&out)[2]) {
     const double h = 1.0 + 9.0 / (double)(c.n - 1) * s[0];
     const double x0 = x[0];
@@ -263,7 +281,8 @@ struct Fn<ZF_ZDT1, 2> {
     out[1] = h * (1.0 - sqrt(x0 / h));
   }
   template <class YL>
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YL& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YL& Y,
+                               double* J,
                                double (&fy)[2]) {
     double s[NF] = {0.0};
     sweep3<double, double>(
@@ -294,21 +313,24 @@ template <>
 struct Fn<ZF_TOI4, 2> {
   static constexpr bool kPointwise = true, kFoldable = false;
   static constexpr int NF = 1, NT = 1;
+  struct Consts {};
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx&) { return Consts{}; }
   template <bool FAST>
   __device__ __forceinline__ static void f_pre(const WarpCtx&, int, double, double (&)[NT], int&) {}
   __device__ __forceinline__ static void f_acc(bool, const double (&)[NT], double (&)[NF]) {}
   __device__ __forceinline__ static void f_finish(const zf_problem& P, const WarpCtx& c,
-                                                  const double* x, const double (&)[NF],
+                                                  const Consts& K, const double* x, const double (&)[NF],
                                                   double (&out)[2]) {
     const double x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3];
     out[0] = x0 * x0 + x1 * x1 + 1.0;
     out[1] = 0.5 * ((x0 - x1) * (x0 - x1) + (x2 - x3) * (x2 - x3)) + 1.0;
   }
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YPlain& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YPlain& Y,
+                               double* J,
                                double (&fy)[2]) {
     const double* y = Y.y;
     double none[NF] = {0.0};
-    f_finish(P, c, y, none, fy);
+    f_finish(P, c, K, y, none, fy);
     if (c.lane == 0) {
       const double y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
       J[0] = 2.0 * y0;
@@ -329,22 +351,25 @@ template <>
 struct Fn<ZF_TRIDIA, 3> {
   static constexpr bool kPointwise = true, kFoldable = false;
   static constexpr int NF = 1, NT = 1;
+  struct Consts {};
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx&) { return Consts{}; }
   template <bool FAST>
   __device__ __forceinline__ static void f_pre(const WarpCtx&, int, double, double (&)[NT], int&) {}
   __device__ __forceinline__ static void f_acc(bool, const double (&)[NT], double (&)[NF]) {}
   __device__ __forceinline__ static void f_finish(const zf_problem& P, const WarpCtx& c,
-                                                  const double* x, const double (&)[NF],
+                                                  const Consts& K, const double* x, const double (&)[NF],
                                                   double (&out)[3]) {
     const double x0 = x[0], x1 = x[1], x2 = x[2];
     out[0] = sq(2.0 * x0 - 1.0);
     out[1] = 2.0 * sq(2.0 * x0 - x1);
     out[2] = 3.0 * sq(2.0 * x1 - x2);
   }
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YPlain& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YPlain& Y,
+                               double* J,
                                double (&fy)[3]) {
     const double* y = Y.y;
     double none[NF] = {0.0};
-    f_finish(P, c, y, none, fy);
+    f_finish(P, c, K, y, none, fy);
     if (c.lane == 0) {
       const double y0 = y[0], y1 = y[1], y2 = y[2];
       J[0] = 8.0 * y0 - 4.0;
@@ -365,6 +390,8 @@ template <int M>
 struct Fn<ZF_LFR1, M> {
   static constexpr bool kPointwise = true, kFoldable = true;
   static constexpr int NF = 1, NT = 2;
+  struct Consts {};
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx&) { return Consts{}; }
   template <bool FAST>
   __device__ __forceinline__ static void f_pre(const WarpCtx& c, int j, double xj,
                                                double (&t)[NT], int& rare) {
@@ -376,13 +403,14 @@ struct Fn<ZF_LFR1, M> {
     s[0] += msk(live, t[0]) * t[1];
   }
   __device__ __forceinline__ static void f_finish(const zf_problem& P, const WarpCtx& c,
-                                                  const double* x, const double (&s)[NF],
+                                                  const Consts& K, const double* x, const double (&s)[NF],
                                                   double (&out)[M]) {
 #pragma unroll
     for (int i = 0; i < M; ++i) out[i] = sq((double)(i + 1) * s[0] - 1.0);
   }
   template <class YL>
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YL& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YL& Y,
+                               double* J,
                                double (&fy)[M]) {
     double s[NF] = {0.0};
     sweep3<double, double>(
@@ -393,7 +421,7 @@ struct Fn<ZF_LFR1, M> {
         },
         [&](int j, bool live, double yj) { Y.store(j, live, yj); });
     warp_sum_k<NF>(s);
-    f_finish(P, c, nullptr, s, fy);
+    f_finish(P, c, K, nullptr, s, fy);
     const double sum = s[0];
 #pragma unroll 1
     for (int j = c.lane; j < c.n; j += 32) {
@@ -412,6 +440,8 @@ template <int M>
 struct Fn<ZF_LSQ_L1, M> {
   static constexpr bool kPointwise = false, kFoldable = false;
   static constexpr int NF = 1, NT = 1;
+  struct Consts {};
+  __device__ __forceinline__ static Consts make_consts(const WarpCtx&) { return Consts{}; }
   // r = A x - b into scratch; returns scale * ||r||^2
   __device__ static double residual(const zf_problem& P, const WarpCtx& c, const double* x) {
     double ss = 0.0;
@@ -433,7 +463,8 @@ struct Fn<ZF_LSQ_L1, M> {
 #pragma unroll
     for (int i = 0; i < M; ++i) out[i] = v;
   }
-  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const YPlain& Y, double* J,
+  __device__ static void f_jac(const zf_problem& P, const WarpCtx& c, const Consts& K, const YPlain& Y,
+                               double* J,
                                double (&fy)[M]) {
     const double v = residual(P, c, Y.y);
 #pragma unroll
@@ -453,7 +484,8 @@ struct Fn<ZF_LSQ_L1, M> {
 
 // Problem.f at a vector in shared memory (all lanes return the same values)
 template <int KIND, int M>
-__device__ void f_eval(const zf_problem& P, const WarpCtx& c, const double* x, double (&out)[M]) {
+__device__ void f_eval(const zf_problem& P, const WarpCtx& c,
+                       const typename Fn<KIND, M>::Consts& K, const double* x, double (&out)[M]) {
   using F = Fn<KIND, M>;
   if constexpr (!F::kPointwise) {
     F::f(P, c, x, out);
@@ -471,7 +503,7 @@ __device__ void f_eval(const zf_problem& P, const WarpCtx& c, const double* x, d
       });
       warp_sum_k<F::NF>(s);
     }
-    F::f_finish(P, c, x, s, out);
+    F::f_finish(P, c, K, x, s, out);
   }
 }
 
@@ -531,16 +563,17 @@ __device__ void g_eval(const zf_problem& P, const WarpCtx& c, const double* x,
 }
 
 // Per-coordinate prox with the reference's stage order (problems.py:126-137).  `wt[i]` is the
-// weight argument of prox_wsum_g (the caller passes lr * w_i).  L1 = the problem has l1_ratios
-// (a template flag: the kernels are instantiated with and without, so that the hot sweeps carry
-// no branch on it).  With TRACK the function also reports whether the coordinate is free
+// weight argument of prox_wsum_g (the caller passes lr * w_i).  GF = which parts g has: ZF_G_L1
+// (l1_ratios given) | ZF_G_BOX (bounds given) -- template flags: the kernels are instantiated per
+// combination, so that the hot sweeps carry neither a branch nor dead work for an absent part.  With TRACK the function also reports whether the coordinate is free
 // (alpha = 1) or pinned at a kink / bound (alpha = 0) and on which side of shift i it sits
 // (eps[i] = +-1); the simplex-Newton dual solver builds its generalised Hessian from these.
 // Branch-free: it runs inside the four-slot sweep bodies.
-template <int KIND, int M, bool L1, bool TRACK>
+template <int KIND, int M, int GF, bool TRACK>
 __device__ __forceinline__ double prox_elem(const zf_problem& P, int j, double v,
                                             const double (&wt)[M], double& alpha,
                                             double (&eps)[M]) {
+  constexpr bool L1 = (GF & ZF_G_L1) != 0, BOX = (GF & ZF_G_BOX) != 0;
   double p = v;
   bool pinned = false;
 #pragma unroll
@@ -582,12 +615,11 @@ __device__ __forceinline__ double prox_elem(const zf_problem& P, int j, double v
       }
     }
   }
-  {
-    // projection_box, as a select on the (warp-uniform) has_bounds flag
+  if constexpr (BOX) {
+    // projection_box (scalar or per-coordinate bounds)
     const double q = fmin(fmax(p, lower_of(P, j)), upper_of(P, j));
-    const bool box = P.has_bounds != 0;
-    if (TRACK) pinned = pinned || (box && q != p);
-    p = box ? q : p;
+    if (TRACK) pinned = pinned || (q != p);
+    p = q;
   }
   alpha = pinned ? 0.0 : 1.0;
   return p;
