@@ -171,6 +171,28 @@ double* zf_lasso_partial(zf_lasso* h, int64_t* n_values); /* device buffer to al
 int zf_lasso_step(zf_lasso* h, int32_t* h_done);           /* prox, line search, momentum */
 int zf_lasso_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
                     int32_t* h_status);
+/* Device-decided form of the same loop (proximal_gradient.py:474-538): lr, t_k, the F values and
+ * the line-search / stop decisions live in device memory and are taken by the kernels, so
+ * nothing below waits for the GPU except zf_lasso_dev_poll(wait = 1) and zf_lasso_dev_finish().
+ * zf_lasso_solve() is built on it (chunks of 32 trials as one CUDA graph launch, the host polling
+ * one chunk behind).  A row-sharded run enqueues the stages of a trial one by one and all-reduces
+ * zf_lasso_partial() between them, on the same stream, without reading anything back:
+ *   dev_begin(sharded = 1); AR(partial[n_cols:]); stage(0);
+ *   repeat { stage(1); AR(partial); stage(2);
+ *            if dev_needs_feval: stage(3); AR(partial[n_cols:]); stage(4) }   -- poll now and then
+ *   if !dev_needs_feval: stage(6); AR(partial[n_cols:]);
+ *   stage(5); dev_finish()
+ * Trials enqueued after the solve has ended do nothing.                                        */
+int zf_lasso_set_stream(zf_lasso* h, void* cuda_stream);
+int zf_lasso_dev_begin(zf_lasso* h, const zf_options* opt, const double* d_x0, int32_t sharded,
+                       int32_t want_trace);
+int zf_lasso_dev_stage(zf_lasso* h, int32_t stage);
+int zf_lasso_dev_needs_feval(zf_lasso* h);
+int zf_lasso_dev_slots(zf_lasso* h, int32_t n_slots);       /* single GPU: whole trials */
+int zf_lasso_dev_poll(zf_lasso* h, int32_t slot /*0|1*/, int32_t wait, int32_t* h_done,
+                      int64_t* h_nit);
+int zf_lasso_dev_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
+                        int32_t* h_status, double* h_lr, double* h_allerrs, double* h_allfuns);
 /* how many times one gradient evaluation reads A from HBM with this handle's kernel choice:
  * 1 (fused A^T(Av-b) kernels) or 2 (residual pass + A^T pass); for the roofline accounting */
 int zf_lasso_passes(zf_lasso* h);

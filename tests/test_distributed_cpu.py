@@ -258,3 +258,181 @@ def test_row_sharded_lasso_world2_matches_oracle(tmp_path):
         solo = zd.run_split_lasso(NumpySplitLasso(A, b, scale, l1, x0, opts), lambda: None)
         assert solo["nit"] == ref["nit"]
         np.testing.assert_allclose(solo["x"], ref["x"], rtol=1e-9, atol=1e-10)
+
+
+class NumpyDeviceLasso:
+    """numpy model of the DEVICE-decided protocol (zf_lasso_dev_* in csrc/zf_lasso.cu) on ONE row
+    shard: stages read and write a state dict exactly as the kernels read and write the device
+    struct, stages enqueued after the end do nothing, and the host only sees snapshots."""
+
+    def __init__(self, A, b, scale, l1, x0, opts):
+        self.A, self.b, self.scale, self.l1, self.x0 = A, b, scale, l1, x0
+        self.o = dict(lr=1.0, tol=1e-5, tol_internal=1e-12, max_iter=1000000,
+                      max_backtrack_iter=100, decay_rate=0.5, nesterov=False,
+                      nesterov_ratio=(0, 0.25), deprecated=False)
+        self.o.update(opts)
+        self.partial = np.zeros(A.shape[1] + 1)
+        self.snaps = [None, None]
+        self.stages_after_done = 0
+
+    def _f(self, ss):
+        return np.sqrt(ss) ** 2 * self.scale
+
+    def needs_feval(self):
+        return self.o["decay_rate"] != 1
+
+    def begin(self):
+        self.xp, self.xn, self.y = self.x0.copy(), self.x0.copy(), self.x0.copy()
+        r = self.A @ self.xp - self.b
+        self.partial[-1] = r @ r
+        self.s = dict(done=False)
+
+    def _next_momentum(self):
+        if not self.o["nesterov"]:
+            return self.s["t"], 0.0
+        a, b = self.o["nesterov_ratio"]
+        t = self.s["t"]
+        t_new = np.sqrt(t * t - a * t + b) + 0.5
+        return t_new, (t - 1) / t_new
+
+    def _accept(self, maxd):
+        s = self.s
+        s["err"] = maxd
+        if maxd < self.o["tol"] or s["nit"] >= self.o["max_iter"]:
+            s.update(status=1 if maxd < self.o["tol"] else 0, done=True, skip_grad=True,
+                     accept=False, result_is_prev=False)
+            return False
+        s["t"], s["mom"] = self._next_momentum()
+        s.update(F_prev=s["F_x"], nit=s["nit"] + 1, phase="grad", skip_grad=False, bt=0)
+        return True
+
+    def stage(self, k):
+        s = self.s
+        if s["done"] and k in (1, 2, 3, 4):
+            self.stages_after_done += 1
+        if k == 0:
+            F0 = self._f(self.partial[-1]) + self.l1 * np.abs(self.xp).sum()
+            s.update(lr=self.o["lr"], t=1.0, F_prev=F0, F_x=F0, nit=1, status=0, phase="grad",
+                     bt=0, accept=False, skip_grad=False, F_known=False, result_is_prev=False)
+        elif k == 1:
+            if not s["skip_grad"]:
+                r = self.A @ self.y - self.b
+                self.gpart, self.sq = self.A.T @ r, r @ r
+            self.partial[:-1], self.partial[-1] = self.gpart, self.sq     # collect
+        elif k == 2:
+            if s["done"]:
+                return
+            retry = s["phase"] == "retry"
+            if not retry:
+                self.g = self.partial[:-1] * (2 * self.scale)
+            lr = s["lr"]
+            v = self.y - lr * self.g
+            xn = np.sign(v) * np.maximum(np.abs(v) - lr * self.l1, 0)
+            d = xn - self.y
+            self.xn = xn
+            s.update(abs1=np.abs(xn).sum(), maxd=np.max(np.abs(d)), accept=False)
+            if not self.needs_feval():
+                _, mom = self._next_momentum()
+                self.y = xn + mom * (xn - self.xp)
+                self.xp = xn.copy()
+                s["F_known"] = False
+                self._accept(s["maxd"])
+            else:
+                if not retry:
+                    s["f_y"] = self._f(self.partial[-1])
+                sub = self.g @ d + self.l1 * s["abs1"] + np.sqrt(d @ d) ** 2 / 2 / lr
+                if not self.o["deprecated"]:
+                    sub += s["f_y"] - s["F_prev"]
+                s["sub"] = sub
+        elif k in (3, 6):
+            if k == 3 and s["done"]:
+                return
+            r = self.A @ self.xn - self.b
+            self.partial[-1] = r @ r
+        elif k == 4:
+            if s["done"]:
+                return
+            f_x = self._f(self.partial[-1])
+            s["F_x"], s["F_known"] = f_x + self.l1 * s["abs1"], True
+            ok = (f_x - s["f_y"] if self.o["deprecated"] else s["F_x"] - s["F_prev"]) \
+                <= s["sub"] + self.o["tol_internal"]
+            if ok:
+                if self._accept(s["maxd"]):
+                    self.y = self.xn + s["mom"] * (self.xn - self.xp)
+                    self.xp = self.xn.copy()
+                return
+            s["lr"] *= self.o["decay_rate"]
+            s["bt"] += 1
+            if s["bt"] >= self.o["max_backtrack_iter"]:
+                s.update(result_is_prev=True, F_x=s["F_prev"], nit=s["nit"] - 1, status=-1,
+                         done=True, skip_grad=True)
+            else:
+                s.update(phase="retry", skip_grad=True)
+        elif k == 5:
+            if not s["F_known"] and not s["result_is_prev"]:
+                s["F_x"] = self._f(self.partial[-1]) + self.l1 * s["abs1"]
+
+    def snapshot(self, slot):
+        self.snaps[slot] = self.s["done"]
+
+    def wait(self, slot):
+        return self.snaps[slot]
+
+    def finish(self):
+        s = self.s
+        assert s["done"]
+        return dict(x=self.xp if s["result_is_prev"] else self.xn, fun=s["F_x"], nit=s["nit"],
+                    status=s["status"], wasted=self.stages_after_done)
+
+
+DEVICE_CASES = (("fista", dict(nesterov=True)), ("ista", dict(nesterov=False, max_iter=50)),
+                ("fixed", dict(nesterov=True, lr=0.5, decay_rate=1, max_iter=200)),
+                ("fail", dict(nesterov=True, lr=1e6, max_backtrack_iter=3)))
+
+
+def _worker_device_lasso(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    A, b, scale, l1, x0 = _lasso_problem()
+    lo, hi = zd.shard_bounds(len(A), rank, world)
+    for tag, opts in DEVICE_CASES:
+        ops = NumpyDeviceLasso(A[lo:hi], b[lo:hi], scale, l1, x0, opts)
+        buf = torch.from_numpy(ops.partial)             # shares memory with ops.partial
+        res = zd.run_device_lasso(ops, lambda: dist.all_reduce(buf),
+                                  lambda: dist.all_reduce(buf[-1:]), chunk=5)
+        np.savez(os.path.join(out_dir, f"dlasso_{tag}_{rank}.npz"), **res)
+    dist.destroy_process_group()
+
+
+def test_device_decided_lasso_world2_matches_oracle(tmp_path):
+    """The device-decided protocol (no host decision inside the loop, the host polling one chunk
+    behind) over two row shards: the same nit / status / x / F as the oracle and as the
+    host-decided protocol, including a line-search failure and a fixed-step run."""
+    import torch.multiprocessing as mp
+
+    from oracle import zfista_oracle as zo
+
+    port = _free_port()
+    mp.spawn(_worker_device_lasso, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    A, b, scale, l1, x0 = _lasso_problem()
+    spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
+    for tag, opts in DEVICE_CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = zo.minimize_proximal_gradient(spec, x0, **opts)
+        outs = [np.load(tmp_path / f"dlasso_{tag}_{r}.npz") for r in range(2)]
+        np.testing.assert_array_equal(outs[0]["x"], outs[1]["x"])      # ranks agree bit for bit
+        for o in outs:
+            assert int(o["nit"]) == ref["nit"], (tag, int(o["nit"]), ref["nit"])
+            assert int(o["status"]) == ref["status"]
+            np.testing.assert_allclose(o["x"], ref["x"], rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(float(o["fun"]), ref["fun"], rtol=1e-10)
+            # at most two chunks of 5 trials (x up to 4 stages) run past the end
+            assert int(o["wasted"]) <= 2 * 5 * 4
+        solo = zd.run_device_lasso(NumpyDeviceLasso(A, b, scale, l1, x0, opts), lambda: None,
+                                   lambda: None, chunk=3)
+        assert solo["nit"] == ref["nit"] and solo["status"] == ref["status"]
+        np.testing.assert_allclose(solo["x"], ref["x"], rtol=1e-9, atol=1e-10)

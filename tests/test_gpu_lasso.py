@@ -271,3 +271,69 @@ def test_baseline_configs3_full_size(gpu):
     np.testing.assert_allclose(m[0].fun, a.fun, rtol=1e-11)
     del A
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n_rows,n_cols", [(300, 120), (700, 4100)])
+def test_device_decided_loop_equals_host_decided_loop(gpu, n_rows, n_cols):
+    """zf_lasso_solve runs the device-decided loop (scalars and decisions in device memory, CUDA
+    graph of 32 trials, no host sync per trial); the split begin / grad / step / finish entry
+    points still take every decision on the host.  Both must produce the SAME bits -- nit, status,
+    x, F and the traces -- with a line search (retries in the first iterations), a fixed step, a
+    line-search failure and max_iter stops, and across repeated solves on one handle (the graph
+    is captured once and replayed)."""
+    import ctypes as C
+
+    import torch
+
+    from zfista_b200 import _lib
+    from zfista_b200.lasso import DenseLasso
+    from zfista_b200.proximal_gradient import _make_options
+
+    rng = np.random.RandomState(n_rows)
+    A = rng.standard_normal((n_rows, n_cols))
+    w = np.zeros(n_cols)
+    w[:10] = rng.standard_normal(10)
+    b = A @ w + 0.01 * rng.standard_normal(n_rows)
+    scale, l1 = 1 / (2 * n_rows), 0.05
+    prob = DenseLasso(A, b, l1, scale=scale)
+    L = _lib.lib()
+    x0 = rng.standard_normal(n_cols) * 0.1
+    lip = 2 * scale * np.linalg.norm(A, 2) ** 2
+
+    def host_loop(opts):
+        o = _make_options(opts.get("lr", 1), opts.get("tol", 1e-5), 1e-12,
+                          opts.get("max_iter", 1000000), 100000,
+                          opts.get("max_backtrack_iter", 100), False, opts.get("decay_rate", 0.5),
+                          opts.get("nesterov", False), opts.get("nesterov_ratio", (0, 0.25)),
+                          opts.get("deprecated", False), "reference", 0)
+        x0d = torch.from_numpy(x0).cuda()
+        xd = torch.empty_like(x0d)
+        fun, nit, status, nxt = C.c_double(), C.c_int64(), C.c_int32(), C.c_int32(0)
+        _lib.check(L.zf_lasso_begin(prob._h, C.byref(o), C.c_void_p(x0d.data_ptr())))
+        _lib.check(L.zf_lasso_step(prob._h, C.byref(nxt)))
+        while nxt.value != 2:
+            _lib.check(L.zf_lasso_grad(prob._h, nxt.value))
+            _lib.check(L.zf_lasso_step(prob._h, C.byref(nxt)))
+        _lib.check(L.zf_lasso_finish(prob._h, C.c_void_p(xd.data_ptr()), C.byref(fun),
+                                     C.byref(nit), C.byref(status)))
+        return xd.cpu().numpy(), fun.value, nit.value, status.value
+
+    cases = [dict(nesterov=True), dict(nesterov=False, max_iter=40),
+             dict(nesterov=True, lr=1 / lip, decay_rate=1, max_iter=300),
+             dict(nesterov=True, lr=1 / lip, decay_rate=1, max_iter=33, tol=0.0),
+             dict(nesterov=True, deprecated=True, lr=8.0),
+             dict(nesterov=True, lr=1e9, max_backtrack_iter=3),
+             dict(nesterov=True, nesterov_ratio=(0.5, 1 / 16))]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for opts in cases + cases[:3]:
+            res = prob.minimize_proximal_gradient(x0, **opts)
+            x, fun, nit, status = host_loop(opts)
+            assert (res.nit, res.status) == (nit, status), (opts, res.nit, nit, res.status, status)
+            np.testing.assert_array_equal(res.x, x)
+            assert res.fun == fun, (opts, res.fun, fun)
+            tr = prob.minimize_proximal_gradient(x0, return_all=True, **opts)
+            assert tr.nit == nit and len(tr.allerrs) == nit and len(tr.allfuns) == nit + 1
+            np.testing.assert_array_equal(tr.x, x)
+            if nit:
+                assert tr.allfuns[-1] == tr.fun

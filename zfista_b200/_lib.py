@@ -61,6 +61,8 @@ EXPORTED_SYMBOLS = [
     "zf_lasso_create", "zf_lasso_destroy", "zf_lasso_solve", "zf_lasso_begin",
     "zf_lasso_grad", "zf_lasso_partial", "zf_lasso_step", "zf_lasso_finish",
     "zf_lasso_gradient_device", "zf_lasso_passes",
+    "zf_lasso_set_stream", "zf_lasso_dev_begin", "zf_lasso_dev_stage", "zf_lasso_dev_needs_feval",
+    "zf_lasso_dev_slots", "zf_lasso_dev_poll", "zf_lasso_dev_finish",
     "zf_lasso_multi_create", "zf_lasso_multi_destroy", "zf_lasso_multi_solve",
     "zf_lasso_multi_begin", "zf_lasso_multi_grad", "zf_lasso_multi_partial",
     "zf_lasso_multi_step", "zf_lasso_multi_finish", "zf_lasso_multi_gradient_device",
@@ -142,8 +144,20 @@ def _bind_lasso(L):
     L.zf_lasso_gradient_device.restype = C.c_int
     L.zf_lasso_passes.argtypes = [C.c_void_p]
     L.zf_lasso_passes.restype = C.c_int
-    # many runs sharing one A (FP64 tensor-core passes)
     V, I32, I64, D = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    # device-decided loop
+    L.zf_lasso_set_stream.argtypes = [V, V]
+    L.zf_lasso_dev_begin.argtypes = [V, C.POINTER(ZfOptions), V, I32, I32]
+    L.zf_lasso_dev_stage.argtypes = [V, I32]
+    L.zf_lasso_dev_needs_feval.argtypes = [V]
+    L.zf_lasso_dev_slots.argtypes = [V, I32]
+    L.zf_lasso_dev_poll.argtypes = [V, I32, I32, c_int32_p, c_int64_p]
+    L.zf_lasso_dev_finish.argtypes = [V, V, V, V, V, V, V, V]
+    for name in ("zf_lasso_set_stream", "zf_lasso_dev_begin", "zf_lasso_dev_stage",
+                 "zf_lasso_dev_needs_feval", "zf_lasso_dev_slots", "zf_lasso_dev_poll",
+                 "zf_lasso_dev_finish"):
+        getattr(L, name).restype = C.c_int
+    # many runs sharing one A (FP64 tensor-core passes)
     L.zf_lasso_multi_create.argtypes = [C.POINTER(V), V, I64, I64, V, I32, I32, D, D, V]
     L.zf_lasso_multi_create.restype = C.c_int
     L.zf_lasso_multi_destroy.argtypes = [V]

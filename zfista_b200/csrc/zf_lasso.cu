@@ -59,7 +59,9 @@ template <bool VEC>
 __global__ void __launch_bounds__(RES_THREADS, 3)
 lasso_residual_kernel(const double* __restrict__ A, const double* __restrict__ b,
                       const double* __restrict__ v, long long n_rows, long long n_cols,
-                      double* __restrict__ r, double* __restrict__ sq_part) {
+                      double* __restrict__ r, double* __restrict__ sq_part,
+                      const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
   constexpr int R = RES_ROWS_PER_WARP;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -140,7 +142,9 @@ constexpr int ATR_ROW_UNROLL = 8;
 template <bool VEC>
 __global__ void __launch_bounds__(ATR_THREADS, 2)
 lasso_atr_kernel(const double* __restrict__ A, const double* __restrict__ r, long long n_rows,
-                 long long n_cols, long long rows_per_block, double* __restrict__ gpart) {
+                 long long n_cols, long long rows_per_block, double* __restrict__ gpart,
+                 const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
   const long long col_base = (long long)blockIdx.x * ATR_SLAB;
   const long long rb = blockIdx.y;
   const long long i0 = rb * rows_per_block;
@@ -241,7 +245,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
 lasso_fused_kernel(const double* __restrict__ A, const double* __restrict__ b,
                    const double* __restrict__ v, long long n_rows, long long n_cols,
                    long long rows_per_cta, double* __restrict__ gpart,
-                   double* __restrict__ sq_part) {
+                   double* __restrict__ sq_part,
+    const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
   extern __shared__ double vsm[];                       // n_cols doubles
   __shared__ double red[2][FUSED_THREADS / 32][FUSED_ROWS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -338,7 +344,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 lasso_fused_cluster_kernel(const double* __restrict__ A, const double* __restrict__ b,
                            const double* __restrict__ v, long long n_rows, long long n_cols,
                            long long rows_per_cluster, long long pairs_per_cta,
-                           double* __restrict__ gpart, double* __restrict__ sq_part) {
+                           double* __restrict__ gpart, double* __restrict__ sq_part,
+    const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -509,7 +517,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
 lasso_fused_tma_pair_kernel(const double* __restrict__ A, const double* __restrict__ b,
                        const double* __restrict__ v, long long n_rows, long long n_cols,
                        long long rows_per_cluster, long long pairs_per_cta,
-                       double* __restrict__ gpart, double* __restrict__ sq_part) {
+                       double* __restrict__ gpart, double* __restrict__ sq_part,
+    const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -636,7 +646,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
 lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ b,
                        const double* __restrict__ v, long long n_rows, long long n_cols,
                        long long rows_per_cluster, long long pairs_per_cta,
-                       double* __restrict__ gpart, double* __restrict__ sq_part) {
+                       double* __restrict__ gpart, double* __restrict__ sq_part,
+    const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -850,7 +862,9 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
                         const double* __restrict__ v, long long n_rows, long long n_cols,
                         long long rows_per_cluster, long long pairs_per_cta,
                         double* __restrict__ gpart, double* __restrict__ sq_part,
-                        int dbg, long long row_begin, long long row_end, int part_base) {
+                        int dbg, long long row_begin, long long row_end, int part_base,
+                        const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -1096,12 +1110,12 @@ lasso_prox_kernel(const double* __restrict__ y, const double* __restrict__ parti
     if (y) {
       const double gj = partial[j] * two_scale;
       const double yj = y[j];
-      const double xj = soft_threshold(yj - lr * gj, thresh);
+      const double xj = soft_threshold(fma(-lr, gj, yj), thresh);
       const double d = xj - yj;
       x[j] = xj;
       if (g_out) g_out[j] = gj;
-      s.gd += gj * d;
-      s.dd += d * d;
+      s.gd = fma(gj, d, s.gd);
+      s.dd = fma(d, d, s.dd);
       s.abs1 += fabs(xj);
       s.maxd = fmax(s.maxd, fabs(d));
     } else {
@@ -1135,7 +1149,7 @@ lasso_momentum_kernel(const double* __restrict__ x, const double* __restrict__ x
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
     const double xj = x[j];
-    y[j] = xj + mom * (xj - xp[j]);
+    y[j] = fma(mom, xj - xp[j], xj);
   }
 }
 
@@ -1150,6 +1164,281 @@ lasso_scale_kernel(const double* __restrict__ partial, double two_scale, double 
     const double nrm = sqrt(partial[n]);
     *f_out = nrm * nrm * scale;
   }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Device-decided loop (zf_lasso_dev_*): the scalars of proximal_gradient.py:474-538 -- lr, t_k,
+// F values, the line-search and stop decisions -- live in ONE device struct, every kernel of an
+// iteration reads what it needs from it, and the last block of the n_cols-sized kernel (or a
+// one-thread kernel) takes the decision the host used to take.  Nothing synchronises with the
+// host inside the loop: the host enqueues "slots" (one trial each) ahead of the GPU, as a CUDA
+// graph when it can, and polls the state every few dozen slots.  Once the state says DONE the
+// remaining slots are no-ops (every kernel tests a flag first).
+//
+// The scalar arithmetic uses the round-to-nearest intrinsics so that nvcc cannot contract it
+// into FMAs: it is bit for bit the host code of zf_lasso_step / accept_candidate above.
+// ---------------------------------------------------------------------------------------
+enum { DV_GRAD = 0, DV_RETRY = 1, DV_DONE = 2 };
+
+struct LassoDevOpts {
+  double lr0, tol, tol_internal, decay, na, nb, scale, l1;
+  long long max_iter;
+  int max_bt, nesterov, deprecated, need_F, cap;
+  double* allerrs;        // device traces (cap, cap + 1) or nullptr
+  double* allfuns;
+};
+
+struct LassoDevState {
+  double lr, t_prev, F_prev, F_x, f_y, sub_fun, err, mom;
+  StepSums sums;          // of the candidate now in x_new
+  long long nit;
+  int status, phase, bt, accept;
+  int skip_grad;          // != 0: the gradient pass of this slot has nothing to do (retry / done)
+  int done;               // != 0: the solve has ended
+  int F_known, result_is_prev;
+  unsigned int ticket;    // last-block election of the update kernel
+  int pad;
+};
+
+__device__ __forceinline__ double dv_f_from_ss(double ss, double scale) {
+  const double nrm = __dsqrt_rn(ss);
+  return __dmul_rn(__dmul_rn(nrm, nrm), scale);
+}
+
+__device__ __forceinline__ void dv_next_momentum(const LassoDevOpts& o, double t, double* t_new,
+                                                 double* mom) {
+  // t_{k+1} = sqrt(t_k^2 - a t_k + b) + 1/2 ; mom = (t_k - 1) / t_{k+1}   (proximal_gradient.py:531-534)
+  if (o.nesterov) {
+    const double tn = __dadd_rn(
+        __dsqrt_rn(__dadd_rn(__dsub_rn(__dmul_rn(t, t), __dmul_rn(o.na, t)), o.nb)), 0.5);
+    *t_new = tn;
+    *mom = __ddiv_rn(__dsub_rn(t, 1.0), tn);
+  } else {
+    *t_new = t;
+    *mom = 0.0;
+  }
+}
+
+// The candidate in x_new was accepted (one thread): stop test, trace, t_{k+1}; returns true if the
+// loop goes on (the caller then applies the momentum / rotation).
+__device__ bool dv_accept(const LassoDevOpts& o, LassoDevState* st, double maxd) {
+  st->err = maxd;
+  const long long nit = st->nit;
+  if (o.cap > 0 && nit <= o.cap) {
+    if (o.allerrs) o.allerrs[nit - 1] = maxd;
+    if (o.allfuns && st->F_known) o.allfuns[nit] = st->F_x;
+  }
+  const bool converged = maxd < o.tol;
+  if (converged || nit >= o.max_iter) {
+    st->status = converged ? 1 : 0;
+    st->result_is_prev = 0;
+    st->phase = DV_DONE;
+    st->done = 1;
+    st->skip_grad = 1;
+    st->accept = 0;
+    return false;
+  }
+  double t_new, mom;
+  dv_next_momentum(o, st->t_prev, &t_new, &mom);
+  st->t_prev = t_new;
+  st->mom = mom;
+  st->F_prev = st->F_x;
+  st->nit = nit + 1;
+  st->phase = DV_GRAD;
+  st->skip_grad = 0;
+  st->bt = 0;
+  return true;
+}
+
+// F(x0) from the residual norm of x0 (ss_src[0]) and ||x0||_1 (sums->abs1)
+__global__ void lasso_dev_init_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
+                                      const StepSums* __restrict__ sums,
+                                      const double* __restrict__ ss_src, int n_sq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const LassoDevOpts o = *op;
+  double ss = 0.0;
+  for (int k = 0; k < n_sq; ++k) ss = __dadd_rn(ss, ss_src[k]);
+  const double F0 = __dadd_rn(dv_f_from_ss(ss, o.scale), __dmul_rn(o.l1, sums->abs1));
+  st->lr = o.lr0;
+  st->t_prev = 1.0;
+  st->F_prev = F0;
+  st->F_x = F0;
+  st->f_y = 0.0;
+  st->sub_fun = 0.0;
+  st->err = CUDART_INF;
+  st->mom = 0.0;
+  st->nit = 1;
+  st->status = 0;
+  st->phase = DV_GRAD;
+  st->bt = 0;
+  st->accept = 0;
+  st->skip_grad = 0;
+  st->done = 0;
+  st->F_known = 0;
+  st->result_is_prev = 0;
+  st->ticket = 0u;
+  if (o.cap > 0 && o.allfuns) o.allfuns[0] = F0;
+}
+
+// One trial:  x_new = soft(y - lr g, lr l1)  with  g = 2 scale A^T(A y - b)  taken from
+//   SRC 0: the row-block partials gpart (the collect pass is folded in; sum r^2 from sq_part),
+//   SRC 1: `partial` (already collected and, in a row-sharded run, all-reduced),
+//   a retry (state.phase == DV_RETRY): the g stored by the trial that computed it.
+// FIXED (decay_rate == 1, no F trace): the step is accepted unconditionally, so the same sweep
+// also writes y^{k+1} = x + mom (x - x_prev) and x_prev = x, and the last block runs the stop test
+// and t_{k+1}: a whole iteration is the gradient pass plus this kernel.
+// Otherwise the last block leaves f(y) and the subproblem value for lasso_dev_decide_kernel.
+template <int SRC, bool FIXED>
+__global__ void __launch_bounds__(VEC_THREADS)
+lasso_dev_update_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
+                        const double* __restrict__ gpart, int n_parts,
+                        const double* __restrict__ sq_part, int n_sq,
+                        const double* __restrict__ partial, long long n,
+                        double* __restrict__ y, double* __restrict__ xp, double* __restrict__ xn,
+                        double* __restrict__ g, StepSums* __restrict__ block_sums) {
+  if (*reinterpret_cast<const volatile int*>(&st->done) != 0) return;
+  __shared__ StepSums sh[VEC_THREADS / 32];
+  __shared__ bool is_last;
+  const LassoDevOpts o = *op;
+  const double lr = st->lr;
+  const bool retry = (st->phase == DV_RETRY);
+  const double two_scale = 2.0 * o.scale;
+  const double thresh = o.l1 * lr;
+  double t_new = 0.0, mom = 0.0;
+  if (FIXED) dv_next_momentum(o, st->t_prev, &t_new, &mom);
+  StepSums s{0.0, 0.0, 0.0, 0.0};
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    double gj;
+    if (retry) {
+      gj = g[j];
+    } else if (SRC == 0) {
+      double acc = 0.0;
+      for (int rb = 0; rb < n_parts; ++rb) acc += gpart[(long long)rb * n + j];
+      gj = acc * two_scale;
+    } else {
+      gj = partial[j] * two_scale;
+    }
+    const double yj = y[j];
+    const double xj = soft_threshold(fma(-lr, gj, yj), thresh);
+    const double d = xj - yj;
+    xn[j] = xj;
+    s.gd = fma(gj, d, s.gd);
+    s.dd = fma(d, d, s.dd);
+    s.abs1 += fabs(xj);
+    s.maxd = fmax(s.maxd, fabs(d));
+    if (FIXED) {
+      y[j] = fma(mom, xj - xp[j], xj);
+      xp[j] = xj;
+    } else if (!retry) {
+      g[j] = gj;
+    }
+  }
+  block_reduce_step(s, sh);
+  if (threadIdx.x == 0) {
+    block_sums[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int done = atomicAdd(&st->ticket, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  StepSums t = block_sums[0];
+  for (unsigned int k = 1; k < gridDim.x; ++k) {
+    const StepSums u = block_sums[k];
+    t.gd += u.gd; t.dd += u.dd; t.abs1 += u.abs1; t.maxd = fmax(t.maxd, u.maxd);
+  }
+  st->ticket = 0u;
+  st->sums = t;
+  st->accept = 0;
+  if (FIXED) {
+    st->F_known = 0;
+    dv_accept(o, st, t.maxd);
+  } else {
+    if (!retry) {
+      double ss = 0.0;
+      if (SRC == 0) {
+        for (int k = 0; k < n_sq; ++k) ss = __dadd_rn(ss, sq_part[k]);
+      } else {
+        ss = partial[n];
+      }
+      st->f_y = dv_f_from_ss(ss, o.scale);
+    }
+    // proximal_gradient.py:149-155 for one objective
+    const double nrm = __dsqrt_rn(t.dd);
+    double fun = __dadd_rn(__dadd_rn(t.gd, __dmul_rn(o.l1, t.abs1)),
+                           __ddiv_rn(__ddiv_rn(__dmul_rn(nrm, nrm), 2.0), lr));
+    if (!o.deprecated) fun = __dadd_rn(fun, __dsub_rn(st->f_y, st->F_prev));
+    st->sub_fun = fun;
+  }
+}
+
+// After the residual pass at the candidate: F(x_new), the line-search test, then either the
+// acceptance logic or a smaller step (one thread).  ss_src: sq_part (n_sq values) or
+// &partial[n_cols] (1 value, all-reduced).
+__global__ void lasso_dev_decide_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
+                                        const double* __restrict__ ss_src, int n_sq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (st->done) return;
+  const LassoDevOpts o = *op;
+  double ss = 0.0;
+  for (int k = 0; k < n_sq; ++k) ss = __dadd_rn(ss, ss_src[k]);
+  const double f_x = dv_f_from_ss(ss, o.scale);
+  st->F_x = __dadd_rn(f_x, __dmul_rn(o.l1, st->sums.abs1));
+  st->F_known = 1;
+  bool ok;
+  if (o.decay == 1.0) ok = true;                                            // proximal_gradient.py:298
+  else if (o.deprecated) ok = (__dsub_rn(f_x, st->f_y) <= __dadd_rn(st->sub_fun, o.tol_internal));
+  else ok = (__dsub_rn(st->F_x, st->F_prev) <= __dadd_rn(st->sub_fun, o.tol_internal));
+  if (ok) {
+    st->accept = dv_accept(o, st, st->sums.maxd) ? 1 : 0;
+    return;
+  }
+  st->lr = __dmul_rn(st->lr, o.decay);
+  st->bt += 1;
+  st->accept = 0;
+  if (st->bt >= o.max_bt) {
+    // RuntimeError("Backtracking failed ...") -> x = x_prev, nit - 1 (proximal_gradient.py:493-509)
+    st->result_is_prev = 1;
+    st->F_x = st->F_prev;
+    st->nit -= 1;
+    st->status = -1;
+    st->phase = DV_DONE;
+    st->done = 1;
+    st->skip_grad = 1;
+  } else {
+    st->phase = DV_RETRY;     // same gradient, smaller step
+    st->skip_grad = 1;
+  }
+}
+
+// y = x + mom (x - x_prev), x_prev = x  when the decide kernel accepted the candidate
+__global__ void __launch_bounds__(VEC_THREADS)
+lasso_dev_momentum_kernel(const LassoDevState* __restrict__ st, long long n,
+                          const double* __restrict__ xn, double* __restrict__ xp,
+                          double* __restrict__ y) {
+  if (st->accept == 0 || st->done != 0) return;
+  const double mom = st->mom;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double xj = xn[j];
+    y[j] = fma(mom, xj - xp[j], xj);
+    xp[j] = xj;
+  }
+}
+
+// res.fun when the loop ran without F evaluations: F(x) from one last residual pass
+__global__ void lasso_dev_final_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
+                                       const double* __restrict__ ss_src, int n_sq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (st->F_known || st->result_is_prev) return;
+  const LassoDevOpts o = *op;
+  double ss = 0.0;
+  for (int k = 0; k < n_sq; ++k) ss = __dadd_rn(ss, ss_src[k]);
+  st->F_x = __dadd_rn(dv_f_from_ss(ss, o.scale), __dmul_rn(o.l1, st->sums.abs1));
+  st->F_known = 1;
 }
 
 }  // namespace zf
@@ -1205,6 +1494,22 @@ struct zf_lasso {
   int status = 0, bt = 0;
   zf::StepSums sums{};
   bool result_is_prev = false;
+  const int* skip = nullptr;    // device flag the gradient-pass kernels test (device-decided loop)
+  // device-decided loop (zf_lasso_dev_*)
+  zf::LassoDevOpts* d_opts = nullptr;
+  zf::LassoDevState* d_state = nullptr;
+  zf::LassoDevState* h_state = nullptr;      // pinned, 2 poll slots
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+  double* d_allerrs = nullptr;
+  double* d_allfuns = nullptr;
+  int dev_cap = 0;
+  bool dev_sharded = false, dev_fixed = false, dev_active = false;
+  zf::LassoDevOpts dev_opts_host{};
+  cudaStream_t st_own = nullptr;             // used when the caller's stream cannot be captured
+  cudaEvent_t ev_own = nullptr;
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [fixed-step slots, line-search slots]
+  int graph_slots = 0;
+  bool graph_failed = false;
   double* h_allerrs = nullptr;
   double* h_allfuns = nullptr;
 };
@@ -1220,10 +1525,10 @@ namespace {
 int launch_residual(zf_lasso* h, const double* v) {
   if (h->vec)
     zf::lasso_residual_kernel<true><<<h->res_blocks, zf::RES_THREADS, 0, h->st>>>(
-        h->A, h->b, v, h->n_rows, h->n_cols, h->r, h->sq_part);
+        h->A, h->b, v, h->n_rows, h->n_cols, h->r, h->sq_part, h->skip);
   else
     zf::lasso_residual_kernel<false><<<h->res_blocks, zf::RES_THREADS, 0, h->st>>>(
-        h->A, h->b, v, h->n_rows, h->n_cols, h->r, h->sq_part);
+        h->A, h->b, v, h->n_rows, h->n_cols, h->r, h->sq_part, h->skip);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -1233,10 +1538,10 @@ int launch_atr(zf_lasso* h) {
   dim3 grid((unsigned)h->n_slabs, (unsigned)h->n_rowblocks);
   if (h->vec)
     zf::lasso_atr_kernel<true><<<grid, zf::ATR_THREADS, 0, h->st>>>(
-        h->A, h->r, h->n_rows, h->n_cols, h->rows_per_block, h->gpart);
+        h->A, h->r, h->n_rows, h->n_cols, h->rows_per_block, h->gpart, h->skip);
   else
     zf::lasso_atr_kernel<false><<<grid, zf::ATR_THREADS, 0, h->st>>>(
-        h->A, h->r, h->n_rows, h->n_cols, h->rows_per_block, h->gpart);
+        h->A, h->r, h->n_rows, h->n_cols, h->rows_per_block, h->gpart, h->skip);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -1248,7 +1553,8 @@ int launch_fused_t(zf_lasso* h, const double* v) {
   const size_t smem = sizeof(double) * (size_t)h->n_cols;
   ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<h->fused_ctas, zf::FUSED_THREADS, smem, h->st>>>(h->A, h->b, v, h->n_rows, h->n_cols,
-                                                       h->fused_rows_per_cta, h->gpart, h->sq_part);
+                                                       h->fused_rows_per_cta, h->gpart, h->sq_part,
+                                                       h->skip);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -1273,7 +1579,7 @@ int launch_fused_cluster_t(zf_lasso* h, const double* v) {
   cfg.numAttrs = 1;
   const long long rows_per_cluster = h->fused_rows_per_cta;
   ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, rows_per_cluster,
-                             h->fused_pairs_per_cta, h->gpart, h->sq_part));
+                             h->fused_pairs_per_cta, h->gpart, h->sq_part, h->skip));
   zf::zf_count_launch();
   return ZF_OK;
 }
@@ -1282,7 +1588,7 @@ template <int PAIRS, int R>
 int launch_fused_tma_t(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
   constexpr int NS = 2;
   void (*k)(const double*, const double*, const double*, long long, long long, long long,
-            long long, double*, double*);
+            long long, double*, double*, const int*);
   if (R == 2) k = zf::lasso_fused_tma_pair_kernel<PAIRS, NS, false>;
   else k = zf::lasso_fused_tma_kernel<PAIRS, NS, (R == 2 ? 3 : R)>;
   const size_t smem = (size_t)h->fused_pairs_per_cta * 16 * (1 + R * NS);
@@ -1305,7 +1611,7 @@ int launch_fused_tma_t(zf_lasso* h, const double* v, bool query_only, int* max_c
   }
   const long long rows_per_cluster = h->fused_rows_per_cta;
   ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, rows_per_cluster,
-                             h->fused_pairs_per_cta, h->gpart, h->sq_part));
+                             h->fused_pairs_per_cta, h->gpart, h->sq_part, h->skip));
   zf::zf_count_launch();
   return ZF_OK;
 }
@@ -1363,7 +1669,7 @@ int launch_fused_ring_t(zf_lasso* h, const double* v, const RingLaunch& L, bool 
   static const int dbg = (ZF_RING_DEBUG && getenv("ZF_LASSO_RING_DBG")) ? 1 : 0;
   ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, L.rows_per_cluster,
                              L.pairs_per_cta, h->gpart, h->sq_part, dbg, L.row_begin,
-                             L.row_end, L.part_base));
+                             L.row_end, L.part_base, h->skip));
   zf::zf_count_launch();
   if (dbg && L.part_base == 0) {
     long long st[8][64], st2[8][64];
@@ -1802,6 +2108,11 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   alloc((void**)&h->d_sums, sizeof(zf::StepSums));
   alloc((void**)&h->counter, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_pin, sizeof(double) * 8);
+  alloc((void**)&h->d_opts, sizeof(zf::LassoDevOpts));
+  alloc((void**)&h->d_state, sizeof(zf::LassoDevState));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_state, 2 * sizeof(zf::LassoDevState));
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+    e = cudaEventCreateWithFlags(&h->ev_poll[k], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), h->st);
   if (e != cudaSuccess) {
     zf_lasso_destroy(h);
@@ -1826,6 +2137,17 @@ extern "C" void zf_lasso_destroy(zf_lasso* h) {
   cudaFree(h->d_sums);
   cudaFree(h->counter);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  cudaFree(h->d_opts);
+  cudaFree(h->d_state);
+  cudaFree(h->d_allerrs);
+  cudaFree(h->d_allfuns);
+  if (h->h_state) cudaFreeHost(h->h_state);
+  for (int k = 0; k < 2; ++k) {
+    if (h->ev_poll[k]) cudaEventDestroy(h->ev_poll[k]);
+    if (h->graph[k]) cudaGraphExecDestroy(h->graph[k]);
+  }
+  if (h->ev_own) cudaEventDestroy(h->ev_own);
+  if (h->st_own) cudaStreamDestroy(h->st_own);
   if (h->st2) cudaStreamDestroy(h->st2);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -2015,9 +2337,20 @@ extern "C" int zf_lasso_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t*
   return ZF_OK;
 }
 
+static int lasso_solve_dev(zf_lasso* h, const zf_options* opt, const double* d_x0, double* d_x,
+                           double* h_fun, int64_t* h_nit, int32_t* h_status, double* h_allerrs,
+                           double* h_allfuns);
+
 extern "C" int zf_lasso_solve(zf_lasso* h, const zf_options* opt, const double* d_x0,
                               double* d_x, double* h_fun, int64_t* h_nit, int32_t* h_status,
                               double* h_allerrs, double* h_allfuns) {
+  // default: the device-decided loop; ZF_LASSO_HOSTLOOP=1 keeps the round-1 loop (one D2H copy +
+  // stream sync per trial, decisions on the host) for A/B measurements
+  static const bool hostloop = getenv("ZF_LASSO_HOSTLOOP") && getenv("ZF_LASSO_HOSTLOOP")[0] == '1';
+  if (!hostloop) {
+    if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+    return lasso_solve_dev(h, opt, d_x0, d_x, h_fun, h_nit, h_status, h_allerrs, h_allfuns);
+  }
   int rc = lasso_begin_impl(h, opt, d_x0, h_allerrs, h_allfuns);
   if (rc != ZF_OK) return rc;
   int32_t next = 0;
@@ -2052,4 +2385,336 @@ extern "C" int zf_lasso_gradient_device(zf_lasso* h, const double* d_x, double* 
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
+}
+
+// =======================================================================================
+// device-decided loop: host side (enqueue only; see the kernels above)
+// =======================================================================================
+namespace {
+
+enum { DS_INIT = 0, DS_GRAD = 1, DS_PROX = 2, DS_FEVAL = 3, DS_DECIDE = 4, DS_FINAL = 5,
+       DS_FEVAL_FINAL = 6 };
+
+// how many partial rows / residual-norm partials the handle's gradient pass leaves behind
+void gradient_part_counts(const zf_lasso* h, int* n_parts, int* n_sq) {
+  if (h->fused_pairs > 0 && h->fused_ring) {
+    *n_parts = h->fused_ctas / h->fused_cluster + h->ring2_ctas / h->ring2_cluster;
+    *n_sq = *n_parts;
+  } else if (h->fused_pairs > 0 && (h->fused_tma || h->fused_cluster > 1)) {
+    *n_parts = h->fused_ctas / h->fused_cluster;
+    *n_sq = *n_parts;
+  } else if (h->fused_pairs > 0) {
+    *n_parts = h->fused_ctas;
+    *n_sq = h->fused_ctas;
+  } else {
+    *n_parts = h->n_rowblocks;
+    *n_sq = h->res_blocks;
+  }
+}
+
+template <int SRC, bool FIXED>
+int launch_dev_update(zf_lasso* h, int n_parts, int n_sq) {
+  zf::lasso_dev_update_kernel<SRC, FIXED><<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
+      h->d_opts, h->d_state, h->gpart, n_parts, h->sq_part, n_sq, h->partial, h->n_cols, h->y,
+      h->xp, h->xn, h->g, h->block_sums);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int dev_stage(zf_lasso* h, int stage) {
+  int rc = ZF_OK, ng = 0, ns = 0;
+  const double* ss_feval = h->dev_sharded ? h->partial + h->n_cols : h->sq_part;
+  const int n_feval = h->dev_sharded ? 1 : h->res_blocks;
+  switch (stage) {
+    case DS_INIT:
+      zf::lasso_dev_init_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss_feval,
+                                                    n_feval);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      return ZF_OK;
+    case DS_GRAD:
+      h->skip = &h->d_state->skip_grad;
+      rc = launch_gradient_pass(h, h->y, &ng, &ns);
+      h->skip = nullptr;
+      if (rc != ZF_OK) return rc;
+      if (h->dev_sharded) rc = launch_collect_n(h, true, ng, ns);   // -> partial, all-reduced next
+      return rc;
+    case DS_PROX:
+      gradient_part_counts(h, &ng, &ns);
+      if (h->dev_sharded)
+        return h->dev_fixed ? launch_dev_update<1, true>(h, ng, ns) : launch_dev_update<1, false>(h, ng, ns);
+      return h->dev_fixed ? launch_dev_update<0, true>(h, ng, ns) : launch_dev_update<0, false>(h, ng, ns);
+    case DS_FEVAL:
+    case DS_FEVAL_FINAL:
+      h->skip = (stage == DS_FEVAL) ? &h->d_state->done : nullptr;
+      rc = launch_residual(h, h->xn);
+      h->skip = nullptr;
+      if (rc != ZF_OK) return rc;
+      if (h->dev_sharded) rc = launch_collect(h, false);            // sum r^2 -> partial[n_cols]
+      return rc;
+    case DS_DECIDE:
+      zf::lasso_dev_decide_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss_feval, n_feval);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      zf::lasso_dev_momentum_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
+          h->d_state, h->n_cols, h->xn, h->xp, h->y);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      return ZF_OK;
+    case DS_FINAL:
+      zf::lasso_dev_final_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss_feval, n_feval);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      return ZF_OK;
+    default:
+      return zf::zf_fail(ZF_ERR_INVALID, "unknown stage");
+  }
+}
+
+// one trial on one GPU (no exchange between the stages)
+int dev_slot(zf_lasso* h) {
+  int rc = dev_stage(h, DS_GRAD);
+  if (rc == ZF_OK) rc = dev_stage(h, DS_PROX);
+  if (rc == ZF_OK && !h->dev_fixed) {
+    rc = dev_stage(h, DS_FEVAL);
+    if (rc == ZF_OK) rc = dev_stage(h, DS_DECIDE);
+  }
+  return rc;
+}
+
+int dev_snapshot(zf_lasso* h, int slot) {
+  ZF_CUDA(cudaMemcpyAsync(&h->h_state[slot], h->d_state, sizeof(zf::LassoDevState),
+                          cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaEventRecord(h->ev_poll[slot], h->st));
+  return ZF_OK;
+}
+
+constexpr int DEV_GRAPH_SLOTS = 32;
+
+// `DEV_GRAPH_SLOTS` slots as one CUDA graph (captured once per handle and mode; every pointer a
+// slot touches is fixed for the life of the handle, the options live in device memory)
+int dev_build_graph(zf_lasso* h) {
+  const int which = h->dev_fixed ? 0 : 1;
+  if (h->graph[which] || h->graph_failed) return ZF_OK;
+  static const bool off = getenv("ZF_LASSO_GRAPH") && getenv("ZF_LASSO_GRAPH")[0] == '0';
+  if (off) { h->graph_failed = true; return ZF_OK; }
+  // warm-up outside the capture: attribute calls and lazy module loading happen here
+  cudaGraph_t g = nullptr;
+  if (cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    h->graph_failed = true;
+    return ZF_OK;
+  }
+  int rc = ZF_OK;
+  for (int k = 0; k < DEV_GRAPH_SLOTS && rc == ZF_OK; ++k) rc = dev_slot(h);
+  const cudaError_t e = cudaStreamEndCapture(h->st, &g);
+  if (rc != ZF_OK || e != cudaSuccess || !g ||
+      cudaGraphInstantiate(&h->graph[which], g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    h->graph[which] = nullptr;
+    h->graph_failed = true;
+  }
+  if (g) cudaGraphDestroy(g);
+  h->graph_slots = DEV_GRAPH_SLOTS;
+  return ZF_OK;
+}
+
+}  // namespace
+
+extern "C" int zf_lasso_set_stream(zf_lasso* h, void* cuda_stream) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (h->dev_active) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_set_stream during a solve");
+  if ((cudaStream_t)cuda_stream != h->st) {
+    for (int k = 0; k < 2; ++k) {        // graphs were captured on the old stream's fork / join
+      if (h->graph[k]) cudaGraphExecDestroy(h->graph[k]);
+      h->graph[k] = nullptr;
+    }
+    h->graph_failed = false;
+  }
+  h->st = (cudaStream_t)cuda_stream;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_dev_begin(zf_lasso* h, const zf_options* opt, const double* d_x0,
+                                  int32_t sharded, int32_t want_trace) {
+  if (!h || !d_x0) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int rc = lasso_check_options(opt);
+  if (rc != ZF_OK) return rc;
+  h->opt = *opt;
+  h->dev_sharded = sharded != 0;
+  const int cap = want_trace ? opt->trace_capacity : 0;
+  if (cap > h->dev_cap) {
+    cudaFree(h->d_allerrs);
+    cudaFree(h->d_allfuns);
+    h->d_allerrs = h->d_allfuns = nullptr;
+    h->dev_cap = 0;
+    ZF_CUDA(cudaMalloc((void**)&h->d_allerrs, sizeof(double) * (size_t)cap));
+    ZF_CUDA(cudaMalloc((void**)&h->d_allfuns, sizeof(double) * ((size_t)cap + 1)));
+    h->dev_cap = cap;
+  }
+  zf::LassoDevOpts& o = h->dev_opts_host;
+  o.lr0 = opt->lr;
+  o.tol = opt->tol;
+  o.tol_internal = opt->tol_internal;
+  o.decay = opt->decay_rate;
+  o.na = opt->nesterov_a;
+  o.nb = opt->nesterov_b;
+  o.scale = h->scale;
+  o.l1 = h->l1;
+  o.max_iter = opt->max_iter;
+  o.max_bt = opt->max_backtrack_iter;
+  o.nesterov = opt->nesterov;
+  o.deprecated = opt->deprecated;
+  o.need_F = (opt->decay_rate != 1.0) || cap > 0;     // the line search, or return_all's allfuns
+  o.cap = cap;
+  o.allerrs = cap > 0 ? h->d_allerrs : nullptr;
+  o.allfuns = cap > 0 ? h->d_allfuns : nullptr;
+  h->dev_fixed = !o.need_F;
+  h->xp = h->vecs;
+  h->xn = h->vecs + h->n_cols;
+  // (pageable source: the runtime stages it before returning, so o may change afterwards)
+  ZF_CUDA(cudaMemcpyAsync(h->d_opts, &o, sizeof(o), cudaMemcpyHostToDevice, h->st));
+  const size_t nb = sizeof(double) * (size_t)h->n_cols;
+  ZF_CUDA(cudaMemcpyAsync(h->xp, d_x0, nb, cudaMemcpyDeviceToDevice, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->xn, d_x0, nb, cudaMemcpyDeviceToDevice, h->st));
+  ZF_CUDA(cudaMemcpyAsync(h->y, d_x0, nb, cudaMemcpyDeviceToDevice, h->st));
+  // F(x0): residual norm of x0 and ||x0||_1
+  rc = launch_residual(h, h->xp);
+  if (rc != ZF_OK) return rc;
+  zf::lasso_prox_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
+      nullptr, nullptr, 0.0, 0.0, 0.0, h->n_cols, h->xp, nullptr, h->block_sums, h->counter,
+      h->d_sums);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  if (h->dev_sharded) {
+    rc = launch_collect(h, false);
+    if (rc != ZF_OK) return rc;
+  }
+  h->dev_active = true;
+  h->phase = LP_IDLE;
+  return ZF_OK;
+}
+
+/* stage: 0 F(x0) | 1 gradient pass at y | 2 prox / update | 3 residual at the candidate |
+ * 4 decide + momentum | 5 res.fun | 6 residual at the final x (before 5 when stage 3/4 never ran) */
+extern "C" int zf_lasso_dev_stage(zf_lasso* h, int32_t stage) {
+  if (!h || !h->dev_active) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_dev_stage before zf_lasso_dev_begin");
+  return dev_stage(h, stage);
+}
+
+/* 1 when every trial needs stages 3 and 4 (line search or F trace), 0 for the fixed-step loop */
+extern "C" int zf_lasso_dev_needs_feval(zf_lasso* h) {
+  return (h && h->dev_active && !h->dev_fixed) ? 1 : 0;
+}
+
+/* enqueue `n_slots` whole trials (single GPU; as CUDA graph launches where possible) */
+extern "C" int zf_lasso_dev_slots(zf_lasso* h, int32_t n_slots) {
+  if (!h || !h->dev_active) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_dev_slots before zf_lasso_dev_begin");
+  if (h->dev_sharded) return zf::zf_fail(ZF_ERR_INVALID, "a row-sharded run enqueues stage by stage");
+  int rc = ZF_OK;
+  const int which = h->dev_fixed ? 0 : 1;
+  if (!h->graph[which] && !h->graph_failed && n_slots > 0) {
+    // the first trial of a mode runs outside the capture: its kernels get loaded and their
+    // attributes set by ordinary launches
+    rc = dev_slot(h);
+    if (rc != ZF_OK) return rc;
+    n_slots -= 1;
+    rc = dev_build_graph(h);
+    if (rc != ZF_OK) return rc;
+  }
+  while (n_slots > 0) {
+    if (h->graph[which] && n_slots >= h->graph_slots) {
+      ZF_CUDA(cudaGraphLaunch(h->graph[which], h->st));
+      zf::zf_count_launch();
+      n_slots -= h->graph_slots;
+    } else {
+      rc = dev_slot(h);
+      if (rc != ZF_OK) return rc;
+      n_slots -= 1;
+    }
+  }
+  return ZF_OK;
+}
+
+/* snapshot the device state after everything enqueued so far (slot 0 / 1), or wait for an
+ * earlier snapshot and read it: done != 0 once the solve has ended */
+extern "C" int zf_lasso_dev_poll(zf_lasso* h, int32_t slot, int32_t wait, int32_t* h_done,
+                                 int64_t* h_nit) {
+  if (!h || !h->dev_active || slot < 0 || slot > 1) return zf::zf_fail(ZF_ERR_INVALID, "bad poll");
+  if (!wait) return dev_snapshot(h, slot);
+  ZF_CUDA(cudaEventSynchronize(h->ev_poll[slot]));
+  if (h_done) *h_done = h->h_state[slot].done;
+  if (h_nit) *h_nit = h->h_state[slot].nit;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_dev_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
+                                   int32_t* h_status, double* h_lr, double* h_allerrs,
+                                   double* h_allfuns) {
+  if (!h || !h->dev_active) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_dev_finish before zf_lasso_dev_begin");
+  h->dev_active = false;
+  ZF_CUDA(cudaMemcpyAsync(&h->h_state[0], h->d_state, sizeof(zf::LassoDevState),
+                          cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  const zf::LassoDevState& s = h->h_state[0];
+  if (!s.done) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_dev_finish before the solve ended");
+  if (d_x) {
+    ZF_CUDA(cudaMemcpyAsync(d_x, s.result_is_prev ? h->xp : h->xn,
+                            sizeof(double) * (size_t)h->n_cols, cudaMemcpyDeviceToDevice, h->st));
+  }
+  const long long k = s.nit < (long long)h->dev_opts_host.cap ? s.nit : (long long)h->dev_opts_host.cap;
+  if (h_allerrs && h->dev_opts_host.cap > 0 && k > 0)
+    ZF_CUDA(cudaMemcpyAsync(h_allerrs, h->d_allerrs, sizeof(double) * (size_t)k,
+                            cudaMemcpyDeviceToHost, h->st));
+  if (h_allfuns && h->dev_opts_host.cap > 0)
+    ZF_CUDA(cudaMemcpyAsync(h_allfuns, h->d_allfuns, sizeof(double) * (size_t)(k + 1),
+                            cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  if (h_fun) *h_fun = s.F_x;
+  if (h_nit) *h_nit = s.nit;
+  if (h_status) *h_status = s.status;
+  if (h_lr) *h_lr = s.lr;
+  return ZF_OK;
+}
+
+// whole solve on one GPU with the device-decided loop: chunks of slots are enqueued one chunk
+// ahead of the poll that looks at the previous one, so the GPU never waits for the host
+static int lasso_solve_dev(zf_lasso* h, const zf_options* opt, const double* d_x0, double* d_x,
+                           double* h_fun, int64_t* h_nit, int32_t* h_status, double* h_allerrs,
+                           double* h_allfuns) {
+  // the caller's stream may be the legacy default stream, which cannot be captured into a
+  // graph: run the loop on the handle's own stream, ordered after / before the caller's
+  cudaStream_t user = h->st;
+  if (!h->st_own) {
+    ZF_CUDA(cudaStreamCreateWithFlags(&h->st_own, cudaStreamNonBlocking));
+    ZF_CUDA(cudaEventCreateWithFlags(&h->ev_own, cudaEventDisableTiming));
+  }
+  ZF_CUDA(cudaEventRecord(h->ev_own, user));
+  ZF_CUDA(cudaStreamWaitEvent(h->st_own, h->ev_own, 0));
+  h->st = h->st_own;
+  int rc = zf_lasso_dev_begin(h, opt, d_x0, 0, (h_allerrs || h_allfuns) ? 1 : 0);
+  if (rc == ZF_OK) rc = dev_stage(h, DS_INIT);
+  const int chunk = DEV_GRAPH_SLOTS;
+  int cur = 0;
+  int32_t done = 0;
+  if (rc == ZF_OK) rc = zf_lasso_dev_slots(h, chunk);
+  if (rc == ZF_OK) rc = dev_snapshot(h, cur);
+  while (rc == ZF_OK) {
+    rc = zf_lasso_dev_slots(h, chunk);
+    if (rc == ZF_OK) rc = dev_snapshot(h, 1 - cur);
+    if (rc == ZF_OK) rc = zf_lasso_dev_poll(h, cur, 1, &done, nullptr);
+    if (rc != ZF_OK || done) break;
+    cur = 1 - cur;
+  }
+  if (rc == ZF_OK && h->dev_fixed) rc = dev_stage(h, DS_FEVAL_FINAL);
+  if (rc == ZF_OK) rc = dev_stage(h, DS_FINAL);
+  if (rc == ZF_OK) rc = zf_lasso_dev_finish(h, d_x, h_fun, h_nit, h_status, nullptr, h_allerrs, h_allfuns);
+  h->dev_active = false;
+  h->st = user;
+  if (rc == ZF_OK) {
+    ZF_CUDA(cudaEventRecord(h->ev_own, h->st_own));
+    ZF_CUDA(cudaStreamWaitEvent(user, h->ev_own, 0));
+  }
+  return rc;
 }

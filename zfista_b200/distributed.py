@@ -91,3 +91,45 @@ def run_split_lasso(ops, allreduce):
         allreduce()
         nxt = ops.step()
     return ops.finish()
+
+
+def run_device_lasso(ops, allreduce_all, allreduce_ss, chunk=16):
+    """Drive one row-sharded solve through the DEVICE-decided protocol of
+    include/zfista_b200.h (zf_lasso_dev_*): every decision is taken on the GPU, the host only
+    enqueues trials -- stage by stage, with the all-reduce of ``partial`` between the stages, all
+    on one stream -- and polls a flag one chunk of trials behind the one it is enqueuing.
+
+    ``ops``: ``begin()``, ``stage(k)``, ``needs_feval() -> bool``, ``snapshot(slot)``,
+    ``wait(slot) -> done``, ``finish()``.  ``allreduce_all()`` sums ``[A^T r | sum r^2]`` over the
+    row shards, ``allreduce_ss()`` only the last value (no-ops on one GPU).  Every rank enqueues
+    the same sequence and sees the same reduced values, so every rank's GPU takes the same
+    decisions."""
+    ops.begin()
+    allreduce_ss()
+    ops.stage(0)
+    feval = ops.needs_feval()
+
+    def enqueue_chunk():
+        for _ in range(chunk):
+            ops.stage(1)
+            allreduce_all()
+            ops.stage(2)
+            if feval:
+                ops.stage(3)
+                allreduce_ss()
+                ops.stage(4)
+
+    cur = 0
+    enqueue_chunk()
+    ops.snapshot(cur)
+    while True:
+        enqueue_chunk()
+        ops.snapshot(1 - cur)
+        if ops.wait(cur):
+            break
+        cur = 1 - cur
+    if not feval:
+        ops.stage(6)
+        allreduce_ss()
+    ops.stage(5)
+    return ops.finish()

@@ -106,6 +106,22 @@ class DenseLasso:
 
             dist.all_reduce(self._partial, group=self.group)
 
+    def _allreduce_ss(self):
+        """all-reduce of the residual-norm partial alone (the last value of ``partial``)"""
+        if self.distributed:
+            import torch.distributed as dist
+
+            dist.all_reduce(self._partial[self.n_features:], group=self.group)
+
+    def _use_current_stream(self):
+        """The library enqueues on the stream it is told; tensors handed in and the NCCL
+        all-reduce are ordered on torch's CURRENT stream, so hand that one over at every entry."""
+        torch = _torch()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if stream != self._stream:
+            _lib.check(_lib.lib().zf_lasso_set_stream(self._h, C.c_void_p(stream)))
+            self._stream = stream
+
     def hbm_passes_per_gradient(self) -> int:
         """1 if this shape uses a fused one-pass A^T(Av - b) kernel, 2 for the two-pass form."""
         return int(_lib.lib().zf_lasso_passes(self._h))
@@ -120,9 +136,11 @@ class DenseLasso:
         fval = torch.empty(1, dtype=torch.float64, device=self.device)
         if self.distributed:
             raise NotImplementedError("gradient() is the single-GPU convenience entry")
-        _lib.check(_lib.lib().zf_lasso_gradient_device(
-            self._h, C.c_void_p(xd.data_ptr()), C.c_void_p(grad.data_ptr()),
-            C.c_void_p(fval.data_ptr())))
+        with torch.cuda.device(self.device):
+            self._use_current_stream()
+            _lib.check(_lib.lib().zf_lasso_gradient_device(
+                self._h, C.c_void_p(xd.data_ptr()), C.c_void_p(grad.data_ptr()),
+                C.c_void_p(fval.data_ptr())))
         return grad, fval
 
     def f(self, x):
@@ -175,6 +193,7 @@ class DenseLasso:
         status = C.c_int32()
         L = _lib.lib()
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             if not self.distributed:
                 _lib.check(L.zf_lasso_solve(
                     self._h, C.byref(opts), C.c_void_p(x0d.data_ptr()), C.c_void_p(xd.data_ptr()),
@@ -182,29 +201,37 @@ class DenseLasso:
                     None if allerrs is None else allerrs.ctypes.data_as(C.c_void_p),
                     None if allfuns is None else allfuns.ctypes.data_as(C.c_void_p)))
             else:
-                if cap:
-                    raise NotImplementedError("return_all is not available on the row-sharded path")
-                from .distributed import run_split_lasso
+                from .distributed import run_device_lasso
 
                 h = self._h
+                want_trace = 1 if cap else 0
+                pe = None if allerrs is None else allerrs.ctypes.data_as(C.c_void_p)
+                pf = None if allfuns is None else allfuns.ctypes.data_as(C.c_void_p)
 
                 class _Ops:
                     def begin(self_):
-                        _lib.check(L.zf_lasso_begin(h, C.byref(opts), C.c_void_p(x0d.data_ptr())))
+                        _lib.check(L.zf_lasso_dev_begin(h, C.byref(opts), C.c_void_p(x0d.data_ptr()),
+                                                        1, want_trace))
 
-                    def grad(self_, which):
-                        _lib.check(L.zf_lasso_grad(h, int(which)))
+                    def stage(self_, k):
+                        _lib.check(L.zf_lasso_dev_stage(h, int(k)))
 
-                    def step(self_):
-                        nxt = C.c_int32(0)
-                        _lib.check(L.zf_lasso_step(h, C.byref(nxt)))
-                        return nxt.value
+                    def needs_feval(self_):
+                        return bool(L.zf_lasso_dev_needs_feval(h))
+
+                    def snapshot(self_, slot):
+                        _lib.check(L.zf_lasso_dev_poll(h, int(slot), 0, None, None))
+
+                    def wait(self_, slot):
+                        done = C.c_int32(0)
+                        _lib.check(L.zf_lasso_dev_poll(h, int(slot), 1, C.byref(done), None))
+                        return bool(done.value)
 
                     def finish(self_):
-                        _lib.check(L.zf_lasso_finish(h, C.c_void_p(xd.data_ptr()), C.byref(fun),
-                                                     C.byref(nit), C.byref(status)))
+                        _lib.check(L.zf_lasso_dev_finish(h, C.c_void_p(xd.data_ptr()), C.byref(fun),
+                                                         C.byref(nit), C.byref(status), None, pe, pf))
 
-                run_split_lasso(_Ops(), self._allreduce)
+                run_device_lasso(_Ops(), self._allreduce, self._allreduce_ss)
         st, k = int(status.value), int(nit.value)
         res = OptimizeResult(
             x=xd if return_device else xd.cpu().numpy(), fun=float(fun.value), nit=k,
