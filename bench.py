@@ -200,12 +200,14 @@ def host_cores():
 def headline_config(spec, world=1):
     """The `config` object of the JSON line: identical in both arms (the reference arm runs a
     bounded SAMPLE of this workload per step and says so in cpu_baseline.sample)."""
-    return {"workload": spec["label"], "options": _json_opts(spec["opts"]),
-            "starts_per_gpu": spec["n_starts"], "l2": "flushed between steps (256 MiB memset)",
-            "inner_solver": "bounded Brent (m=2) / simplex Newton (m>=3)",
-            "options_note": ("max_iter_internal=100 bounds the CPU arm only (reference default "
-                             "100000: one start does not finish in 50 min of trust-constr); the "
-                             "device's exact dual solver does not use it")}
+    cfg = {"workload": spec["label"], "options": _json_opts(spec["opts"]),
+           "starts_per_gpu": spec["n_starts"], "l2": "flushed between steps (256 MiB memset)",
+           "inner_solver": "bounded Brent (m=2) / simplex Newton (m>=3)"}
+    if "max_iter_internal" in spec["opts"]:
+        cfg["options_note"] = ("max_iter_internal=100 bounds the CPU arm only (reference default "
+                               "100000: one start does not finish in 50 min of trust-constr); "
+                               "the device's exact dual solver does not use it")
+    return cfg
 
 
 def run_reference_arm(args):
@@ -264,7 +266,7 @@ def run_reference_arm(args):
     value = solves / total if total > 0 else 0.0
     sample = (f"{n_sample} starts per step ({len(times)} steps timed of {args.steps} requested, "
               f"budget {args.ref_budget_s:.0f} s) of the same workload; oracle port of zfista "
-              "(numpy + scipy trust-constr, max_iter_internal=100), one process per start; all "
+              "(numpy + scipy inner solver, options as in config), one process per start; all "
               "solves counted, converged or not")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
@@ -273,7 +275,7 @@ def run_reference_arm(args):
         "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": headline_config(spec),
-        "same_config": False,
+        "same_config": n_sample == spec["n_starts"],
         "same_config_note": (f"same problem and options; {n_sample} starts per CPU step against "
                              f"{spec['n_starts']} per GPU step (throughput per start is what is "
                              "compared)"),
@@ -295,14 +297,148 @@ def _json_opts(opts):
 
 
 # --------------------------------------------------------------------------- GPU arm
+class BatchedRunner:
+    """One batched workload on this rank's GPU: device-resident steps through
+    zf_solve_batched_device and end-to-end steps through the public API on pinned host arrays."""
+
+    def __init__(self, spec, dev, rank, world, total_steps, n_starts=None, seed0=1000):
+        import torch
+
+        from zfista_b200 import _lib
+        import zfista_b200.problems as zp
+        from zfista_b200.proximal_gradient import _make_options
+
+        self.spec, self.dev = spec, dev
+        self.prob = getattr(zp, spec["cls"])(**spec["kw"])
+        self.n, self.m = self.prob.n_features, self.prob.n_objectives
+        self.S = S = int(n_starts if n_starts is not None else spec["n_starts"])
+        sp = dict(spec, n_starts=S)
+        # every step gets its own batch of starts; each rank its own slice of the seed space
+        self.host_batches = [make_starts(sp, seed0 + step * world + rank, self.n)
+                             for step in range(total_steps)]
+        self.dev_batches = [torch.from_numpy(b).to(dev) for b in self.host_batches]
+        self.out = dict(x=torch.empty(S, self.n, dtype=torch.float64, device=dev),
+                        fun=torch.empty(S, self.m, dtype=torch.float64, device=dev),
+                        nit=torch.empty(S, dtype=torch.int64, device=dev),
+                        status=torch.empty(S, dtype=torch.int32, device=dev),
+                        n_dual=torch.empty(S, dtype=torch.int64, device=dev),
+                        nfev=torch.empty(S, dtype=torch.int64, device=dev))
+        self.res = _lib.ZfResult()
+        for k, t in self.out.items():
+            setattr(self.res, k, t.data_ptr())
+        o = spec["opts"]
+        self.opts = _make_options(1.0, 1e-5, o["tol_internal"], o["max_iter"],
+                                  o.get("max_iter_internal", 100000), 100, False, 0.5,
+                                  o.get("nesterov", False), (0, 0.25), False, "reference", 0)
+        self.desc, self.keep = self.prob.descriptor()
+        self.stream = torch.cuda.current_stream()
+        self.L = _lib.lib()
+        self._lib = _lib
+
+    def device_step(self, i):
+        self._lib.check(self.L.zf_solve_batched_device(
+            C.byref(self.desc), C.byref(self.opts), self.S,
+            C.c_void_p(self.dev_batches[i].data_ptr()), None, C.byref(self.res),
+            C.c_void_p(self.stream.cuda_stream)))
+
+    def run_device(self, warmup, steps, flush, barrier):
+        """-> dict(ms (sum over steps), converged, nit_sum, nit_max, ndual_sum, nits (last step))"""
+        import torch
+
+        for i in range(warmup):
+            self.device_step(i)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        r = dict(converged=0, nit_sum=0, nit_max=0, ndual_sum=0)
+        for k in range(steps):
+            flush.zero_()
+            ev[k][0].record(self.stream)
+            self.device_step(warmup + k)
+            ev[k][1].record(self.stream)
+            ev[k][1].synchronize()
+            n = self.S
+            r["converged"] += int((self.out["status"][:n] == 1).sum().item())
+            r["nit_sum"] += int(self.out["nit"][:n].sum().item())
+            r["nit_max"] = max(r["nit_max"], int(self.out["nit"][:n].max().item()))
+            r["ndual_sum"] += int(self.out["n_dual"][:n].sum().item())
+        barrier()
+        r["ms"] = sum(a.elapsed_time(b) for a, b in ev)
+        r["nits"] = self.out["nit"][:self.S].cpu().numpy()
+        return r
+
+    def run_e2e(self, warmup, steps, flush, barrier):
+        """public API on pinned host arrays: H2D of the starts and D2H of the results inside the
+        timed region -> (seconds, converged)"""
+        import torch
+
+        pinned = [torch.from_numpy(b).pin_memory() for b in self.host_batches]
+        for i in range(min(warmup, 2)):
+            self.prob.minimize_proximal_gradient_batched(pinned[i].numpy(), **self.spec["opts"])
+        barrier()
+        secs, conv = 0.0, 0
+        for k in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            br = self.prob.minimize_proximal_gradient_batched(pinned[warmup + k].numpy(),
+                                                              **self.spec["opts"])
+            secs += time.perf_counter() - t0
+            conv += int((br.status == 1).sum())
+        return secs, conv
+
+    def io_bytes(self):
+        S, n, m = self.S, self.n, self.m
+        return S * n * 8, S * (n * 8 + m * 8 + 8 + 4 + 8 + 8 + 8 + 8)
+
+
+def nit_histogram(nits):
+    """iteration counts of one batch: the kernel runs one warp per start, so its duration is the
+    LONGEST start's while the average warp is busy mean/max of that time"""
+    nits = np.asarray(nits)
+    edges = [0, 50, 100, 200, 300, 400, 500, 600, 800, 1000, 10 ** 9]
+    hist, _ = np.histogram(nits, bins=edges)
+    return {"bins": [f"{a}-{b - 1}" if b < 10 ** 9 else f">={a}" for a, b in zip(edges, edges[1:])],
+            "counts": hist.tolist(), "mean": float(nits.mean()), "max": int(nits.max()),
+            "mean_over_max_utilisation": float(nits.mean() / max(1, nits.max()))}
+
+
+def fp64_roofline(kernel_s, start_iterations, clocks):
+    """roofline of batched_fista_kernel: it keeps a start's state in shared memory and touches
+    HBM for x0 and the results only (~1 MB per launch), so the roof that bounds it is the FP64
+    pipe.  FP64 flops per launch = (flops per start-iteration counted by ncu on this very kernel,
+    profiles/r02_fp64_calib.json) x the start-iterations of the timed launches."""
+    cal_p = os.path.join(ROOT, "profiles", "r02_fp64_calib.json")
+    with open(cal_p) as fh:
+        cal = json.load(fh)
+    flops = cal["flops_per_start_iteration"] * start_iterations
+    achieved = flops / kernel_s / 1e12
+    peak = 148 * 64 * 2 * 1.965e9 / 1e12
+    return {
+        "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak, "traffic": cal["dram_bytes_read"] + cal["dram_bytes_write"],
+        "peak_source": "148 SMs x 64 FP64 FMA lanes x 2 x 1.965 GHz (ncu: "
+                       "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained = 9472 "
+                       "per cycle); MEASURED_PEAKS.json has no FP64 figure",
+        "flops_per_start_iteration": cal["flops_per_start_iteration"],
+        "ncu": {"fp64_pipe_active_pct": cal["fp64_pipe_active_pct"],
+                "issue_slots_active_pct": cal["issue_slots_active_pct"],
+                "warp_occupancy_pct": cal["warp_occupancy_pct"],
+                "dominant_stall": "wait 43 % (dependent FP64 chains), selected 28 %, "
+                                  "no_instruction 9 %",
+                "source": "profiles/r02_batched_fista_full.txt"},
+        "note": ("latency bound: 1024 warps on 592 schedulers, each a chain of dependent FP64 "
+                 "operations; the launch lasts as long as its longest start (nit_histogram), so "
+                 "the pipe fraction grows with the batch (also.batch_scaling) -- DESIGN.md 3.1"),
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from zfista_b200 import _lib
     from zfista_b200 import build as zbuild
-    import zfista_b200.problems as zp
-    from zfista_b200.proximal_gradient import _make_options
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -318,31 +454,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     zbuild.build()
-    L = _lib.lib()
 
     spec = workload_spec(args.workload)
-    prob = getattr(zp, spec["cls"])(**spec["kw"])
-    n, m, S = prob.n_features, prob.n_objectives, spec["n_starts"]
     total_steps = args.warmup + args.steps
-    # every step gets its own batch of starts; each rank its own slice of the seed space
-    host_batches = [make_starts(spec, 1000 + step * world + rank, n) for step in range(total_steps)]
-    dev_batches = [torch.from_numpy(b).to(dev) for b in host_batches]
-    out_x = torch.empty(S, n, dtype=torch.float64, device=dev)
-    out_fun = torch.empty(S, m, dtype=torch.float64, device=dev)
-    out_nit = torch.empty(S, dtype=torch.int64, device=dev)
-    out_status = torch.empty(S, dtype=torch.int32, device=dev)
-    out_ndual = torch.empty(S, dtype=torch.int64, device=dev)
-    out_nfev = torch.empty(S, dtype=torch.int64, device=dev)
-    res = _lib.ZfResult()
-    res.x, res.fun, res.nit, res.status = (out_x.data_ptr(), out_fun.data_ptr(),
-                                           out_nit.data_ptr(), out_status.data_ptr())
-    res.n_dual, res.nfev = out_ndual.data_ptr(), out_nfev.data_ptr()
-    o = spec["opts"]
-    opts = _make_options(1.0, 1e-5, o["tol_internal"], o["max_iter"],
-                         o.get("max_iter_internal", 100000), 100, False, 0.5,
-                         o.get("nesterov", False), (0, 0.25), False, "reference", 0)
-    desc, keep = prob.descriptor()
-    stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -350,134 +464,161 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step(i):
-        _lib.check(L.zf_solve_batched_device(
-            C.byref(desc), C.byref(opts), S, C.c_void_p(dev_batches[i].data_ptr()), None,
-            C.byref(res), C.c_void_p(stream.cuda_stream)))
+    def reduce_max_sum(tmax, csum):
+        t = torch.tensor(tmax, dtype=torch.float64, device=dev)
+        c = torch.tensor(csum, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        return t.tolist(), c.tolist()
 
-    # ---------------- value: device-resident, CUDA events per step, L2 flushed between steps
-    for i in range(args.warmup):
-        device_step(i)
-    barrier()
+    # ---------------- headline: value (device-resident, CUDA events per step, L2 flushed between
+    # steps) and e2e (public API, pinned host arrays in, host arrays out)
+    head = BatchedRunner(spec, dev, rank, world, total_steps)
+    S, n, m = head.S, head.n, head.m
     sampler = ClockSampler(local_rank)
+    barrier()
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    converged = 0
-    nit_sum = 0
-    ndual_sum = 0
-    nit_max = 0
-    barrier()
-    for k in range(args.steps):
-        flush.zero_()
-        ev[k][0].record(stream)
-        device_step(args.warmup + k)
-        ev[k][1].record(stream)
-        ev[k][1].synchronize()
-        converged += int((out_status == 1).sum().item())
-        nit_sum += int(out_nit.sum().item())
-        nit_max = max(nit_max, int(out_nit.max().item()))
-        ndual_sum += int(out_ndual.sum().item())
-    barrier()
-    launches = _lib.launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dv = head.run_device(args.warmup, args.steps, flush, barrier)
+    launches = _lib.launch_count() - launches0 - args.warmup
     clocks = sampler.stop() if rank == 0 else None
-
-    # ---------------- e2e: public API, pinned host arrays in, host arrays out
-    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
-    for i in range(min(args.warmup, 2)):
-        prob.minimize_proximal_gradient_batched(pinned[i].numpy(), **spec["opts"])
-    barrier()
-    e2e_s = 0.0
-    e2e_conv = 0
-    for k in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        br = prob.minimize_proximal_gradient_batched(pinned[args.warmup + k].numpy(),
-                                                     **spec["opts"])
-        e2e_s += time.perf_counter() - t0
-        e2e_conv += int((br.status == 1).sum())
-    h2d = S * n * 8
-    d2h = S * (n * 8 + m * 8 + 8 + 4 + 8 + 8 + 8 + 8)
-
-    # ---------------- reduce over ranks: time = max, counts = sum
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    c = torch.tensor([converged, e2e_conv, nit_sum, ndual_sum, launches], dtype=torch.float64,
-                     device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = t.tolist()
-    conv_all, e2e_conv_all, nit_all, ndual_all, launches_all = c.tolist()
+    e2e_s, e2e_conv = head.run_e2e(args.warmup, args.steps, flush, barrier)
+    h2d, d2h = head.io_bytes()
+    (dev_ms_max, e2e_ms_max), (conv_all, e2e_conv_all, nit_all, ndual_all, launches_all) = \
+        reduce_max_sum([dv["ms"], e2e_s * 1e3],
+                       [dv["converged"], e2e_conv, dv["nit_sum"], dv["ndual_sum"], launches])
 
     line = None
     if rank == 0:
         value = conv_all / (dev_ms_max / 1e3)
         e2e_value = e2e_conv_all / (e2e_ms_max / 1e3)
-        peaks = _measured_peaks()
-        # dominant kernel = batched_fista_kernel: one launch per step.  Algorithmic HBM bytes
-        # per start: x0 in; x, fun, nit, status, n_dual, nfev out (DESIGN.md "Measurement").
-        bytes_per_start = n * 8 + n * 8 + m * 8 + 8 + 4 + 8 + 8
-        ker_s = (dev_ms / 1e3) / args.steps
-        achieved = S * bytes_per_start / ker_s / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": spec["label"], "options": _json_opts(spec["opts"]),
-                       "starts_per_gpu": S, "l2": "flushed between steps (256 MiB memset)",
-                       "inner_solver": "bounded Brent (m=2) / simplex Newton (m>=3)"},
+            "config": headline_config(spec, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "nit_mean": nit_all / (S * world * args.steps), "nit_max_rank0": nit_max,
+            "nit_mean": nit_all / (S * world * args.steps), "nit_max_rank0": dv["nit_max"],
+            "nit_histogram_last_step_rank0": nit_histogram(dv["nits"]),
             "dual_evals_per_solve": ndual_all / (S * world * args.steps),
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": 1239808.0,
-                "ncu": {"fp64_pipe_active_pct": 16.6, "issue_slots_active_pct": 34.8,
-                        "warp_occupancy_pct": 7.0, "dominant_stall": "wait (dependent FP64 ops)",
-                        "source": "profiles/r01e_batched_fista_final.txt"},
-                "peak_source": peaks["source"],
-                "note": ("batched_fista_kernel keeps each start's state in shared memory and "
-                         "touches HBM only for x0 and the results; it is FP64-latency bound, "
-                         "not HBM bound (profiles/), so this fraction is tiny by design. The "
-                         "HBM-bound kernel of the path is the dense LASSO pass: also.lasso")},
+            "roofline": fp64_roofline((dv["ms"] / 1e3), dv["nit_sum"], clocks),
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             ns = ref_sample_size(spec, args, cores)
-            cconv, cdt, cn = cpu_reference_step(spec, host_batches[args.warmup][:ns], cores)
+            cconv, cdt, cn = cpu_reference_step(spec, head.host_batches[args.warmup][:ns], cores)
             line["cpu_baseline"] = {
-                "value": cconv / cdt if cdt > 0 else 0.0, "unit": UNIT, "cores": cores,
-                "kind": "port", "seconds": cdt, "nit": cn,
-                "sample": (f"{ns} starts of this step's batch, oracle port "
-                           "of zfista (numpy + scipy trust-constr), one process per start")}
+                "value": ns / cdt if cdt > 0 else 0.0, "unit": UNIT, "cores": cores,
+                "kind": "port", "seconds": cdt, "nit": cn, "converged": int(cconv),
+                "sample": (f"{ns} starts of this step's batch (all counted, {cconv} converged), "
+                           "oracle port of zfista (numpy + scipy trust-constr, "
+                           "max_iter_internal=100), one process per start")}
         else:
             line["cpu_baseline"] = None
-    if rank == 0 or world > 1:
-        also = {}
-        if not args.no_extras:
-            for name, fn in (("lasso", bench_lasso), ("lasso_multi", bench_lasso_multi),
-                             ("cameraman", bench_cameraman),
-                             ("ab_sweep", bench_sweep), ("batch_scaling", bench_batch_scaling),
-                             ("lasso_configs3", bench_lasso_configs3)):
-                try:
-                    also[name] = fn(args, dev, rank, world)
-                except Exception as e:  # extras must never lose the headline line
-                    also[name] = {"error": repr(e)}
-        if rank == 0:
-            line["also"] = also
-            emit(line)
-    del keep
+    del head
+
+    # ---------------- the other BASELINE configs, each measured the same way
+    def section(name, fn, store):
+        try:
+            store[name] = fn(args, dev, rank, world)
+        except Exception as e:  # a failing extra must never lose the headline line
+            store[name] = {"error": repr(e)}
+
+    configs, also = {}, {}
+    if not args.no_extras:
+        ctx = dict(flush=flush, barrier=barrier, reduce_max_sum=reduce_max_sum)
+        args._ctx = ctx
+        section("configs0_jos1_n5_1000_starts", bench_configs0, configs)
+        section("configs2_fds_1024_starts_sharded", bench_configs2_strong, configs)
+        section("configs4_ab_sweep_jos1", bench_sweep, configs)
+        section("configs4_ab_sweep_fds", bench_sweep_fds, configs)
+        section("configs1_cameraman", bench_cameraman, configs)
+        section("batch_scaling", bench_batch_scaling, also)
+        section("lasso", bench_lasso, also)
+        section("lasso_multi", bench_lasso_multi, also)
+        section("multigpu_parity", bench_multigpu_parity, also)
+        del flush
+        ctx["flush"] = None
+        torch.cuda.empty_cache()
+        section("configs3_lasso_200000x20000", bench_lasso_configs3, configs)
+    if rank == 0:
+        c3 = configs.get("configs3_lasso_200000x20000", {})
+        if isinstance(c3, dict) and "roofline" in c3:
+            # the HBM-bound kernel of the path, at BASELINE configs[3]'s size: second half of the
+            # metric ("LASSO FISTA iters/sec vs HBM roofline")
+            line["roofline_hbm"] = c3["roofline"]
+            line["lasso"] = {"metric": "LASSO FISTA iters/sec vs HBM roofline", "unit": "it/s",
+                             "value": c3.get("single_fista_iters_per_s"),
+                             "config": c3.get("A"), "roofline_frac": c3["roofline"]["frac"],
+                             "e2e": "A resident in HBM (29.8 GiB: loading it is not part of an "
+                                    "iteration); x0 / x cross PCIe once per solve"}
+        line["configs"] = configs
+        line["also"] = also
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_configs0(args, dev, rank, world):
+    """BASELINE configs[0]: JOS1 bi-objective n = 5, FISTA, 1000 uniform(-2, 4) starts
+    (benchmarks/benchmark.py:413-419, 463), the reference's own CPU-runnable case.  m = 2 is the
+    like-for-like comparison: the device runs the reference's own inner solver (bounded Brent,
+    same update order), parity tier 1 (same nit, 1e-8).  CPU arm: all 1000 starts of one step."""
+    spec = workload_spec("jos1")
+    ctx = args._ctx
+    steps, warmup = max(3, min(args.steps, 10)), 3
+    r = BatchedRunner(spec, dev, rank, world, steps + warmup, seed0=5000)
+    dv = r.run_device(warmup, steps, ctx["flush"], ctx["barrier"])
+    e2e_s, e2e_conv = r.run_e2e(warmup, steps, ctx["flush"], ctx["barrier"])
+    (ms, e2e_ms), (conv, e2e_c, nit) = ctx["reduce_max_sum"](
+        [dv["ms"], e2e_s * 1e3], [dv["converged"], e2e_conv, dv["nit_sum"]])
+    out = {"workload": spec["label"], "options": _json_opts(spec["opts"]), "steps": steps,
+           "value": conv / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+           "e2e": {"value": e2e_c / (e2e_ms / 1e3), "unit": UNIT,
+                   "h2d_bytes_per_step": r.io_bytes()[0], "d2h_bytes_per_step": r.io_bytes()[1]},
+           "nit_mean": nit / (r.S * world * steps), "nit_max_rank0": dv["nit_max"]}
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cores = host_cores()
+        cconv, cdt, cn = cpu_reference_step(spec, r.host_batches[warmup], cores)
+        out["cpu_baseline"] = {"value": len(cn) / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "seconds": cdt, "converged": int(cconv),
+                               "sample": f"all {len(cn)} starts of one step, oracle port "
+                                         "(numpy + scipy bounded Brent), one process per start"}
+        out["e2e_over_cpu"] = out["e2e"]["value"] / out["cpu_baseline"]["value"]
+    return out
+
+
+def bench_configs2_strong(args, dev, rank, world):
+    """BASELINE configs[2] as written: 1024 starts IN TOTAL, sharded over the N GPUs (strong
+    scaling, 1024 / N starts per GPU, no collective).  The kernel's duration is its longest
+    start's (one warp per start), so fewer starts per GPU barely shorten it: this line is the
+    latency floor of the batch, the weak-scaling headline is the throughput."""
+    spec = workload_spec("fds")
+    ctx = args._ctx
+    total = 1024
+    from zfista_b200.distributed import shard_bounds
+
+    lo, hi = shard_bounds(total, rank, world)
+    steps, warmup = max(3, min(args.steps, 10)), 3
+    r = BatchedRunner(spec, dev, rank, 1, steps + warmup, n_starts=total, seed0=7000)
+    # every rank draws the SAME 1024 starts per step and keeps its own slice
+    r.S = hi - lo
+    r.dev_batches = [b[lo:hi].contiguous() for b in r.dev_batches]
+    r.host_batches = [b[lo:hi] for b in r.host_batches]
+    dv = r.run_device(warmup, steps, ctx["flush"], ctx["barrier"])
+    (ms,), (conv, nit) = ctx["reduce_max_sum"]([dv["ms"]], [dv["converged"], dv["nit_sum"]])
+    return {"workload": f"FDS n=100 + L1, FISTA, {total} starts in total = {hi - lo} per GPU",
+            "scaling": "strong", "value": conv / (ms / 1e3), "unit": UNIT,
+            "ms_per_step": ms / steps, "steps": steps, "nit_mean": nit / (total * steps),
+            "nit_max_rank0": dv["nit_max"],
+            "us_per_iteration_of_the_longest_start": 1e3 * (dv["ms"] / steps) / max(1, dv["nit_max"])}
 
 
 def _measured_peaks():
@@ -586,14 +727,180 @@ def bench_lasso_multi(args, dev, rank, world):
     return out
 
 
-def bench_lasso_configs3(args, dev, rank, world):
-    """BASELINE configs[3]: dense LASSO A 200000 x 20000 fp64 (29.8 GiB), rows sharded over the
-    ranks (strong scaling: 200000 / world rows per GPU), A^T r all-reduced over NCCL.  Single-run
-    path (one-pass fused gradient) and 16 runs sharing A (two FP64 tensor-core passes)."""
+def _fista_iters_per_s(solve, n_short, n_long, dev, world):
+    """Iterations per second of a fixed-step run with everything that happens once per solve
+    (begin(): copies + the F(x0) pass over A, the final F pass, the tail of the last chunk of
+    trials) outside the measurement: (n_long - n_short) / (T(n_long) - T(n_short)), both runs timed
+    with a device synchronise on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    ts = []
+    for n in (n_short, n_short, n_long):          # the first one warms up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nit = solve(n)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ts.append((nit, tt.item()))
+    (n1, t1), (n2, t2) = ts[1], ts[2]
+    return (n2 - n1) / (t2 - t1), n2 / t2, n2 - n1
+
+
+def _sustained_gradient_ms(prob, x, reps, multi=False):
+    """ms per gradient pass, `reps` launches back to back (so the clocks are those of a running
+    solve, not of a burst), at a NON-ZERO iterate (zeros draw less power)."""
+    import torch
+
+    stream = torch.cuda.current_stream()
+    for _ in range(3):
+        prob.gradient(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        prob.gradient(x)
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _hbm_roofline(a_bytes, vec_bytes, ms, passes, peaks, traffic_note):
+    alg = a_bytes + vec_bytes
+    ach = alg / (ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):            # ncu-measured DRAM bytes / |A| per kernel form
+        with open(tp) as fh:
+            tj = json.load(fh)
+        keys = (["lasso_fused_ring_kernel"] if passes == 1
+                else ["lasso_residual_kernel", "lasso_atr_kernel"])
+        traffic = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"])
+                      / tj[k]["algorithmic_bytes"] for k in keys) * a_bytes
+    return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+            "traffic_source": "NOT measured at this shape: ncu dram bytes / |A| of the same kernel "
+                              "at 32768x16384 and 32768x20000 (1.0001, profiles/r01_traffic.json, "
+                              "profiles/r01g_*) scaled to this A" + traffic_note,
+            "ms_per_gradient": ms, "hbm_passes_over_A": passes,
+            "timing": "50 launches back to back at a non-zero iterate (sustained clocks)",
+            "peak_source": peaks["source"]}
+
+
+def bench_lasso(args, dev, rank, world):
+    """Dense LASSO (the HBM-bound kernels): A rows x cols fp64 per GPU, rows sharded over the
+    ranks (weak: every rank holds `rows` rows), A^T r all-reduced over NCCL.  Reports the
+    roofline of one gradient pass and FISTA iterations/s of a fixed-step run (device-decided
+    loop), and their ratio: how much of the gradient-bound rate the solver keeps."""
+    import warnings
+
+    import torch
+
+    from zfista_b200.lasso import DenseLasso
+
+    rows, cols = args.lasso_rows, args.lasso_cols
+    A, b = _lasso_data(rows, cols, dev, rank)
+    prob = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows * world),
+                      distributed=world > 1)
+    x = torch.zeros(cols, dtype=torch.float64, device=dev)
+    a_bytes = rows * cols * 8
+    out = {"A": f"{rows}x{cols} fp64 per GPU ({a_bytes / 2**30:.1f} GiB, > L2)"}
+    kw = dict(lr=0.5, decay_rate=1, nesterov=True, tol=0.0, return_device=True)
+
+    def solve(n):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return prob.minimize_proximal_gradient(x, max_iter=n, **kw).nit
+
+    rate, rate_whole, n_it = _fista_iters_per_s(solve, 20, 20 + args.lasso_iters, dev, world)
+    out.update(fista_iters_per_s=rate, fista_iters_per_s_whole_call=rate_whole, fista_iters=n_it,
+               global_rows=rows * world)
+    if world == 1:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            xk = prob.minimize_proximal_gradient(x, max_iter=5, **kw).x
+        ms = _sustained_gradient_ms(prob, xk, 50)
+        out["roofline"] = _hbm_roofline(a_bytes, (2 * cols + 2 * rows) * 8, ms,
+                                        prob.hbm_passes_per_gradient(), _measured_peaks(), "")
+        out["solver_over_gradient_bound"] = rate * ms / 1e3
+    return out
+
+
+def bench_multigpu_parity(args, dev, rank, world):
+    """Driver-visible multi-GPU parity: the row-sharded LASSO (NCCL all-reduce of A^T r between
+    the device-decided stages) against the same solve on ONE GPU with the whole A, and the CPU
+    oracle; asserted.  At N = 1 the sharded code path runs on a one-rank group."""
     import warnings
 
     import torch
     import torch.distributed as dist
+
+    from oracle import zfista_oracle as zo
+    from zfista_b200.distributed import shard_bounds
+    from zfista_b200.lasso import DenseLasso
+
+    if world == 1 and not dist.is_initialized():
+        import socket
+
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0,
+                                world_size=1, device_id=dev)
+        own_group = True
+    else:
+        own_group = False
+    rng = np.random.RandomState(11)
+    n_rows, n_cols = 4003, 1300
+    A = rng.standard_normal((n_rows, n_cols))
+    w = np.zeros(n_cols)
+    w[:8] = rng.standard_normal(8)
+    b = A @ w + 0.01 * rng.standard_normal(n_rows)
+    scale, l1, x0 = 1 / (2 * n_rows), 0.03, np.zeros(n_cols)
+    lo, hi = shard_bounds(n_rows, rank, world)
+    sharded = DenseLasso(A[lo:hi], b[lo:hi], l1, scale=scale, distributed=True)
+    single = DenseLasso(A, b, l1, scale=scale)
+    spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
+    out = {"A": f"{n_rows}x{n_cols}, rows sharded over {world} rank(s)", "cases": []}
+    for opts in (dict(nesterov=True), dict(nesterov=True, lr=0.2, decay_rate=1, max_iter=400)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r_sh = sharded.minimize_proximal_gradient(x0, **opts)
+            r_1 = single.minimize_proximal_gradient(x0, **opts)
+            ref = zo.minimize_proximal_gradient(spec, x0, **opts) if rank == 0 else None
+        dx = float(np.max(np.abs(r_sh.x - r_1.x)))
+        case = {"options": {k: v for k, v in opts.items()}, "nit_sharded": r_sh.nit,
+                "nit_single_gpu": r_1.nit, "max_abs_dx_sharded_vs_single": dx}
+        assert r_sh.nit == r_1.nit, case
+        assert dx <= 1e-8 * max(1.0, float(np.max(np.abs(r_1.x)))), case
+        if ref is not None:
+            case["nit_oracle"] = int(ref["nit"])
+            case["max_abs_dx_vs_oracle"] = float(np.max(np.abs(r_sh.x - ref["x"])))
+            assert r_sh.nit == ref["nit"], case
+            assert case["max_abs_dx_vs_oracle"] <= 1e-8 * max(1.0, float(np.max(np.abs(ref["x"])))), case
+        out["cases"].append(case)
+    del sharded, single
+    if own_group:
+        dist.destroy_process_group()
+    out["ok"] = True
+    return out
+
+
+def bench_lasso_configs3(args, dev, rank, world):
+    """BASELINE configs[3]: dense LASSO A 200000 x 20000 fp64 (29.8 GiB), rows sharded over the
+    ranks (strong scaling: 200000 / world rows per GPU), A^T r all-reduced over NCCL.  Single-run
+    path (one-pass fused gradient, device-decided loop) and 16 runs sharing A (two FP64
+    tensor-core passes).  Iterations/s exclude what happens once per solve (_fista_iters_per_s);
+    `efficiency_vs_gradient_bound` = iterations/s x this rank's sustained gradient-pass time: 1.0
+    means the loop costs nothing but its gradient passes (the 1-GPU pass time divides by N when
+    the rows are split, so this is also the strong-scaling efficiency a perfect split would keep)."""
+    import warnings
+
+    import torch
 
     from zfista_b200.lasso import DenseLasso, DenseLassoMulti
 
@@ -609,130 +916,56 @@ def bench_lasso_configs3(args, dev, rank, world):
     a_bytes = rows * cols * 8
     out = {"A": f"{rows_total}x{cols} fp64, {rows} rows per GPU ({a_bytes / 2**30:.1f} GiB per GPU)"}
     x = torch.zeros(cols, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
     single = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows_total), distributed=world > 1)
     multi = DenseLassoMulti(A, b, 1e-3, K, scale=1.0 / (2 * rows_total), distributed=world > 1)
-    if world == 1:
-        X = torch.zeros(K, cols, dtype=torch.float64, device=dev)
-        for name, fn, n_pass in (("single_run_gradient", lambda: single.gradient(x), 1),
-                                 ("multi_run_gradient", lambda: multi.gradient(X), 2)):
-            fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(3):
-                fn()
-            e1.record(stream)
-            e1.synchronize()
-            ms = e0.elapsed_time(e1) / 3
-            ach = n_pass * a_bytes / (ms / 1e3) / 1e9
-            out[name] = {"bound": "hbm", "ms": ms, "algorithmic_passes_over_A": n_pass,
-                         "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"]}
-        out["multi_run_gradient"]["runs"] = K
-        out["multi_run_gradient"]["ms_per_run"] = out["multi_run_gradient"]["ms"] / K
     kw = dict(lr=0.5, decay_rate=1, nesterov=True, tol=0.0, return_device=True)
     grid = [AB_GRID[k % len(AB_GRID)] for k in range(K)]
+
+    def solve_single(n):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return single.minimize_proximal_gradient(x, max_iter=n, **kw).nit
+
+    def solve_multi(n):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return sum(r.nit for r in multi.minimize_proximal_gradient_batched(x, grid, max_iter=n, **kw))
+
+    rate, whole, n_it = _fista_iters_per_s(solve_single, 10, 70, dev, world)
+    out.update(single_fista_iters_per_s=rate, single_fista_iters_per_s_whole_call=whole,
+               single_fista_iters_timed=n_it)
+    mrate, mwhole, mn = _fista_iters_per_s(solve_multi, 5, 25, dev, world)
+    out.update(multi_fista_run_iters_per_s=mrate, multi_fista_run_iters_per_s_whole_call=mwhole,
+               multi_runs=K)
+    # this rank's gradient pass alone (a local single-GPU handle over the same rows: no exchange)
+    local = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows_total))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        for name, run in (("single", lambda n: [single.minimize_proximal_gradient(x, max_iter=n, **kw)]),
-                          ("multi", lambda n: multi.minimize_proximal_gradient_batched(x, grid, max_iter=n, **kw))):
-            run(2)
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res = run(10)
-            torch.cuda.synchronize()
-            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            out[f"{name}_fista_run_iters_per_s"] = sum(r.nit for r in res) / tt.item()
-    del single, multi
+        xk = local.minimize_proximal_gradient(x, max_iter=3, **kw).x
+    ms = _sustained_gradient_ms(local, xk, 50)
+    roof = _hbm_roofline(a_bytes, (2 * cols + 2 * rows) * 8, ms, local.hbm_passes_per_gradient(),
+                         peaks, "")
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["roofline"] = roof
+    out["gradient_ms_max_over_ranks"] = t.item()
+    out["efficiency_vs_gradient_bound"] = rate * t.item() / 1e3
+    if world == 1:
+        local_m = DenseLassoMulti(A, b, 1e-3, K, scale=1.0 / (2 * rows_total))
+        X = xk.expand(K, -1).contiguous()
+        msm = _sustained_gradient_ms(local_m, X, 20)
+        achm = 2 * a_bytes / (msm / 1e3) / 1e9
+        out["multi_run_gradient"] = {"bound": "hbm", "ms": msm, "algorithmic_passes_over_A": 2,
+                                     "achieved": achm, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": achm / peaks["hbm_gbs"], "runs": K,
+                                     "ms_per_run": msm / K}
+        del local_m
+    del single, multi, local
     _LASSO_DATA.clear()
     torch.cuda.empty_cache()
-    return out
-
-
-def bench_lasso(args, dev, rank, world):
-    """Dense LASSO gradient pass (the HBM-bound kernels): A rows x cols fp64 per GPU, rows
-    sharded over ranks (weak: every rank holds `rows` rows), A^T r all-reduced over NCCL.
-    Reports FISTA iterations/s of a fixed-step run and the roofline of one gradient."""
-    import torch
-    import torch.distributed as dist
-
-    from zfista_b200 import _lib
-    from zfista_b200.lasso import DenseLasso
-
-    rows, cols = args.lasso_rows, args.lasso_cols
-    A, b = _lasso_data(rows, cols, dev, rank)
-    prob = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows * world),
-                      distributed=world > 1)
-    x = torch.zeros(cols, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
-    a_bytes = rows * cols * 8
-    out = {"A": f"{rows}x{cols} fp64 per GPU ({a_bytes / 2**30:.1f} GiB, > L2)"}
-    if world == 1:
-        # kernel-level: one gradient = residual pass + A^T pass (2 x |A| from HBM)
-        for _ in range(3):
-            prob.gradient(x)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record(stream)
-        for _ in range(reps):
-            prob.gradient(x)
-        e1.record(stream)
-        e1.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        peaks = _measured_peaks()
-        # Algorithmic bytes of one gradient A^T(A v - b): A once (a fused kernel keeps the row
-        # on chip between the dot product and the rank-1 update) plus the vectors.  The
-        # two-pass kernels read A twice; `passes` says which form this shape runs.
-        vec_bytes = (2 * cols + 2 * rows) * 8
-        alg = a_bytes + vec_bytes
-        passes = prob.hbm_passes_per_gradient()
-        ach = alg / (ms / 1e3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):        # ncu-measured DRAM bytes / |A| per kernel form
-            with open(tp) as fh:
-                tj = json.load(fh)
-            keys = (["lasso_fused_ring_kernel"] if passes == 1
-                    else ["lasso_residual_kernel", "lasso_atr_kernel"])
-            traffic = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"])
-                          / tj[k]["algorithmic_bytes"] for k in keys) * a_bytes
-        out["roofline"] = {
-            "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
-            "traffic_source": "ncu dram bytes / |A| per kernel (profiles/r01_traffic.json, "
-                              "measured at 32768x16384), scaled to this A",
-            "ms_per_gradient": ms, "hbm_passes_over_A": passes,
-            "dram_GBps": passes * a_bytes / (ms / 1e3) / 1e9,
-            "peak_source": peaks["source"]}
-    # solver-level: fixed-step FISTA iterations per second (A stays resident)
-    iters = args.lasso_iters
-    lr = 0.5
-    prob.minimize_proximal_gradient(x, lr=lr, decay_rate=1, nesterov=True, max_iter=3, tol=0.0,
-                                    return_device=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    import warnings
-
-    t0 = time.perf_counter()
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        res = prob.minimize_proximal_gradient(x, lr=lr, decay_rate=1, nesterov=True,
-                                              max_iter=iters, tol=0.0, return_device=True)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    out["fista_iters_per_s"] = res.nit / tt.item()
-    out["fista_iters"] = res.nit
-    out["global_rows"] = rows * world
     return out
 
 
@@ -909,6 +1142,36 @@ def bench_sweep(args, dev, rank, world):
                           "nit_mean": float(bn.nit.mean()),
                           "dual_evals_per_solve": float(bn.n_dual.mean())}
     return out
+
+
+def bench_sweep_fds(args, dev, rank, world):
+    """BASELINE configs[4], FDS half: the 15 (a, b) pairs x 1024 starts of the headline problem
+    (FDS n = 100 + L1) as ONE launch of 15360 starts per GPU (per-start (a, b) table), timed
+    through the public API on host arrays."""
+    import torch
+
+    from zfista_b200.distributed import momentum_grid
+    import zfista_b200.problems as zp
+
+    spec = workload_spec("fds")
+    prob = zp.FDS(**spec["kw"])
+    rng = np.random.RandomState(177 + rank)
+    X0 = rng.uniform(spec["low"], spec["high"], size=(1024, prob.n_features))
+    Xg, AB, _, gi = momentum_grid(X0, AB_GRID)
+    kw = dict(nesterov=True, tol_internal=1e-11, max_iter=100000000)
+    prob.minimize_proximal_gradient_batched(Xg[:64], nesterov_ratio=AB[:64], **kw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    br = prob.minimize_proximal_gradient_batched(Xg, nesterov_ratio=AB, **kw)
+    dt = time.perf_counter() - t0
+    per_pair = {f"({a:.4g}, {b:.4g})": float(br.nit[gi == g].mean())
+                for g, (a, b) in enumerate(AB_GRID)}
+    return {"workload": "FDS n=100 +L1, 15 (a,b) pairs x 1024 starts in one launch per GPU "
+                        "(e2e call)", "solves": int(len(Xg)),
+            "converged": int((br.status == 1).sum()),
+            "solves_per_s": float((br.status == 1).sum() / dt), "seconds": dt,
+            "nit_mean": float(br.nit.mean()), "nit_max": int(br.nit.max()),
+            "nit_mean_per_pair": per_pair}
 
 
 _JSON_FD = None
