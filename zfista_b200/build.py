@@ -121,6 +121,67 @@ def _build_locked(fp: str, verbose: bool) -> str:
     return LIB_PATH
 
 
+SASS_MNEMONICS = ("UBLKCP", "UTMALDG", "DMMA", "STAS", "SYNCS", "UCGABAR", "DFMA", "LDGSTS")
+
+
+def sass_counts(out_path: str | None = None) -> str:
+    """Per-kernel counts of the SASS mnemonics that prove what the kernels are made of (bulk TMA
+    UBLKCP, tensor-map TMA UTMALDG, FP64 tensor-core DMMA, st.async STAS, mbarrier SYNCS, cluster
+    barrier UCGABAR, plain DFMA), from `cuobjdump -sass` of the objects build() made.  Returns
+    the table as text and writes it to `out_path` (profiles/sass_counts.txt) when given."""
+    import collections
+    import re
+
+    cuobjdump = os.path.join(os.path.dirname(_nvcc()), "cuobjdump") if os.path.isabs(_nvcc()) \
+        else "cuobjdump"
+    rows = []
+    for obj in sorted(f for f in os.listdir(BUILD_DIR) if f.endswith(".o")):
+        r = subprocess.run([cuobjdump, "-sass", os.path.join(BUILD_DIR, obj)],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            continue
+        fn, arch = None, "?"
+        counts = collections.OrderedDict()
+        for ln in r.stdout.splitlines():
+            m = re.match(r"\s*arch = (sm_\w+)", ln)
+            if m:
+                arch = m.group(1)
+            m = re.match(r"\s*Function : (\S+)", ln)
+            if m:
+                fn = m.group(1)
+                counts[fn] = collections.Counter(arch=arch)
+                continue
+            if fn is None:
+                continue
+            m = re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", ln)
+            if m:
+                op = m.group(1)
+                counts[fn]["total"] += 1
+                for mn in SASS_MNEMONICS:
+                    if op.startswith(mn):
+                        counts[fn][mn] += 1
+        for fn, c in counts.items():
+            r2 = subprocess.run(["c++filt", fn], capture_output=True, text=True)
+            name = (r2.stdout.strip() or fn).split("(")[0].replace("void ", "")
+            rows.append((obj, name[:70], c["arch"], c["total"], [c[mn] for mn in SASS_MNEMONICS]))
+    head = f"{'object':28s} {'kernel':70s} {'arch':8s} {'instr':>7s} " + " ".join(
+        f"{mn:>7s}" for mn in SASS_MNEMONICS)
+    lines = ["# cuobjdump -sass of zfista_b200/build/*.o (written by __graft_entry__.build())", head]
+    for obj, name, arch, total, cs in rows:
+        lines.append(f"{obj:28s} {name:70s} {arch:8s} {total:7d} " + " ".join(f"{c:7d}" for c in cs))
+    text = "\n".join(lines) + "\n"
+    if out_path:
+        with open(out_path, "w") as fh:
+            fh.write(text)
+    return text
+
+
+def sass_stale(out_path: str) -> bool:
+    """True if `out_path` is missing or older than the library (so build() rewrites it once)."""
+    return (not os.path.exists(out_path)) or (
+        os.path.exists(LIB_PATH) and os.path.getmtime(out_path) < os.path.getmtime(LIB_PATH))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
