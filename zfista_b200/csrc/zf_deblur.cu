@@ -73,7 +73,62 @@ struct DeblurBufs {
   int run0, group;                          // this launch covers runs run0 .. run0 + gridDim.y - 1
 };
 
-__constant__ double c_kernel[81];
+// The blur kernel travels as a kernel PARAMETER (constant bank, indexed with compile-time
+// offsets after unrolling): every handle has its own taps, nothing process-wide to race on.
+//   k   : the (2R+1)^2 taps, row major (general and column-symmetric forms)
+//   a, b: when the kernel is an outer product k[u][v] = a[u] b[v] (to within rounding: every
+//         Gaussian-like PSF built as window(...) x window(...), examples/cameraman.ipynb), the
+//         SEPARABLE form runs two 1-D passes per correlation: 2 (2R+1) FMAs per pixel, not (2R+1)^2
+struct DeblurTaps {
+  double k[81];
+  double a[9], b[9];
+};
+enum { DK_GENERAL = 0, DK_SYM = 1, DK_SEP = 2 };
+
+// 1-D horizontal pass of the separable form over `rows` x `cols` outputs:
+//   out[r][c] = sum_v tb[v] * in[r][c + v + OFF]
+// A thread owns 8 consecutive outputs of one row (16 loads feed 72 FMAs); consecutive lanes own
+// consecutive ROWS, so with odd pitches every shared-memory access is conflict free.  `in` and
+// `out` may be the same array (the first pass runs in place): every thread first loads all its
+// inputs, then the block synchronises, then it stores.  At most two tasks per thread (<= 48 rows
+// x 5 strips on 128 threads).
+template <int R, int OFF, int IN_PITCH, int OUT_PITCH, bool IN_PLACE>
+__device__ __forceinline__ void db_hpass(const double (*in)[IN_PITCH], double (*out)[OUT_PITCH],
+                                         int rows, int cols, const double (&tb)[9], int tid) {
+  constexpr int K = 2 * R + 1, S = 8, NIN = S + 2 * R;
+  const int strips = (cols + S - 1) / S;
+  const int n_tasks = rows * strips;
+  double reg[2][NIN];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int task = tid + t * DB_THREADS;
+    if (task < n_tasks) {
+      const int r = task % rows, c0 = S * (task / rows);
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) reg[t][k] = in[r][c0 + k + OFF];
+    }
+  }
+  if (IN_PLACE) __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int task = tid + t * DB_THREADS;
+    if (task < n_tasks) {
+      const int r = task % rows, c0 = S * (task / rows);
+      double acc[S];
+#pragma unroll
+      for (int o = 0; o < S; ++o) acc[o] = 0.0;
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        const double w = tb[v];
+#pragma unroll
+        for (int o = 0; o < S; ++o) acc[o] = fma(w, reg[t][o + v], acc[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < S; ++o)
+        if (c0 + o < cols) out[r][c0 + o] = acc[o];
+    }
+  }
+}
 
 __device__ __forceinline__ int db_reflect(int i, int n) {
   int r = i < 0 ? -i - 1 : (i >= n ? 2 * n - i - 1 : i);
@@ -188,9 +243,12 @@ __device__ void deblur_decide(const DeblurDims& d, const DeblurCtl& c, const Deb
 // SYM: the blur kernel is mirror symmetric in its columns (K[u][v] == K[u][2R-v], true for
 // every Gaussian-like PSF): the two mirrored input columns are added first and share their
 // multiplications -- 8+2R adds + 8K FMAs per column pair instead of 16K FMAs (-35 % FP64 work).
-template <int R, int MODE, bool SYM>
-__global__ void __launch_bounds__(DB_THREADS)
-deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int count) {
+template <int R, int MODE, int KIND>
+__global__ void __launch_bounds__(DB_THREADS, KIND == DK_SEP ? 7 : 1)
+deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, const __grid_constant__ DeblurTaps taps,
+                   int decide, int count) {
+  constexpr bool SYM = (KIND == DK_SYM);
+  constexpr bool SEP = (KIND == DK_SEP);
   constexpr int T = DB_T;
   constexpr int HV = (MODE == 0) ? R : 0;         // halo of V
   // halo of U, rounded up to even so that the region is aligned to the 2x2 Haar blocks
@@ -225,6 +283,16 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
   const int tyo = (blockIdx.x / d.tiles_x) * T, txo = (blockIdx.x % d.tiles_x) * T;
   const long long q = (long long)d.h2 * d.w2;
   double abs_acc = 0.0;
+  // ---- 0. (separable form) the observed image on the V region goes into V's storage now: these
+  // loads fly while the coefficient gather below waits for its own, and step 2 subtracts from
+  // shared memory instead of stalling on global loads between its two passes
+  if constexpr (SEP) {
+    for (int idx = tid; idx < VR * VR; idx += DB_THREADS) {
+      const int li = idx / VR, lj = idx % VR;
+      const int gi = tyo - HV + li, gj = txo - HV + lj;
+      V[li][lj] = (gi >= 0 && gi < d.H && gj >= 0 && gj < d.W) ? B.b[(long long)gi * d.W + gj] : 0.0;
+    }
+  }
   // ---- 1. U = W y on the halo region, by 2x2 blocks (one coefficient quadruple each)
   constexpr int UB = UR / 2;
   // fully unrolled (<= 5 trips): all of a thread's coefficient loads are in flight at once --
@@ -268,6 +336,12 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
   double fsum = 0.0;
   constexpr int S = DB_STRIP;
   constexpr int VS = (VR + S - 1) / S;
+  if constexpr (SEP) {
+    // horizontal pass in place: U[r][lj] <- sum_v b[v] U[r][lj + v + OFF] on the rows the
+    // vertical pass reads (OFF .. OFF + VR + 2R - 1; row indices are shifted by -OFF on the way)
+    db_hpass<R, OFF, DB_UR + 1, DB_UR + 1, true>(U + OFF, U + OFF, VR + 2 * R, VR, taps.b, tid);
+    __syncthreads();
+  }
   for (int task = tid; task < VS * VR; task += DB_THREADS) {
     const int li0 = S * (task / VR), lj = task % VR;
     const int gj = txo - HV + lj;
@@ -277,8 +351,21 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
     for (int o = 0; o < S; ++o) {       // observed image values: loaded before the FMA loop
       const int gi = tyo - HV + li0 + o;
       acc[o] = 0.0;
-      bv[o] = (col_ok && li0 + o < VR && gi >= 0 && gi < d.H) ? B.b[(long long)gi * d.W + gj] : 0.0;
+      if constexpr (SEP) bv[o] = (li0 + o < VR) ? V[li0 + o][lj] : 0.0;
+      else bv[o] = (col_ok && li0 + o < VR && gi >= 0 && gi < d.H) ? B.b[(long long)gi * d.W + gj] : 0.0;
     }
+    if constexpr (SEP) {
+      // vertical pass of the separable form: one column of the row-filtered U
+      double col[S + 2 * R];
+#pragma unroll
+      for (int k = 0; k < S + 2 * R; ++k) col[k] = U[li0 + k + OFF][lj];
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        const double w = taps.a[u];
+#pragma unroll
+        for (int o = 0; o < S; ++o) acc[o] = fma(w, col[o + u], acc[o]);
+      }
+    } else {
 #pragma unroll
     for (int v = 0; v < (SYM ? R + 1 : K); ++v) {
       double col[S + 2 * R];
@@ -289,10 +376,11 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
       }
 #pragma unroll
       for (int u = 0; u < K; ++u) {
-        const double w = c_kernel[u * K + v];
+        const double w = taps.k[u * K + v];
 #pragma unroll
         for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
       }
+    }
     }
     if (col_ok) {
 #pragma unroll
@@ -324,6 +412,28 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
     }
     __syncthreads();
     // ---- 4. Wimg = R V on the tile (vertical strips of DB_STRIP), into U's storage
+    // (separable form: rows of V filtered into U's storage, then the columns of that back into
+    // V's storage -- V is dead once its rows have been read -- and step 5 reads Wimg from V)
+    if constexpr (SEP) {
+      db_hpass<R, 0, DB_VR + 1, DB_UR + 1, false>(V, U, T + 2 * R, T, taps.b, tid);
+      __syncthreads();
+      for (int task = tid; task < (T / S) * T; task += DB_THREADS) {
+        const int li0 = S * (task / T), lj = task % T;
+        double acc[S], col[S + 2 * R];
+#pragma unroll
+        for (int o = 0; o < S; ++o) acc[o] = 0.0;
+#pragma unroll
+        for (int k = 0; k < S + 2 * R; ++k) col[k] = U[li0 + k][lj];
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+          const double w = taps.a[u];
+#pragma unroll
+          for (int o = 0; o < S; ++o) acc[o] = fma(w, col[o + u], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < S; ++o) V[li0 + o][lj] = acc[o];
+      }
+    } else
     for (int task = tid; task < (T / S) * T; task += DB_THREADS) {
       const int li0 = S * (task / T), lj = task % T;
       double acc[S];
@@ -339,7 +449,7 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
         }
 #pragma unroll
         for (int u = 0; u < K; ++u) {
-          const double w = c_kernel[u * K + v];
+          const double w = taps.k[u * K + v];
 #pragma unroll
           for (int o = 0; o < S; ++o) acc[o] += w * col[o + u];
         }
@@ -355,8 +465,14 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, int decide, int coun
       const int bi = blk / (T / 2), bj = blk % (T / 2);
       const int gi = tyo + 2 * bi, gj = txo + 2 * bj;
       if (gi < d.H && gj < d.W) {
-        const double p00 = U[2 * bi][2 * bj], p01 = U[2 * bi][2 * bj + 1];
-        const double p10 = U[2 * bi + 1][2 * bj], p11 = U[2 * bi + 1][2 * bj + 1];
+        double p00, p01, p10, p11;
+        if constexpr (SEP) {
+          p00 = V[2 * bi][2 * bj]; p01 = V[2 * bi][2 * bj + 1];
+          p10 = V[2 * bi + 1][2 * bj]; p11 = V[2 * bi + 1][2 * bj + 1];
+        } else {
+          p00 = U[2 * bi][2 * bj]; p01 = U[2 * bi][2 * bj + 1];
+          p10 = U[2 * bi + 1][2 * bj]; p11 = U[2 * bi + 1][2 * bj + 1];
+        }
         const long long o = (long long)(gi >> 1) * d.w2 + (gj >> 1);
         double g4[4];
         g4[0] = 2.0 * ((((p00 + p01) + p10) + p11) / 2.0);
@@ -495,8 +611,10 @@ struct zf_deblur {
   cudaStream_t own_st = nullptr;     // created when the caller passes no stream (graphs cannot
                                      // be captured on the legacy default stream)
   bool capturing = false;
-  bool sym = false;                  // kernel columns mirror symmetric (exactly): folded stencil
-  double kernel_host[81];
+  int kind = zf::DK_GENERAL;         // DK_SYM: kernel columns mirror symmetric (exactly): folded
+                                     // stencil; DK_SEP: outer product (to rounding): two 1-D passes
+  zf::DeblurTaps taps{};
+  int device = 0;                    // the device the handle's buffers live on
   std::mutex mu;
 };
 
@@ -519,21 +637,28 @@ int launch_tile_g(zf_deblur* h, const RunGroup& g, const zf::DeblurCtl& c, bool 
   zf::DeblurBufs B = h->B;
   B.run0 = g.run0;
   B.group = g.group;
-  if (h->sym) {
-    switch (h->d.R) {
-      case 1: zf::deblur_tile_kernel<1, MODE, true><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-      case 2: zf::deblur_tile_kernel<2, MODE, true><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-      case 3: zf::deblur_tile_kernel<3, MODE, true><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-      default: zf::deblur_tile_kernel<4, MODE, true><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-    }
-  } else {
-    switch (h->d.R) {
-      case 1: zf::deblur_tile_kernel<1, MODE, false><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-      case 2: zf::deblur_tile_kernel<2, MODE, false><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-      case 3: zf::deblur_tile_kernel<3, MODE, false><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-      default: zf::deblur_tile_kernel<4, MODE, false><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, dd, cc); break;
-    }
+  // (the separable form is built for 7 CTAs per SM -- 72 registers, 7 x 32.4 KB of shared memory:
+  // ask for the largest shared-memory carve-out so that all of them fit)
+#define ZF_DB_LAUNCH(RR, KK)                                                                  \
+  do {                                                                                        \
+    if (KK == zf::DK_SEP)                                                                     \
+      cudaFuncSetAttribute(zf::deblur_tile_kernel<RR, MODE, KK>,                               \
+                           cudaFuncAttributePreferredSharedMemoryCarveout, 100);              \
+    zf::deblur_tile_kernel<RR, MODE, KK><<<grid, zf::DB_THREADS, 0, g.st>>>(h->d, c, B, h->taps, \
+                                                                           dd, cc);           \
+  } while (0)
+#define ZF_DB_LAUNCH_R(KK)                                                                    \
+  switch (h->d.R) {                                                                          \
+    case 1: ZF_DB_LAUNCH(1, KK); break;                                                       \
+    case 2: ZF_DB_LAUNCH(2, KK); break;                                                       \
+    case 3: ZF_DB_LAUNCH(3, KK); break;                                                       \
+    default: ZF_DB_LAUNCH(4, KK); break;                                                      \
   }
+  if (h->kind == zf::DK_SEP) { ZF_DB_LAUNCH_R(zf::DK_SEP) }
+  else if (h->kind == zf::DK_SYM) { ZF_DB_LAUNCH_R(zf::DK_SYM) }
+  else { ZF_DB_LAUNCH_R(zf::DK_GENERAL) }
+#undef ZF_DB_LAUNCH_R
+#undef ZF_DB_LAUNCH
   ZF_CUDA(cudaGetLastError());
   if (!h->capturing) zf::zf_count_launch();
   return ZF_OK;
@@ -746,14 +871,45 @@ extern "C" int zf_deblur_create(zf_deblur** out, int32_t height, int32_t width,
     }
     h->st = h->own_st;
   }
-  std::memcpy(h->kernel_host, h_kernel, sizeof(double) * ksize * ksize);
+  cudaGetDevice(&h->device);
+  std::memcpy(h->taps.k, h_kernel, sizeof(double) * ksize * ksize);
   {
+    // which stencil form.  Column symmetry is tested exactly.  Separability: with the centre row
+    // and column as factors, a[u] = k[u][c] / sqrt(k[c][c]), b[v] = k[c][v] / sqrt(k[c][c]), every
+    // tap must be a[u] b[v] to within a few ulps of the largest tap (an outer product that was
+    // normalised afterwards, as in examples/cameraman.ipynb, is rank one only up to rounding; the
+    // separable operator then differs from the given one by ~1e-16 relative, far below the 1e-8
+    // parity tolerance).  ZF_DEBLUR_FORM=general|sym|sep overrides (sym / sep only if they apply).
     bool sym = true;
     for (int u = 0; u < ksize && sym; ++u)
       for (int v = 0; v < ksize / 2; ++v)
         if (h_kernel[u * ksize + v] != h_kernel[u * ksize + (ksize - 1 - v)]) { sym = false; break; }
-    const char* env = getenv("ZF_DEBLUR_SYM");
-    h->sym = env ? (env[0] != '0' && sym) : sym;
+    const int cc = ksize / 2;
+    const double centre = h_kernel[cc * ksize + cc];
+    bool sep = centre > 0.0;
+    if (sep) {
+      const double root = std::sqrt(centre);
+      double kmax = 0.0;
+      for (int i = 0; i < ksize * ksize; ++i) kmax = std::fmax(kmax, std::fabs(h_kernel[i]));
+      for (int u = 0; u < ksize; ++u) {
+        h->taps.a[u] = h_kernel[u * ksize + cc] / root;
+        h->taps.b[u] = h_kernel[cc * ksize + u] / root;
+      }
+      for (int u = 0; u < ksize && sep; ++u)
+        for (int v = 0; v < ksize; ++v)
+          if (std::fabs(h->taps.a[u] * h->taps.b[v] - h_kernel[u * ksize + v]) > 8 * 2.3e-16 * kmax) {
+            sep = false;
+            break;
+          }
+    }
+    h->kind = sep ? zf::DK_SEP : (sym ? zf::DK_SYM : zf::DK_GENERAL);
+    if (const char* env = getenv("ZF_DEBLUR_FORM")) {
+      if (env[0] == 'g') h->kind = zf::DK_GENERAL;
+      else if (env[0] == 's' && env[1] == 'y' && sym) h->kind = zf::DK_SYM;
+      else if (env[0] == 's' && env[1] == 'e' && sep) h->kind = zf::DK_SEP;
+    }
+    if (const char* env = getenv("ZF_DEBLUR_SYM"))       // round-1 switch: 0 = never fold
+      if (env[0] == '0' && h->kind == zf::DK_SYM) h->kind = zf::DK_GENERAL;
   }
   const size_t vb = sizeof(double) * (size_t)max_runs * (size_t)d.n;
   cudaError_t e = cudaSuccess;
@@ -804,12 +960,15 @@ extern "C" void zf_deblur_destroy(zf_deblur* h) {
   delete h;
 }
 
-static int deblur_load_kernel(zf_deblur* h) {
-  const int K = 2 * h->d.R + 1;
-  ZF_CUDA(cudaMemcpyToSymbolAsync(zf::c_kernel, h->kernel_host, sizeof(double) * K * K, 0,
-                                  cudaMemcpyHostToDevice, h->st));
-  return ZF_OK;
-}
+// a handle works on the device it was created on, whatever the caller's current device is
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // x0: n_runs x n when x0_is_batched, else one vector shared by every run.
 static int deblur_solve_impl(zf_deblur* h, const zf_options* opt, int64_t n_runs,
@@ -824,8 +983,7 @@ static int deblur_solve_impl(zf_deblur* h, const zf_options* opt, int64_t n_runs
   if (!out->x || !out->fun || !out->nit || !out->status)
     return zf::zf_fail(ZF_ERR_INVALID, "result.x/fun/nit/status are required");
   std::lock_guard<std::mutex> lock(h->mu);
-  rc = deblur_load_kernel(h);
-  if (rc != ZF_OK) return rc;
+  DeviceGuard on_device(h->device);
   const size_t nb = sizeof(double) * (size_t)h->d.n;
   const cudaMemcpyKind kin = x0_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   for (int64_t r = 0; r < n_runs; ++r) {
@@ -896,8 +1054,8 @@ extern "C" int zf_deblur_eval_host(zf_deblur* h, int64_t n_points, const double*
     return zf::zf_fail(ZF_ERR_INVALID, "n_points outside 0..max_runs");
   if (n_points == 0) return ZF_OK;
   std::lock_guard<std::mutex> lock(h->mu);
-  int rc = deblur_load_kernel(h);
-  if (rc != ZF_OK) return rc;
+  DeviceGuard on_device(h->device);
+  int rc = ZF_OK;
   const int n = (int)n_points;
   const size_t nb = sizeof(double) * (size_t)h->d.n * n;
   ZF_CUDA(cudaMemcpyAsync(h->B.X[0], h_X, nb, cudaMemcpyHostToDevice, h->st));
