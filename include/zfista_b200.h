@@ -108,6 +108,13 @@ typedef struct {
   double* allerrs;  /* n_starts x cap                                          */
   double* allfuns;  /* n_starts x (cap + 1) x n_objectives, entry 0 = F(x0)    */
   double* allvecs;  /* n_starts x (cap + 1) x n_features,   entry 0 = x0       */
+  /* RAGGED traces (NULL: the dense layout above).  n_starts + 1 offsets, off[0] = 0: start s
+   * records at most off[s+1] - off[s] iterations; its errors start at allerrs[off[s]], its
+   * F values at allfuns[(off[s] + s) * n_objectives], its iterates at
+   * allvecs[(off[s] + s) * n_features] (one more entry than errors: entry 0 = x0).  With the
+   * iteration counts of a first, trace-less solve as capacities nothing is allocated that is
+   * not written (benchmarks/benchmark.py:320-372 asks return_all for every start).           */
+  const int64_t* trace_offsets;
 } zf_result;
 
 int zf_abi_version(void);

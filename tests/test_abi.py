@@ -50,7 +50,8 @@ int main(void) {
          offsetof(zf_problem, A), offsetof(zf_problem, scale), offsetof(zf_problem, l1));
   printf("%zu %zu %zu %zu\\n", offsetof(zf_options, max_iter), offsetof(zf_options, decay_rate),
          offsetof(zf_options, deprecated), offsetof(zf_options, trace_capacity));
-  printf("%zu %zu\\n", offsetof(zf_result, lr), offsetof(zf_result, allvecs));
+  printf("%zu %zu %zu\\n", offsetof(zf_result, lr), offsetof(zf_result, allvecs),
+         offsetof(zf_result, trace_offsets));
   return 0;
 }
 ''')
@@ -64,7 +65,7 @@ int main(void) {
         C.sizeof(P), C.sizeof(O), C.sizeof(R),
         P.l1_shifts.offset, P.lower_v.offset, P.A.offset, P.scale.offset, P.l1.offset,
         O.max_iter.offset, O.decay_rate.offset, O.deprecated.offset, O.trace_capacity.offset,
-        R.lr.offset, R.allvecs.offset,
+        R.lr.offset, R.allvecs.offset, R.trace_offsets.offset,
     ]
 
 

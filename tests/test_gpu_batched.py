@@ -495,3 +495,66 @@ def test_largest_benchmark_dimension_matches_oracle(gpu):
             _rel_close(br.fun[i], r["fun"])
     with pytest.raises(Exception, match="shared memory"):
         zp.JOS1(n_features=20000).minimize_proximal_gradient_batched(np.zeros((1, 20000)))
+
+
+def test_return_all_is_ragged_and_survives_the_benchmark_shape(gpu):
+    """benchmarks/benchmark.py:320-372 asks return_all=True for every one of its starts.  The
+    traces are ragged (exactly nit_i entries per start), so 1000 starts x n = 1000 with iterates
+    is ~0.2 GB, not n_starts x capacity x n; the traces equal the single-start call's."""
+    import zfista_b200.problems as zp
+
+    n, S = 1000, 1000
+    prob = zp.JOS1(n_features=n)
+    X0 = np.random.RandomState(12).uniform(-2, 4, size=(S, n))
+    br = prob.minimize_proximal_gradient_batched(X0, nesterov=True, tol_internal=1e-11,
+                                                 return_all=True)
+    assert np.all(br.status == 1) and not br.trace_truncated
+    total = int(br.nit.sum())
+    assert br.allerrs.flat.shape == (total,)
+    assert br.allfuns.flat.shape == (total + S, 2)
+    assert br.allvecs.flat.shape == (total + S, n)
+    assert br.allvecs.nbytes < 1 << 30
+    for i in (0, 17, S - 1):
+        k = int(br.nit[i])
+        assert br.allerrs[i].shape == (k,) and br.allvecs[i].shape == (k + 1, n)
+        np.testing.assert_array_equal(br.allvecs[i][0], X0[i])
+        np.testing.assert_array_equal(br.allvecs[i][-1], br.x[i])
+        np.testing.assert_array_equal(br.allfuns[i][-1], br.fun[i])
+        assert br.allerrs[i][-1] == br.err[i] and br.allerrs[i][-1] < 1e-5
+        one = prob.minimize_proximal_gradient(X0[i], nesterov=True, tol_internal=1e-11,
+                                              return_all=True)
+        assert one.nit == k
+        np.testing.assert_array_equal(np.array(one.allvecs), br.allvecs[i])
+        np.testing.assert_array_equal(np.array(one.allfuns), br.allfuns[i])
+        np.testing.assert_array_equal(np.array(one.allerrs), br.allerrs[i])
+    # F and errors only; a capacity truncates every start's trace and says so
+    funs = prob.minimize_proximal_gradient_batched(X0[:50], nesterov=True, tol_internal=1e-11,
+                                                   return_all="funs", trace_capacity=5)
+    assert funs.allvecs is None and funs.trace_truncated
+    for i in range(50):
+        np.testing.assert_array_equal(funs.allerrs[i], br.allerrs[i][:5])
+        np.testing.assert_array_equal(funs.allfuns[i], br.allfuns[i][:6])
+    with pytest.raises(ValueError):
+        prob.minimize_proximal_gradient_batched(X0[:2], return_all="vecs")
+
+
+def test_return_all_goes_through_the_device_in_groups(gpu, monkeypatch):
+    """With a small device budget the iterates are fetched in several groups of starts: the
+    result must not depend on the grouping."""
+    import zfista_b200.problems as zp
+    from zfista_b200 import proximal_gradient as pg
+
+    prob = zp.FDS(n_features=40, l1_ratios=(np.arange(3) + 1) / 40, l1_shifts=np.arange(3.0))
+    X0 = np.random.RandomState(4).uniform(-2, 2, size=(37, 40))
+    kw = dict(nesterov=True, tol_internal=1e-11, return_all=True)
+    whole = prob.minimize_proximal_gradient_batched(X0, **kw)
+    monkeypatch.setattr(pg, "_TRACE_DEVICE_BYTES", 200_000)
+    parts = prob.minimize_proximal_gradient_batched(X0, **kw)
+    np.testing.assert_array_equal(parts.nit, whole.nit)
+    np.testing.assert_array_equal(parts.allvecs.flat, whole.allvecs.flat)
+    np.testing.assert_array_equal(parts.allfuns.flat, whole.allfuns.flat)
+    np.testing.assert_array_equal(parts.allerrs.flat, whole.allerrs.flat)
+    # the single-objective problem classes return shape-(1,) objective arrays, as the reference's do
+    lfr = zp.LinearFunctionRank1(n_features=6, n_objectives=1)
+    one = lfr.minimize_proximal_gradient(np.ones(6) * 0.3, return_all=True, max_iter=20)
+    assert np.shape(one.fun) == (1,) and np.shape(one.allfuns[0]) == (1,)

@@ -50,6 +50,7 @@ class ZfResult(C.Structure):
         ("x", C.c_void_p), ("fun", C.c_void_p), ("nit", C.c_void_p), ("status", C.c_void_p),
         ("lr", C.c_void_p), ("nfev", C.c_void_p), ("n_dual", C.c_void_p), ("err", C.c_void_p),
         ("allerrs", C.c_void_p), ("allfuns", C.c_void_p), ("allvecs", C.c_void_p),
+        ("trace_offsets", C.c_void_p),
     ]
 
 

@@ -239,12 +239,22 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
   cudaStream_t st = 0;
   const size_t N = (size_t)n_starts, n = problem->n_features, m = problem->n_objectives;
   const size_t cap = (size_t)opt->trace_capacity;
+  // trace sizes: dense (cap entries per start) or ragged (h_out->trace_offsets, host array)
+  const int64_t* h_off = h_out->trace_offsets;
+  if (h_off && (h_off[0] != 0 || h_off[N] < 0))
+    return zf::zf_fail(ZF_ERR_INVALID, "trace_offsets must start at 0 and be non-decreasing");
+  const bool tracing = h_off != nullptr || cap > 0;
+  const size_t n_err = h_off ? (size_t)h_off[N] : N * cap;          // error entries
+  const size_t n_fx = h_off ? (size_t)h_off[N] + N : N * (cap + 1);  // F / x entries
   std::lock_guard<std::mutex> lock(g_arena.mu);
   {
     size_t total = DevProblem::bytes(*problem) + 2 * pad256(N * n * 8) + pad256(N * 16) +
-                   pad256(N * m * 8) + 6 * pad256(N * 8);
-    if (cap > 0)
-      total += pad256(N * cap * 8) + pad256(N * (cap + 1) * m * 8) + pad256(N * (cap + 1) * n * 8);
+                   pad256(N * m * 8) + 6 * pad256(N * 8) + pad256((N + 1) * 8);
+    if (tracing) {
+      if (h_out->allerrs) total += pad256(n_err * 8);
+      if (h_out->allfuns) total += pad256(n_fx * m * 8);
+      if (h_out->allvecs) total += pad256(n_fx * n * 8);
+    }
     rc = g_arena.reset(total);
     if (rc != ZF_OK) return rc;
   }
@@ -271,20 +281,26 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
   if (h_out->nfev) { nfev.take(N * 8); R.nfev = nfev.as<int64_t>(); }
   if (h_out->n_dual) { ndual.take(N * 8); R.n_dual = ndual.as<int64_t>(); }
   if (h_out->err) { err.take(N * 8); R.err = err.as<double>(); }
-  if (cap > 0) {
+  DevBuf toff;
+  if (tracing) {
+    if (h_off) {
+      toff.take((N + 1) * 8);
+      ZF_CUDA(cudaMemcpyAsync(toff.p, h_off, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+      R.trace_offsets = toff.as<int64_t>();
+    }
     if (h_out->allerrs) {
-      allerrs.take(N * cap * 8);
-      ZF_CUDA(cudaMemsetAsync(allerrs.p, 0, N * cap * 8, st));
+      allerrs.take(n_err * 8);
+      ZF_CUDA(cudaMemsetAsync(allerrs.p, 0, n_err * 8, st));
       R.allerrs = allerrs.as<double>();
     }
     if (h_out->allfuns) {
-      allfuns.take(N * (cap + 1) * m * 8);
-      ZF_CUDA(cudaMemsetAsync(allfuns.p, 0, N * (cap + 1) * m * 8, st));
+      allfuns.take(n_fx * m * 8);
+      ZF_CUDA(cudaMemsetAsync(allfuns.p, 0, n_fx * m * 8, st));
       R.allfuns = allfuns.as<double>();
     }
     if (h_out->allvecs) {
-      allvecs.take(N * (cap + 1) * n * 8);
-      ZF_CUDA(cudaMemsetAsync(allvecs.p, 0, N * (cap + 1) * n * 8, st));
+      allvecs.take(n_fx * n * 8);
+      ZF_CUDA(cudaMemsetAsync(allvecs.p, 0, n_fx * n * 8, st));
       R.allvecs = allvecs.as<double>();
     }
   }
@@ -299,9 +315,9 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
   if (R.nfev) ZF_CUDA(cudaMemcpyAsync(h_out->nfev, R.nfev, N * 8, cudaMemcpyDeviceToHost, st));
   if (R.n_dual) ZF_CUDA(cudaMemcpyAsync(h_out->n_dual, R.n_dual, N * 8, cudaMemcpyDeviceToHost, st));
   if (R.err) ZF_CUDA(cudaMemcpyAsync(h_out->err, R.err, N * 8, cudaMemcpyDeviceToHost, st));
-  if (R.allerrs) ZF_CUDA(cudaMemcpyAsync(h_out->allerrs, R.allerrs, N * cap * 8, cudaMemcpyDeviceToHost, st));
-  if (R.allfuns) ZF_CUDA(cudaMemcpyAsync(h_out->allfuns, R.allfuns, N * (cap + 1) * m * 8, cudaMemcpyDeviceToHost, st));
-  if (R.allvecs) ZF_CUDA(cudaMemcpyAsync(h_out->allvecs, R.allvecs, N * (cap + 1) * n * 8, cudaMemcpyDeviceToHost, st));
+  if (R.allerrs && n_err) ZF_CUDA(cudaMemcpyAsync(h_out->allerrs, R.allerrs, n_err * 8, cudaMemcpyDeviceToHost, st));
+  if (R.allfuns) ZF_CUDA(cudaMemcpyAsync(h_out->allfuns, R.allfuns, n_fx * m * 8, cudaMemcpyDeviceToHost, st));
+  if (R.allvecs) ZF_CUDA(cudaMemcpyAsync(h_out->allvecs, R.allvecs, n_fx * n * 8, cudaMemcpyDeviceToHost, st));
   ZF_CUDA(cudaStreamSynchronize(st));
   return ZF_OK;
 }

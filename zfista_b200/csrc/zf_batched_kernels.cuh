@@ -256,14 +256,20 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
   for (long long s = (long long)blockIdx.x * warps_per_block + warp_in_block; s < n_starts;
        s += total_warps) {
     const double* xs = x0 + s * n;
-    const int cap = O.trace_capacity;
+    // return_all traces: dense (trace_capacity entries per start) or ragged (zf_result.trace_offsets)
+    const bool ragged = R.trace_offsets != nullptr;
+    const long long cap = ragged ? (long long)(R.trace_offsets[s + 1] - R.trace_offsets[s])
+                                 : (long long)O.trace_capacity;
+    const bool tracing = ragged || cap > 0;
+    const long long ebase = ragged ? (long long)R.trace_offsets[s] : s * cap;           // errors
+    const long long fbase = ragged ? (long long)R.trace_offsets[s] + s : s * (cap + 1);  // F, x
 #pragma unroll 1
     for (int j = lane; j < n; j += 32) {
       const double v = xs[j];
       c.y[j] = v;
       c.xp[j] = v;
       c.xn[j] = v;
-      if (cap > 0 && R.allvecs) R.allvecs[(s * (cap + 1)) * n + j] = v;
+      if (tracing && R.allvecs) R.allvecs[fbase * n + j] = v;
     }
     __syncwarp();
     const double na = ab ? ab[2 * s] : O.nesterov_a;
@@ -278,9 +284,9 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
       Fprev[i] = fx[i] + gx[i];
       Fx[i] = Fprev[i];
     }
-    if (cap > 0 && R.allfuns && lane == 0) {
+    if (tracing && R.allfuns && lane == 0) {
 #pragma unroll
-      for (int i = 0; i < M; ++i) R.allfuns[(s * (cap + 1)) * M + i] = Fprev[i];
+      for (int i = 0; i < M; ++i) R.allfuns[fbase * M + i] = Fprev[i];
     }
     long long nfev = 1, ndual = 0;
     double wwarm[M];
@@ -346,15 +352,15 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
         break;
       }
       err = ev.err;
-      if (cap > 0 && it <= cap) {
-        if (R.allerrs && lane == 0) R.allerrs[s * cap + (it - 1)] = err;
+      if (tracing && it <= cap) {
+        if (R.allerrs && lane == 0) R.allerrs[ebase + (it - 1)] = err;
         if (R.allfuns && lane == 0) {
 #pragma unroll
-          for (int i = 0; i < M; ++i) R.allfuns[(s * (cap + 1) + it) * M + i] = Fx[i];
+          for (int i = 0; i < M; ++i) R.allfuns[(fbase + it) * M + i] = Fx[i];
         }
         if (R.allvecs) {
 #pragma unroll 1
-          for (int j = lane; j < n; j += 32) R.allvecs[(s * (cap + 1) + it) * n + j] = c.xn[j];
+          for (int j = lane; j < n; j += 32) R.allvecs[(fbase + it) * n + j] = c.xn[j];
         }
       }
       if (err < O.tol) { status = 1; break; }

@@ -27,7 +27,34 @@ TERMINATION_MESSAGES = {
 }
 
 DUAL_SOLVERS = {"reference": 0, "newton": 1}
-_DEFAULT_TRACE = 4096
+# return_all: most bytes of iterates (allvecs) one launch may hold on the device, and the most the
+# host may be asked to keep before the call refuses (return_all="funs" keeps F and the errors only)
+_TRACE_DEVICE_BYTES = 1 << 30
+_TRACE_HOST_BYTES = 16 << 30
+
+
+class RaggedTrace:
+    """Per-start traces of different lengths stored flat: ``t[i]`` is the array of start i
+    (``(len_i,)`` or ``(len_i, width)``), ``t[i, :k]`` its first k entries."""
+
+    def __init__(self, flat: np.ndarray, offsets: np.ndarray):
+        self.flat, self.offsets = flat, offsets
+
+    def __len__(self) -> int:
+        return len(self.offsets) - 1
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            i, rest = key[0], key[1:]
+            return self.flat[self.offsets[i]:self.offsets[i + 1]][rest if len(rest) > 1 else rest[0]]
+        return self.flat[self.offsets[key]:self.offsets[key + 1]]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.flat.nbytes)
 
 
 def _resolve_problem(f, g, jac_f, prox_wsum_g) -> Problem:
@@ -84,9 +111,10 @@ class BatchResult:
     n_dual: np.ndarray     # dual-function evaluations
     err: np.ndarray        # last max|x^k - y^k|
     time: float            # wall time of the call, seconds
-    allerrs: np.ndarray | None = None
-    allfuns: np.ndarray | None = None
-    allvecs: np.ndarray | None = None
+    trace_truncated: bool = False   # trace_capacity cut at least one start's trace short
+    allerrs: RaggedTrace | None = None      # start i: (nit_i,)
+    allfuns: RaggedTrace | None = None      # start i: (nit_i + 1, n_objectives), entry 0 = F(x0)
+    allvecs: RaggedTrace | None = None      # start i: (nit_i + 1, n_features); None with "funs"
 
     @property
     def success(self) -> np.ndarray:
@@ -95,12 +123,9 @@ class BatchResult:
     def __len__(self) -> int:
         return len(self.nit)
 
-    def to_results(self) -> list[OptimizeResult]:
+    def to_results(self, scalar_fun: bool = False) -> list[OptimizeResult]:
         """One ``OptimizeResult`` per start with the reference's fields."""
-        out = []
-        for i in range(len(self)):
-            out.append(_one_result(self, i))
-        return out
+        return [_one_result(self, i, scalar_fun) for i in range(len(self))]
 
 
 def _message(status: int) -> str:
@@ -111,20 +136,52 @@ def _message(status: int) -> str:
     return "Error: Backtracking failed to find a suitable stepsize."
 
 
-def _one_result(br: BatchResult, i: int) -> OptimizeResult:
+def _one_result(br: BatchResult, i: int, scalar_fun: bool = False) -> OptimizeResult:
+    """``scalar_fun``: the objective closures return scalars (LeastSquaresL1 with one objective,
+    the closures of tests/test_proximal_gradient.py:49-63), so ``fun`` / ``allfuns`` are
+    scalars too; every zfista.problems class returns shape-(m,) arrays, also for m = 1."""
     status = int(br.status[i])
     nit = int(br.nit[i])
     fun = br.fun[i].copy()
     res = OptimizeResult(
-        x=br.x[i].copy(), fun=fun if fun.shape[0] > 1 else fun[0], nit=nit,
+        x=br.x[i].copy(), fun=fun[0] if scalar_fun else fun, nit=nit,
         success=status == 1, status=status, message=_message(status),
         nfev=int(br.nfev[i]), lr=float(br.lr[i]), time=br.time,
         allvecs=None, allfuns=None, allerrs=None)
     if br.allerrs is not None:
-        res.allerrs = list(br.allerrs[i, :nit])
-        res.allfuns = [row if row.shape[0] > 1 else row[0] for row in br.allfuns[i, :nit + 1]]
-        res.allvecs = list(br.allvecs[i, :nit + 1])
+        res.allerrs = list(br.allerrs[i])
+        res.allfuns = [row[0] if scalar_fun else row for row in br.allfuns[i]]
+        res.allvecs = None if br.allvecs is None else list(br.allvecs[i])
     return res
+
+
+def _solve_host(problem, X0, ab_arr, opts, offsets=None, want_vecs=False):
+    """One call of zf_solve_batched_host -> (BatchResult without traces, allerrs, allfuns,
+    allvecs flat arrays or None)."""
+    n_starts, n = X0.shape
+    m = problem.n_objectives
+    desc, keep = problem.descriptor()
+    out = BatchResult(
+        x=np.empty((n_starts, n)), fun=np.empty((n_starts, m)),
+        nit=np.zeros(n_starts, dtype=np.int64), status=np.zeros(n_starts, dtype=np.int32),
+        lr=np.empty(n_starts), nfev=np.zeros(n_starts, dtype=np.int64),
+        n_dual=np.zeros(n_starts, dtype=np.int64), err=np.empty(n_starts), time=0.0)
+    r = _lib.ZfResult()
+    r.x, r.fun, r.nit, r.status = _ptr(out.x), _ptr(out.fun), _ptr(out.nit), _ptr(out.status)
+    r.lr, r.nfev, r.n_dual, r.err = _ptr(out.lr), _ptr(out.nfev), _ptr(out.n_dual), _ptr(out.err)
+    errs = funs = vecs = None
+    if offsets is not None:
+        total = int(offsets[-1])
+        errs = np.zeros(total)
+        funs = np.zeros((total + n_starts, m))
+        r.allerrs, r.allfuns, r.trace_offsets = _ptr(errs), _ptr(funs), _ptr(offsets)
+        if want_vecs:
+            vecs = np.zeros((total + n_starts, n))
+            r.allvecs = _ptr(vecs)
+    _lib.check(_lib.lib().zf_solve_batched_host(C.byref(desc), C.byref(opts), n_starts, _ptr(X0),
+                                                _ptr(ab_arr), C.byref(r)))
+    del keep
+    return out, errs, funs, vecs
 
 
 def minimize_proximal_gradient_batched(problem: Problem, X0, lr=1, tol=1e-5,
@@ -141,12 +198,23 @@ def minimize_proximal_gradient_batched(problem: Problem, X0, lr=1, tol=1e-5,
     pair or an array of shape (n_starts, 2) giving each start its own pair, which is
     how the (a, b) sweep grid is batched.  Host arrays in, host arrays out (H2D and
     D2H copies are inside the call).
+
+    ``return_all`` (benchmark.py passes it for every start): ``True`` records ``allerrs``,
+    ``allfuns`` and ``allvecs`` as the reference does, ``"funs"`` leaves the iterates out.  The
+    traces are RAGGED (:class:`RaggedTrace`): a first launch without traces gives every start's
+    iteration count, a second one (the solver is deterministic) writes each start's trace into
+    exactly the space it needs -- nothing of size ``n_starts x capacity x n_features`` is ever
+    allocated.  The iterates go through the device in groups of starts of at most 1 GiB.
+    ``trace_capacity`` truncates every start's trace to its first ``trace_capacity`` iterations
+    (``BatchResult.trace_truncated`` says whether that cut anything).
     """
     if not isinstance(problem, Problem):
         raise TypeError("problem must be a zfista_b200.problems.Problem")
     X0 = _as_f64(X0)
     if X0.ndim != 2 or X0.shape[1] != problem.n_features:
         raise ValueError(f"X0 must have shape (n_starts, {problem.n_features})")
+    if return_all not in (False, True, "funs"):
+        raise ValueError('return_all must be False, True or "funs"')
     n_starts, n = X0.shape
     m = problem.n_objectives
     ab = np.asarray(nesterov_ratio, dtype=np.float64)
@@ -158,37 +226,50 @@ def minimize_proximal_gradient_batched(problem: Problem, X0, lr=1, tol=1e-5,
         pair = (0.0, 0.25)
     else:
         pair = (float(ab[0]), float(ab[1]))
-    cap = 0
-    if return_all:
-        cap = int(trace_capacity) if trace_capacity is not None else min(int(max_iter),
-                                                                       _DEFAULT_TRACE)
     t0 = time.time()
-    while True:
-        opts = _make_options(lr, tol, tol_internal, max_iter, max_iter_internal,
-                             max_backtrack_iter, warm_start, decay_rate, nesterov, pair,
-                             deprecated, dual_solver, cap)
-        desc, keep = problem.descriptor()
-        out = BatchResult(
-            x=np.empty((n_starts, n)), fun=np.empty((n_starts, m)),
-            nit=np.zeros(n_starts, dtype=np.int64), status=np.zeros(n_starts, dtype=np.int32),
-            lr=np.empty(n_starts), nfev=np.zeros(n_starts, dtype=np.int64),
-            n_dual=np.zeros(n_starts, dtype=np.int64), err=np.empty(n_starts), time=0.0)
-        r = _lib.ZfResult()
-        r.x, r.fun, r.nit, r.status = _ptr(out.x), _ptr(out.fun), _ptr(out.nit), _ptr(out.status)
-        r.lr, r.nfev, r.n_dual, r.err = _ptr(out.lr), _ptr(out.nfev), _ptr(out.n_dual), _ptr(out.err)
-        if cap > 0:
-            out.allerrs = np.zeros((n_starts, cap))
-            out.allfuns = np.zeros((n_starts, cap + 1, m))
-            out.allvecs = np.zeros((n_starts, cap + 1, n))
-            r.allerrs, r.allfuns, r.allvecs = _ptr(out.allerrs), _ptr(out.allfuns), _ptr(out.allvecs)
-        L = _lib.lib()
-        _lib.check(L.zf_solve_batched_host(C.byref(desc), C.byref(opts), n_starts, _ptr(X0),
-                                           _ptr(ab_arr), C.byref(r)))
-        del keep
-        if cap > 0 and n_starts and int(out.nit.max()) > cap and trace_capacity is None:
-            cap = int(out.nit.max())      # trace overflowed: rerun once with room for all
-            continue
-        break
+    opts = _make_options(lr, tol, tol_internal, max_iter, max_iter_internal, max_backtrack_iter,
+                         warm_start, decay_rate, nesterov, pair, deprecated, dual_solver, 0)
+    out, _, _, _ = _solve_host(problem, X0, ab_arr, opts)
+    if return_all and n_starts:
+        want_vecs = return_all is True
+        lens = out.nit.copy()
+        if trace_capacity is not None:
+            lens = np.minimum(lens, int(trace_capacity))
+        out.trace_truncated = bool(np.any(lens < out.nit))
+        offsets = np.zeros(n_starts + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        total = int(offsets[-1])
+        vec_bytes = (total + n_starts) * n * 8 if want_vecs else 0
+        if vec_bytes > _TRACE_HOST_BYTES:
+            raise MemoryError(
+                f"return_all=True would keep {vec_bytes / 2**30:.1f} GiB of iterates (allvecs) on "
+                'the host; pass return_all="funs" for allfuns / allerrs only, or trace_capacity')
+        errs = np.zeros(total)
+        funs = np.zeros((total + n_starts, m))
+        vecs = np.zeros((total + n_starts, n)) if want_vecs else None
+        # groups of consecutive starts whose iterates fit the device budget
+        per_start = (lens + 1) * n * 8 if want_vecs else np.zeros(n_starts, dtype=np.int64)
+        lo = 0
+        while lo < n_starts:
+            hi, acc = lo, 0
+            while hi < n_starts and (hi == lo or acc + per_start[hi] <= _TRACE_DEVICE_BYTES):
+                acc += int(per_start[hi])
+                hi += 1
+            goff = np.ascontiguousarray(offsets[lo:hi + 1] - offsets[lo])
+            part, e, f_, v = _solve_host(problem, X0[lo:hi],
+                                         None if ab_arr is None else ab_arr[lo:hi], opts, goff,
+                                         want_vecs)
+            if not np.array_equal(part.nit, out.nit[lo:hi]):
+                raise RuntimeError("the trace pass did not reproduce the first pass's iterations")
+            errs[offsets[lo]:offsets[hi]] = e
+            funs[offsets[lo] + lo:offsets[hi] + hi] = f_
+            if want_vecs:
+                vecs[offsets[lo] + lo:offsets[hi] + hi] = v
+            lo = hi
+        out.allerrs = RaggedTrace(errs, offsets)
+        foff = offsets + np.arange(n_starts + 1)
+        out.allfuns = RaggedTrace(funs, foff)
+        out.allvecs = RaggedTrace(vecs, foff) if want_vecs else None
     out.time = time.time() - t0
     return out
 
@@ -237,9 +318,13 @@ def minimize_proximal_gradient(f, g, jac_f, prox_wsum_g, x0, lr=1, tol=1e-5,
         problem, x0[None, :], lr=lr, tol=tol, tol_internal=tol_internal, max_iter=max_iter,
         max_iter_internal=max_iter_internal, max_backtrack_iter=max_backtrack_iter,
         warm_start=warm_start, decay_rate=decay_rate, nesterov=nesterov,
-        nesterov_ratio=nesterov_ratio, return_all=return_all or verbose,
+        nesterov_ratio=nesterov_ratio,
+        return_all=return_all if return_all else ("funs" if verbose else False),
         deprecated=deprecated, dual_solver=dual_solver)
-    one = _one_result(br, 0)
+    from .problems import LeastSquaresL1
+
+    one = _one_result(br, 0, scalar_fun=isinstance(problem, LeastSquaresL1)
+                      and problem.n_objectives == 1)
     if verbose:
         print(f"|{'niter':^7}|{'max(abs(xk - yk)))':^20}|{'learning rate':^13}|")
         for k, e in enumerate(one.allerrs, start=1):
