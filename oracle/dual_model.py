@@ -109,11 +109,14 @@ def fmin_bounded(func, a=0.0, b=1.0, xatol=1e-12, maxfun=100000):
 def prox_chain(v, coef, shifts, lower, upper, has_l1):
     """The reference's prox chain (problems.py:126-137) on the vector v, returning
     also, per coordinate, alpha (1 if p moves with v, 0 if pinned at a kink or a
-    bound) and eps[i] = +1/-1: side of shift i the free coordinate lies on."""
+    bound), eps[i] = +1/-1: side of shift i the free coordinate lies on, and the piece code
+    of zf_problems.cuh:prox_elem (two bits per L1 stage: 2 pinned at its kink, 1 / 0 above /
+    below it; two bits for the box: 1 clipped at the upper bound, 2 at the lower)."""
     n = v.shape[0]
     m = coef.shape[0]
     alpha = np.ones(n)
     eps = np.zeros((m, n))
+    code = np.zeros(n, dtype=np.int64)
     p = v
     if has_l1:
         a0 = p + np.sum(coef[1:]) - shifts[0] + shifts[0]
@@ -121,17 +124,20 @@ def prox_chain(v, coef, shifts, lower, upper, has_l1):
         stuck = np.abs(a0) <= coef[0]
         alpha = np.where(stuck, 0.0, alpha)
         eps[0] = np.where(a0 > coef[0], 1.0, -1.0)
+        code |= np.where(stuck, 2, np.where(a0 > coef[0], 1, 0))
         for i in range(1, m):
             ai = p - coef[i] - shifts[i]
             p = np.sign(ai) * np.maximum(np.abs(ai) - coef[i], 0.0) + shifts[i]
             stuck = np.abs(ai) <= coef[i]
             alpha = np.where(stuck, 0.0, alpha)
             eps[i] = np.where(ai > coef[i], 1.0, -1.0)
+            code |= np.where(stuck, 2, np.where(ai > coef[i], 1, 0)) << (2 * i)
     if lower is not None:
         q = np.clip(p, lower, upper)
         alpha = np.where(q != p, 0.0, alpha)
+        code |= np.where(q < p, 1, np.where(q > p, 2, 0)) << (2 * m)
         p = q
-    return p, alpha, eps
+    return p, alpha, eps, code
 
 
 def dual_eval(w, y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun):
@@ -142,7 +148,7 @@ def dual_eval(w, y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun):
     v = y - lr * wj
     lam = l1_ratios if has_l1 else np.zeros(m)
     sh = l1_shifts if has_l1 else np.zeros(m)
-    p, alpha, eps = prox_chain(v, lr * w * lam, sh, lower, upper, has_l1)
+    p, alpha, eps, _ = prox_chain(v, lr * w * lam, sh, lower, upper, has_l1)
     gp = g_fun(p)
     D = np.inner(w, gp) + np.sum((p - v) ** 2) / 2 / lr - lr / 2 * np.sum(wj ** 2) \
         + np.inner(w, c)
@@ -215,15 +221,6 @@ def simplex_qp(Q, G, w_cur):
     return best_w
 
 
-def piece_codes(alpha, eps):
-    """Per coordinate: which linear piece of the prox chain it is on -- 0 if pinned at a kink or
-    a bound (alpha = 0), else 1 | the side of every shift it lies on (zf_dual.cuh:piece_code)."""
-    code = np.ones(alpha.shape[0], dtype=np.int64)
-    for i in range(eps.shape[0]):
-        code |= (eps[i] > 0).astype(np.int64) << (i + 1)
-    return np.where(alpha == 0.0, 0, code)
-
-
 def simplex_newton(y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun, w0=None,
                    max_iter=60, shortcut=True, info=None):
     """Maximise the dual over the simplex.  Returns (w, D(w), p(w), dual evaluations).
@@ -246,8 +243,8 @@ def simplex_newton(y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun, w0=No
     def full(wq):
         Dq, Gq, Qq, pq = dual_eval(wq, *args)
         vq = y - lr * (wq @ J)
-        _, al, ep = prox_chain(vq, lr * wq * lam, sh, lower, upper, has_l1)
-        return Dq, Gq, Qq, piece_codes(al, ep)
+        _, _, _, codes = prox_chain(vq, lr * wq * lam, sh, lower, upper, has_l1)
+        return Dq, Gq, Qq, codes
 
     wt = w.copy()
     d = np.zeros(m)
@@ -284,8 +281,8 @@ def simplex_newton(y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun, w0=No
             break
         if shortcut:
             vn = y - lr * (wn @ J)
-            pn, al, ep = prox_chain(vn, lr * wn * lam, sh, lower, upper, has_l1)
-            if np.array_equal(piece_codes(al, ep), pat):
+            pn, _, _, codes = prox_chain(vn, lr * wn * lam, sh, lower, upper, has_l1)
+            if np.array_equal(codes, pat):
                 w = wn
                 D = D + pred
                 x_ready = pn
@@ -294,7 +291,7 @@ def simplex_newton(y, J, lr, c, l1_ratios, l1_shifts, lower, upper, g_fun, w0=No
         wt = wn.copy()
     if x_ready is None:
         v = y - lr * (w @ J)
-        x_ready, _, _ = prox_chain(v, lr * w * lam, sh, lower, upper, has_l1)
+        x_ready, _, _, _ = prox_chain(v, lr * w * lam, sh, lower, upper, has_l1)
     if info is not None:
         info["evals"] = evals
     return w, D, x_ready, evals

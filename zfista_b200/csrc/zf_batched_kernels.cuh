@@ -19,7 +19,7 @@
 namespace zf {
 
 __host__ __device__ __forceinline__ size_t warp_smem_doubles(int n, int m, int n_rows) {
-  return (size_t)(3 + m) * n + n_rows + (size_t)(n + 7) / 8;     // + n pattern bytes
+  return (size_t)(3 + m) * n + n_rows + (size_t)(n + 3) / 4;     // + n 16-bit piece codes
 }
 
 template <int M>
@@ -89,12 +89,12 @@ __device__ bool fused_primal_eval(const zf_problem& P, const WarpCtx& c,
       same = 1;
       bad = 0;
       int rare = 0;
-      struct In { CoordIn<M> c; unsigned char pat; };
+      struct In { CoordIn<M> c; unsigned short pat; };
       sweep3<In, double>(
           c.n, c.lane,
           [&](int j, bool live) {
             const int jc = live ? j : 0;
-            return In{load_coord<M>(c, jc), PROBE ? c.pat[jc] : (unsigned char)0};
+            return In{load_coord<M>(c, jc), PROBE ? c.pat[jc] : (unsigned short)0};
           },
           [&](const In& in, int j, bool live) {
             const int jc = live ? j : 0;
@@ -104,8 +104,9 @@ __device__ bool fused_primal_eval(const zf_problem& P, const WarpCtx& c,
             const double yj = in.c.y;
             const double v = yj - lr * wj;
             double alpha, eps[M];
-            const double p = prox_elem<KIND, M, GF, PROBE>(P, jc, v, wt, alpha, eps);
-            if constexpr (PROBE) same &= live ? (int)(piece_code<M>(alpha, eps) == in.pat) : 1;
+            unsigned pcode;
+            const double p = prox_elem<KIND, M, GF, PROBE>(P, jc, v, wt, alpha, eps, pcode);
+            if constexpr (PROBE) same &= live ? (int)((unsigned short)pcode == in.pat) : 1;
             double t[F::NT];
             F::template f_pre<FAST>(c, jc, p, t, rare);
             F::f_acc(live, t, sf);
@@ -175,7 +176,8 @@ __device__ void solve_subproblem(const zf_problem& P, const zf_options& O, const
       const double yj = c.y[j];
       const double gj = c.J[j];
       double alpha, eps[1];
-      const double p = prox_elem<KIND, 1, GF, false>(P, j, yj - lr * gj, wt, alpha, eps);
+            unsigned pcode;
+      const double p = prox_elem<KIND, 1, GF, false>(P, j, yj - lr * gj, wt, alpha, eps, pcode);
       c.xn[j] = p;
       s[0] += gj * (p - yj);
       s[1] += (p - yj) * (p - yj);
@@ -248,7 +250,7 @@ batched_fista_kernel(zf_problem P, zf_options O, long long n_starts, const doubl
   c.xn = base + 2 * (size_t)n;
   c.J = base + 3 * (size_t)n;
   c.scratch = base + (size_t)(3 + M) * n;
-  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
+  c.pat = reinterpret_cast<unsigned short*>(c.scratch + n_rows);
 
   using F = Fn<KIND, M>;
   const typename F::Consts K = F::make_consts(c);
@@ -431,7 +433,7 @@ subproblem_kernel(zf_problem P, zf_options O, long long n_items, const double* _
   c.lane = lane; c.n = n;
   c.y = base; c.xp = base + n; c.xn = base + 2 * (size_t)n; c.J = base + 3 * (size_t)n;
   c.scratch = base + (size_t)(3 + M) * n;
-  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
+  c.pat = reinterpret_cast<unsigned short*>(c.scratch + n_rows);
   using F = Fn<KIND, M>;
   const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
   if (s >= n_items) return;
@@ -481,7 +483,7 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
   c.lane = lane; c.n = n;
   c.y = base; c.xp = base + n; c.xn = base + 2 * (size_t)n; c.J = base + 3 * (size_t)n;
   c.scratch = base + (size_t)(3 + M) * n;
-  c.pat = reinterpret_cast<unsigned char*>(c.scratch + n_rows);
+  c.pat = reinterpret_cast<unsigned short*>(c.scratch + n_rows);
   using F = Fn<KIND, M>;
   const long long s = (long long)blockIdx.x * warps_per_block + warp_in_block;
   if (s >= n_items) return;
@@ -514,7 +516,8 @@ problem_eval_kernel(zf_problem P, long long n_items, const double* __restrict__ 
 #pragma unroll 1
     for (int j = lane; j < n; j += 32) {
       double alpha, eps[M];
-      po[s * n + j] = prox_elem<KIND, M, GF, false>(P, j, c.y[j], wt, alpha, eps);
+            unsigned pcode;
+      po[s * n + j] = prox_elem<KIND, M, GF, false>(P, j, c.y[j], wt, alpha, eps, pcode);
     }
   }
 }

@@ -63,7 +63,8 @@ __device__ double neg_dual_value(const zf_problem& P, const WarpCtx& c, const Du
     for (int i = 0; i < M; ++i) wj += w[i] * c.J[i * c.n + jc];
     const double v = c.y[jc] - d.lr * wj;
     double alpha, eps[M];
-    const double p = prox_elem<KIND, M, GF, false>(P, jc, v, wt, alpha, eps);
+            unsigned pcode;
+    const double p = prox_elem<KIND, M, GF, false>(P, jc, v, wt, alpha, eps, pcode);
     if (lsq) {
       s[0] += msk(live, fabs(p));
     } else if (L1) {
@@ -109,7 +110,8 @@ __device__ void primal_from_weights(const zf_problem& P, const WarpCtx& c, doubl
         for (int i = 0; i < M; ++i) wj += w[i] * in.J[i];
         const double v = in.y - lr * wj;
         double alpha, eps[M];
-        return prox_elem<KIND, M, GF, false>(P, live ? j : 0, v, wt, alpha, eps);
+            unsigned pcode;
+        return prox_elem<KIND, M, GF, false>(P, live ? j : 0, v, wt, alpha, eps, pcode);
       },
       [&](int j, bool live, double p) {
         if (live) out[j] = p;
@@ -209,18 +211,9 @@ __device__ double dual_brent(const zf_problem& P, const WarpCtx& c, const DualDa
 //   max_{w' in simplex}  (G + Qm w) . w' - 1/2 w'^T Qm w'
 // is then solved exactly in registers by enumerating the 2^M - 1 faces.
 // ------------------------------------------------------------------------------------
-// Which linear piece of the prox chain a coordinate is on: 0 if pinned at a kink / bound
-// (alpha = 0), else 1 | the side of every shift it lies on.  The dual is one quadratic wherever
-// these codes do not change.
-template <int M>
-__device__ __forceinline__ unsigned char piece_code(double alpha, const double (&eps)[M]) {
-  if (alpha == 0.0) return 0;
-  unsigned code = 1u;
-#pragma unroll
-  for (int i = 0; i < M; ++i) code |= (eps[i] > 0.0 ? 1u : 0u) << (i + 1);
-  return (unsigned char)code;
-}
-
+// Which linear piece of the prox chain a coordinate is on: the code prox_elem<.., TRACK> builds
+// (zf_problems.cuh): per L1 stage pinned / above / below its kink, and the box state.  The dual
+// is one quadratic wherever these codes do not change.
 // x = prox_wsum_g(lr * w, y - lr * w @ J) into `out`, and whether every coordinate is on the
 // same piece as at the last full dual evaluation (c.pat)
 template <int KIND, int M, int GF>
@@ -230,7 +223,7 @@ __device__ bool primal_probe(const zf_problem& P, const WarpCtx& c, double lr,
 #pragma unroll
   for (int i = 0; i < M; ++i) wt[i] = lr * w[i];
   int same = 1;
-  struct In { CoordIn<M> c; unsigned char pat; };
+  struct In { CoordIn<M> c; unsigned short pat; };
   sweep3<In, double>(
       c.n, c.lane,
       [&](int j, bool live) {
@@ -243,8 +236,9 @@ __device__ bool primal_probe(const zf_problem& P, const WarpCtx& c, double lr,
         for (int i = 0; i < M; ++i) wj += w[i] * in.c.J[i];
         const double v = in.c.y - lr * wj;
         double alpha, eps[M];
-        const double p = prox_elem<KIND, M, GF, true>(P, live ? j : 0, v, wt, alpha, eps);
-        same &= live ? (int)(piece_code<M>(alpha, eps) == in.pat) : 1;
+            unsigned pcode;
+        const double p = prox_elem<KIND, M, GF, true>(P, live ? j : 0, v, wt, alpha, eps, pcode);
+        same &= live ? (int)((unsigned short)pcode == in.pat) : 1;
         return p;
       },
       [&](int j, bool live, double p) {
@@ -282,7 +276,7 @@ __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<
     if (lsq) lam[i] = P.l1;
     else if (L1) { lam[i] = P.l1_ratios[i]; shift[i] = P.l1_shifts[i]; }
   }
-  sweep3<CoordIn<M>, unsigned char>(
+  sweep3<CoordIn<M>, unsigned short>(
       c.n, c.lane, [&](int j, bool live) { return load_coord<M>(c, live ? j : 0); },
       [&](const CoordIn<M>& in, int j, bool live) {
         double wj = 0.0;
@@ -291,7 +285,8 @@ __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<
         const double yj = in.y;
         const double v = yj - d.lr * wj;
         double alpha, eps[M];
-        const double p = prox_elem<KIND, M, GF, true>(P, live ? j : 0, v, wt, alpha, eps);
+            unsigned pcode;
+        const double p = prox_elem<KIND, M, GF, true>(P, live ? j : 0, v, wt, alpha, eps, pcode);
         // a dead slot contributes exact zeros: its alpha, p - y, p - v and w.J are masked
         const double am = msk(live, alpha);
         const double dy = msk(live, p - yj);
@@ -310,9 +305,9 @@ __device__ void dual_full(const zf_problem& P, const WarpCtx& c, const DualData<
 #pragma unroll
           for (int l = i; l < M; ++l) s[k++] += mcol[i] * mcol[l];
         }
-        return piece_code<M>(alpha, eps);
+        return (unsigned short)pcode;
       },
-      [&](int j, bool live, unsigned char code) {
+      [&](int j, bool live, unsigned short code) {
         if (live) c.pat[j] = code;
       });
   warp_sum_k<NS>(s);

@@ -572,10 +572,16 @@ __device__ void g_eval(const zf_problem& P, const WarpCtx& c, const double* x,
 template <int KIND, int M, int GF, bool TRACK>
 __device__ __forceinline__ double prox_elem(const zf_problem& P, int j, double v,
                                             const double (&wt)[M], double& alpha,
-                                            double (&eps)[M]) {
+                                            double (&eps)[M], unsigned& code) {
+  // code (TRACK): which linear piece of the chain the coordinate is on -- two bits per L1 stage
+  // (2: pinned at that stage's kink, 1 / 0: above / below it) and two for the box (1: clipped at
+  // the upper bound, 2: at the lower bound).  Two points with equal codes in every coordinate
+  // lie on ONE quadratic piece of the dual; pinned at a different kink or bound is a different
+  // piece even though alpha is 0 in both.
   constexpr bool L1 = (GF & ZF_G_L1) != 0, BOX = (GF & ZF_G_BOX) != 0;
   double p = v;
   bool pinned = false;
+  code = 0u;
 #pragma unroll
   for (int i = 0; i < M; ++i) eps[i] = 0.0;
   if constexpr (KIND == ZF_LSQ_L1) {
@@ -588,6 +594,7 @@ __device__ __forceinline__ double prox_elem(const zf_problem& P, int j, double v
       pinned = fabs(v) <= t;
 #pragma unroll
       for (int i = 0; i < M; ++i) eps[i] = v > t ? 1.0 : -1.0;
+      code = pinned ? 2u : (v > t ? 1u : 0u);
     }
     alpha = pinned ? 0.0 : 1.0;
     return p;
@@ -604,21 +611,27 @@ __device__ __forceinline__ double prox_elem(const zf_problem& P, int j, double v
     if (TRACK) {
       pinned = fabs(a0) <= coef[0];
       eps[0] = a0 > coef[0] ? 1.0 : -1.0;
+      code = pinned ? 2u : (a0 > coef[0] ? 1u : 0u);
     }
 #pragma unroll
     for (int i = 1; i < M; ++i) {
       const double ai = p - coef[i] - P.l1_shifts[i];
       p = soft_threshold(ai, coef[i]) + P.l1_shifts[i];
       if (TRACK) {
-        pinned = pinned || (fabs(ai) <= coef[i]);
+        const bool pin_i = fabs(ai) <= coef[i];
+        pinned = pinned || pin_i;
         eps[i] = ai > coef[i] ? 1.0 : -1.0;
+        code |= (pin_i ? 2u : (ai > coef[i] ? 1u : 0u)) << (2 * i);
       }
     }
   }
   if constexpr (BOX) {
     // projection_box (scalar or per-coordinate bounds)
     const double q = fmin(fmax(p, lower_of(P, j)), upper_of(P, j));
-    if (TRACK) pinned = pinned || (q != p);
+    if (TRACK) {
+      pinned = pinned || (q != p);
+      code |= (q < p ? 1u : (q > p ? 2u : 0u)) << (2 * M);
+    }
     p = q;
   }
   alpha = pinned ? 0.0 : 1.0;
