@@ -161,6 +161,15 @@ def test_large_a_properties(gpu):
     ({"ZF_LASSO_RING": "2"}, (640, 20000), 1),             # BASELINE configs[3] row width
     ({"ZF_LASSO_RING": "4"}, (1300, 8200), 1),             # cluster 4: few rows per cluster
     ({"ZF_LASSO_RING": "2"}, (640, 6), 1),                 # one short chunk, slices of 2 and 1 pairs
+    ({"ZF_LASSO_RING": "3"}, (700, 20000), 1),             # odd cluster sizes: 3 x 4 chunks
+    ({"ZF_LASSO_RING": "5"}, (650, 36002), 1),             # 5 CTAs, ragged last chunk
+    ({"ZF_LASSO_RING": "6"}, (640, 40000), 1),
+    ({"ZF_LASSO_RING": "7"}, (610, 30000), 1),
+    ({}, (1200, 20000), 1),                                # create-time probe (4-CTA + 2-CTA split or not)
+    ({"ZF_LASSO_TUNE": "v"}, (900, 36000), 1),             # probe over 5..8-CTA clusters, table printed
+    ({"ZF_LASSO_TUNE": "0"}, (900, 36000), 1),             # static policy: 5-CTA clusters
+    ({"ZF_LASSO_NSM": "100"}, (900, 24000), 1),            # planned for a part with fewer SMs
+    ({"ZF_LASSO_NSM": "37", "ZF_LASSO_TUNE": "0"}, (640, 20000), 1),
 ])
 def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     """Each form of the A^T(A v - b) pass (csrc/zf_lasso.cu) forced through its environment
@@ -170,7 +179,7 @@ def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     from zfista_b200.lasso import DenseLasso
 
     for k in ("ZF_LASSO_FUSED", "ZF_LASSO_CLUSTER", "ZF_LASSO_THREADS", "ZF_LASSO_TMA",
-              "ZF_LASSO_TMA_ROWS", "ZF_LASSO_RING"):
+              "ZF_LASSO_TMA_ROWS", "ZF_LASSO_RING", "ZF_LASSO_TUNE", "ZF_LASSO_NSM"):
         monkeypatch.delenv(k, raising=False)
     rows, cols = shape
     g = torch.Generator(device="cuda").manual_seed(rows + cols)

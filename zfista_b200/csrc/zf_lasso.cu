@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include <cooperative_groups.h>
 
@@ -1479,6 +1480,9 @@ struct zf_lasso {
   // 132 of 148 SMs): 2-CTA clusters over the last rows, on its own stream
   int ring2_ctas = 0, ring2_nch = 0, ring2_cluster = 2, ring1_clusters = 0;
   long long ring2_row0 = 0, ring2_rows_per_cluster = 0, ring2_pairs_per_cta = 0;
+  long long ring_rows = 0;            // rows the ring plan covers (n_rows; a prefix while tuning)
+  int tuned_cluster = 0;              // what the create-time probe chose (0: static policy)
+  double tuned_rate2 = 0.0;
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fused_tma = false;             // TMA / shared-memory-resident form
@@ -1702,7 +1706,7 @@ int launch_fused_ring_n(zf_lasso* h, const double* v, int nch, const RingLaunch&
 
 int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
   RingLaunch L1{h->fused_ctas, h->fused_cluster, h->fused_rows_per_cta, h->fused_pairs_per_cta, 0,
-                h->ring2_ctas > 0 ? h->ring2_row0 : h->n_rows, 0, h->st};
+                h->ring2_ctas > 0 ? h->ring2_row0 : h->ring_rows, 0, h->st};
   if (query_only || h->ring2_ctas == 0)
     return launch_fused_ring_n(h, v, h->fused_pairs, L1, query_only, max_clusters);
   // fork: the wide launch first (it takes every SM a 4-CTA cluster fits on), then the 2-CTA
@@ -1712,7 +1716,7 @@ int launch_fused_ring(zf_lasso* h, const double* v, bool query_only, int* max_cl
   int rc = launch_fused_ring_n(h, v, h->fused_pairs, L1, false, nullptr);
   if (rc != ZF_OK) return rc;
   RingLaunch L2{h->ring2_ctas, h->ring2_cluster, h->ring2_rows_per_cluster, h->ring2_pairs_per_cta, h->ring2_row0,
-                h->n_rows, h->ring1_clusters, h->st2};
+                h->ring_rows, h->ring1_clusters, h->st2};
   rc = launch_fused_ring_n(h, v, h->ring2_nch, L2, false, nullptr);
   if (rc != ZF_OK) return rc;
   ZF_CUDA(cudaEventRecord(h->ev_join, h->st2));
@@ -1893,6 +1897,141 @@ int accept_candidate(zf_lasso* h, int* next) {
 
 }  // namespace
 
+namespace {
+
+// Configure the chunk-ring gradient pass for clusters of `c` CTAs over rows [0, rows) (the
+// handle's full row count, or a prefix while zf_lasso_create times the candidates).  Returns
+// false if a row slice does not fit (more than 5 chunks of 2048 columns per CTA).
+// 4-CTA clusters leave SMs idle (33 clusters = 132 of 148 SMs on B200).  When a 2-CTA cluster can
+// still hold the row slice (<= 5 chunks) and rate2 > 0, a second launch of 2-CTA clusters takes
+// the last rows on those SMs, concurrently, on its own stream; its share of the rows follows the
+// per-SM rates 0.82 (4-CTA, <= 3 chunks per row) : rate2 (2-CTA, 5 chunks).
+// (8-CTA clusters + a 4-CTA second launch was measured: the 4-CTA clusters do not fit on the
+// idle SMs and run afterwards, 0.38 instead of 0.59 at 36000 columns -- only c == 4 splits.)
+bool ring_plan(zf_lasso* h, int c, double rate2, long long rows, int max_smem) {
+  const long long n2 = h->n_cols / 2;
+  h->fused_ring = false;
+  h->fused_pairs = 0;
+  h->ring2_ctas = 0;
+  h->ring_rows = rows;
+  if (c < 1 || c > zf::RING_MAX_CLUSTER || !h->vec || n2 < c || rows < 1) return false;
+  const long long ppc = (n2 + c - 1) / c;
+  const long long nchunks = (ppc + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
+  if (nchunks > 5 || (size_t)zf::RING_SLOTS * zf::RING_CH_PAIRS * 16 + 4096 > (size_t)max_smem)
+    return false;
+  h->fused_ring = true;
+  h->fused_cluster = c;
+  h->fused_pairs_per_cta = ppc;
+  h->fused_pairs = (int)nchunks;
+  int n_clusters = h->n_sm / c;
+  if (n_clusters < 1) { h->fused_ring = false; h->fused_pairs = 0; return false; }
+  h->fused_ctas = n_clusters * c;
+  h->fused_rows_per_cta = 1;
+  int active = 0;
+  if (launch_fused_ring(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
+    n_clusters = active;
+  const int idle = h->n_sm - n_clusters * c;
+  const int c2 = c / 2;                                  // cluster size of the second launch
+  const long long ppc2 = c2 > 0 ? (n2 + c2 - 1) / c2 : n2;
+  const long long nch2 = (ppc2 + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
+  if (c == 4 && idle >= c2 && nch2 <= 5 && rate2 > 0.0) {
+    const int clusters2 = idle / c2;
+    const double w1 = 0.82 * n_clusters * c, w2 = rate2 * clusters2 * c2;
+    const long long rows2 = (long long)((double)rows * w2 / (w1 + w2));
+    bool have = h->st2 != nullptr;
+    if (!have)
+      have = cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (rows2 >= clusters2 && have) {
+      h->ring2_row0 = rows - rows2;
+      h->ring2_rows_per_cluster = (rows2 + clusters2 - 1) / clusters2;
+      h->ring2_cluster = c2;
+      h->ring2_ctas = c2 * (int)((rows2 + h->ring2_rows_per_cluster - 1) / h->ring2_rows_per_cluster);
+      h->ring2_pairs_per_cta = ppc2;
+      h->ring2_nch = (int)nch2;
+    }
+  }
+  // rows of the first launch over its clusters
+  const long long rows1 = h->ring2_ctas > 0 ? h->ring2_row0 : rows;
+  h->fused_rows_per_cta = (rows1 + n_clusters - 1) / n_clusters;
+  const int used = (int)((rows1 + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
+  h->fused_ctas = used * c;
+  h->ring1_clusters = used;
+  return true;
+}
+
+}  // namespace
+
+namespace {
+
+// One-off timed probe at zf_lasso_create (n_cols > 16384, where no single rule fits: how well a
+// cluster size does depends on how full its last 2048-column chunk is, on how the clusters pack
+// into the GPCs, and -- for the 4-CTA + concurrent 2-CTA form -- on the row share of the second
+// launch).  Every candidate plan is timed on the first 64 rows per SM of the caller's own A (two
+// launches after a warm-up one, CUDA events) and the fastest is kept; the static choice stays
+// unless something beats it by more than 3 %, so that timing noise does not flip the kernel form
+// (and with it the summation order of A^T r) between two handles of the same shape.
+// ZF_LASSO_TUNE=0 switches the probe off, ZF_LASSO_TUNE=v prints the table.
+void ring_autotune(zf_lasso* h, int max_smem) {
+  struct Cand { int c; double rate2; float ms; };
+  const int c_static = h->fused_cluster;
+  const double r_static = h->ring2_ctas > 0 ? 0.57 : 0.0;
+  std::vector<Cand> cands;
+  cands.push_back(Cand{c_static, r_static, 0.f});
+  const long long n2 = h->n_cols / 2;
+  for (int c = 1; c <= zf::RING_MAX_CLUSTER; ++c) {
+    const long long ppc = (n2 + c - 1) / c;
+    if ((ppc + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS > 4) continue;
+    for (double r : {0.0, 0.45, 0.57, 0.7}) {
+      if (r > 0.0 && c != 4) continue;
+      if (c == c_static && r == r_static) continue;
+      cands.push_back(Cand{c, r, 0.f});
+    }
+  }
+  const long long probe_rows = h->n_rows < 64LL * h->n_sm ? h->n_rows : 64LL * h->n_sm;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+    if (e0) cudaEventDestroy(e0);
+    ring_plan(h, c_static, r_static, h->n_rows, max_smem);
+    return;
+  }
+  cudaMemsetAsync(h->y, 0, sizeof(double) * (size_t)h->n_cols, h->st);
+  int best = -1;
+  for (size_t k = 0; k < cands.size(); ++k) {
+    Cand& cd = cands[k];
+    cd.ms = -1.f;
+    if (!ring_plan(h, cd.c, cd.rate2, probe_rows, max_smem)) continue;
+    if (cd.rate2 > 0.0 && h->ring2_ctas == 0) continue;           // the split did not apply
+    bool ok = launch_fused_ring(h, h->y, false, nullptr) == ZF_OK;
+    ok = ok && cudaEventRecord(e0, h->st) == cudaSuccess;
+    for (int rep = 0; rep < 2 && ok; ++rep) ok = launch_fused_ring(h, h->y, false, nullptr) == ZF_OK;
+    ok = ok && cudaEventRecord(e1, h->st) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); continue; }
+    cudaEventElapsedTime(&cd.ms, e0, e1);
+    cd.ms *= 0.5f;
+    if (best < 0 || cd.ms < cands[best].ms) best = (int)k;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  int pick = 0;
+  if (best > 0 && (cands[0].ms <= 0.f || cands[best].ms < cands[0].ms / 1.03f)) pick = best;
+  if (const char* ev = getenv("ZF_LASSO_TUNE")) {
+    if (ev[0] == 'v') {
+      for (size_t k = 0; k < cands.size(); ++k)
+        fprintf(stderr, "[zf_lasso tune %lldx%lld] cluster %d split %.2f : %.4f ms%s%s\n", h->n_rows,
+                h->n_cols, cands[k].c, cands[k].rate2, cands[k].ms, k == 0 ? " (static)" : "",
+                (int)k == pick ? " <- chosen" : "");
+    }
+  }
+  if (!ring_plan(h, cands[pick].c, cands[pick].rate2, h->n_rows, max_smem))
+    ring_plan(h, c_static, r_static, h->n_rows, max_smem);
+  h->tuned_cluster = h->fused_cluster;
+  h->tuned_rate2 = h->ring2_ctas > 0 ? cands[pick].rate2 : 0.0;
+}
+
+}  // namespace
+
 extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* d_b,
                                int64_t n_rows, int64_t n_cols, double scale, double l1,
                                void* cuda_stream) {
@@ -1913,6 +2052,10 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (h->n_sm < 1) h->n_sm = 148;
+  if (const char* e_sm = getenv("ZF_LASSO_NSM")) {     // plan for fewer SMs (tests: a non-148 part)
+    const int v_sm = atoi(e_sm);
+    if (v_sm >= 1 && v_sm < h->n_sm) h->n_sm = v_sm;
+  }
   // residual: 3 CTAs per SM, never more warps than row groups
   const long long n_groups = (n_rows + zf::RES_ROWS_PER_WARP - 1) / zf::RES_ROWS_PER_WARP;
   long long rb = (n_groups + 7) / 8;
@@ -1988,61 +2131,16 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       return true;
     };
     auto try_ring = [&](int c) -> bool {
-      if (!(c == 1 || c == 2 || c == 4 || c == 8) || !big_enough || n2 < c) return false;
-      const long long ppc = (n2 + c - 1) / c;
-      const long long nchunks = (ppc + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
-      if (nchunks > 5 || (size_t)zf::RING_SLOTS * zf::RING_CH_PAIRS * 16 + 4096 > (size_t)max_smem)
-        return false;
-      h->fused_ring = true;
-      h->fused_cluster = c;
-      h->fused_pairs_per_cta = ppc;
-      h->fused_pairs = (int)nchunks;
-      int n_clusters = h->n_sm / c;
-      h->fused_ctas = n_clusters * c;
-      h->fused_rows_per_cta = 1;
-      int active = 0;
-      if (launch_fused_ring(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
-        n_clusters = active;
-      // 4-CTA clusters leave SMs idle (33 clusters = 132 of 148 SMs on B200).  When a 2-CTA
-      // cluster can still hold the row slice (<= 5 chunks), a second launch of 2-CTA clusters
-      // takes the last rows on those SMs, concurrently, on its own stream.  Its share of the rows
-      // follows the per-SM rates (4-CTA, 3 chunks per row : 2-CTA, 5 chunks), tuned below.
-      const int idle = h->n_sm - n_clusters * c;
-      const int c2 = c / 2;                                  // cluster size of the second launch
-      const long long ppc2 = c2 > 0 ? (n2 + c2 - 1) / c2 : n2;
-      const long long nch2 = (ppc2 + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
+      if (!big_enough) return false;
       const char* env_split = getenv("ZF_LASSO_RING_SPLIT");
-      // (8-CTA clusters + a 4-CTA second launch was measured: the 4-CTA clusters do not fit on the
-      // idle SMs and run afterwards, 0.38 instead of 0.59 at 36000 columns -- only c == 4 splits)
-      if (c == 4 && idle >= c2 && nch2 <= 5 && !(env_split && env_split[0] == '0')) {
-        const int clusters2 = idle / c2;
-        double rate2 = 0.57;       // 200000 x 20000: none 0.851, .5: 0.913, .55: 0.920, .6: 0.926,
-                                   // .65: 0.872, .7: 0.815 (second launch becomes the long pole)
-        if (env_split && atof(env_split) > 0.0) rate2 = atof(env_split);      // experiment knob
-        const double w1 = 0.82 * n_clusters * c, w2 = rate2 * clusters2 * c2;
-        long long rows2 = (long long)((double)n_rows * w2 / (w1 + w2));
-        if (rows2 >= clusters2 && cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess) {
-          h->ring2_row0 = n_rows - rows2;
-          h->ring2_rows_per_cluster = (rows2 + clusters2 - 1) / clusters2;
-          h->ring2_cluster = c2;
-          h->ring2_ctas = c2 * (int)((rows2 + h->ring2_rows_per_cluster - 1) / h->ring2_rows_per_cluster);
-          h->ring2_pairs_per_cta = ppc2;
-          h->ring2_nch = (int)nch2;
-        }
-      }
-      {
-        // rows of the first launch over its clusters
-        const long long rows1 = h->ring2_ctas > 0 ? h->ring2_row0 : n_rows;
-        h->fused_rows_per_cta = (rows1 + n_clusters - 1) / n_clusters;
-        const int used = (int)((rows1 + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
-        h->fused_ctas = used * c;
-        h->ring1_clusters = used;
-        const size_t parts = (size_t)used + (size_t)(h->ring2_ctas / h->ring2_cluster);
-        if (parts > h->gpart_rows) h->gpart_rows = parts;
-        if (parts > sq_rows) sq_rows = parts;
-      }
+      double rate2 = 0.57;       // 200000 x 20000: none 0.851, .5: 0.913, .55: 0.920, .6: 0.926,
+                                 // .65: 0.872, .7: 0.815 (second launch becomes the long pole)
+      if (env_split && env_split[0] == '0') rate2 = 0.0;
+      else if (env_split && atof(env_split) > 0.0) rate2 = atof(env_split);   // experiment knob
+      if (!ring_plan(h, c, rate2, n_rows, max_smem)) return false;
+      const size_t parts = (size_t)h->ring1_clusters + (size_t)(h->ring2_ctas / h->ring2_cluster);
+      if (parts > h->gpart_rows) h->gpart_rows = parts;
+      if (parts > sq_rows) sq_rows = parts;
       return true;
     };
     auto try_cluster = [&](int c) -> bool {
@@ -2086,8 +2184,12 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
     } else if (n_cols < 4096) {
       try_single();
     } else {
-      // chunk ring: the smallest cluster whose row slice is at most 4 chunks (8192 columns)
-      const int c = n_cols <= 8192 ? 1 : n_cols <= 16384 ? 2 : n_cols <= 32768 ? 4 : 8;
+      // chunk ring: the smallest cluster whose row slice is at most 4 chunks (8192 columns); 7-CTA
+      // clusters pack badly into the GPCs and are never the static choice (sustained, B200:
+      // 36000 columns 5 / 6 / 8 CTAs 0.89 / 0.92 / 0.70, 40000: 0.97 / 0.81 / 0.77, 50000 and
+      // 60000: 8 CTAs 0.73 / 0.85).  Above 16384 columns the create-time probe below re-decides.
+      const int c = n_cols <= 8192 ? 1 : n_cols <= 16384 ? 2 : n_cols <= 32768 ? 4
+                  : n_cols <= 40960 ? 5 : n_cols <= 49152 ? 6 : 8;
       if (!try_ring(c) && !try_ring(8)) {
         if (n_cols <= 8192) { if (!try_tma(2)) try_single(); }
         else if (n_cols <= 16384) try_cluster(2);
@@ -2099,6 +2201,12 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   auto alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
+  const bool tune = h->fused_ring && n_cols > 16384 && !getenv("ZF_LASSO_RING") &&
+                    !(getenv("ZF_LASSO_TUNE") && getenv("ZF_LASSO_TUNE")[0] == '0');
+  if (tune) {                     // any candidate plan leaves at most one partial row per SM
+    if ((size_t)h->n_sm > h->gpart_rows) h->gpart_rows = (size_t)h->n_sm;
+    if ((size_t)h->n_sm > sq_rows) sq_rows = (size_t)h->n_sm;
+  }
   alloc((void**)&h->vecs, sizeof(double) * 4 * (size_t)n_cols);
   alloc((void**)&h->r, sizeof(double) * (size_t)n_rows);
   alloc((void**)&h->gpart, sizeof(double) * h->gpart_rows * (size_t)n_cols);
@@ -2122,6 +2230,11 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   h->xn = h->vecs + n_cols;
   h->y = h->vecs + 2 * n_cols;
   h->g = h->vecs + 3 * n_cols;
+  if (tune) {
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    ring_autotune(h, max_smem);
+  }
   *out = h;
   return ZF_OK;
 }
