@@ -933,7 +933,23 @@ def bench_lasso_configs3(args, dev, rank, world):
 
     rate, whole, n_it = _fista_iters_per_s(solve_single, 10, 70, dev, world)
     out.update(single_fista_iters_per_s=rate, single_fista_iters_per_s_whole_call=whole,
-               single_fista_iters_timed=n_it)
+               single_fista_iters_timed=n_it,
+               exchange=("NVLink peer memory, folded into the prox kernel" if single.peer_exchange
+                         else "NCCL all-reduce between the stages" if world > 1 else "none (1 GPU)"))
+    if world > 1 and single.peer_exchange:
+        # the same run with the NCCL all-reduce instead of the in-kernel peer exchange
+        os.environ["ZF_LASSO_P2P"] = "0"
+        nccl = DenseLasso(A, b, l1_ratio=1e-3, scale=1.0 / (2 * rows_total), distributed=True)
+        del os.environ["ZF_LASSO_P2P"]
+
+        def solve_nccl(n):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                return nccl.minimize_proximal_gradient(x, max_iter=n, **kw).nit
+
+        out["single_fista_iters_per_s_nccl_exchange"] = _fista_iters_per_s(solve_nccl, 10, 70, dev,
+                                                                           world)[0]
+        del nccl
     mrate, mwhole, mn = _fista_iters_per_s(solve_multi, 5, 25, dev, world)
     out.update(multi_fista_run_iters_per_s=mrate, multi_fista_run_iters_per_s_whole_call=mwhole,
                multi_runs=K)

@@ -200,6 +200,18 @@ int zf_lasso_dev_poll(zf_lasso* h, int32_t slot /*0|1*/, int32_t wait, int32_t* 
                       int64_t* h_nit);
 int zf_lasso_dev_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
                         int32_t* h_status, double* h_lr, double* h_allerrs, double* h_allfuns);
+/* Row-sharded runs on ONE node: the exchange folded into the kernels over NVLink peer memory
+ * instead of an NCCL all-reduce between the stages.  Each rank exports a 64-byte
+ * cudaIpcMemHandle_t of its exchange buffer, the caller all-gathers the handles over its control
+ * plane and attaches them (<= 8 ranks).  From then on stage 1 publishes this rank's
+ * [A^T r | sum r^2] into its own buffer and stage 2 (the prox kernel) sums every rank's partials
+ * straight out of peer memory, in rank order -- bit-identical on every rank; stages 3 / 6
+ * exchange the residual norm the same way.  The caller skips its all-reduces when
+ * zf_lasso_p2p_active() returns 1.  A peer that never publishes ends the solve with status -3
+ * after ~2 s instead of hanging the GPU.                                                  */
+int zf_lasso_p2p_export(zf_lasso* h, void* handle_out /* 64 bytes */);
+int zf_lasso_p2p_attach(zf_lasso* h, int32_t rank, int32_t world, const void* handles /* world x 64 */);
+int zf_lasso_p2p_active(zf_lasso* h);
 /* how many times one gradient evaluation reads A from HBM with this handle's kernel choice:
  * 1 (fused A^T(Av-b) kernels) or 2 (residual pass + A^T pass); for the roofline accounting */
 int zf_lasso_passes(zf_lasso* h);

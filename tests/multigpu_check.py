@@ -37,25 +37,43 @@ def main():
     b = A @ w + 0.01 * rng.standard_normal(n_rows)
     scale, l1, x0 = 1 / (2 * n_rows), 0.03, np.zeros(n_cols)
     lo, hi = zd.shard_bounds(n_rows, rank, world)
+    # the exchange of [A^T r | sum r^2]: folded into the kernels over NVLink peer memory
+    # (default on one node), and the NCCL all-reduce between the stages (ZF_LASSO_P2P=0)
     sharded = DenseLasso(A[lo:hi], b[lo:hi], l1, scale=scale, distributed=True)
+    os.environ["ZF_LASSO_P2P"] = "0"
+    sharded_nccl = DenseLasso(A[lo:hi], b[lo:hi], l1, scale=scale, distributed=True)
+    del os.environ["ZF_LASSO_P2P"]
+    assert not sharded_nccl.peer_exchange
+    kinds = [None] * world
+    dist.all_gather_object(kinds, sharded.peer_exchange)
+    assert len(set(kinds)) == 1, kinds            # every rank took the same decision
     single = DenseLasso(A, b, l1, scale=scale)
     spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
     for opts in (dict(nesterov=True), dict(nesterov=False, max_iter=80),
-                 dict(nesterov=True, lr=0.2, decay_rate=1, nesterov_ratio=(0.25, 1 / 64))):
+                 dict(nesterov=True, lr=0.2, decay_rate=1, nesterov_ratio=(0.25, 1 / 64)),
+                 dict(nesterov=True, return_all=True), dict(nesterov=True, lr=1e9, max_backtrack_iter=3)):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            r_sh = sharded.minimize_proximal_gradient(x0, **opts)
             r_1 = single.minimize_proximal_gradient(x0, **opts)
             ref = zo.minimize_proximal_gradient(spec, x0, **opts)
-        assert r_sh.nit == r_1.nit == ref["nit"], (r_sh.nit, r_1.nit, ref["nit"])
-        np.testing.assert_allclose(r_sh.x, r_1.x, rtol=1e-9, atol=1e-10)
-        np.testing.assert_allclose(r_sh.x, ref["x"], rtol=1e-8, atol=1e-9)
-        np.testing.assert_allclose(r_sh.fun, ref["fun"], rtol=1e-9)
-        # all ranks hold the same replicated x
-        xs = [None] * world
-        dist.all_gather_object(xs, r_sh.x)
-        for other in xs[1:]:
-            np.testing.assert_array_equal(other, xs[0])
+        for prob in (sharded, sharded_nccl, sharded):     # (the first one again: repeated solves)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                r_sh = prob.minimize_proximal_gradient(x0, **opts)
+            assert r_sh.nit == r_1.nit == ref["nit"], (r_sh.nit, r_1.nit, ref["nit"])
+            assert r_sh.status == r_1.status == ref["status"]
+            np.testing.assert_allclose(r_sh.x, r_1.x, rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(r_sh.x, ref["x"], rtol=1e-8, atol=1e-9)
+            np.testing.assert_allclose(r_sh.fun, ref["fun"], rtol=1e-9)
+            if opts.get("return_all"):
+                np.testing.assert_allclose(r_sh.allfuns, np.ravel(ref["allfuns"]), rtol=1e-9)
+                np.testing.assert_allclose(r_sh.allerrs, ref["allerrs"], rtol=1e-6, atol=1e-12)
+            # all ranks hold the same replicated x
+            xs = [None] * world
+            dist.all_gather_object(xs, r_sh.x)
+            for other in xs[1:]:
+                np.testing.assert_array_equal(other, xs[0])
+    peer = sharded.peer_exchange
     grid = [(0.0, 0.25), (0.5, 1 / 16), (0.25, 17 / 128), (0.0, 0.0), (0.75, 0.25)]
     X0m = np.random.RandomState(5).standard_normal((len(grid), n_cols)) * 0.1
     msh = DenseLassoMulti(A[lo:hi], b[lo:hi], l1, len(grid), scale=scale, distributed=True)
@@ -76,7 +94,7 @@ def main():
     np.testing.assert_array_equal(full.x, one.x)
     dist.barrier()
     if rank == 0:
-        print(f"MULTIGPU_OK world={world}")
+        print(f"MULTIGPU_OK world={world} peer_exchange={peer}")
     dist.destroy_process_group()
 
 

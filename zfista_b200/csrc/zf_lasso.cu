@@ -1199,8 +1199,123 @@ struct LassoDevState {
   int done;               // != 0: the solve has ended
   int F_known, result_is_prev;
   unsigned int ticket;    // last-block election of the update kernel
-  int pad;
+  int p2p_error;          // a peer's flag did not arrive in time (row-sharded peer exchange)
+  unsigned long long gseq, sseq;   // gradient / residual-norm exchanges published so far
 };
+
+// ---------------------------------------------------------------------------------------
+// Row-sharded runs on one node: the exchange of [A^T r | sum r^2] folded into the kernels.
+// Every rank owns one P2PBuf in its own HBM, mapped into every other rank of the node
+// (cudaIpc handles, NVLink peer access).  A rank PUBLISHES its collected partials into its own
+// buffer and then bumps the buffer's flag; the consumers -- the same update / decide kernels
+// that a single GPU runs -- wait for every peer's flag and add the peers' partials straight out
+// of peer memory, in rank order, so every rank forms bit-identical sums.  No NCCL launch, no
+// extra pass: the all-reduce IS the operand fetch of the prox kernel.  Buffers alternate with the
+// exchange's sequence number; a rank reaches exchange k + 2 (which overwrites buffer k & 1) only
+// after its own exchange k + 1 saw every peer's flag k + 1, i.e. after every peer finished
+// reading exchange k.  Flags are monotonic, waits are bounded (an error flag, never a hang).
+// ---------------------------------------------------------------------------------------
+constexpr int P2P_MAX_RANKS = 8;
+struct P2PBuf {
+  unsigned long long flag_g[2];      // sequence number of the gradient partials in data[p]
+  unsigned long long flag_s[2];      // sequence number of ss[p]
+  double ss[2];
+  double pad[2];
+  double data[1];                    // [2][stride]: A^T r partial (n_cols) | sum r^2
+};
+struct P2PPeers {
+  P2PBuf* buf[P2P_MAX_RANKS];        // every rank's buffer, own included, in rank order
+  long long stride;                  // doubles per data slot (>= n_cols + 1)
+  int world, rank;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until *flag >= seq (one thread); false after ~2 s
+__device__ bool p2p_wait(const unsigned long long* flag, unsigned long long seq) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys_u64(flag) < seq) {
+    __nanosleep(64);
+    if (clock64() - t0 > (1LL << 32)) return false;
+  }
+  return true;
+}
+
+// publish the collected gradient partials: mine->data[p][j] = sum_rb gpart[rb][j], [n_cols] = ss
+__global__ void __launch_bounds__(256)
+lasso_p2p_publish_kernel(LassoDevState* st, const double* __restrict__ gpart, int n_parts,
+                         const double* __restrict__ sq_part, int n_sq, long long n_cols,
+                         P2PPeers pp, unsigned int* __restrict__ ticket) {
+  if (st->done != 0 || st->skip_grad != 0) return;
+  const unsigned long long seq = st->gseq + 1ull;
+  P2PBuf* mine = pp.buf[pp.rank];
+  double* out = mine->data + (seq & 1ull) * pp.stride;
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_cols) {
+    double acc = 0.0;
+    for (int rb = 0; rb < n_parts; ++rb) acc += gpart[(long long)rb * n_cols + j];
+    out[j] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int k = 0; k < n_sq; ++k) acc = __dadd_rn(acc, sq_part[k]);
+    out[n_cols] = acc;
+  }
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    *ticket = 0u;
+    __threadfence_system();
+    st_release_sys_u64(&mine->flag_g[seq & 1ull], seq);
+    st->gseq = seq;
+  }
+}
+
+// publish this rank's sum r^2 (residual pass at the candidate / x0 / the final x)
+__global__ void lasso_p2p_publish_ss_kernel(LassoDevState* st, const double* __restrict__ sq_part,
+                                            int n_sq, P2PPeers pp, int force) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (st->done != 0 && !force) return;
+  const unsigned long long seq = st->sseq + 1ull;
+  P2PBuf* mine = pp.buf[pp.rank];
+  double acc = 0.0;
+  for (int k = 0; k < n_sq; ++k) acc = __dadd_rn(acc, sq_part[k]);
+  mine->ss[seq & 1ull] = acc;
+  __threadfence_system();
+  st_release_sys_u64(&mine->flag_s[seq & 1ull], seq);
+  st->sseq = seq;
+}
+
+// every rank's sum r^2 of the exchange just published, in rank order, into local memory
+__global__ void lasso_p2p_gather_ss_kernel(LassoDevState* st, P2PPeers pp, double* __restrict__ out,
+                                           int force) {
+  if (blockIdx.x != 0 || (int)threadIdx.x >= pp.world) return;
+  if (st->done != 0 && !force) return;
+  const unsigned long long seq = st->sseq;
+  const P2PBuf* peer = pp.buf[threadIdx.x];
+  if (!p2p_wait(&peer->flag_s[seq & 1ull], seq)) {
+    atomicExch(&st->p2p_error, 1);
+    out[threadIdx.x] = 0.0;
+    return;
+  }
+  out[threadIdx.x] = ld_relaxed_sys_f64(&peer->ss[seq & 1ull]);
+}
 
 __device__ __forceinline__ double dv_f_from_ss(double ss, double scale) {
   const double nrm = __dsqrt_rn(ss);
@@ -1279,6 +1394,13 @@ __global__ void lasso_dev_init_kernel(const LassoDevOpts* __restrict__ op, Lasso
   st->F_known = 0;
   st->result_is_prev = 0;
   st->ticket = 0u;
+  // (gseq / sseq run on across solves; p2p_error is sticky: the F(x0) exchange precedes this kernel)
+  if (st->p2p_error) {
+    st->status = -3;
+    st->phase = DV_DONE;
+    st->done = 1;
+    st->skip_grad = 1;
+  }
   if (o.cap > 0 && o.allfuns) o.allfuns[0] = F0;
 }
 
@@ -1297,13 +1419,25 @@ lasso_dev_update_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
                         const double* __restrict__ sq_part, int n_sq,
                         const double* __restrict__ partial, long long n,
                         double* __restrict__ y, double* __restrict__ xp, double* __restrict__ xn,
-                        double* __restrict__ g, StepSums* __restrict__ block_sums) {
+                        double* __restrict__ g, StepSums* __restrict__ block_sums, P2PPeers pp) {
   if (*reinterpret_cast<const volatile int*>(&st->done) != 0) return;
   __shared__ StepSums sh[VEC_THREADS / 32];
   __shared__ bool is_last;
   const LassoDevOpts o = *op;
   const double lr = st->lr;
   const bool retry = (st->phase == DV_RETRY);
+  // SRC 2: the gradient is the sum of every rank's published partials, read from peer memory
+  const unsigned long long gseq = (SRC == 2) ? st->gseq : 0ull;
+  const double* peer_data[P2P_MAX_RANKS];
+  if (SRC == 2 && !retry) {
+    if ((int)threadIdx.x < pp.world) {
+      if (!p2p_wait(&pp.buf[threadIdx.x]->flag_g[gseq & 1ull], gseq)) atomicExch(&st->p2p_error, 1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+      peer_data[r] = (r < pp.world) ? pp.buf[r]->data + (gseq & 1ull) * pp.stride : nullptr;
+  }
   const double two_scale = 2.0 * o.scale;
   const double thresh = o.l1 * lr;
   double t_new = 0.0, mom = 0.0;
@@ -1317,6 +1451,12 @@ lasso_dev_update_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
     } else if (SRC == 0) {
       double acc = 0.0;
       for (int rb = 0; rb < n_parts; ++rb) acc += gpart[(long long)rb * n + j];
+      gj = acc * two_scale;
+    } else if (SRC == 2) {
+      double acc = 0.0;
+#pragma unroll
+      for (int r = 0; r < P2P_MAX_RANKS; ++r)
+        if (r < pp.world) acc += ld_relaxed_sys_f64(peer_data[r] + j);
       gj = acc * two_scale;
     } else {
       gj = partial[j] * two_scale;
@@ -1354,6 +1494,13 @@ lasso_dev_update_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
   st->ticket = 0u;
   st->sums = t;
   st->accept = 0;
+  if (SRC == 2 && st->p2p_error) {      // a peer never published: stop with an error status
+    st->status = -3;
+    st->phase = DV_DONE;
+    st->done = 1;
+    st->skip_grad = 1;
+    return;
+  }
   if (FIXED) {
     st->F_known = 0;
     dv_accept(o, st, t.maxd);
@@ -1362,6 +1509,8 @@ lasso_dev_update_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
       double ss = 0.0;
       if (SRC == 0) {
         for (int k = 0; k < n_sq; ++k) ss = __dadd_rn(ss, sq_part[k]);
+      } else if (SRC == 2) {
+        for (int r = 0; r < pp.world; ++r) ss = __dadd_rn(ss, ld_relaxed_sys_f64(peer_data[r] + n));
       } else {
         ss = partial[n];
       }
@@ -1383,6 +1532,14 @@ __global__ void lasso_dev_decide_kernel(const LassoDevOpts* __restrict__ op, Las
                                         const double* __restrict__ ss_src, int n_sq) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (st->done) return;
+  if (st->p2p_error) {                 // a peer's residual norm never arrived
+    st->status = -3;
+    st->phase = DV_DONE;
+    st->done = 1;
+    st->skip_grad = 1;
+    st->accept = 0;
+    return;
+  }
   const LassoDevOpts o = *op;
   double ss = 0.0;
   for (int k = 0; k < n_sq; ++k) ss = __dadd_rn(ss, ss_src[k]);
@@ -1511,6 +1668,13 @@ struct zf_lasso {
   zf::LassoDevOpts dev_opts_host{};
   cudaStream_t st_own = nullptr;             // used when the caller's stream cannot be captured
   cudaEvent_t ev_own = nullptr;
+  // row-sharded peer exchange (zf_lasso_p2p_*)
+  zf::P2PPeers pp{};
+  zf::P2PBuf* p2p_mine = nullptr;
+  void* p2p_opened[zf::P2P_MAX_RANKS] = {};
+  bool p2p_on = false;
+  double* ss_gather = nullptr;               // every rank's sum r^2, in rank order
+  unsigned int* p2p_ticket = nullptr;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [fixed-step slots, line-search slots]
   int graph_slots = 0;
   bool graph_failed = false;
@@ -2218,6 +2382,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_pin, sizeof(double) * 8);
   alloc((void**)&h->d_opts, sizeof(zf::LassoDevOpts));
   alloc((void**)&h->d_state, sizeof(zf::LassoDevState));
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->d_state, 0, sizeof(zf::LassoDevState), h->st);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_state, 2 * sizeof(zf::LassoDevState));
   for (int k = 0; k < 2 && e == cudaSuccess; ++k)
     e = cudaEventCreateWithFlags(&h->ev_poll[k], cudaEventDisableTiming);
@@ -2250,6 +2415,11 @@ extern "C" void zf_lasso_destroy(zf_lasso* h) {
   cudaFree(h->d_sums);
   cudaFree(h->counter);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  for (int r = 0; r < zf::P2P_MAX_RANKS; ++r)
+    if (h->p2p_opened[r]) cudaIpcCloseMemHandle(h->p2p_opened[r]);
+  cudaFree(h->p2p_mine);
+  cudaFree(h->ss_gather);
+  cudaFree(h->p2p_ticket);
   cudaFree(h->d_opts);
   cudaFree(h->d_state);
   cudaFree(h->d_allerrs);
@@ -2529,7 +2699,18 @@ template <int SRC, bool FIXED>
 int launch_dev_update(zf_lasso* h, int n_parts, int n_sq) {
   zf::lasso_dev_update_kernel<SRC, FIXED><<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
       h->d_opts, h->d_state, h->gpart, n_parts, h->sq_part, n_sq, h->partial, h->n_cols, h->y,
-      h->xp, h->xn, h->g, h->block_sums);
+      h->xp, h->xn, h->g, h->block_sums, h->pp);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+// publish this rank's sum r^2 and collect every rank's (peer exchange)
+int p2p_exchange_ss(zf_lasso* h, int force) {
+  zf::lasso_p2p_publish_ss_kernel<<<1, 32, 0, h->st>>>(h->d_state, h->sq_part, h->res_blocks, h->pp, force);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  zf::lasso_p2p_gather_ss_kernel<<<1, 32, 0, h->st>>>(h->d_state, h->pp, h->ss_gather, force);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -2537,8 +2718,9 @@ int launch_dev_update(zf_lasso* h, int n_parts, int n_sq) {
 
 int dev_stage(zf_lasso* h, int stage) {
   int rc = ZF_OK, ng = 0, ns = 0;
-  const double* ss_feval = h->dev_sharded ? h->partial + h->n_cols : h->sq_part;
-  const int n_feval = h->dev_sharded ? 1 : h->res_blocks;
+  const bool p2p = h->dev_sharded && h->p2p_on;
+  const double* ss_feval = p2p ? h->ss_gather : h->dev_sharded ? h->partial + h->n_cols : h->sq_part;
+  const int n_feval = p2p ? h->pp.world : h->dev_sharded ? 1 : h->res_blocks;
   switch (stage) {
     case DS_INIT:
       zf::lasso_dev_init_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss_feval,
@@ -2551,10 +2733,20 @@ int dev_stage(zf_lasso* h, int stage) {
       rc = launch_gradient_pass(h, h->y, &ng, &ns);
       h->skip = nullptr;
       if (rc != ZF_OK) return rc;
+      if (p2p) {                      // collect into this rank's exchange buffer and raise its flag
+        const int blocks = (int)((h->n_cols + 255) / 256);
+        zf::lasso_p2p_publish_kernel<<<blocks, 256, 0, h->st>>>(h->d_state, h->gpart, ng, h->sq_part,
+                                                               ns, h->n_cols, h->pp, h->p2p_ticket);
+        ZF_CUDA(cudaGetLastError());
+        zf::zf_count_launch();
+        return ZF_OK;
+      }
       if (h->dev_sharded) rc = launch_collect_n(h, true, ng, ns);   // -> partial, all-reduced next
       return rc;
     case DS_PROX:
       gradient_part_counts(h, &ng, &ns);
+      if (p2p)
+        return h->dev_fixed ? launch_dev_update<2, true>(h, ng, ns) : launch_dev_update<2, false>(h, ng, ns);
       if (h->dev_sharded)
         return h->dev_fixed ? launch_dev_update<1, true>(h, ng, ns) : launch_dev_update<1, false>(h, ng, ns);
       return h->dev_fixed ? launch_dev_update<0, true>(h, ng, ns) : launch_dev_update<0, false>(h, ng, ns);
@@ -2564,6 +2756,7 @@ int dev_stage(zf_lasso* h, int stage) {
       rc = launch_residual(h, h->xn);
       h->skip = nullptr;
       if (rc != ZF_OK) return rc;
+      if (p2p) return p2p_exchange_ss(h, stage == DS_FEVAL_FINAL ? 1 : 0);
       if (h->dev_sharded) rc = launch_collect(h, false);            // sum r^2 -> partial[n_cols]
       return rc;
     case DS_DECIDE:
@@ -2700,7 +2893,10 @@ extern "C" int zf_lasso_dev_begin(zf_lasso* h, const zf_options* opt, const doub
       h->d_sums);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
-  if (h->dev_sharded) {
+  if (h->dev_sharded && h->p2p_on) {
+    rc = p2p_exchange_ss(h, 1);
+    if (rc != ZF_OK) return rc;
+  } else if (h->dev_sharded) {
     rc = launch_collect(h, false);
     if (rc != ZF_OK) return rc;
   }
@@ -2831,3 +3027,58 @@ static int lasso_solve_dev(zf_lasso* h, const zf_options* opt, const double* d_x
   }
   return rc;
 }
+
+
+/* ---- row-sharded runs on one node: exchange through peer memory instead of NCCL ----------
+ * zf_lasso_p2p_export: allocate this rank's exchange buffer and write its 64-byte
+ * cudaIpcMemHandle_t to `handle_out`.  zf_lasso_p2p_attach: `handles` = the world x 64 bytes of
+ * every rank's export (all-gathered by the caller over its control plane); maps the peers'
+ * buffers (NVLink peer access).  Afterwards a sharded device-decided run needs no all-reduce
+ * between its stages (zf_lasso_p2p_active() == 1).                                        */
+extern "C" int zf_lasso_p2p_export(zf_lasso* h, void* handle_out) {
+  if (!h || !handle_out) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  if (!h->p2p_mine) {
+    const long long stride = ((h->n_cols + 1 + 31) / 32) * 32;
+    const size_t bytes = sizeof(zf::P2PBuf) + sizeof(double) * 2 * (size_t)stride;
+    ZF_CUDA(cudaMalloc((void**)&h->p2p_mine, bytes));
+    ZF_CUDA(cudaMemset(h->p2p_mine, 0, bytes));
+    ZF_CUDA(cudaMalloc((void**)&h->ss_gather, sizeof(double) * zf::P2P_MAX_RANKS));
+    ZF_CUDA(cudaMalloc((void**)&h->p2p_ticket, sizeof(unsigned int)));
+    ZF_CUDA(cudaMemset(h->p2p_ticket, 0, sizeof(unsigned int)));
+    h->pp.stride = stride;
+  }
+  cudaIpcMemHandle_t hd;
+  ZF_CUDA(cudaIpcGetMemHandle(&hd, h->p2p_mine));
+  std::memcpy(handle_out, &hd, sizeof(hd));
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_p2p_attach(zf_lasso* h, int32_t rank, int32_t world, const void* handles) {
+  if (h && world == 0) {           // the ranks did not all succeed: back to the caller's all-reduce
+    h->p2p_on = false;
+    return ZF_OK;
+  }
+  if (!h || !handles || !h->p2p_mine) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_p2p_attach before export");
+  if (world < 1 || world > zf::P2P_MAX_RANKS || rank < 0 || rank >= world)
+    return zf::zf_fail(ZF_ERR_UNSUPPORTED, "peer exchange supports 1..%d ranks of one node", zf::P2P_MAX_RANKS);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->pp.buf[r] = h->p2p_mine; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const char*>(handles) + 64 * (size_t)r, sizeof(hd));
+    void* ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return zf::zf_fail_cuda(e, "cudaIpcOpenMemHandle (peer exchange unavailable)");
+    }
+    h->p2p_opened[r] = ptr;
+    h->pp.buf[r] = static_cast<zf::P2PBuf*>(ptr);
+  }
+  h->pp.world = world;
+  h->pp.rank = rank;
+  h->p2p_on = true;
+  return ZF_OK;
+}
+
+extern "C" int zf_lasso_p2p_active(zf_lasso* h) { return (h && h->p2p_on) ? 1 : 0; }

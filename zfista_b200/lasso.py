@@ -80,6 +80,40 @@ class DenseLasso:
         n = C.c_int64()
         ptr = _lib.lib().zf_lasso_partial(self._h, C.byref(n))
         self._partial = torch.as_tensor(_DevView(int(ptr), int(n.value)), device=self.device)
+        self.peer_exchange = False
+        if self.distributed:
+            self._setup_peer_exchange()
+
+    def _setup_peer_exchange(self):
+        """One node, <= 8 ranks: map every rank's exchange buffer into every other rank
+        (cudaIpc handles all-gathered over the control plane) so that the all-reduce of
+        ``[A^T r | sum r^2]`` becomes peer-memory reads inside the prox kernel
+        (csrc/zf_lasso.cu, P2PBuf).  Falls back to the NCCL all-reduce -- on every rank, by
+        agreement -- if any rank cannot map its peers (ZF_LASSO_P2P=0 forces the fallback)."""
+        import os
+
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        L = _lib.lib()
+        buf = C.create_string_buffer(64)
+        ok = os.environ.get("ZF_LASSO_P2P", "1") != "0" and 1 <= world <= 8
+        with _torch().cuda.device(self.device):
+            if ok:
+                ok = L.zf_lasso_p2p_export(self._h, buf) == 0
+            handles = [None] * world
+            dist.all_gather_object(handles, (bool(ok), bytes(buf.raw)), group=self.group)
+            ok = all(h[0] for h in handles)
+            if ok:
+                blob = b"".join(h[1] for h in handles)
+                ok = L.zf_lasso_p2p_attach(self._h, rank, world, blob) == 0
+            agreed = [None] * world
+            dist.all_gather_object(agreed, bool(ok), group=self.group)
+            if not all(agreed):
+                L.zf_lasso_p2p_attach(self._h, 0, 0, None)      # world = 0: switch it off again
+        self.peer_exchange = all(agreed) and bool(L.zf_lasso_p2p_active(self._h))
 
     def _to_dev(self, a, ndim):
         torch = _torch()
@@ -101,14 +135,14 @@ class DenseLasso:
 
     # ------------------------------------------------------------------ closures
     def _allreduce(self):
-        if self.distributed:
+        if self.distributed and not self.peer_exchange:
             import torch.distributed as dist
 
             dist.all_reduce(self._partial, group=self.group)
 
     def _allreduce_ss(self):
         """all-reduce of the residual-norm partial alone (the last value of ``partial``)"""
-        if self.distributed:
+        if self.distributed and not self.peer_exchange:
             import torch.distributed as dist
 
             dist.all_reduce(self._partial[self.n_features:], group=self.group)
@@ -233,6 +267,9 @@ class DenseLasso:
 
                 run_device_lasso(_Ops(), self._allreduce, self._allreduce_ss)
         st, k = int(status.value), int(nit.value)
+        if st == -3:
+            raise RuntimeError("row-sharded LASSO: a peer rank never published its partials "
+                               "(peer-memory exchange timed out)")
         res = OptimizeResult(
             x=xd if return_device else xd.cpu().numpy(), fun=float(fun.value), nit=k,
             success=st == 1, status=st, message=_message(st), time=time.time() - start,
