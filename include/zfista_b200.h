@@ -200,6 +200,9 @@ int zf_lasso_dev_poll(zf_lasso* h, int32_t slot /*0|1*/, int32_t wait, int32_t* 
                       int64_t* h_nit);
 int zf_lasso_dev_finish(zf_lasso* h, double* d_x, double* h_fun, int64_t* h_nit,
                         int32_t* h_status, double* h_lr, double* h_allerrs, double* h_allfuns);
+/* return_all's allvecs for the NEXT solve with traces: rows x n_cols doubles on the host,
+ * row k = x^k; rows 0 .. min(nit, rows - 1) are written (proximal_gradient.py:471, 522)      */
+int zf_lasso_set_allvecs(zf_lasso* h, double* h_allvecs, int64_t rows);
 /* Row-sharded runs on ONE node: the exchange folded into the kernels over NVLink peer memory
  * instead of an NCCL all-reduce between the stages.  Each rank exports a 64-byte
  * cudaIpcMemHandle_t of its exchange buffer, the caller all-gathers the handles over its control
@@ -237,6 +240,7 @@ int zf_lasso_multi_create(zf_lasso_multi** out, const double* d_A, int64_t n_row
                           int64_t n_cols, const double* d_b, int32_t b_is_batched,
                           int32_t n_runs, double scale, double l1, void* cuda_stream);
 void zf_lasso_multi_destroy(zf_lasso_multi* h);
+int zf_lasso_multi_set_stream(zf_lasso_multi* h, void* cuda_stream);
 int zf_lasso_multi_solve(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
                          int32_t x0_is_batched, const double* h_ab, double* d_x, double* h_fun,
                          int64_t* h_nit, int32_t* h_status, double* h_lr, double* h_err,

@@ -346,3 +346,42 @@ def test_device_decided_loop_equals_host_decided_loop(gpu, n_rows, n_cols):
             np.testing.assert_array_equal(tr.x, x)
             if nit:
                 assert tr.allfuns[-1] == tr.fun
+
+
+def test_return_all_records_the_iterates(gpu):
+    """return_all=True on the large-n path: allvecs = [x^0, ..., x^nit] as the reference records
+    them (proximal_gradient.py:471, 522), with line-search retries in the first iterations (a
+    rejected candidate must not be recorded); a byte budget truncates; "funs" leaves them out."""
+    from oracle import zfista_oracle as zo
+    from zfista_b200.lasso import DenseLasso
+
+    rng = np.random.RandomState(7)
+    n_rows, n_cols = 250, 140
+    A = rng.standard_normal((n_rows, n_cols))
+    w = np.zeros(n_cols)
+    w[:9] = rng.standard_normal(9)
+    b = A @ w + 0.01 * rng.standard_normal(n_rows)
+    scale, l1 = 1 / (2 * n_rows), 0.04
+    spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
+    prob = DenseLasso(A, b, l1, scale=scale)
+    x0 = rng.standard_normal(n_cols) * 0.1
+    for opts in (dict(nesterov=True, lr=16.0), dict(nesterov=False, max_iter=60)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = zo.minimize_proximal_gradient(spec, x0, return_all=True, **opts)
+            res = prob.minimize_proximal_gradient(x0, return_all=True, **opts)
+        assert res.nit == ref["nit"] and len(res.allvecs) == res.nit + 1
+        assert not res.allvecs_truncated
+        _close(np.array(res.allvecs), np.array(ref["allvecs"]))
+        np.testing.assert_array_equal(res.allvecs[0], x0)
+        np.testing.assert_array_equal(res.allvecs[-1], res.x)
+        _close(np.ravel(res.allfuns), np.ravel(ref["allfuns"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cut = prob.minimize_proximal_gradient(x0, return_all=True, nesterov=True,
+                                              allvecs_bytes=5 * n_cols * 8)
+        funs = prob.minimize_proximal_gradient(x0, return_all="funs", nesterov=True)
+    assert len(cut.allvecs) == 5 and cut.allvecs_truncated and len(cut.allerrs) == cut.nit
+    full = prob.minimize_proximal_gradient(x0, return_all=True, nesterov=True)
+    np.testing.assert_array_equal(np.array(cut.allvecs), np.array(full.allvecs[:5]))
+    assert funs.allvecs is None and len(funs.allfuns) == funs.nit + 1

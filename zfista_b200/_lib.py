@@ -64,8 +64,9 @@ EXPORTED_SYMBOLS = [
     "zf_lasso_gradient_device", "zf_lasso_passes",
     "zf_lasso_set_stream", "zf_lasso_dev_begin", "zf_lasso_dev_stage", "zf_lasso_dev_needs_feval",
     "zf_lasso_dev_slots", "zf_lasso_dev_poll", "zf_lasso_dev_finish",
-    "zf_lasso_p2p_export", "zf_lasso_p2p_attach", "zf_lasso_p2p_active",
-    "zf_lasso_multi_create", "zf_lasso_multi_destroy", "zf_lasso_multi_solve",
+    "zf_lasso_p2p_export", "zf_lasso_p2p_attach", "zf_lasso_p2p_active", "zf_lasso_set_allvecs",
+    "zf_lasso_multi_create", "zf_lasso_multi_destroy", "zf_lasso_multi_set_stream",
+    "zf_lasso_multi_solve",
     "zf_lasso_multi_begin", "zf_lasso_multi_grad", "zf_lasso_multi_partial",
     "zf_lasso_multi_step", "zf_lasso_multi_finish", "zf_lasso_multi_gradient_device",
     "zf_lasso_multi_pass_device",
@@ -155,6 +156,8 @@ def _bind_lasso(L):
     L.zf_lasso_dev_slots.argtypes = [V, I32]
     L.zf_lasso_dev_poll.argtypes = [V, I32, I32, c_int32_p, c_int64_p]
     L.zf_lasso_dev_finish.argtypes = [V, V, V, V, V, V, V, V]
+    L.zf_lasso_set_allvecs.argtypes = [V, V, I64]
+    L.zf_lasso_set_allvecs.restype = C.c_int
     L.zf_lasso_p2p_export.argtypes = [V, V]
     L.zf_lasso_p2p_attach.argtypes = [V, I32, I32, V]
     L.zf_lasso_p2p_active.argtypes = [V]
@@ -169,6 +172,8 @@ def _bind_lasso(L):
     L.zf_lasso_multi_create.restype = C.c_int
     L.zf_lasso_multi_destroy.argtypes = [V]
     L.zf_lasso_multi_destroy.restype = None
+    L.zf_lasso_multi_set_stream.argtypes = [V, V]
+    L.zf_lasso_multi_set_stream.restype = C.c_int
     L.zf_lasso_multi_solve.argtypes = [V, C.POINTER(ZfOptions), V, I32, V, V, V, V, V, V, V, V, V]
     L.zf_lasso_multi_solve.restype = C.c_int
     L.zf_lasso_multi_begin.argtypes = [V, C.POINTER(ZfOptions), V, I32, V]

@@ -1188,6 +1188,8 @@ struct LassoDevOpts {
   int max_bt, nesterov, deprecated, need_F, cap;
   double* allerrs;        // device traces (cap, cap + 1) or nullptr
   double* allfuns;
+  double* allvecs;        // (vec_rows x n_cols) iterates x^0 .. or nullptr (zf_lasso_set_allvecs)
+  long long vec_rows;
 };
 
 struct LassoDevState {
@@ -1195,6 +1197,7 @@ struct LassoDevState {
   StepSums sums;          // of the candidate now in x_new
   long long nit;
   int status, phase, bt, accept;
+  long long record_nit;   // > 0: the momentum kernel stores x_new as iterate `record_nit` (allvecs)
   int skip_grad;          // != 0: the gradient pass of this slot has nothing to do (retry / done)
   int done;               // != 0: the solve has ended
   int F_known, result_is_prev;
@@ -1341,6 +1344,7 @@ __device__ __forceinline__ void dv_next_momentum(const LassoDevOpts& o, double t
 __device__ bool dv_accept(const LassoDevOpts& o, LassoDevState* st, double maxd) {
   st->err = maxd;
   const long long nit = st->nit;
+  st->record_nit = (o.allvecs && nit < o.vec_rows) ? nit : 0;
   if (o.cap > 0 && nit <= o.cap) {
     if (o.allerrs) o.allerrs[nit - 1] = maxd;
     if (o.allfuns && st->F_known) o.allfuns[nit] = st->F_x;
@@ -1393,6 +1397,7 @@ __global__ void lasso_dev_init_kernel(const LassoDevOpts* __restrict__ op, Lasso
   st->done = 0;
   st->F_known = 0;
   st->result_is_prev = 0;
+  st->record_nit = 0;
   st->ticket = 0u;
   // (gseq / sseq run on across solves; p2p_error is sticky: the F(x0) exchange precedes this kernel)
   if (st->p2p_error) {
@@ -1541,6 +1546,7 @@ __global__ void lasso_dev_decide_kernel(const LassoDevOpts* __restrict__ op, Las
     return;
   }
   const LassoDevOpts o = *op;
+  st->record_nit = 0;                  // set again by dv_accept if this candidate is accepted
   double ss = 0.0;
   for (int k = 0; k < n_sq; ++k) ss = __dadd_rn(ss, ss_src[k]);
   const double f_x = dv_f_from_ss(ss, o.scale);
@@ -1574,9 +1580,19 @@ __global__ void lasso_dev_decide_kernel(const LassoDevOpts* __restrict__ op, Las
 
 // y = x + mom (x - x_prev), x_prev = x  when the decide kernel accepted the candidate
 __global__ void __launch_bounds__(VEC_THREADS)
-lasso_dev_momentum_kernel(const LassoDevState* __restrict__ st, long long n,
+lasso_dev_momentum_kernel(const LassoDevOpts* __restrict__ op,
+                          const LassoDevState* __restrict__ st, long long n,
                           const double* __restrict__ xn, double* __restrict__ xp,
                           double* __restrict__ y) {
+  // return_all's allvecs: the accepted candidate is iterate `record_nit` (also when the solve
+  // ends with it; slots after the end rewrite the same row with the same values)
+  const long long rec = st->record_nit;
+  if (rec > 0) {
+    double* row = op->allvecs + rec * n;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (long long)gridDim.x * blockDim.x)
+      row[j] = xn[j];
+  }
   if (st->accept == 0 || st->done != 0) return;
   const double mom = st->mom;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
@@ -1664,6 +1680,10 @@ struct zf_lasso {
   double* d_allerrs = nullptr;
   double* d_allfuns = nullptr;
   int dev_cap = 0;
+  double* h_allvecs = nullptr;               // zf_lasso_set_allvecs: host target of the next solve
+  long long h_allvecs_rows = 0;
+  double* d_allvecs = nullptr;
+  long long d_allvecs_rows = 0;
   bool dev_sharded = false, dev_fixed = false, dev_active = false;
   zf::LassoDevOpts dev_opts_host{};
   cudaStream_t st_own = nullptr;             // used when the caller's stream cannot be captured
@@ -2424,6 +2444,7 @@ extern "C" void zf_lasso_destroy(zf_lasso* h) {
   cudaFree(h->d_state);
   cudaFree(h->d_allerrs);
   cudaFree(h->d_allfuns);
+  cudaFree(h->d_allvecs);
   if (h->h_state) cudaFreeHost(h->h_state);
   for (int k = 0; k < 2; ++k) {
     if (h->ev_poll[k]) cudaEventDestroy(h->ev_poll[k]);
@@ -2634,6 +2655,8 @@ extern "C" int zf_lasso_solve(zf_lasso* h, const zf_options* opt, const double* 
     if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
     return lasso_solve_dev(h, opt, d_x0, d_x, h_fun, h_nit, h_status, h_allerrs, h_allfuns);
   }
+  h->h_allvecs = nullptr;          // the host-decided loop does not record iterates
+  h->h_allvecs_rows = 0;
   int rc = lasso_begin_impl(h, opt, d_x0, h_allerrs, h_allfuns);
   if (rc != ZF_OK) return rc;
   int32_t next = 0;
@@ -2764,7 +2787,7 @@ int dev_stage(zf_lasso* h, int stage) {
       ZF_CUDA(cudaGetLastError());
       zf::zf_count_launch();
       zf::lasso_dev_momentum_kernel<<<h->vec_blocks, zf::VEC_THREADS, 0, h->st>>>(
-          h->d_state, h->n_cols, h->xn, h->xp, h->y);
+          h->d_opts, h->d_state, h->n_cols, h->xn, h->xp, h->y);
       ZF_CUDA(cudaGetLastError());
       zf::zf_count_launch();
       return ZF_OK;
@@ -2876,6 +2899,23 @@ extern "C" int zf_lasso_dev_begin(zf_lasso* h, const zf_options* opt, const doub
   o.cap = cap;
   o.allerrs = cap > 0 ? h->d_allerrs : nullptr;
   o.allfuns = cap > 0 ? h->d_allfuns : nullptr;
+  o.allvecs = nullptr;
+  o.vec_rows = 0;
+  if (cap > 0 && h->h_allvecs && h->h_allvecs_rows > 0) {
+    // iterates x^0 .. x^{rows-1} (return_all's allvecs); rows is bounded by the caller's buffer
+    long long rows = h->h_allvecs_rows < (long long)cap + 1 ? h->h_allvecs_rows : (long long)cap + 1;
+    if (rows > h->d_allvecs_rows) {
+      cudaFree(h->d_allvecs);
+      h->d_allvecs = nullptr;
+      h->d_allvecs_rows = 0;
+      ZF_CUDA(cudaMalloc((void**)&h->d_allvecs, sizeof(double) * (size_t)rows * (size_t)h->n_cols));
+      h->d_allvecs_rows = rows;
+    }
+    o.allvecs = h->d_allvecs;
+    o.vec_rows = rows;
+    ZF_CUDA(cudaMemcpyAsync(h->d_allvecs, d_x0, sizeof(double) * (size_t)h->n_cols,
+                            cudaMemcpyDeviceToDevice, h->st));
+  }
   h->dev_fixed = !o.need_F;
   h->xp = h->vecs;
   h->xn = h->vecs + h->n_cols;
@@ -2979,11 +3019,29 @@ extern "C" int zf_lasso_dev_finish(zf_lasso* h, double* d_x, double* h_fun, int6
   if (h_allfuns && h->dev_opts_host.cap > 0)
     ZF_CUDA(cudaMemcpyAsync(h_allfuns, h->d_allfuns, sizeof(double) * (size_t)(k + 1),
                             cudaMemcpyDeviceToHost, h->st));
+  if (h->dev_opts_host.allvecs && h->h_allvecs) {
+    long long rows = s.nit + 1 < h->dev_opts_host.vec_rows ? s.nit + 1 : h->dev_opts_host.vec_rows;
+    ZF_CUDA(cudaMemcpyAsync(h->h_allvecs, h->d_allvecs,
+                            sizeof(double) * (size_t)rows * (size_t)h->n_cols,
+                            cudaMemcpyDeviceToHost, h->st));
+  }
+  h->h_allvecs = nullptr;                  // one solve per zf_lasso_set_allvecs
+  h->h_allvecs_rows = 0;
   ZF_CUDA(cudaStreamSynchronize(h->st));
   if (h_fun) *h_fun = s.F_x;
   if (h_nit) *h_nit = s.nit;
   if (h_status) *h_status = s.status;
   if (h_lr) *h_lr = s.lr;
+  return ZF_OK;
+}
+
+/* return_all's allvecs for the NEXT device-decided solve with traces (zf_lasso_solve with
+ * h_allerrs / h_allfuns, or zf_lasso_dev_begin(want_trace = 1)): rows x n_cols doubles on the
+ * host, row k = x^k, rows 0 .. min(nit, rows - 1) are written (proximal_gradient.py:471, 522). */
+extern "C" int zf_lasso_set_allvecs(zf_lasso* h, double* h_allvecs, int64_t rows) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  h->h_allvecs = rows > 0 ? h_allvecs : nullptr;
+  h->h_allvecs_rows = h_allvecs ? rows : 0;
   return ZF_OK;
 }
 

@@ -962,6 +962,15 @@ extern "C" int zf_lasso_multi_grad(zf_lasso_multi* h, int which) {
   return zf::zf_fail(ZF_ERR_INVALID, "which must be 0 or 1");
 }
 
+/* the stream every later call enqueues on (callers whose current stream changes hand it over) */
+extern "C" int zf_lasso_multi_set_stream(zf_lasso_multi* h, void* cuda_stream) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (h->phase != MP_IDLE && h->phase != MP_DONE)
+    return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_set_stream during a solve");
+  h->st = (cudaStream_t)cuda_stream;
+  return ZF_OK;
+}
+
 extern "C" double* zf_lasso_multi_partial(zf_lasso_multi* h, int64_t* n_values) {
   if (!h) return nullptr;
   if (n_values) *n_values = (int64_t)h->kp * h->pitch_c + h->kp;

@@ -199,10 +199,11 @@ class DenseLasso:
                                    max_backtrack_iter=100, warm_start=False, decay_rate=0.5,
                                    nesterov=False, nesterov_ratio=(0, 0.25), return_all=False,
                                    verbose=False, deprecated=False, trace_capacity=None,
-                                   return_device=False) -> OptimizeResult:
+                                   return_device=False, allvecs_bytes=512 << 20) -> OptimizeResult:
         """Same keyword arguments and OptimizeResult fields as the reference
-        (proximal_gradient.py:311-555).  ``allvecs`` is not recorded on this path (n is
-        large); ``allerrs`` / ``allfuns`` are."""
+        (proximal_gradient.py:311-555).  ``return_all=True`` records ``allerrs``, ``allfuns``
+        and -- as long as they fit ``allvecs_bytes`` (default 512 MiB; n is large on this path)
+        -- the iterates ``allvecs``; ``return_all="funs"`` leaves the iterates out."""
         from .proximal_gradient import _make_options, _message
 
         torch = _torch()
@@ -221,6 +222,11 @@ class DenseLasso:
                              nesterov_ratio, deprecated, "reference", cap)
         allerrs = np.zeros(cap) if cap else None
         allfuns = np.zeros(cap + 1) if cap else None
+        # iterates: at most allvecs_bytes of them (rows x^0 .. x^{vec_rows - 1})
+        vec_rows = 0
+        if return_all is True and cap:
+            vec_rows = int(min(cap + 1, max(1, allvecs_bytes // (8 * self.n_features))))
+        allvecs = np.zeros((vec_rows, self.n_features)) if vec_rows else None
         xd = torch.empty_like(x0d)
         fun = C.c_double()
         nit = C.c_int64()
@@ -228,6 +234,9 @@ class DenseLasso:
         L = _lib.lib()
         with torch.cuda.device(self.device):
             self._use_current_stream()
+            if allvecs is not None:
+                _lib.check(L.zf_lasso_set_allvecs(self._h, allvecs.ctypes.data_as(C.c_void_p),
+                                                  vec_rows))
             if not self.distributed:
                 _lib.check(L.zf_lasso_solve(
                     self._h, C.byref(opts), C.c_void_p(x0d.data_ptr()), C.c_void_p(xd.data_ptr()),
@@ -277,6 +286,9 @@ class DenseLasso:
         if return_all:
             res.allerrs = list(allerrs[:k])
             res.allfuns = list(allfuns[:k + 1])
+            if allvecs is not None:
+                res.allvecs = list(allvecs[:min(k + 1, vec_rows)])
+                res.allvecs_truncated = k + 1 > vec_rows
         if verbose:
             print(f"|{'niter':^7}|{'max(abs(xk - yk)))':^20}|")
             for i, e in enumerate(allerrs[:k], start=1):
@@ -360,6 +372,13 @@ class DenseLassoMulti:
 
             dist.all_reduce(self._partial, group=self.group)
 
+    def _use_current_stream(self):
+        """as DenseLasso._use_current_stream: the library enqueues on torch's CURRENT stream"""
+        stream = _torch().cuda.current_stream(self.device).cuda_stream
+        if stream != self._stream:
+            _lib.check(_lib.lib().zf_lasso_multi_set_stream(self._h, C.c_void_p(stream)))
+            self._stream = stream
+
     def _x_batch(self, x):
         """(tensor, is_batched): one vector shared by all runs or (n_runs, n_features)."""
         torch = _torch()
@@ -380,9 +399,11 @@ class DenseLassoMulti:
             xd = xd.expand(self.n_runs, -1).contiguous()
         grad = torch.empty(self.n_runs, self.n_features, dtype=torch.float64, device=self.device)
         fval = torch.empty(self.n_runs, dtype=torch.float64, device=self.device)
-        _lib.check(_lib.lib().zf_lasso_multi_gradient_device(
-            self._h, C.c_void_p(xd.data_ptr()), C.c_void_p(grad.data_ptr()),
-            C.c_void_p(fval.data_ptr())))
+        with torch.cuda.device(self.device):
+            self._use_current_stream()
+            _lib.check(_lib.lib().zf_lasso_multi_gradient_device(
+                self._h, C.c_void_p(xd.data_ptr()), C.c_void_p(grad.data_ptr()),
+                C.c_void_p(fval.data_ptr())))
         return grad, fval
 
     def minimize_proximal_gradient_batched(self, x0, nesterov_ratios=None, lr=1, tol=1e-5,
@@ -425,6 +446,7 @@ class DenseLassoMulti:
             allfuns = np.zeros((K, cap + 1)) if cap else None
             p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
             with torch.cuda.device(self.device):
+                self._use_current_stream()
                 if not self.distributed:
                     _lib.check(L.zf_lasso_multi_solve(
                         self._h, C.byref(opts), C.c_void_p(x0d.data_ptr()), int(batched), p(ab),
