@@ -211,3 +211,72 @@ def test_large_a_properties(gpu):
         gs, fs = single.gradient(X[k])
         _close(G16[k], gs.cpu().numpy(), rel=1e-11)
         _close(f16[k], fs.item(), rel=1e-12)
+
+
+def test_device_decided_rounds_equal_host_decided_rounds(gpu):
+    """zf_lasso_multi_solve runs the device-decided rounds (per-run scalars and the run masks in
+    device memory, one-warp decision kernels, the host polling one chunk of trials behind); the
+    split begin / grad / step / finish entry points still decide on the host.  Same bits: nit,
+    status, x, F, lr of every run -- runs retrying their line search and stopping at different
+    rounds, a fixed step, failures, max_iter, traces."""
+    import ctypes as C
+
+    import torch
+
+    from zfista_b200 import _lib
+    from zfista_b200.lasso import DenseLassoMulti
+    from zfista_b200.proximal_gradient import _make_options
+
+    n_rows, n_cols = 310, 144
+    grid = helpers.AB_GRID[:11]
+    K = len(grid)
+    A, b, X0 = _dataset(77, n_rows, n_cols, K, True)
+    scale, l1 = 1 / (2 * n_rows), 0.05
+    prob = DenseLassoMulti(A, b, l1, K, scale=scale)
+    L = _lib.lib()
+    lip = 2 * scale * np.linalg.norm(A, 2) ** 2
+    ab = np.ascontiguousarray(np.array(grid, dtype=np.float64))
+
+    def host_rounds(opts):
+        o = _make_options(opts.get("lr", 1), opts.get("tol", 1e-5), 1e-12,
+                          opts.get("max_iter", 1000000), 100000,
+                          opts.get("max_backtrack_iter", 100), False, opts.get("decay_rate", 0.5),
+                          opts.get("nesterov", False), (0, 0.25), opts.get("deprecated", False),
+                          "reference", 0)
+        x0d = torch.from_numpy(X0).cuda()
+        xd = torch.empty_like(x0d)
+        fun, lrs, err = np.empty(K), np.empty(K), np.empty(K)
+        nit, status = np.zeros(K, dtype=np.int64), np.zeros(K, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        nxt = C.c_int32(0)
+        _lib.check(L.zf_lasso_multi_begin(prob._h, C.byref(o), C.c_void_p(x0d.data_ptr()), 1, p(ab)))
+        _lib.check(L.zf_lasso_multi_step(prob._h, C.byref(nxt)))
+        while nxt.value != 2:
+            _lib.check(L.zf_lasso_multi_grad(prob._h, nxt.value))
+            _lib.check(L.zf_lasso_multi_step(prob._h, C.byref(nxt)))
+        _lib.check(L.zf_lasso_multi_finish(prob._h, C.c_void_p(xd.data_ptr()), p(fun), p(nit),
+                                           p(status), p(lrs), p(err)))
+        return xd.cpu().numpy(), fun, nit, status, lrs
+
+    cases = [dict(nesterov=True), dict(nesterov=False, max_iter=30),
+             dict(nesterov=True, lr=1 / lip, decay_rate=1, max_iter=250),
+             dict(nesterov=True, lr=1 / lip, decay_rate=1, max_iter=19, tol=0.0),
+             dict(nesterov=True, deprecated=True, lr=8.0),
+             dict(nesterov=True, lr=1e9, max_backtrack_iter=3)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for opts in cases + cases[:2]:
+            got = prob.minimize_proximal_gradient_batched(X0, grid, **opts)
+            x, fun, nit, status, lrs = host_rounds(opts)
+            assert [r.nit for r in got] == nit.tolist(), (opts, [r.nit for r in got], nit.tolist())
+            assert [r.status for r in got] == status.tolist()
+            for k, r in enumerate(got):
+                np.testing.assert_array_equal(r.x, x[k])
+                assert r.fun == fun[k] and r.lr == lrs[k], (opts, k)
+            tr = prob.minimize_proximal_gradient_batched(X0, grid, return_all=True, **opts)
+            for k, r in enumerate(tr):
+                assert r.nit == nit[k] and len(r.allerrs) == nit[k]
+                np.testing.assert_array_equal(r.x, x[k])
+                if nit[k]:
+                    assert r.allfuns[-1] == r.fun
+    assert len(set(nit.tolist())) >= 1

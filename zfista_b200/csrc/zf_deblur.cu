@@ -460,7 +460,7 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, const __grid_constan
     __syncthreads();
     // ---- 5. gradient coefficients = 2 * dwt2(Wimg) per 2x2 block, and the prox candidate
     double* xn = B.X[st.nxt] + (long long)run * d.n;
-    const double lr = st.lr, thr = c.l1 * lr;
+    const double lr = st.lr, thr = __dmul_rn(c.l1, lr);
     for (int blk = tid; blk < (T / 2) * (T / 2); blk += DB_THREADS) {
       const int bi = blk / (T / 2), bj = blk % (T / 2);
       const int gi = tyo + 2 * bi, gj = txo + 2 * bj;
@@ -484,7 +484,7 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, const __grid_constan
           const long long oo = sb * q + o;
           const double yj = db_extrap(xa[oo], xb[oo], mom);
           const double gj4 = g4[sb];
-          const double xj = soft_threshold(yj - lr * gj4, thr);
+          const double xj = soft_threshold(fma(-lr, gj4, yj), thr);
           const double dd = xj - yj;
           xn[oo] = xj;
           if (c.store_yg) {
@@ -556,12 +556,12 @@ deblur_prox_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B) {
   double* xn = B.X[st.nxt] + (long long)run * d.n;
   const double* y = B.Y + (long long)run * d.n;
   const double* g = B.G + (long long)run * d.n;
-  const double lr = st.lr, thr = c.l1 * lr;
+  const double lr = st.lr, thr = __dmul_rn(c.l1, lr);
   DeblurSums s{0.0, 0.0, 0.0, 0.0};
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < d.n;
        j += (long long)gridDim.x * blockDim.x) {
     const double gj = g[j], yj = y[j];
-    const double xj = soft_threshold(yj - lr * gj, thr);
+    const double xj = soft_threshold(fma(-lr, gj, yj), thr);
     const double dd = xj - yj;
     xn[j] = xj;
     s.gd += gj * dd;

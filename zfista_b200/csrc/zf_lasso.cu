@@ -1444,7 +1444,9 @@ lasso_dev_update_kernel(const LassoDevOpts* __restrict__ op, LassoDevState* st,
       peer_data[r] = (r < pp.world) ? pp.buf[r]->data + (gseq & 1ull) * pp.stride : nullptr;
   }
   const double two_scale = 2.0 * o.scale;
-  const double thresh = o.l1 * lr;
+  // the rounded product, as the host-decided loop passes it and as numpy forms l1 * lr: nvcc must
+  // not contract it into the subtraction inside soft_threshold
+  const double thresh = __dmul_rn(o.l1, lr);
   double t_new = 0.0, mom = 0.0;
   if (FIXED) dv_next_momentum(o, st->t_prev, &t_new, &mom);
   StepSums s{0.0, 0.0, 0.0, 0.0};

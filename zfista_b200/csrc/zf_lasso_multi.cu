@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 multi_residual_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmV,
                       long long n_rows, long long n_cols, const double* __restrict__ b,
                       long long b_stride, double* __restrict__ R, long long pitch_r,
-                      double* __restrict__ sq_part) {
+                      double* __restrict__ sq_part, const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop
   using C_ = Cfg<NT>;
   constexpr int KP = C_::KP, NS = C_::NS1, BOX_A = C_::BOX_A, BOX_V = C_::BOX_V, STAGE = C_::STAGE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -278,7 +279,8 @@ template <int NT>
 __global__ void __launch_bounds__(THREADS, 1)
 multi_atr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR,
                  long long n_rows, long long n_cols, long long rows_per_split, int n_splits,
-                 double* __restrict__ gpart, long long pitch_c) {
+                 double* __restrict__ gpart, long long pitch_c, const int* __restrict__ skip) {
+  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop
   using C_ = Cfg<NT>;
   constexpr int KP = C_::KP, NS = C_::NS2, BOX_A = C_::BOX_A, BOX_R = C_::BOX_V, STAGE = C_::STAGE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -448,7 +450,9 @@ multi_prox_kernel(StepArgs a, const double* __restrict__ Y, const double* __rest
   const double* y = Y + (long long)k * pitch_c;
   const double* gs = src + (long long)k * pitch_c;
   double* go = g_out ? g_out + (long long)k * pitch_c : nullptr;
-  const double lr = a.lr[k], thresh = lr * l1;
+  // (thresh is the ROUNDED product, as numpy forms l1 * lr; left to nvcc it may or may not be
+  // contracted into the subtraction inside soft_threshold, differently in different kernels)
+  const double lr = a.lr[k], thresh = __dmul_rn(lr, l1);
   StepSums s{0.0, 0.0, 0.0, 0.0};
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
@@ -457,12 +461,12 @@ multi_prox_kernel(StepArgs a, const double* __restrict__ Y, const double* __rest
     } else {
       const double gj = gs[j] * two_scale;
       const double yj = y[j];
-      const double xj = soft_threshold(yj - lr * gj, thresh);
+      const double xj = soft_threshold(fma(-lr, gj, yj), thresh);
       const double d = xj - yj;
       xn[j] = xj;
       if (go) go[j] = gj;
-      s.gd += gj * d;
-      s.dd += d * d;
+      s.gd = fma(gj, d, s.gd);
+      s.dd = fma(d, d, s.dd);
       s.abs1 += fabs(xj);
       s.maxd = fmax(s.maxd, fabs(d));
     }
@@ -513,9 +517,308 @@ multi_momentum_kernel(StepArgs a, double* __restrict__ Xp, const double* __restr
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
     const double xj = xn[j];
-    y[j] = xj + mom * (xj - xp[j]);
+    y[j] = fma(mom, xj - xp[j], xj);
     xp[j] = xj;
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-decided rounds (as zf_lasso.cu's zf_lasso_dev_*, for K runs in lockstep): the per-run
+// scalars of proximal_gradient.py:474-538 and the run masks (active / on trial / advancing) live
+// in device memory, one-warp kernels take the decisions lane k for run k, the n_cols-sized
+// kernels read their step sizes, momentum factors and masks from there.  A slot is
+//   [gradient of all runs at Y: two DGEMM passes + collect]   (skipped while a retry is pending)
+//   prox of the runs on trial -> after_prox (sums, f(y), subproblem values; fixed step: accept)
+//   [residual DGEMM at the candidates + collect -> decide]    (line search / F trace only)
+//   momentum of the runs that advance
+// and slots enqueued after every run has ended do nothing.  Scalar arithmetic in *_rn
+// intrinsics: bit for bit the host-decided loop below.
+// ---------------------------------------------------------------------------------------
+enum { MD_GRAD = 0, MD_RETRY = 1, MD_DONE = 2 };
+
+struct MultiDevOpts {
+  double lr0, tol, tol_internal, decay, scale, l1;
+  long long max_iter, pitch_c, n;
+  int max_bt, nesterov, deprecated, need_F, cap, n_runs, kp, pad;
+  double* allerrs;             // [n_runs][cap]
+  double* allfuns;             // [n_runs][cap + 1]
+  double na[MAX_RUNS], nb[MAX_RUNS];
+};
+
+struct MultiDevRun {
+  double lr, t_prev, F_prev, F_x, f_y, sub_fun, err, mom;
+  StepSums sums;
+  long long nit;
+  int status, bt, F_known, result_is_prev;
+};
+
+struct MultiDevState {
+  MultiDevRun run[MAX_RUNS];
+  unsigned active, trial, accepted, adv;
+  int phase, skip_grad, done, pad;
+};
+
+__device__ __forceinline__ double md_f_from_ss(double ss, double scale) {
+  const double nrm = __dsqrt_rn(ss);
+  return __dmul_rn(__dmul_rn(nrm, nrm), scale);
+}
+
+__device__ __forceinline__ double md_subproblem_fun(const MultiDevOpts& o, const MultiDevRun& r) {
+  const double nrm = __dsqrt_rn(r.sums.dd);
+  double fun = __dadd_rn(__dadd_rn(r.sums.gd, __dmul_rn(o.l1, r.sums.abs1)),
+                         __ddiv_rn(__ddiv_rn(__dmul_rn(nrm, nrm), 2.0), r.lr));
+  if (!o.deprecated) fun = __dadd_rn(fun, __dsub_rn(r.f_y, r.F_prev));
+  return fun;
+}
+
+// one warp, lane k = run k: the runs in `accepted` have an accepted candidate -- stop tests,
+// traces, t_{k+1}; then the masks and the phase of the next slot
+__device__ void md_advance(const MultiDevOpts& o, MultiDevState* st, unsigned accepted, int lane) {
+  bool stops = false, advances = false;
+  if (lane < o.n_runs && ((accepted >> lane) & 1u)) {
+    MultiDevRun& r = st->run[lane];
+    r.err = r.sums.maxd;
+    if (o.cap > 0 && r.nit <= o.cap) {
+      if (o.allerrs) o.allerrs[(long long)lane * o.cap + r.nit - 1] = r.err;
+      if (o.allfuns && r.F_known) o.allfuns[(long long)lane * (o.cap + 1) + r.nit] = r.F_x;
+    }
+    const bool converged = r.err < o.tol;
+    if (converged || r.nit >= o.max_iter) {
+      r.status = converged ? 1 : 0;
+      stops = true;
+    } else {
+      double mom = 0.0;
+      if (o.nesterov) {
+        const double t = r.t_prev;
+        const double tn = __dadd_rn(
+            __dsqrt_rn(__dadd_rn(__dsub_rn(__dmul_rn(t, t), __dmul_rn(o.na[lane], t)), o.nb[lane])), 0.5);
+        mom = __ddiv_rn(__dsub_rn(t, 1.0), tn);
+        r.t_prev = tn;
+      }
+      r.mom = mom;
+      r.F_prev = r.F_x;
+      r.nit += 1;
+      advances = true;
+    }
+  }
+  const unsigned stop_mask = __ballot_sync(0xffffffffu, stops);
+  const unsigned adv_mask = __ballot_sync(0xffffffffu, advances);
+  if (lane == 0) {
+    st->active &= ~stop_mask;
+    st->adv = adv_mask;
+    st->accepted = 0u;
+    st->trial = 0u;
+    if (st->active) {
+      st->phase = MD_GRAD;
+      st->skip_grad = 0;
+    } else {
+      st->phase = MD_DONE;
+      st->skip_grad = 1;
+      st->done = 1;
+    }
+  }
+}
+
+__global__ void multi_dev_init_kernel(const MultiDevOpts* __restrict__ op, MultiDevState* st,
+                                      const StepSums* __restrict__ sums,
+                                      const double* __restrict__ ss) {
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0 || lane >= 32) return;
+  const MultiDevOpts& o = *op;
+  if (lane < o.n_runs) {
+    MultiDevRun& r = st->run[lane];
+    const double F0 = __dadd_rn(md_f_from_ss(ss[lane], o.scale), __dmul_rn(o.l1, sums[lane].abs1));
+    r.lr = o.lr0; r.t_prev = 1.0; r.F_prev = F0; r.F_x = F0; r.f_y = 0.0; r.sub_fun = 0.0;
+    r.err = CUDART_INF; r.mom = 0.0; r.sums = sums[lane]; r.nit = 1; r.status = 0; r.bt = 0;
+    r.F_known = 0; r.result_is_prev = 0;
+    if (o.cap > 0 && o.allfuns) o.allfuns[(long long)lane * (o.cap + 1)] = F0;
+  }
+  if (lane == 0) {
+    st->active = (o.n_runs == 32) ? 0xffffffffu : ((1u << o.n_runs) - 1u);
+    st->trial = 0u; st->accepted = 0u; st->adv = 0u;
+    st->phase = MD_GRAD; st->skip_grad = 0; st->done = 0;
+  }
+}
+
+// prox of the runs on trial: first trial of an iteration (phase GRAD: every active run, g from
+// the collected partials, stored to G) or a retry (the runs still on trial, g from G)
+__global__ void __launch_bounds__(VEC_THREADS)
+multi_dev_prox_kernel(const MultiDevOpts* __restrict__ op, const MultiDevState* __restrict__ st,
+                      const double* __restrict__ Y, double* __restrict__ Xn,
+                      const double* __restrict__ partial, double* __restrict__ G,
+                      StepSums* __restrict__ block_sums, unsigned int* __restrict__ counter,
+                      StepSums* __restrict__ out) {
+  if (st->done != 0) return;
+  const int k = blockIdx.y;
+  const bool first = (st->phase == MD_GRAD);
+  const unsigned mask = first ? st->active : st->trial;
+  if (!((mask >> k) & 1u)) return;
+  __shared__ StepSums sh[VEC_THREADS / 32];
+  __shared__ bool is_last;
+  const long long pitch_c = op->pitch_c, n = op->n;
+  double* xn = Xn + (long long)k * pitch_c;
+  const double* y = Y + (long long)k * pitch_c;
+  const double* gs = (first ? partial : G) + (long long)k * pitch_c;
+  double* go = G + (long long)k * pitch_c;
+  const double two_scale = first ? 2.0 * op->scale : 1.0;
+  const double lr = st->run[k].lr, thresh = __dmul_rn(lr, op->l1);
+  StepSums s{0.0, 0.0, 0.0, 0.0};
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double gj = gs[j] * two_scale;
+    const double yj = y[j];
+    const double xj = soft_threshold(fma(-lr, gj, yj), thresh);
+    const double d = xj - yj;
+    xn[j] = xj;
+    if (first) go[j] = gj;
+    s.gd = fma(gj, d, s.gd);
+    s.dd = fma(d, d, s.dd);
+    s.abs1 += fabs(xj);
+    s.maxd = fmax(s.maxd, fabs(d));
+  }
+  s.gd = warp_sum(s.gd);
+  s.dd = warp_sum(s.dd);
+  s.abs1 = warp_sum(s.abs1);
+  s.maxd = warp_max(s.maxd);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    StepSums t = sh[0];
+    for (int w = 1; w < VEC_THREADS / 32; ++w) {
+      t.gd += sh[w].gd; t.dd += sh[w].dd; t.abs1 += sh[w].abs1; t.maxd = fmax(t.maxd, sh[w].maxd);
+    }
+    block_sums[(long long)k * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    is_last = (atomicAdd(&counter[k], 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    const StepSums* bs = block_sums + (long long)k * gridDim.x;
+    StepSums t = bs[0];
+    for (unsigned int i = 1; i < gridDim.x; ++i) {
+      const StepSums u = bs[i];
+      t.gd += u.gd; t.dd += u.dd; t.abs1 += u.abs1; t.maxd = fmax(t.maxd, u.maxd);
+    }
+    out[k] = t;
+    counter[k] = 0u;
+  }
+}
+
+// one warp after the prox: the trial runs' sums, f(y) (first trial) and subproblem values; with a
+// fixed step and no F trace every trial is accepted here
+__global__ void multi_dev_after_prox_kernel(const MultiDevOpts* __restrict__ op, MultiDevState* st,
+                                            const StepSums* __restrict__ sums,
+                                            const double* __restrict__ ss) {
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0 || lane >= 32 || st->done != 0) return;
+  const MultiDevOpts& o = *op;
+  const bool first = (st->phase == MD_GRAD);
+  const unsigned mask = first ? st->active : st->trial;
+  if (lane < o.n_runs && ((mask >> lane) & 1u)) {
+    MultiDevRun& r = st->run[lane];
+    r.sums = sums[lane];
+    if (first) {
+      r.bt = 0;
+      r.f_y = md_f_from_ss(ss[lane], o.scale);
+      r.F_known = 0;
+    }
+    r.sub_fun = md_subproblem_fun(o, r);
+  }
+  __syncwarp();
+  if (!o.need_F) {
+    md_advance(o, st, mask, lane);
+  } else if (lane == 0) {
+    st->trial = mask;
+    st->adv = 0u;
+  }
+}
+
+// one warp after the residual pass at the candidates: F(x_new) and the line-search test of every
+// run on trial; accepted runs wait until no run is on trial any more, then all advance together
+__global__ void multi_dev_decide_kernel(const MultiDevOpts* __restrict__ op, MultiDevState* st,
+                                        const double* __restrict__ ss) {
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0 || lane >= 32 || st->done != 0) return;
+  const MultiDevOpts& o = *op;
+  const unsigned trial = st->trial;
+  bool acc = false, fail = false;
+  if (lane < o.n_runs && ((trial >> lane) & 1u)) {
+    MultiDevRun& r = st->run[lane];
+    const double f_x = md_f_from_ss(ss[lane], o.scale);
+    r.F_x = __dadd_rn(f_x, __dmul_rn(o.l1, r.sums.abs1));
+    r.F_known = 1;
+    bool ok;
+    if (o.decay == 1.0) ok = true;                                        // proximal_gradient.py:298
+    else if (o.deprecated) ok = (__dsub_rn(f_x, r.f_y) <= __dadd_rn(r.sub_fun, o.tol_internal));
+    else ok = (__dsub_rn(r.F_x, r.F_prev) <= __dadd_rn(r.sub_fun, o.tol_internal));
+    if (ok) {
+      acc = true;
+    } else {
+      r.lr = __dmul_rn(r.lr, o.decay);
+      r.bt += 1;
+      if (r.bt >= o.max_bt) {
+        // RuntimeError("Backtracking failed ...") -> x = x_prev, nit - 1 (proximal_gradient.py:493-509)
+        r.result_is_prev = 1;
+        r.F_x = r.F_prev;
+        r.nit -= 1;
+        r.status = -1;
+        fail = true;
+      }
+    }
+  }
+  const unsigned acc_mask = __ballot_sync(0xffffffffu, acc);
+  const unsigned fail_mask = __ballot_sync(0xffffffffu, fail);
+  const unsigned left = trial & ~(acc_mask | fail_mask);
+  const unsigned accepted = st->accepted | acc_mask;
+  __syncwarp();
+  if (lane == 0) {
+    st->active &= ~fail_mask;
+    st->accepted = accepted;
+    st->trial = left;
+  }
+  __syncwarp();
+  if (left) {
+    if (lane == 0) {
+      st->phase = MD_RETRY;          // same gradients, smaller steps for the runs still on trial
+      st->skip_grad = 1;
+      st->adv = 0u;
+    }
+  } else {
+    md_advance(o, st, accepted, lane);
+  }
+}
+
+// y = x_new + mom (x_new - x_prev), x_prev = x_new for the runs that advance
+__global__ void __launch_bounds__(VEC_THREADS)
+multi_dev_momentum_kernel(const MultiDevOpts* __restrict__ op, const MultiDevState* __restrict__ st,
+                          double* __restrict__ Xp, const double* __restrict__ Xn,
+                          double* __restrict__ Y) {
+  const int k = blockIdx.y;
+  if (!((st->adv >> k) & 1u)) return;
+  const long long pitch_c = op->pitch_c, n = op->n;
+  double* xp = Xp + (long long)k * pitch_c;
+  const double* xn = Xn + (long long)k * pitch_c;
+  double* y = Y + (long long)k * pitch_c;
+  const double mom = st->run[k].mom;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double xj = xn[j];
+    y[j] = fma(mom, xj - xp[j], xj);
+    xp[j] = xj;
+  }
+}
+
+// res.fun of the runs that never evaluated F at their result
+__global__ void multi_dev_final_kernel(const MultiDevOpts* __restrict__ op, MultiDevState* st,
+                                       const double* __restrict__ ss) {
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0 || lane >= op->n_runs) return;
+  MultiDevRun& r = st->run[lane];
+  if (r.F_known || r.result_is_prev) return;
+  r.F_x = __dadd_rn(md_f_from_ss(ss[lane], op->scale), __dmul_rn(op->l1, r.sums.abs1));
+  r.F_known = 1;
 }
 
 // grad[k][j] = partial[k][j] * 2*scale ; f[k] = ||r_k||^2 * scale   (bench / closures)
@@ -582,6 +885,15 @@ struct zf_lasso_multi {
   RunState run[zf::multi::MAX_RUNS];
   double* h_allerrs = nullptr;
   double* h_allfuns = nullptr;
+  // device-decided rounds
+  const int* skip = nullptr;                     // flag the DGEMM passes test
+  zf::multi::MultiDevOpts* d_opts = nullptr;
+  zf::multi::MultiDevState* d_state = nullptr;
+  zf::multi::MultiDevState* h_state = nullptr;   // pinned, 2 snapshots
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+  double* d_allerrs = nullptr;
+  double* d_allfuns = nullptr;
+  size_t dev_trace = 0;
 };
 
 namespace {
@@ -604,7 +916,7 @@ int launch_residual_t(zf_lasso_multi* h, int which) {
                                (int)Cfg<NT>::P1_SMEM));
   k<<<h->grid, zf::multi::THREADS, Cfg<NT>::P1_SMEM, h->st>>>(
       h->tmA, which == 0 ? h->tmY : h->tmXn, h->n_rows, h->n_cols, h->bcopy,
-      h->b_batched ? h->pitch_r : 0, h->R, h->pitch_r, h->sq_part);
+      h->b_batched ? h->pitch_r : 0, h->R, h->pitch_r, h->sq_part, h->skip);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -625,7 +937,8 @@ int launch_atr_t(zf_lasso_multi* h) {
   ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)Cfg<NT>::P2_SMEM));
   k<<<h->grid, zf::multi::THREADS, Cfg<NT>::P2_SMEM, h->st>>>(
-      h->tmA, h->tmR, h->n_rows, h->n_cols, h->rows_per_split, h->n_splits, h->gpart, h->pitch_c);
+      h->tmA, h->tmR, h->n_rows, h->n_cols, h->rows_per_split, h->n_splits, h->gpart, h->pitch_c,
+      h->skip);
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
@@ -928,6 +1241,13 @@ extern "C" int zf_lasso_multi_create(zf_lasso_multi** out, const double* d_A, in
 
 extern "C" void zf_lasso_multi_destroy(zf_lasso_multi* h) {
   if (!h) return;
+  cudaFree(h->d_opts);
+  cudaFree(h->d_state);
+  cudaFree(h->d_allerrs);
+  cudaFree(h->d_allfuns);
+  if (h->h_state) cudaFreeHost(h->h_state);
+  for (int k = 0; k < 2; ++k)
+    if (h->ev_poll[k]) cudaEventDestroy(h->ev_poll[k]);
   cudaFree(h->vecs);
   cudaFree(h->bcopy);
   cudaFree(h->R);
@@ -1119,11 +1439,182 @@ extern "C" int zf_lasso_multi_finish(zf_lasso_multi* h, double* d_x, double* h_f
   return ZF_OK;
 }
 
+// ---- device-decided rounds (single GPU): nothing in the loop waits for the GPU except the poll
+namespace {
+
+int multi_dev_alloc(zf_lasso_multi* h) {
+  if (h->d_state) return ZF_OK;
+  ZF_CUDA(cudaMalloc((void**)&h->d_opts, sizeof(zf::multi::MultiDevOpts)));
+  ZF_CUDA(cudaMalloc((void**)&h->d_state, sizeof(zf::multi::MultiDevState)));
+  ZF_CUDA(cudaMemset(h->d_state, 0, sizeof(zf::multi::MultiDevState)));
+  ZF_CUDA(cudaMallocHost((void**)&h->h_state, 2 * sizeof(zf::multi::MultiDevState)));
+  for (int k = 0; k < 2; ++k)
+    ZF_CUDA(cudaEventCreateWithFlags(&h->ev_poll[k], cudaEventDisableTiming));
+  return ZF_OK;
+}
+
+// one trial of the runs on trial
+int multi_dev_slot(zf_lasso_multi* h, bool need_F) {
+  using namespace zf::multi;
+  const double* ss = h->partial + (long long)h->kp * h->pitch_c;
+  dim3 vgrid(VEC_BLOCKS, (unsigned)h->n_runs);
+  h->skip = &h->d_state->skip_grad;
+  int rc = gradient_pass(h);                          // both DGEMM passes + collect (or nothing)
+  h->skip = nullptr;
+  if (rc != ZF_OK) return rc;
+  multi_dev_prox_kernel<<<vgrid, VEC_THREADS, 0, h->st>>>(h->d_opts, h->d_state, h->Y, h->Xn,
+                                                          h->partial, h->G, h->block_sums,
+                                                          h->counter, h->d_sums);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  multi_dev_after_prox_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  if (need_F) {
+    h->skip = &h->d_state->done;
+    rc = launch_residual(h, 1);
+    h->skip = nullptr;
+    if (rc != ZF_OK) return rc;
+    rc = launch_collect(h, false);
+    if (rc != ZF_OK) return rc;
+    multi_dev_decide_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss);
+    ZF_CUDA(cudaGetLastError());
+    zf::zf_count_launch();
+  }
+  multi_dev_momentum_kernel<<<vgrid, VEC_THREADS, 0, h->st>>>(h->d_opts, h->d_state, h->Xp, h->Xn, h->Y);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  return ZF_OK;
+}
+
+int multi_solve_dev(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                    int32_t x0_is_batched, const double* h_ab, double* d_x, double* h_fun,
+                    int64_t* h_nit, int32_t* h_status, double* h_lr, double* h_err,
+                    double* h_allerrs, double* h_allfuns) {
+  using namespace zf::multi;
+  if (!h || !d_x0) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
+  int rc = check_options(opt);
+  if (rc != ZF_OK) return rc;
+  rc = multi_dev_alloc(h);
+  if (rc != ZF_OK) return rc;
+  h->opt = *opt;
+  const int cap = (h_allerrs || h_allfuns) ? opt->trace_capacity : 0;
+  const size_t need = (size_t)h->n_runs * ((size_t)cap + 1);
+  if (cap > 0 && need > h->dev_trace) {
+    cudaFree(h->d_allerrs);
+    cudaFree(h->d_allfuns);
+    h->d_allerrs = h->d_allfuns = nullptr;
+    h->dev_trace = 0;
+    ZF_CUDA(cudaMalloc((void**)&h->d_allerrs, sizeof(double) * need));
+    ZF_CUDA(cudaMalloc((void**)&h->d_allfuns, sizeof(double) * need));
+    h->dev_trace = need;
+  }
+  MultiDevOpts o{};
+  o.lr0 = opt->lr; o.tol = opt->tol; o.tol_internal = opt->tol_internal; o.decay = opt->decay_rate;
+  o.scale = h->scale; o.l1 = h->l1; o.max_iter = opt->max_iter; o.pitch_c = h->pitch_c;
+  o.n = h->n_cols; o.max_bt = opt->max_backtrack_iter; o.nesterov = opt->nesterov;
+  o.deprecated = opt->deprecated; o.cap = cap; o.n_runs = h->n_runs; o.kp = h->kp;
+  o.need_F = (opt->decay_rate != 1.0) || (cap > 0 && h_allfuns != nullptr);
+  o.allerrs = (cap > 0 && h_allerrs) ? h->d_allerrs : nullptr;
+  o.allfuns = (cap > 0 && h_allfuns) ? h->d_allfuns : nullptr;
+  for (int k = 0; k < h->n_runs; ++k) {
+    o.na[k] = h_ab ? h_ab[2 * k] : opt->nesterov_a;
+    o.nb[k] = h_ab ? h_ab[2 * k + 1] : opt->nesterov_b;
+  }
+  ZF_CUDA(cudaMemcpyAsync(h->d_opts, &o, sizeof(o), cudaMemcpyHostToDevice, h->st));
+  if (cap > 0) {
+    if (o.allerrs) ZF_CUDA(cudaMemsetAsync(h->d_allerrs, 0, sizeof(double) * (size_t)h->n_runs * cap, h->st));
+    if (o.allfuns) ZF_CUDA(cudaMemsetAsync(h->d_allfuns, 0, sizeof(double) * need, h->st));
+  }
+  for (int k = 0; k < h->n_runs; ++k) {
+    const double* src = d_x0 + (x0_is_batched ? (long long)k * h->n_cols : 0);
+    const size_t nb = sizeof(double) * (size_t)h->n_cols;
+    const long long off = (long long)k * h->pitch_c;
+    ZF_CUDA(cudaMemcpyAsync(h->Xp + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->Xn + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+    ZF_CUDA(cudaMemcpyAsync(h->Y + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
+  }
+  // F(x0): residual norms and |x0|_1 of every run
+  const double* ss = h->partial + (long long)h->kp * h->pitch_c;
+  rc = launch_residual(h, 0);
+  if (rc == ZF_OK) rc = launch_collect(h, false);
+  if (rc != ZF_OK) return rc;
+  h->active = (h->n_runs == 32) ? 0xffffffffu : ((1u << h->n_runs) - 1u);
+  for (int k = 0; k < h->n_runs; ++k) h->run[k].lr = opt->lr;     // run_prox reads the host copy
+  rc = run_prox(h, h->active, false, true);
+  if (rc != ZF_OK) return rc;
+  multi_dev_init_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  // chunks of slots, the poll one chunk behind
+  const int chunk = 8;
+  auto snapshot = [&](int slot) -> int {
+    ZF_CUDA(cudaMemcpyAsync(&h->h_state[slot], h->d_state, sizeof(MultiDevState),
+                            cudaMemcpyDeviceToHost, h->st));
+    ZF_CUDA(cudaEventRecord(h->ev_poll[slot], h->st));
+    return ZF_OK;
+  };
+  int cur = 0;
+  for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = multi_dev_slot(h, o.need_F != 0);
+  if (rc == ZF_OK) rc = snapshot(cur);
+  while (rc == ZF_OK) {
+    for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = multi_dev_slot(h, o.need_F != 0);
+    if (rc == ZF_OK) rc = snapshot(1 - cur);
+    if (rc != ZF_OK) break;
+    ZF_CUDA(cudaEventSynchronize(h->ev_poll[cur]));
+    if (h->h_state[cur].done) break;
+    cur = 1 - cur;
+  }
+  if (rc != ZF_OK) return rc;
+  if (!o.need_F) {                       // res.fun = F(x): one residual pass at the results
+    rc = launch_residual(h, 1);
+    if (rc == ZF_OK) rc = launch_collect(h, false);
+    if (rc != ZF_OK) return rc;
+  }
+  multi_dev_final_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss);
+  ZF_CUDA(cudaGetLastError());
+  zf::zf_count_launch();
+  ZF_CUDA(cudaMemcpyAsync(&h->h_state[0], h->d_state, sizeof(MultiDevState), cudaMemcpyDeviceToHost,
+                          h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  const MultiDevState& S = h->h_state[0];
+  for (int k = 0; k < h->n_runs; ++k) {
+    const MultiDevRun& r = S.run[k];
+    if (d_x) {
+      const double* prev = h->Xp + (long long)k * h->pitch_c;
+      const double* cand = h->Xn + (long long)k * h->pitch_c;
+      ZF_CUDA(cudaMemcpyAsync(d_x + (long long)k * h->n_cols, r.result_is_prev ? prev : cand,
+                              sizeof(double) * (size_t)h->n_cols, cudaMemcpyDeviceToDevice, h->st));
+    }
+    if (h_fun) h_fun[k] = r.F_x;
+    if (h_nit) h_nit[k] = r.nit;
+    if (h_status) h_status[k] = r.status;
+    if (h_lr) h_lr[k] = r.lr;
+    if (h_err) h_err[k] = r.err;
+  }
+  if (cap > 0 && h_allerrs)
+    ZF_CUDA(cudaMemcpyAsync(h_allerrs, h->d_allerrs, sizeof(double) * (size_t)h->n_runs * cap,
+                            cudaMemcpyDeviceToHost, h->st));
+  if (cap > 0 && h_allfuns)
+    ZF_CUDA(cudaMemcpyAsync(h_allfuns, h->d_allfuns, sizeof(double) * need, cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaStreamSynchronize(h->st));
+  h->phase = MP_IDLE;
+  return ZF_OK;
+}
+
+}  // namespace
+
 extern "C" int zf_lasso_multi_solve(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
                                     int32_t x0_is_batched, const double* h_ab, double* d_x,
                                     double* h_fun, int64_t* h_nit, int32_t* h_status,
                                     double* h_lr, double* h_err, double* h_allerrs,
                                     double* h_allfuns) {
+  // default: the device-decided rounds; ZF_LASSO_HOSTLOOP=1 keeps the round-1 loop (decisions on
+  // the host, one D2H copy + stream sync per trial) for A/B measurements
+  static const bool hostloop = getenv("ZF_LASSO_HOSTLOOP") && getenv("ZF_LASSO_HOSTLOOP")[0] == '1';
+  if (!hostloop)
+    return multi_solve_dev(h, opt, d_x0, x0_is_batched, h_ab, d_x, h_fun, h_nit, h_status, h_lr,
+                           h_err, h_allerrs, h_allfuns);
   int rc = begin_impl(h, opt, d_x0, x0_is_batched, h_ab, h_allerrs, h_allfuns);
   if (rc != ZF_OK) return rc;
   int32_t next = 0;
