@@ -707,23 +707,24 @@ def bench_lasso_multi(args, dev, rank, world):
         out["ms_per_gradient_per_run"] = ms2 / K
     iters = args.lasso_iters
     kw = dict(lr=0.5, decay_rate=1, nesterov=True, tol=0.0, return_device=True)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        prob.minimize_proximal_gradient_batched(X, grid, max_iter=3, **kw)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = prob.minimize_proximal_gradient_batched(X, grid, max_iter=iters, **kw)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    n_it = sum(r.nit for r in res)
-    out["fista_run_iters_per_s"] = n_it / tt.item()
-    out["fista_iters_per_run"] = res[0].nit
+
+    def solve(n):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return sum(r.nit for r in prob.minimize_proximal_gradient_batched(X, grid, max_iter=n, **kw))
+
+    rate, whole, n_it = _fista_iters_per_s(solve, 10, 10 + iters, dev, world)
+    out["fista_run_iters_per_s"] = rate
+    out["fista_run_iters_per_s_whole_call"] = whole
+    out["fista_iters_per_run"] = iters
     out["global_rows"] = rows * world
+    if world == 1:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Xk = torch.stack([r.x for r in prob.minimize_proximal_gradient_batched(X, grid, max_iter=5, **kw)])
+        ms = _sustained_gradient_ms(prob, Xk, 30)
+        out["ms_per_gradient_of_all_runs_sustained"] = ms
+        out["solver_over_gradient_bound"] = rate * ms / 1e3 / K
     return out
 
 
