@@ -2,6 +2,7 @@
 // kernels (the whole minimize_proximal_gradient loop, proximal_gradient.py:474-555, on device,
 // one warp per starting point) are in zf_batched_kernels.cuh.
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 
 #include "zf_batched_kernels.cuh"
@@ -150,6 +151,24 @@ struct Arena {
   char* base = nullptr;
   size_t cap = 0, off = 0;
   int device = -1;
+  // pinned host staging for the per-start results: ONE device-to-host copy per call instead of
+  // eight small ones into pageable memory (each of those is its own synchronous transfer)
+  char* h_stage = nullptr;
+  size_t h_cap = 0;
+  char* stage(size_t need) {
+    if (need > h_cap) {
+      if (h_stage) cudaFreeHost(h_stage);
+      h_stage = nullptr;
+      h_cap = 0;
+      const size_t want = need + (need >> 2) + (1u << 16);
+      if (cudaMallocHost((void**)&h_stage, want) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      h_cap = want;
+    }
+    return h_stage;
+  }
   int reset(size_t need) {
     int dev = 0;
     ZF_CUDA(cudaGetDevice(&dev));
@@ -268,6 +287,7 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
     ab.take(N * 2 * 8);
     ZF_CUDA(cudaMemcpyAsync(ab.p, h_ab, N * 2 * 8, cudaMemcpyHostToDevice, st));
   }
+  const size_t res_begin = g_arena.off;     // x .. err are carved back to back: one D2H range
   x.take(N * n * 8);
   fun.take(N * m * 8);
   nit.take(N * 8);
@@ -281,6 +301,7 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
   if (h_out->nfev) { nfev.take(N * 8); R.nfev = nfev.as<int64_t>(); }
   if (h_out->n_dual) { ndual.take(N * 8); R.n_dual = ndual.as<int64_t>(); }
   if (h_out->err) { err.take(N * 8); R.err = err.as<double>(); }
+  const size_t res_end = g_arena.off;
   DevBuf toff;
   if (tracing) {
     if (h_off) {
@@ -307,18 +328,38 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
   rc = zf_solve_batched_device(&dp.P, opt, n_starts, x0.as<double>(),
                                h_ab ? ab.as<double>() : nullptr, &R, st);
   if (rc != ZF_OK) return rc;
-  ZF_CUDA(cudaMemcpyAsync(h_out->x, R.x, N * n * 8, cudaMemcpyDeviceToHost, st));
-  ZF_CUDA(cudaMemcpyAsync(h_out->fun, R.fun, N * m * 8, cudaMemcpyDeviceToHost, st));
-  ZF_CUDA(cudaMemcpyAsync(h_out->nit, R.nit, N * 8, cudaMemcpyDeviceToHost, st));
-  ZF_CUDA(cudaMemcpyAsync(h_out->status, R.status, N * 4, cudaMemcpyDeviceToHost, st));
-  if (R.lr) ZF_CUDA(cudaMemcpyAsync(h_out->lr, R.lr, N * 8, cudaMemcpyDeviceToHost, st));
-  if (R.nfev) ZF_CUDA(cudaMemcpyAsync(h_out->nfev, R.nfev, N * 8, cudaMemcpyDeviceToHost, st));
-  if (R.n_dual) ZF_CUDA(cudaMemcpyAsync(h_out->n_dual, R.n_dual, N * 8, cudaMemcpyDeviceToHost, st));
-  if (R.err) ZF_CUDA(cudaMemcpyAsync(h_out->err, R.err, N * 8, cudaMemcpyDeviceToHost, st));
+  char* stage = g_arena.stage(res_end - res_begin);
+  if (stage) {
+    // one transfer of the whole result block into pinned memory, then host copies
+    ZF_CUDA(cudaMemcpyAsync(stage, g_arena.base + res_begin, res_end - res_begin,
+                            cudaMemcpyDeviceToHost, st));
+  } else {
+    ZF_CUDA(cudaMemcpyAsync(h_out->x, R.x, N * n * 8, cudaMemcpyDeviceToHost, st));
+    ZF_CUDA(cudaMemcpyAsync(h_out->fun, R.fun, N * m * 8, cudaMemcpyDeviceToHost, st));
+    ZF_CUDA(cudaMemcpyAsync(h_out->nit, R.nit, N * 8, cudaMemcpyDeviceToHost, st));
+    ZF_CUDA(cudaMemcpyAsync(h_out->status, R.status, N * 4, cudaMemcpyDeviceToHost, st));
+    if (R.lr) ZF_CUDA(cudaMemcpyAsync(h_out->lr, R.lr, N * 8, cudaMemcpyDeviceToHost, st));
+    if (R.nfev) ZF_CUDA(cudaMemcpyAsync(h_out->nfev, R.nfev, N * 8, cudaMemcpyDeviceToHost, st));
+    if (R.n_dual) ZF_CUDA(cudaMemcpyAsync(h_out->n_dual, R.n_dual, N * 8, cudaMemcpyDeviceToHost, st));
+    if (R.err) ZF_CUDA(cudaMemcpyAsync(h_out->err, R.err, N * 8, cudaMemcpyDeviceToHost, st));
+  }
   if (R.allerrs && n_err) ZF_CUDA(cudaMemcpyAsync(h_out->allerrs, R.allerrs, n_err * 8, cudaMemcpyDeviceToHost, st));
   if (R.allfuns) ZF_CUDA(cudaMemcpyAsync(h_out->allfuns, R.allfuns, n_fx * m * 8, cudaMemcpyDeviceToHost, st));
   if (R.allvecs) ZF_CUDA(cudaMemcpyAsync(h_out->allvecs, R.allvecs, n_fx * n * 8, cudaMemcpyDeviceToHost, st));
   ZF_CUDA(cudaStreamSynchronize(st));
+  if (stage) {
+    auto back = [&](void* dst, const void* dev, size_t bytes) {
+      std::memcpy(dst, stage + (static_cast<const char*>(dev) - (g_arena.base + res_begin)), bytes);
+    };
+    back(h_out->x, R.x, N * n * 8);
+    back(h_out->fun, R.fun, N * m * 8);
+    back(h_out->nit, R.nit, N * 8);
+    back(h_out->status, R.status, N * 4);
+    if (R.lr) back(h_out->lr, R.lr, N * 8);
+    if (R.nfev) back(h_out->nfev, R.nfev, N * 8);
+    if (R.n_dual) back(h_out->n_dual, R.n_dual, N * 8);
+    if (R.err) back(h_out->err, R.err, N * 8);
+  }
   return ZF_OK;
 }
 
