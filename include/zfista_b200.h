@@ -211,7 +211,7 @@ int zf_lasso_set_allvecs(zf_lasso* h, double* h_allvecs, int64_t rows);
  * straight out of peer memory, in rank order -- bit-identical on every rank; stages 3 / 6
  * exchange the residual norm the same way.  The caller skips its all-reduces when
  * zf_lasso_p2p_active() returns 1.  A peer that never publishes ends the solve with status -3
- * after ~2 s instead of hanging the GPU.                                                  */
+ * after ~10 s instead of hanging the GPU.                                                  */
 int zf_lasso_p2p_export(zf_lasso* h, void* handle_out /* 64 bytes */);
 int zf_lasso_p2p_attach(zf_lasso* h, int32_t rank, int32_t world, const void* handles /* world x 64 */);
 int zf_lasso_p2p_active(zf_lasso* h);

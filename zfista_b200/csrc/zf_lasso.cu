@@ -1245,12 +1245,14 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
-// wait until *flag >= seq (one thread); false after ~2 s
+// wait until *flag >= seq (one thread); false after ~10 s (2^34 cycles): ranks enter a solve
+// within milliseconds of each other (the wrapper puts a barrier in front of it), a peer that
+// is this late has died
 __device__ bool p2p_wait(const unsigned long long* flag, unsigned long long seq) {
   const long long t0 = clock64();
   while (ld_acquire_sys_u64(flag) < seq) {
     __nanosleep(64);
-    if (clock64() - t0 > (1LL << 32)) return false;
+    if (clock64() - t0 > (1LL << 34)) return false;
   }
   return true;
 }

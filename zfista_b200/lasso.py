@@ -274,6 +274,13 @@ class DenseLasso:
                         _lib.check(L.zf_lasso_dev_finish(h, C.c_void_p(xd.data_ptr()), C.byref(fun),
                                                          C.byref(nit), C.byref(status), None, pe, pf))
 
+                if self.peer_exchange:
+                    # the peer exchange spins on the peers' flags inside kernels (bounded, ~10 s):
+                    # line the ranks up first so that a rank that was busy elsewhere is not
+                    # mistaken for a dead one
+                    import torch.distributed as dist
+
+                    dist.barrier(group=self.group)
                 run_device_lasso(_Ops(), self._allreduce, self._allreduce_ss)
         st, k = int(status.value), int(nit.value)
         if st == -3:
