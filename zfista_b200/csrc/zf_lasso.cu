@@ -12,17 +12,21 @@
 //                                     earlier cluster forms, kept behind ZF_LASSO_* switches)
 //                                    or two passes where a row is too wide for them:
 //                                    lasso_residual_kernel (r = A y - b), lasso_atr_kernel (A^T r)
-//   x = soft(y - lr*2*scale*q, lr*l1) + the four sums the line search / stop test need
-//                                    lasso_prox_kernel       (n_cols work)
-//   [line search]  ||A x - b||^2     lasso_residual_kernel   (one pass per trial)
-//   y = x + mom*(x - x_prev)         lasso_momentum_kernel
+//   x = soft(y - lr*2*scale*q, lr*l1) + the four sums the line search / stop test need,
+//   collect of the row-block partials, y = x + mom*(x - x_prev), stop test, t_{k+1}
+//                                    lasso_dev_update_kernel (n_cols work, ONE kernel)
+//   [line search]  ||A x - b||^2     lasso_residual_kernel   (one pass per trial), then
+//                                    lasso_dev_decide_kernel + lasso_dev_momentum_kernel
 // Every reduction has a fixed order (no floating-point atomics), so a solve is bit
-// reproducible run to run.  Scalars (lr, t_k, F values, accept/stop decisions) live on the
-// host: one small D2H copy + stream sync per trial, negligible against a >= 1 ms pass.
+// reproducible run to run.  Scalars (lr, t_k, F values, accept / stop decisions) live in DEVICE
+// memory (LassoDevState): zf_lasso_solve enqueues trials as CUDA graphs of 32 and polls a flag
+// one chunk behind; the round-1 host-decided loop (zf_lasso_begin / grad / step / finish, one
+// D2H copy + stream sync per trial) is kept as the split API and the A/B baseline.
 //
-// Row-sharded multi-GPU: each rank owns a block of rows and the same replicated vectors;
-// the only exchange is the all-reduce of `partial` = [A^T r (n_cols) | sum r^2] between
-// zf_lasso_grad() and zf_lasso_step() (done by the caller, NCCL over NVLink).
+// Row-sharded multi-GPU: each rank owns a block of rows and the same replicated vectors; the
+// only exchange is the sum over ranks of `partial` = [A^T r (n_cols) | sum r^2], done INSIDE the
+// update kernel by reading every rank's published partials from NVLink peer memory (P2PBuf,
+// zf_lasso_p2p_*), or by the caller's NCCL all-reduce between the stages.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
