@@ -561,3 +561,34 @@ def test_return_all_goes_through_the_device_in_groups(gpu, monkeypatch):
     lfr = zp.LinearFunctionRank1(n_features=6, n_objectives=1)
     one = lfr.minimize_proximal_gradient(np.ones(6) * 0.3, return_all=True, max_iter=20)
     assert np.shape(one.fun) == (1,) and np.shape(one.allfuns[0]) == (1,)
+
+
+def test_host_entry_points_from_several_threads(gpu):
+    """The *_host entry points keep their device scratch and their stream per calling thread
+    (round 1: one process-wide arena behind a mutex on the legacy stream): concurrent calls from
+    four threads -- ctypes releases the GIL -- give exactly the serial results."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import zfista_b200.problems as zp
+
+    probs = [zp.JOS1(n_features=30), zp.FDS(n_features=40, l1_ratios=(np.arange(3) + 1) / 40,
+                                           l1_shifts=np.arange(3.0)),
+             zp.JOS1(n_features=8, l1_ratios=(0.1, 0.2), l1_shifts=(0.0, 1.0)), zp.SD()]
+    rng = np.random.RandomState(21)
+    starts = [rng.uniform(0.5, 2.0, size=(200 + 37 * k, p.n_features)) for k, p in enumerate(probs)]
+    kw = dict(nesterov=True, tol_internal=1e-11)
+    serial = [p.minimize_proximal_gradient_batched(X, **kw) for p, X in zip(probs, starts)]
+
+    def work(k):
+        out = []
+        for _ in range(4):
+            out.append(probs[k].minimize_proximal_gradient_batched(starts[k], **kw))
+        return out
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        results = list(ex.map(work, range(4)))
+    for k in range(4):
+        for br in results[k]:
+            np.testing.assert_array_equal(br.nit, serial[k].nit)
+            np.testing.assert_array_equal(br.x, serial[k].x)
+            np.testing.assert_array_equal(br.fun, serial[k].fun)

@@ -143,11 +143,26 @@ namespace {
     if (_e != cudaSuccess) return zf::zf_fail_cuda(_e, #call);      \
   } while (0)
 
-// Device scratch of the *_host entry points: one grow-only block per process, carved per
-// call (cudaMalloc / cudaFree cost ~0.3 ms each and cudaFree synchronises; a 1024-start
-// solve is ~1 ms of kernel).  Calls through the host entry points are serialised by the lock.
+// Device scratch of the *_host entry points: one grow-only block PER CALLING THREAD, carved per
+// call (cudaMalloc / cudaFree cost ~0.3 ms each and cudaFree synchronises; a 1024-start solve is
+// ~1 ms of kernel), with its own non-blocking stream: host calls from different threads neither
+// serialise on a lock nor on the legacy default stream (round 1: one process-wide arena, a
+// mutex, stream 0).
 struct Arena {
-  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaStream_t get_stream() {
+    if (!stream && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      stream = nullptr;              // fall back to the default stream
+    }
+    return stream;
+  }
+  ~Arena() {                         // thread exit (errors at process teardown are harmless)
+    if (base) cudaFree(base);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (stream) cudaStreamDestroy(stream);
+    cudaGetLastError();
+  }
   char* base = nullptr;
   size_t cap = 0, off = 0;
   int device = -1;
@@ -176,6 +191,7 @@ struct Arena {
       if (base) {
         cudaSetDevice(device);
         cudaFree(base);
+        if (stream && dev != device) { cudaStreamDestroy(stream); stream = nullptr; }
         cudaSetDevice(dev);
         base = nullptr;
         cap = 0;
@@ -194,7 +210,7 @@ struct Arena {
     return p;
   }
 };
-Arena g_arena;
+thread_local Arena g_arena;
 inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 // a slice of the arena (same interface the RAII buffers had)
@@ -255,7 +271,7 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
     return zf::zf_fail(ZF_ERR_INVALID, "result.x/fun/nit/status are required");
   rc = zf::zf_require_device();
   if (rc != ZF_OK) return rc;
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
   const size_t N = (size_t)n_starts, n = problem->n_features, m = problem->n_objectives;
   const size_t cap = (size_t)opt->trace_capacity;
   // trace sizes: dense (cap entries per start) or ragged (h_out->trace_offsets, host array)
@@ -265,7 +281,6 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
   const bool tracing = h_off != nullptr || cap > 0;
   const size_t n_err = h_off ? (size_t)h_off[N] : N * cap;          // error entries
   const size_t n_fx = h_off ? (size_t)h_off[N] + N : N * (cap + 1);  // F / x entries
-  std::lock_guard<std::mutex> lock(g_arena.mu);
   {
     size_t total = DevProblem::bytes(*problem) + 2 * pad256(N * n * 8) + pad256(N * 16) +
                    pad256(N * m * 8) + 6 * pad256(N * 8) + pad256((N + 1) * 8);
@@ -277,6 +292,7 @@ extern "C" int zf_solve_batched_host(const zf_problem* problem, const zf_options
     rc = g_arena.reset(total);
     if (rc != ZF_OK) return rc;
   }
+  st = g_arena.get_stream();
   DevProblem dp;
   rc = dp.upload(*problem, st);
   if (rc != ZF_OK) return rc;
@@ -374,12 +390,12 @@ extern "C" int zf_solve_subproblem_host(const zf_problem* problem, const zf_opti
   if (n <= 0) return n == 0 ? ZF_OK : zf::zf_fail(ZF_ERR_INVALID, "n < 0");
   rc = zf::zf_require_device();
   if (rc != ZF_OK) return rc;
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
   const size_t N = (size_t)n, nf = problem->n_features, m = problem->n_objectives;
-  std::lock_guard<std::mutex> lock(g_arena.mu);
   rc = g_arena.reset(DevProblem::bytes(*problem) + 3 * pad256(N * nf * 8) + 3 * pad256(N * 8) +
                      pad256(N * m * 8));
   if (rc != ZF_OK) return rc;
+  st = g_arena.get_stream();
   DevProblem dp;
   rc = dp.upload(*problem, st);
   if (rc != ZF_OK) return rc;
@@ -427,12 +443,12 @@ extern "C" int zf_problem_eval_host(const zf_problem* problem, int64_t n, const 
   if (n <= 0) return n == 0 ? ZF_OK : zf::zf_fail(ZF_ERR_INVALID, "n < 0");
   int rc = zf::zf_require_device();
   if (rc != ZF_OK) return rc;
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
   const size_t N = (size_t)n, nf = problem->n_features, m = problem->n_objectives;
-  std::lock_guard<std::mutex> lock(g_arena.mu);
   rc = g_arena.reset(DevProblem::bytes(*problem) + 2 * pad256(N * nf * 8) + 3 * pad256(N * m * 8) +
                      pad256(N * m * nf * 8));
   if (rc != ZF_OK) return rc;
+  st = g_arena.get_stream();
   DevProblem dp;
   rc = dp.upload(*problem, st);
   if (rc != ZF_OK) return rc;
