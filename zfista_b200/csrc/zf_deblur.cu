@@ -409,14 +409,28 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, const __grid_constan
     // ---- 3. symmetric reflection of V into the out-of-image halo positions (border tiles only)
     const bool touches_border = (tyo - HV < 0) || (txo - HV < 0) || (tyo + T + HV > d.H) ||
                                 (txo + T + HV > d.W);
-    if (touches_border)
-    for (int idx = tid; idx < VR * VR; idx += DB_THREADS) {
-      const int li = idx / VR, lj = idx % VR;
-      const int gi = tyo - HV + li, gj = txo - HV + lj;
-      if (gi < 0 || gi >= d.H || gj < 0 || gj >= d.W) {
+    if (touches_border) {
+      // only the out-of-image strips are visited: the rows above / below the image over their
+      // whole width, then the columns left / right of it over the in-image rows
+      const int r_lo = (tyo - HV < 0) ? -(tyo - HV) : 0;
+      const int r_hi = (d.H - (tyo - HV) < VR) ? d.H - (tyo - HV) : VR;
+      const int c_lo = (txo - HV < 0) ? -(txo - HV) : 0;
+      const int c_hi = (d.W - (txo - HV) < VR) ? d.W - (txo - HV) : VR;
+      auto fill = [&](int li, int lj) {
+        const int gi = tyo - HV + li, gj = txo - HV + lj;
         const int si = db_reflect(gi, d.H) - (tyo - HV), sj = db_reflect(gj, d.W) - (txo - HV);
         if (si >= 0 && si < VR && sj >= 0 && sj < VR) V[li][lj] = V[si][sj];
         else V[li][lj] = 0.0;   // never read by an in-image output
+      };
+      const int out_rows = r_lo + (VR - r_hi);
+      for (int idx = tid; idx < out_rows * VR; idx += DB_THREADS) {
+        const int rr = idx / VR, lj = idx % VR;
+        fill(rr < r_lo ? rr : r_hi + (rr - r_lo), lj);
+      }
+      const int out_cols = c_lo + (VR - c_hi);
+      for (int idx = tid; idx < (r_hi - r_lo) * out_cols; idx += DB_THREADS) {
+        const int rr = idx / out_cols, cc = idx % out_cols;
+        fill(r_lo + rr, cc < c_lo ? cc : c_hi + (cc - c_lo));
       }
     }
     __syncthreads();
@@ -509,11 +523,13 @@ deblur_tile_kernel(DeblurDims d, DeblurCtl c, DeblurBufs B, const __grid_constan
     }
   }
   // ---- block reduction of the partials (fixed order), ticket, decision by the last CTA
-  fsum = warp_sum(fsum);
-  abs_acc = warp_sum(abs_acc);
-  ps.gd = warp_sum(ps.gd);
-  ps.dd = warp_sum(ps.dd);
-  ps.abs1 = warp_sum(ps.abs1);
+  {
+    // five sums in one recursive-halving reduction (zf_common.cuh: 13 double shuffles instead of
+    // 25, bit-identical to five butterflies)
+    double v5[5] = {fsum, abs_acc, ps.gd, ps.dd, ps.abs1};
+    warp_sum_k<5>(v5);
+    fsum = v5[0]; abs_acc = v5[1]; ps.gd = v5[2]; ps.dd = v5[3]; ps.abs1 = v5[4];
+  }
   ps.maxd = warp_max(ps.maxd);
   if ((tid & 31) == 0) {
     const int w = tid >> 5;
