@@ -828,11 +828,21 @@ def _hbm_roofline(a_bytes, vec_bytes, ms, passes, peaks, traffic_note, ms_burst=
                 else ["lasso_residual_kernel", "lasso_atr_kernel"])
         traffic = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"])
                       / tj[k]["algorithmic_bytes"] for k in keys) * a_bytes
+    traffic_source = ("NOT measured at this shape: ncu dram bytes / |A| of the same kernel at "
+                      "32768x16384 and 32768x20000 (1.0001, profiles/r01_traffic.json, "
+                      "profiles/r01g_*) scaled to this A")
+    mp = os.path.join(ROOT, "profiles", "r02_traffic_configs3.json")
+    if os.path.exists(mp):            # the bench shape itself, measured
+        with open(mp) as fh:
+            mj = json.load(fh)
+        if mj["algorithmic_bytes"] == a_bytes and passes == 1:
+            traffic = mj["dram_bytes_read"] + mj["dram_bytes_write"]
+            traffic_source = ("measured at this shape: ncu dram__bytes_read.sum + dram__bytes_write.sum "
+                              "of one gradient pass (both concurrent launches), "
+                              "profiles/r02_traffic_configs3.json: 1.00008 x |A|")
     return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
-            "traffic_source": "NOT measured at this shape: ncu dram bytes / |A| of the same kernel "
-                              "at 32768x16384 and 32768x20000 (1.0001, profiles/r01_traffic.json, "
-                              "profiles/r01g_*) scaled to this A" + traffic_note,
+            "traffic_source": traffic_source + traffic_note,
             "ms_per_gradient": ms, "hbm_passes_over_A": passes,
             "timing": "50 launches back to back at a non-zero iterate (sustained clocks)",
             "burst": (None if ms_burst is None else
