@@ -161,15 +161,21 @@ def test_batched_solve_matches_reference(gpu, case):
         _rel_close(br.allerrs[0, :n0], d["allerrs0"], rel=1e-6, floor=1e-9)
         _rel_close(br.allfuns[0, :n0 + 1], d["allfuns0"])
         return
+    # the reference's own envelope: its dual value perturbed by ONE ulp, 8 seeds.  Measured on
+    # B200 (profiles/r02_envelope_probe.py, all 15 such cases): the device's iteration counts are
+    # inside 1.0x that envelope on every case (e.g. JOS1 n=50 +L1 FISTA: 16 against 30; TOI4 +L1
+    # FISTA: 8 against 15; 7 cases 0 against 0), x inside 1.33x (1.29e-3 against 9.7e-4 on
+    # JOS1_n50_l1nb FISTA, <= 1.0x elsewhere), F inside 1.07x.  Asserted: 1x, 1.5x, 1.5x.
     env = helpers.oracle_noise_envelope(helpers.oracle_spec(cls, kw), d["x0"], d["x"], d["fun"],
                                         d["nit"], opts,
-                                        n_starts=16 if prob.n_features <= 10 else 4)
+                                        n_starts=16 if prob.n_features <= 10 else 4,
+                                        seeds=tuple(range(8)))
     dnit = np.abs(br.nit - d["nit"])
     dx = np.max(np.abs(br.x - d["x"]))
     dF = np.max(np.abs(br.fun - d["fun"]) / np.maximum(1.0, np.abs(d["fun"])))
-    assert dnit.max() <= 2 * env["dnit"] + max(3, 0.05 * d["nit"].max()), (dnit, env)
-    assert dx <= 4 * env["dx"] + 1e-6, (dx, env)
-    assert dF <= 4 * env["dF"] + 1e-7, (dF, env)
+    assert dnit.max() <= env["dnit"], (dnit, env)
+    assert dx <= 1.5 * env["dx"] + 1e-8, (dx, env)
+    assert dF <= 1.5 * env["dF"] + 1e-8, (dF, env)
     # the first iterations (before the noise is amplified) still agree tightly
     k = min(5, int(min(br.nit[0], d["nit"][0])))
     _rel_close(br.allerrs[0, :k], d["allerrs0"][:k], rel=1e-5, floor=1e-8)
