@@ -28,9 +28,9 @@ if which in ("all", "lasso"):
     from zfista_b200.lasso import DenseLasso
 
     for env, shape in [({"ZF_LASSO_FUSED": "0"}, (700, 1030)), ({}, (700, 2050)),
-                       ({"ZF_LASSO_CLUSTER": "2"}, (701, 3000)), ({"ZF_LASSO_TMA": "2"}, (900, 2000)),
-                       ({"ZF_LASSO_TMA": "4"}, (1000, 5000)), ({}, (50, 201))]:
-        for k in ("ZF_LASSO_FUSED", "ZF_LASSO_CLUSTER", "ZF_LASSO_TMA"):
+                       ({"ZF_LASSO_RING": "2"}, (701, 3000)), ({"ZF_LASSO_RING": "3"}, (900, 20000)),
+                       ({"ZF_LASSO_RING": "1"}, (1000, 5000)), ({}, (50, 201))]:
+        for k in ("ZF_LASSO_FUSED", "ZF_LASSO_RING"):
             os.environ.pop(k, None)
         os.environ.update(env)
         rows, cols = shape

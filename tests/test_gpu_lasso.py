@@ -149,12 +149,9 @@ def test_large_a_properties(gpu):
 @pytest.mark.parametrize("env,shape,passes", [
     ({"ZF_LASSO_FUSED": "0"}, (700, 1030), 2),            # two-pass kernels
     ({}, (700, 2050), 1),                                  # single-CTA fused (default policy)
-    ({"ZF_LASSO_CLUSTER": "2"}, (701, 3000), 1),           # 2-CTA cluster, L2 re-read, odd rows
-    ({"ZF_LASSO_CLUSTER": "2", "ZF_LASSO_THREADS": "1024"}, (1200, 9000), 1),
-    ({"ZF_LASSO_TMA": "2"}, (900, 2000), 1),               # TMA ring, cluster 2
-    ({"ZF_LASSO_TMA": "4"}, (1000, 5002), 1),              # TMA ring, cluster 4, ragged slices
-    ({"ZF_LASSO_TMA": "2", "ZF_LASSO_TMA_ROWS": "3"}, (911, 2000), 1),   # 3 rows per stage, ragged
-    ({"ZF_LASSO_TMA": "4", "ZF_LASSO_TMA_ROWS": "4"}, (1001, 3000), 1),  # 4 rows per stage
+    ({"ZF_LASSO_FUSED": "1"}, (701, 3000), 1),             # single-CTA fused forced, odd rows
+    ({}, (1200, 9000), 1),                                 # default: chunk ring, cluster 2
+    ({}, (900, 4100), 1),                                  # default: chunk ring, no cluster
     ({"ZF_LASSO_RING": "1"}, (903, 2050), 1),              # chunk ring, no cluster, 2 chunks (ragged)
     ({"ZF_LASSO_RING": "1"}, (700, 10240), 1),             # 5 full chunks per row
     ({"ZF_LASSO_RING": "2"}, (1001, 5002), 1),             # cluster 2, ragged slices and chunks
@@ -178,8 +175,7 @@ def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     import torch
     from zfista_b200.lasso import DenseLasso
 
-    for k in ("ZF_LASSO_FUSED", "ZF_LASSO_CLUSTER", "ZF_LASSO_THREADS", "ZF_LASSO_TMA",
-              "ZF_LASSO_TMA_ROWS", "ZF_LASSO_RING", "ZF_LASSO_TUNE", "ZF_LASSO_NSM"):
+    for k in ("ZF_LASSO_FUSED", "ZF_LASSO_RING", "ZF_LASSO_TUNE", "ZF_LASSO_NSM"):
         monkeypatch.delenv(k, raising=False)
     rows, cols = shape
     g = torch.Generator(device="cuda").manual_seed(rows + cols)

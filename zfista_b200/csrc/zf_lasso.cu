@@ -7,9 +7,7 @@
 //   q = A^T (A y - b), sum r^2       ONE pass over A with a fused kernel chosen per shape
 //                                    (lasso_fused_ring_kernel: warp-specialised TMA chunk
 //                                     ring, the default from 4096 columns up;
-//                                     lasso_fused_kernel: single CTA, L2 re-read, below that;
-//                                     lasso_fused_cluster_kernel / lasso_fused_tma_kernel:
-//                                     earlier cluster forms, kept behind ZF_LASSO_* switches)
+//                                     lasso_fused_kernel: single CTA, L2 re-read, below that)
 //                                    or two passes where a row is too wide for them:
 //                                    lasso_residual_kernel (r = A y - b), lasso_atr_kernel (A^T r)
 //   x = soft(y - lr*2*scale*q, lr*l1) + the four sums the line search / stop test need,
@@ -336,152 +334,10 @@ lasso_fused_kernel(const double* __restrict__ A, const double* __restrict__ b,
 }
 
 // ------------------------------------------------------------------------------------
-// Cluster form of the fused pass for wide A.  The columns are split over the CTAs of a thread
-// block cluster (2 or 4 SMs): each CTA keeps only its slice of v in shared memory and its slice
-// of the A^T r partial in registers (PAIRS <= 10 column pairs per thread: no spills at 20000
-// columns), computes the partial dot products of a row pair over its slice, and the CTAs
-// exchange those partials through distributed shared memory (one cluster barrier per row
-// pair).  The row stream is software pipelined: the loads of pair k+1 for the dot products are
-// issued before the rank-1 update of pair k, so the HBM pipe never drains at the barrier.
-// ------------------------------------------------------------------------------------
-template <int PAIRS, int THREADS, int CHUNK>
-__global__ void __launch_bounds__(THREADS, 1)
-lasso_fused_cluster_kernel(const double* __restrict__ A, const double* __restrict__ b,
-                           const double* __restrict__ v, long long n_rows, long long n_cols,
-                           long long rows_per_cluster, long long pairs_per_cta,
-                           double* __restrict__ gpart, double* __restrict__ sq_part,
-    const int* __restrict__ skip) {
-  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
-  const int csize = (int)cluster.num_blocks();
-  const long long cid = blockIdx.x / csize;                 // cluster index = row block
-  extern __shared__ double vsm[];                           // this CTA's slice of v
-  __shared__ double red[THREADS / 32][FUSED_ROWS];
-  __shared__ double xch[2][FUSED_ROWS][8];                   // [parity][row][cluster rank]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long n2 = n_cols >> 1;
-  const long long p_lo = (long long)crank * pairs_per_cta;
-  const long long p_hi = (p_lo + pairs_per_cta < n2) ? p_lo + pairs_per_cta : n2;
-  const long long my_pairs = p_hi > p_lo ? p_hi - p_lo : 0;
-  for (long long p = tid; p < my_pairs; p += THREADS)
-    reinterpret_cast<double2*>(vsm)[p] = __ldg(reinterpret_cast<const double2*>(v) + p_lo + p);
-  __syncthreads();
-  const unsigned long long keep_pol = l2_policy_evict_last();
-  const unsigned long long last_pol = l2_policy_evict_first();
-  double2 q[PAIRS];
-#pragma unroll
-  for (int k = 0; k < PAIRS; ++k) q[k] = make_double2(0.0, 0.0);
-  const long long i0 = cid * rows_per_cluster;
-  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
-  double ss = 0.0;
-  int parity = 0;
-  // column-pair offsets of this thread (clamped: inactive slots read pair 0 and are masked)
-  auto dots = [&](const double* row0, const double* row1, double (&acc)[FUSED_ROWS]) {
-    acc[0] = acc[1] = 0.0;
-#pragma unroll
-    for (int k0 = 0; k0 < PAIRS; k0 += CHUNK) {
-      double2 a0[CHUNK], a1[CHUNK];
-#pragma unroll
-      for (int u = 0; u < CHUNK; ++u) {
-        if (k0 + u < PAIRS) {          // compile time: no load is issued for a slot past PAIRS
-          const long long p = tid + (long long)(k0 + u) * THREADS;
-          const long long pc = (p < my_pairs) ? p : 0;
-          a0[u] = ld_hint2(row0 + 2 * (p_lo + pc), keep_pol);
-          a1[u] = ld_hint2(row1 + 2 * (p_lo + pc), keep_pol);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < CHUNK; ++u) {
-        const long long p = tid + (long long)(k0 + u) * THREADS;
-        if (k0 + u < PAIRS && p < my_pairs) {
-          const double2 vv = reinterpret_cast<const double2*>(vsm)[p];
-          acc[0] += a0[u].x * vv.x + a0[u].y * vv.y;
-          acc[1] += a1[u].x * vv.x + a1[u].y * vv.y;
-        }
-      }
-    }
-  };
-  double acc[FUSED_ROWS];
-  if (i0 < i1) {
-    const double* r0p = A + i0 * n_cols;
-    dots(r0p, (i0 + 1 < i1) ? r0p + n_cols : r0p, acc);
-  }
-  for (long long i = i0; i < i1; i += FUSED_ROWS) {
-    const bool two = (i + 1 < i1);
-    const double* row0 = A + i * n_cols;
-    const double* row1 = two ? row0 + n_cols : row0;
-    // ---- CTA partial dots of this pair -> every CTA of the cluster
-    warp_sum_k<FUSED_ROWS>(acc);
-    if (lane == 0) { red[warp][0] = acc[0]; red[warp][1] = acc[1]; }
-    __syncthreads();
-    if (tid < csize) {
-      double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-      for (int w = 0; w < THREADS / 32; ++w) { p0 += red[w][0]; p1 += red[w][1]; }
-      double* remote = cluster.map_shared_rank(&xch[0][0][0], tid);
-      remote[(parity * FUSED_ROWS + 0) * 8 + crank] = p0;
-      remote[(parity * FUSED_ROWS + 1) * 8 + crank] = p1;
-    }
-    // ---- prefetch: dot-product loads of the NEXT pair are in flight across the barrier
-    double nacc[FUSED_ROWS] = {0.0, 0.0};
-    const long long in = i + FUSED_ROWS;
-    if (in < i1) {
-      const double* n0 = A + in * n_cols;
-      dots(n0, (in + 1 < i1) ? n0 + n_cols : n0, nacc);
-    }
-    cluster.sync();
-    double r0 = 0.0, r1 = 0.0;
-    for (int c = 0; c < csize; ++c) { r0 += xch[parity][0][c]; r1 += xch[parity][1][c]; }
-    parity ^= 1;
-    r0 -= b[i];
-    r1 = two ? r1 - b[i + 1] : 0.0;
-    ss += r0 * r0;
-    ss += r1 * r1;
-    // ---- rank-1 updates of the thread's columns (rows re-read from L2)
-#pragma unroll
-    for (int k0 = 0; k0 < PAIRS; k0 += CHUNK) {
-      double2 a0[CHUNK], a1[CHUNK];
-#pragma unroll
-      for (int u = 0; u < CHUNK; ++u) {
-        if (k0 + u < PAIRS) {
-          const long long p = tid + (long long)(k0 + u) * THREADS;
-          const long long pc = (p < my_pairs) ? p : 0;
-          a0[u] = ld_hint2(row0 + 2 * (p_lo + pc), last_pol);
-          a1[u] = ld_hint2(row1 + 2 * (p_lo + pc), last_pol);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < CHUNK; ++u) {
-        if (k0 + u < PAIRS) {
-          q[k0 + u].x += r0 * a0[u].x; q[k0 + u].y += r0 * a0[u].y;
-          q[k0 + u].x += r1 * a1[u].x; q[k0 + u].y += r1 * a1[u].y;
-        }
-      }
-    }
-    acc[0] = nacc[0];
-    acc[1] = nacc[1];
-  }
-  double* out = gpart + cid * n_cols;
-#pragma unroll
-  for (int k = 0; k < PAIRS; ++k) {
-    const long long p = tid + (long long)k * THREADS;
-    if (p < my_pairs) reinterpret_cast<double2*>(out)[p_lo + p] = q[k];
-  }
-  if (tid == 0 && crank == 0) sq_part[cid] = ss;
-  cluster.sync();        // no CTA may exit while a peer can still write into its shared memory
-}
-
-// ------------------------------------------------------------------------------------
-// TMA form of the fused pass: the row pair never leaves the chip between the dot products and
-// the rank-1 update.  The columns are split over a cluster of CS CTAs; each CTA keeps its
-// slice of v, and a ring of NS stages, each one row PAIR's slice, in shared memory.  One
-// elected thread streams the stages in with 1-D bulk TMA copies (cp.async.bulk ->
-// mbarrier complete_tx); all threads wait on the stage's mbarrier, form the partial dot
-// products from shared memory, exchange them across the cluster through distributed shared
-// memory (one cluster barrier per pair), apply the rank-1 update from the SAME shared-memory
-// stage, and hand the stage back for the pair NS ahead.  HBM sees A once, L2 is not re-read.
+// mbarrier / bulk-TMA helpers of the chunk-ring kernel below.  (Round 1 also had a 2-CTA cluster
+// form that re-read the row pair from L2 and two TMA forms with one block reduction + one
+// cluster barrier per stage, 0.65-0.77 of the one-pass bound; the ring kernel superseded them
+// on every shape and they were removed in round 2 -- their numbers stay in DESIGN.md 3.3.)
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
@@ -512,276 +368,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   }
 }
 
-constexpr int TMA_THREADS = 512;
-
-// Two rows per stage, hand-specialised (measured 5-10 % faster than the generic kernel below
-// instantiated at R = 2).  PIPE (dot products of pair k+1 between the cluster barrier's arrive
-// and wait of pair k) was measured slower and is instantiated off.
-template <int PAIRS, int NS, bool PIPE>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
-lasso_fused_tma_pair_kernel(const double* __restrict__ A, const double* __restrict__ b,
-                       const double* __restrict__ v, long long n_rows, long long n_cols,
-                       long long rows_per_cluster, long long pairs_per_cta,
-                       double* __restrict__ gpart, double* __restrict__ sq_part,
-    const int* __restrict__ skip) {
-  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
-  const int csize = (int)cluster.num_blocks();
-  const long long cid = blockIdx.x / csize;
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ double red[TMA_THREADS / 32][FUSED_ROWS];
-  __shared__ double xch[2][FUSED_ROWS][8];
-  __shared__ __align__(8) unsigned long long full[NS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long n2 = n_cols >> 1;
-  const long long p_lo = (long long)crank * pairs_per_cta;
-  const long long p_hi = (p_lo + pairs_per_cta < n2) ? p_lo + pairs_per_cta : n2;
-  const long long my_pairs = p_hi > p_lo ? p_hi - p_lo : 0;
-  const unsigned slice_bytes = (unsigned)(my_pairs * 16);
-  const size_t slice_stride = (size_t)pairs_per_cta * 16;        // bytes reserved per row slice
-  double2* vsm = reinterpret_cast<double2*>(dyn);
-  unsigned char* ring = dyn + slice_stride;                      // NS x 2 row slices
-  for (long long p = tid; p < my_pairs; p += TMA_THREADS)
-    vsm[p] = __ldg(reinterpret_cast<const double2*>(v) + p_lo + p);
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const long long i0 = cid * rows_per_cluster;
-  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
-  const long long n_pairs = (i1 > i0) ? (i1 - i0 + 1) / 2 : 0;
-  auto issue = [&](long long k) {        // elected thread: stream pair k into stage k % NS
-    const int s = (int)(k % NS);
-    const long long i = i0 + 2 * k;
-    const double* row0 = A + i * n_cols + 2 * p_lo;
-    const double* row1 = (i + 1 < i1) ? row0 + n_cols : row0;
-    unsigned char* dst = ring + (size_t)s * 2 * slice_stride;
-    mbar_expect_tx(&full[s], 2 * slice_bytes);
-    tma_load_1d(dst, row0, slice_bytes, &full[s]);
-    tma_load_1d(dst + slice_stride, row1, slice_bytes, &full[s]);
-  };
-  if (tid == 0 && my_pairs > 0)
-    for (long long k = 0; k < NS && k < n_pairs; ++k) issue(k);
-  double2 q[PAIRS];
-#pragma unroll
-  for (int k = 0; k < PAIRS; ++k) q[k] = make_double2(0.0, 0.0);
-  double ss = 0.0;
-  int parity = 0;
-  // partial dot products of pair k over this CTA's columns, from its shared-memory stage
-  auto dots = [&](long long k, double (&acc)[FUSED_ROWS]) {
-    const int s = (int)(k % NS);
-    const double2* a0 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride);
-    const double2* a1 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride + slice_stride);
-    if (my_pairs > 0) mbar_wait(&full[s], (unsigned)((k / NS) & 1));
-    acc[0] = acc[1] = 0.0;
-#pragma unroll
-    for (int u = 0; u < PAIRS; ++u) {
-      const long long p = tid + (long long)u * TMA_THREADS;
-      if (p < my_pairs) {
-        const double2 vv = vsm[p], x0 = a0[p], x1 = a1[p];
-        acc[0] += x0.x * vv.x + x0.y * vv.y;
-        acc[1] += x1.x * vv.x + x1.y * vv.y;
-      }
-    }
-  };
-  double acc[FUSED_ROWS] = {0.0, 0.0};
-  if (n_pairs > 0) dots(0, acc);
-  for (long long k = 0; k < n_pairs; ++k) {
-    const int s = (int)(k % NS);
-    const long long i = i0 + 2 * k;
-    const bool two = (i + 1 < i1);
-    const double2* a0 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride);
-    const double2* a1 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * slice_stride + slice_stride);
-    // ---- this CTA's partials of pair k -> every CTA of the cluster (DSMEM), barrier ARRIVE
-    warp_sum_k<FUSED_ROWS>(acc);
-    if (lane == 0) { red[warp][0] = acc[0]; red[warp][1] = acc[1]; }
-    __syncthreads();
-    if (tid < csize) {
-      double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-      for (int w = 0; w < TMA_THREADS / 32; ++w) { p0 += red[w][0]; p1 += red[w][1]; }
-      double* remote = cluster.map_shared_rank(&xch[0][0][0], tid);
-      remote[(parity * FUSED_ROWS + 0) * 8 + crank] = p0;
-      remote[(parity * FUSED_ROWS + 1) * 8 + crank] = p1;
-    }
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    // ---- while the barrier completes: the dot products of pair k+1 (nothing of it depends
-    //      on pair k)
-    double nacc[FUSED_ROWS] = {0.0, 0.0};
-    if (PIPE && k + 1 < n_pairs) dots(k + 1, nacc);
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    double r0 = 0.0, r1 = 0.0;
-    for (int c = 0; c < csize; ++c) { r0 += xch[parity][0][c]; r1 += xch[parity][1][c]; }
-    parity ^= 1;
-    r0 -= b[i];
-    r1 = two ? r1 - b[i + 1] : 0.0;
-    ss += r0 * r0;
-    ss += r1 * r1;
-    // ---- phase 2: rank-1 update from the same shared-memory stage
-#pragma unroll
-    for (int u = 0; u < PAIRS; ++u) {
-      const long long p = tid + (long long)u * TMA_THREADS;
-      if (p < my_pairs) {
-        const double2 x0 = a0[p], x1 = a1[p];
-        q[u].x += r0 * x0.x; q[u].y += r0 * x0.y;
-        q[u].x += r1 * x1.x; q[u].y += r1 * x1.y;
-      }
-    }
-    __syncthreads();                      // every thread is done with stage s
-    if (tid == 0 && my_pairs > 0 && k + NS < n_pairs) issue(k + NS);
-    if (PIPE) { acc[0] = nacc[0]; acc[1] = nacc[1]; }
-    else if (k + 1 < n_pairs) dots(k + 1, acc);
-  }
-  double* out = gpart + cid * n_cols;
-#pragma unroll
-  for (int u = 0; u < PAIRS; ++u) {
-    const long long p = tid + (long long)u * TMA_THREADS;
-    if (p < my_pairs) reinterpret_cast<double2*>(out)[p_lo + p] = q[u];
-  }
-  if (tid == 0 && crank == 0) sq_part[cid] = ss;
-  cluster.sync();
-}
-
-// R: rows per stage (one cluster barrier per R rows); NS: stages of the ring.
-template <int PAIRS, int NS, int R>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
-lasso_fused_tma_kernel(const double* __restrict__ A, const double* __restrict__ b,
-                       const double* __restrict__ v, long long n_rows, long long n_cols,
-                       long long rows_per_cluster, long long pairs_per_cta,
-                       double* __restrict__ gpart, double* __restrict__ sq_part,
-    const int* __restrict__ skip) {
-  if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;   // device-decided loop: nothing to do
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
-  const int csize = (int)cluster.num_blocks();
-  const long long cid = blockIdx.x / csize;
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ double red[TMA_THREADS / 32][R];
-  __shared__ double xch[2][R][8];                    // [parity][row][cluster rank]
-  __shared__ __align__(8) unsigned long long full[NS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long n2 = n_cols >> 1;
-  const long long p_lo = (long long)crank * pairs_per_cta;
-  const long long p_hi = (p_lo + pairs_per_cta < n2) ? p_lo + pairs_per_cta : n2;
-  const long long my_pairs = p_hi > p_lo ? p_hi - p_lo : 0;
-  const unsigned slice_bytes = (unsigned)(my_pairs * 16);
-  const size_t slice_stride = (size_t)pairs_per_cta * 16;        // bytes reserved per row slice
-  double2* vsm = reinterpret_cast<double2*>(dyn);
-  unsigned char* ring = dyn + slice_stride;                      // NS stages x R row slices
-  for (long long p = tid; p < my_pairs; p += TMA_THREADS)
-    vsm[p] = __ldg(reinterpret_cast<const double2*>(v) + p_lo + p);
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const long long i0 = cid * rows_per_cluster;
-  const long long i1 = (i0 + rows_per_cluster < n_rows) ? i0 + rows_per_cluster : n_rows;
-  const long long n_groups = (i1 > i0) ? (i1 - i0 + R - 1) / R : 0;
-  auto issue = [&](long long k) {        // elected thread: stream row group k into stage k % NS
-    const int s = (int)(k % NS);
-    const long long i = i0 + (long long)R * k;
-    unsigned char* dst = ring + (size_t)s * R * slice_stride;
-    mbar_expect_tx(&full[s], R * slice_bytes);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const long long row = (i + r < i1) ? i + r : i;          // rows past the end: a duplicate,
-      tma_load_1d(dst + (size_t)r * slice_stride,               // its residual is forced to 0
-                  A + row * n_cols + 2 * p_lo, slice_bytes, &full[s]);
-    }
-  };
-  if (tid == 0 && my_pairs > 0)
-    for (long long k = 0; k < NS && k < n_groups; ++k) issue(k);
-  double2 q[PAIRS];
-#pragma unroll
-  for (int k = 0; k < PAIRS; ++k) q[k] = make_double2(0.0, 0.0);
-  double ss = 0.0;
-  int parity = 0;
-  for (long long k = 0; k < n_groups; ++k) {
-    const int s = (int)(k % NS);
-    const long long i = i0 + (long long)R * k;
-    const double2* rowp[R];               // the R row slices of this stage
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      rowp[r] = reinterpret_cast<const double2*>(ring + ((size_t)s * R + r) * slice_stride);
-    if (my_pairs > 0) mbar_wait(&full[s], (unsigned)((k / NS) & 1));
-    // ---- phase 1: partial dot products of the R rows over this CTA's columns
-    double acc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0;
-#pragma unroll
-    for (int u = 0; u < PAIRS; ++u) {
-      const long long p = tid + (long long)u * TMA_THREADS;
-      if (p < my_pairs) {
-        const double2 vv = vsm[p];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const double2 x = rowp[r][p];
-          acc[r] += x.x * vv.x + x.y * vv.y;
-        }
-      }
-    }
-    warp_sum_k<R>(acc);
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) red[warp][r] = acc[r];
-    }
-    __syncthreads();
-    if (tid < csize) {
-      double* remote = cluster.map_shared_rank(&xch[0][0][0], tid);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < TMA_THREADS / 32; ++w) t += red[w][r];
-        remote[(parity * R + r) * 8 + crank] = t;
-      }
-    }
-    cluster.sync();
-    double res[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      double t = 0.0;
-      for (int c = 0; c < csize; ++c) t += xch[parity][r][c];
-      res[r] = (i + r < i1) ? t - b[i + r] : 0.0;
-      ss += res[r] * res[r];
-    }
-    parity ^= 1;
-    // ---- phase 2: rank-1 updates from the same shared-memory stage
-#pragma unroll
-    for (int u = 0; u < PAIRS; ++u) {
-      const long long p = tid + (long long)u * TMA_THREADS;
-      if (p < my_pairs) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const double2 x = rowp[r][p];
-          q[u].x += res[r] * x.x;
-          q[u].y += res[r] * x.y;
-        }
-      }
-    }
-    __syncthreads();                      // every thread is done with stage s
-    if (tid == 0 && my_pairs > 0 && k + NS < n_groups) issue(k + NS);
-  }
-  double* out = gpart + cid * n_cols;
-#pragma unroll
-  for (int u = 0; u < PAIRS; ++u) {
-    const long long p = tid + (long long)u * TMA_THREADS;
-    if (p < my_pairs) reinterpret_cast<double2*>(out)[p_lo + p] = q[u];
-  }
-  if (tid == 0 && crank == 0) sq_part[cid] = ss;
-  cluster.sync();
-}
-
 // ------------------------------------------------------------------------------------
 // Fused one-pass gradient, warp-specialised chunk ring (round-1 final form).
-// The TMA kernels above pay one block reduction + one cluster barrier per stage in the
-// critical path of every thread, and with 4-CTA clusters only 132 of the 148 SMs can be
-// co-resident.  Here the roles are split and nothing waits for a barrier it does not need:
+// The roles are split over warps and nothing waits for a barrier it does not need:
 //   * producer warp: streams each row of the CTA's column slice as 16 KB
 //     chunks (1-D bulk TMA) into a ring of RING_SLOTS chunks -- rows simply follow each other
 //     through the ring, a slot is refilled as soon as the update warps release it, so HBM
@@ -1655,7 +1244,6 @@ struct zf_lasso {
   int fused_pairs = 0, fused_ctas = 0;
   long long fused_rows_per_cta = 0;
   int fused_cluster = 1;              // CTAs per cluster (1: single-CTA kernel)
-  int fused_threads = 512;            // threads per CTA of the cluster form
   bool fused_ring = false;            // warp-specialised chunk ring (lasso_fused_ring_kernel)
   // second, concurrent ring launch on the SMs the first one cannot use (4-CTA clusters fit on
   // 132 of 148 SMs): 2-CTA clusters over the last rows, on its own stream
@@ -1666,8 +1254,6 @@ struct zf_lasso {
   double tuned_rate2 = 0.0;
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool fused_tma = false;             // TMA / shared-memory-resident form
-  int tma_rows = 2;                   // rows per TMA stage (one cluster barrier per stage)
   long long fused_pairs_per_cta = 0;  // column pairs per CTA (cluster form)
   size_t gpart_rows = 0;
   // solver state (host scalars)
@@ -1754,83 +1340,6 @@ int launch_fused_t(zf_lasso* h, const double* v) {
   ZF_CUDA(cudaGetLastError());
   zf::zf_count_launch();
   return ZF_OK;
-}
-
-template <int PAIRS, int THREADS, int CHUNK>
-int launch_fused_cluster_t(zf_lasso* h, const double* v) {
-  auto k = zf::lasso_fused_cluster_kernel<PAIRS, THREADS, CHUNK>;
-  const size_t smem = sizeof(double) * 2 * (size_t)h->fused_pairs_per_cta;
-  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)h->fused_ctas);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)h->fused_cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  const long long rows_per_cluster = h->fused_rows_per_cta;
-  ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, rows_per_cluster,
-                             h->fused_pairs_per_cta, h->gpart, h->sq_part, h->skip));
-  zf::zf_count_launch();
-  return ZF_OK;
-}
-
-template <int PAIRS, int R>
-int launch_fused_tma_t(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
-  constexpr int NS = 2;
-  void (*k)(const double*, const double*, const double*, long long, long long, long long,
-            long long, double*, double*, const int*);
-  if (R == 2) k = zf::lasso_fused_tma_pair_kernel<PAIRS, NS, false>;
-  else k = zf::lasso_fused_tma_kernel<PAIRS, NS, (R == 2 ? 3 : R)>;
-  const size_t smem = (size_t)h->fused_pairs_per_cta * 16 * (1 + R * NS);
-  ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)h->fused_ctas);
-  cfg.blockDim = dim3(zf::TMA_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)h->fused_cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (query_only) {
-    ZF_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, k, &cfg));
-    return ZF_OK;
-  }
-  const long long rows_per_cluster = h->fused_rows_per_cta;
-  ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, rows_per_cluster,
-                             h->fused_pairs_per_cta, h->gpart, h->sq_part, h->skip));
-  zf::zf_count_launch();
-  return ZF_OK;
-}
-
-template <int R>
-int launch_fused_tma_r(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
-  switch (h->fused_pairs) {
-    case 1: return launch_fused_tma_t<1, R>(h, v, query_only, max_clusters);
-    case 2: return launch_fused_tma_t<2, R>(h, v, query_only, max_clusters);
-    case 3: return launch_fused_tma_t<3, R>(h, v, query_only, max_clusters);
-    case 4: return launch_fused_tma_t<4, R>(h, v, query_only, max_clusters);
-    case 5: return launch_fused_tma_t<5, R>(h, v, query_only, max_clusters);
-    case 6: return launch_fused_tma_t<6, R>(h, v, query_only, max_clusters);
-    default: return launch_fused_tma_t<8, R>(h, v, query_only, max_clusters);
-  }
-}
-
-int launch_fused_tma(zf_lasso* h, const double* v, bool query_only, int* max_clusters) {
-  switch (h->tma_rows) {
-    case 4: return launch_fused_tma_r<4>(h, v, query_only, max_clusters);
-    case 3: return launch_fused_tma_r<3>(h, v, query_only, max_clusters);
-    default: return launch_fused_tma_r<2>(h, v, query_only, max_clusters);
-  }
 }
 
 struct RingLaunch {
@@ -1923,35 +1432,6 @@ int launch_gradient_pass(zf_lasso* h, const double* v, int* n_gpart_rows, int* n
     const int rc = launch_fused_ring(h, v, false, nullptr);
     *n_gpart_rows = h->fused_ctas / h->fused_cluster + h->ring2_ctas / h->ring2_cluster;
     *n_sq = *n_gpart_rows;
-    return rc;
-  }
-  if (h->fused_pairs > 0 && h->fused_tma) {
-    const int rc = launch_fused_tma(h, v, false, nullptr);
-    *n_gpart_rows = h->fused_ctas / h->fused_cluster;
-    *n_sq = h->fused_ctas / h->fused_cluster;
-    return rc;
-  }
-  if (h->fused_pairs > 0 && h->fused_cluster > 1) {
-    int rc;
-    if (h->fused_threads == 1024) {
-      switch (h->fused_pairs) {
-        case 1: rc = launch_fused_cluster_t<1, 1024, 1>(h, v); break;
-        case 2: rc = launch_fused_cluster_t<2, 1024, 2>(h, v); break;
-        case 3: rc = launch_fused_cluster_t<3, 1024, 3>(h, v); break;
-        case 4: rc = launch_fused_cluster_t<4, 1024, 2>(h, v); break;
-        default: rc = launch_fused_cluster_t<5, 1024, 3>(h, v); break;
-      }
-    } else {
-      switch (h->fused_pairs) {
-        case 2: rc = launch_fused_cluster_t<2, 512, 2>(h, v); break;
-        case 4: rc = launch_fused_cluster_t<4, 512, 4>(h, v); break;
-        case 6: rc = launch_fused_cluster_t<6, 512, 4>(h, v); break;
-        case 8: rc = launch_fused_cluster_t<8, 512, 4>(h, v); break;
-        default: rc = launch_fused_cluster_t<10, 512, 4>(h, v); break;
-      }
-    }
-    *n_gpart_rows = h->fused_ctas / h->fused_cluster;
-    *n_sq = h->fused_ctas / h->fused_cluster;
     return rc;
   }
   if (h->fused_pairs > 0) {
@@ -2268,15 +1748,13 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
   // ---- which kernels compute A^T(A v - b) for this shape.  Measured on B200 (DESIGN.md 3.3,
   // fraction of the one-pass HBM bound).  Warp-specialised chunk ring: 0.89 at 4096 columns,
   // 0.97-0.99 at 6000-8192 (no cluster), 0.95-0.98 at 12000-16384 (cluster 2), 0.82 at 30000
-  // (cluster 4: 132 of 148 SMs).  The older forms, kept behind the overrides and as fall-backs:
-  // single-CTA fused 0.83 at 4096 columns, 0.52 at 6000;
-  // TMA / shared-memory-resident form 0.72 at 6000 and 0.76 at 8192 (cluster 2, 4 / 3 rows per
-  // stage), 0.67-0.72 at 20000 (cluster 4) but 0.69 at 16384; 2-CTA cluster with L2 re-read
-  // 0.77 at 16384, 0.70 at 12000, 0.65 at 20000; two-pass kernels 0.53 everywhere.
+  // (cluster 4: 132 of 148 SMs).  Below 4096 columns the single-CTA fused kernel (0.83 at 4096
+  // columns, 0.52 at 6000); two-pass kernels 0.53 everywhere.  (The round-1 cluster / TMA forms,
+  // 0.65-0.77, were removed in round 2: nothing selected them any more.)
   // Environment overrides for experiments:
-  //   ZF_LASSO_FUSED=0 (two-pass), ZF_LASSO_CLUSTER=2|4, ZF_LASSO_THREADS=512|1024,
-  //   ZF_LASSO_TMA=2|4|8, ZF_LASSO_TMA_ROWS=2|3|4, ZF_LASSO_RING=1|2|4|8,
-  //   ZF_LASSO_RING_SPLIT=0 (no second launch on the idle SMs) | .NN (its per-SM rate).
+  //   ZF_LASSO_FUSED=0 (two-pass) | 1 (single-CTA fused), ZF_LASSO_RING=1..8 (cluster size),
+  //   ZF_LASSO_RING_SPLIT=0 (no second launch on the idle SMs) | .NN (its per-SM rate),
+  //   ZF_LASSO_TUNE=0|v, ZF_LASSO_NSM=n.
   h->gpart_rows = (size_t)h->n_rowblocks;
   size_t sq_rows = (size_t)h->res_blocks;
   {
@@ -2286,42 +1764,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const bool big_enough = h->vec && n_rows >= 4LL * h->n_sm;
     const char* env_fused = getenv("ZF_LASSO_FUSED");
-    const char* env_cluster = getenv("ZF_LASSO_CLUSTER");
-    const char* env_tma = getenv("ZF_LASSO_TMA");
     const bool off = env_fused && env_fused[0] == '0';
-    auto finish_cluster_grid = [&](int cluster, int n_clusters, int row_multiple) {
-      h->fused_rows_per_cta = (n_rows + n_clusters - 1) / n_clusters;      // rows per cluster
-      while (h->fused_rows_per_cta % row_multiple) h->fused_rows_per_cta += 1;
-      const int used = (int)((n_rows + h->fused_rows_per_cta - 1) / h->fused_rows_per_cta);
-      h->fused_ctas = used * cluster;
-      if ((size_t)used > h->gpart_rows) h->gpart_rows = (size_t)used;
-      if ((size_t)used > sq_rows) sq_rows = (size_t)used;
-    };
-    auto try_tma = [&](int c) -> bool {
-      if (!(c == 2 || c == 4 || c == 8) || !big_enough) return false;
-      const long long ppc = (n2 + c - 1) / c;
-      const long long ppt = (ppc + zf::TMA_THREADS - 1) / zf::TMA_THREADS;
-      // rows per stage: as many as fit (v slice + 2 stages x R row slices in shared memory),
-      // up to 4 -- one block reduction + one cluster barrier is paid per stage
-      int R = 4;
-      if (const char* e2 = getenv("ZF_LASSO_TMA_ROWS")) { R = atoi(e2); if (R < 2 || R > 4) R = 2; }
-      while (R > 2 && (size_t)ppc * 16 * (1 + 2 * R) + 2048 > (size_t)max_smem) --R;
-      h->tma_rows = R;
-      const size_t smem = (size_t)ppc * 16 * (1 + 2 * R);
-      if (ppt > 8 || smem + 2048 > (size_t)max_smem) return false;
-      h->fused_tma = true;
-      h->fused_cluster = c;
-      h->fused_pairs_per_cta = ppc;
-      h->fused_pairs = (int)(ppt == 7 ? 8 : ppt);
-      int n_clusters = h->n_sm / c;
-      h->fused_ctas = n_clusters * c;
-      h->fused_rows_per_cta = 2;
-      int active = 0;
-      if (launch_fused_tma(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
-        n_clusters = active;              // only clusters that can be co-resident: one wave
-      finish_cluster_grid(c, n_clusters, h->tma_rows);
-      return true;
-    };
     auto try_ring = [&](int c) -> bool {
       if (!big_enough) return false;
       const char* env_split = getenv("ZF_LASSO_RING_SPLIT");
@@ -2333,22 +1776,6 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       const size_t parts = (size_t)h->ring1_clusters + (size_t)(h->ring2_ctas / h->ring2_cluster);
       if (parts > h->gpart_rows) h->gpart_rows = parts;
       if (parts > sq_rows) sq_rows = parts;
-      return true;
-    };
-    auto try_cluster = [&](int c) -> bool {
-      if (!(c == 2 || c == 4) || !big_enough) return false;
-      const long long ppc = (n2 + c - 1) / c;
-      long long ppt = (ppc + zf::FUSED_THREADS - 1) / zf::FUSED_THREADS;
-      int threads = 512;
-      if (const char* tenv = getenv("ZF_LASSO_THREADS")) threads = atoi(tenv) == 1024 ? 1024 : 512;
-      else if (ppt > 8) threads = 1024;      // 9-10 pairs per thread spill at 512 threads
-      if (threads == 1024) ppt = (ppc + 1023) / 1024;
-      if (ppt > (threads == 1024 ? 5 : 10) || (size_t)ppc * 16 + 2048 > (size_t)max_smem) return false;
-      h->fused_cluster = c;
-      h->fused_threads = threads;
-      h->fused_pairs_per_cta = ppc;
-      h->fused_pairs = threads == 1024 ? (int)ppt : (int)(((ppt + 1) / 2) * 2);
-      finish_cluster_grid(c, h->n_sm / c, 2);
       return true;
     };
     auto try_single = [&]() -> bool {
@@ -2367,10 +1794,6 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       // two-pass kernels
     } else if (env_ring) {
       try_ring(atoi(env_ring));
-    } else if (env_tma) {
-      try_tma(atoi(env_tma));
-    } else if (env_cluster) {
-      try_cluster(atoi(env_cluster));
     } else if (env_fused) {
       try_single();
     } else if (n_cols < 4096) {
@@ -2382,11 +1805,9 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
       // 60000: 8 CTAs 0.73 / 0.85).  Above 16384 columns the create-time probe below re-decides.
       const int c = n_cols <= 8192 ? 1 : n_cols <= 16384 ? 2 : n_cols <= 32768 ? 4
                   : n_cols <= 40960 ? 5 : n_cols <= 49152 ? 6 : 8;
-      if (!try_ring(c) && !try_ring(8)) {
-        if (n_cols <= 8192) { if (!try_tma(2)) try_single(); }
-        else if (n_cols <= 16384) try_cluster(2);
-        else if (!try_tma(4)) try_cluster(2);
-      }
+      // (rows wider than 8 x 5 chunks = 81920 columns, an odd column count or an unaligned A:
+      // the two-pass kernels)
+      if (!try_ring(c) && !try_ring(8)) try_single();
     }
   }
   cudaError_t e = cudaSuccess;
@@ -2713,9 +2134,6 @@ enum { DS_INIT = 0, DS_GRAD = 1, DS_PROX = 2, DS_FEVAL = 3, DS_DECIDE = 4, DS_FI
 void gradient_part_counts(const zf_lasso* h, int* n_parts, int* n_sq) {
   if (h->fused_pairs > 0 && h->fused_ring) {
     *n_parts = h->fused_ctas / h->fused_cluster + h->ring2_ctas / h->ring2_cluster;
-    *n_sq = *n_parts;
-  } else if (h->fused_pairs > 0 && (h->fused_tma || h->fused_cluster > 1)) {
-    *n_parts = h->fused_ctas / h->fused_cluster;
     *n_sq = *n_parts;
   } else if (h->fused_pairs > 0) {
     *n_parts = h->fused_ctas;
