@@ -840,16 +840,24 @@ def _hbm_roofline(a_bytes, vec_bytes, ms, passes, peaks, traffic_note, ms_burst=
             traffic_source = ("measured at this shape: ncu dram__bytes_read.sum + dram__bytes_write.sum "
                               "of one gradient pass (both concurrent launches), "
                               "profiles/r02_traffic_configs3.json: 1.00008 x |A|")
-    return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+    sustained = {"ms_per_gradient": ms, "achieved": ach, "frac": ach / peaks["hbm_gbs"],
+                 "timing": "50 launches back to back at a non-zero iterate: the clocks of a running "
+                           "solve (power cap), against the same BURST peak"}
+    if ms_burst is None:
+        head_ms, timing = ms, sustained["timing"]
+    else:
+        # MEASURED_PEAKS.json's HBM figure is a burst figure (best of 10 copies): the fraction that
+        # compares like with like is the kernel timed alone the same way; the sustained figure is
+        # reported next to it
+        head_ms = ms_burst
+        timing = ("kernel timed alone: 5 launches after a 0.5 s pause, CUDA events (the way the "
+                  "MEASURED_PEAKS copy peak and round 1 were timed)")
+    head = alg / (head_ms / 1e3) / 1e9
+    return {"bound": "hbm", "achieved": head, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": head / peaks["hbm_gbs"], "traffic": traffic,
             "traffic_source": traffic_source + traffic_note,
-            "ms_per_gradient": ms, "hbm_passes_over_A": passes,
-            "timing": "50 launches back to back at a non-zero iterate (sustained clocks)",
-            "burst": (None if ms_burst is None else
-                      {"ms_per_gradient": ms_burst, "frac": alg / (ms_burst / 1e3) / 1e9 / peaks["hbm_gbs"],
-                       "timing": "5 launches after a 0.5 s pause (boost clocks; how round 1 and the "
-                                 "MEASURED_PEAKS copy test were timed)"}),
-            "peak_source": peaks["source"]}
+            "ms_per_gradient": head_ms, "hbm_passes_over_A": passes, "timing": timing,
+            "sustained": sustained, "peak_source": peaks["source"]}
 
 
 def bench_lasso(args, dev, rank, world):
@@ -888,7 +896,7 @@ def bench_lasso(args, dev, rank, world):
         out["roofline"] = _hbm_roofline(a_bytes, (2 * cols + 2 * rows) * 8, ms,
                                         prob.hbm_passes_per_gradient(), _measured_peaks(), "",
                                         ms_burst=_burst_gradient_ms(prob, xk))
-        out["solver_over_gradient_bound"] = rate * ms / 1e3
+        out["solver_over_gradient_bound"] = rate * ms / 1e3       # against the SUSTAINED pass time
     return out
 
 
@@ -1033,10 +1041,11 @@ def bench_lasso_configs3(args, dev, rank, world):
         local = None
         cp = _copy_bandwidth_here(dev)
         roof["copy_test_on_this_box"] = cp
-        roof["frac_of_sustained_copy_here"] = roof["achieved"] / cp["sustained_GBps"]
+        roof["sustained"]["frac_of_sustained_copy_here"] = (roof["sustained"]["achieved"]
+                                                            / cp["sustained_GBps"])
     out["roofline"] = roof
     out["gradient_ms_max_over_ranks"] = t.item()
-    out["efficiency_vs_gradient_bound"] = rate * t.item() / 1e3
+    out["efficiency_vs_gradient_bound"] = rate * t.item() / 1e3      # (sustained gradient time)
     if world == 1:
         local_m = DenseLassoMulti(A, b, 1e-3, K, scale=1.0 / (2 * rows_total))
         X = xk.expand(K, -1).contiguous()
