@@ -430,7 +430,7 @@ __device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, uns
 }
 
 // Timing experiment: compile with -DZF_RING_DEBUG=1 and run with ZF_LASSO_RING_DBG=1 to get
-// clock64 stamps of rows 64..127 of CTA 0: [0] first chunk issued, [1] dot warp 0 done, [6] all
+// clock64 stamps of rows 64..127 of CTA <ZF_LASSO_RING_DBG>: [0] first chunk issued, [1] dot warp 0 done, [6] all
 // dot warps in, [2] part posted, [3] update warps saw `ready`, [4] last chunk released; dbg2 =
 // per-dot-warp completion.  (The numbers quoted in DESIGN.md 3.3 come from these.)  The stamps
 // are compiled out by default: their predicates were ~15 of the ~45 instructions an update
@@ -442,9 +442,9 @@ __device__ long long zf_ring_dbg[8][64];
 __device__ long long zf_ring_dbg2[8][64];
 #if ZF_RING_DEBUG
 #define RING_STAMP(k, row) \
-  do { if (dbg && blockIdx.x == 0 && (row) >= 64 && (row) < 128) zf_ring_dbg[k][(row) - 64] = clock64(); } while (0)
+  do { if (dbg && (int)blockIdx.x == dbg - 1 && (row) >= 64 && (row) < 128) zf_ring_dbg[k][(row) - 64] = clock64(); } while (0)
 #define RING_STAMP2(w, row) \
-  do { if (dbg && blockIdx.x == 0 && (row) >= 64 && (row) < 128) zf_ring_dbg2[w][(row) - 64] = clock64(); } while (0)
+  do { if (dbg && (int)blockIdx.x == dbg - 1 && (row) >= 64 && (row) < 128) zf_ring_dbg2[w][(row) - 64] = clock64(); } while (0)
 #else
 #define RING_STAMP(k, row) do { } while (0)
 #define RING_STAMP2(w, row) do { } while (0)
@@ -1371,7 +1371,9 @@ int launch_fused_ring_t(zf_lasso* h, const double* v, const RingLaunch& L, bool 
     ZF_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, k, &cfg));
     return ZF_OK;
   }
-  static const int dbg = (ZF_RING_DEBUG && getenv("ZF_LASSO_RING_DBG")) ? 1 : 0;
+  // ZF_LASSO_RING_DBG=<block index>: which CTA of the grid writes its stamps
+  static const int dbg = (ZF_RING_DEBUG && getenv("ZF_LASSO_RING_DBG"))
+                             ? atoi(getenv("ZF_LASSO_RING_DBG")) + 1 : 0;
   ZF_CUDA(cudaLaunchKernelEx(&cfg, k, h->A, h->b, v, h->n_rows, h->n_cols, L.rows_per_cluster,
                              L.pairs_per_cta, h->gpart, h->sq_part, dbg, L.row_begin,
                              L.row_end, L.part_base, h->skip));
