@@ -175,7 +175,7 @@ def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     import torch
     from zfista_b200.lasso import DenseLasso
 
-    for k in ("ZF_LASSO_FUSED", "ZF_LASSO_RING", "ZF_LASSO_TUNE", "ZF_LASSO_NSM"):
+    for k in ("ZF_LASSO_FUSED", "ZF_LASSO_RING", "ZF_LASSO_TUNE", "ZF_LASSO_NSM", "ZF_LASSO_RING_RPS"):
         monkeypatch.delenv(k, raising=False)
     rows, cols = shape
     g = torch.Generator(device="cuda").manual_seed(rows + cols)
@@ -204,6 +204,41 @@ def test_every_gradient_kernel_form(gpu, monkeypatch, env, shape, passes):
     assert a.nit == c.nit and a.status == c.status
     np.testing.assert_allclose(a.x, c.x, rtol=0, atol=1e-9)
     np.testing.assert_allclose(a.fun, c.fun, rtol=1e-11)
+
+
+@pytest.mark.parametrize("cluster,shape", [
+    ("4", (901, 20000)), ("4", (1200, 8192)), ("6", (641, 36000)), ("8", (777, 40000)),
+    ("3", (610, 12000)), ("2", (650, 4000)),
+])
+def test_ring_rows_per_exchange_step_is_bit_identical(gpu, monkeypatch, cluster, shape):
+    """Two rows per exchange step (the default for row slices of <= 3 chunks: one dot-product
+    reduction, one exchange and one `ready` wait per ROW PAIR; ZF_LASSO_RING_RPS=1 switches it
+    off) changes the schedule of the chunk-ring kernel, not its arithmetic: gradient and f must
+    equal the one-row-per-step kernel's bit for bit, also when the rows of a cluster are odd in
+    number (a last step of one row)."""
+    import torch
+    from zfista_b200.lasso import DenseLasso
+
+    for k in ("ZF_LASSO_FUSED", "ZF_LASSO_RING", "ZF_LASSO_TUNE", "ZF_LASSO_NSM", "ZF_LASSO_RING_RPS"):
+        monkeypatch.delenv(k, raising=False)
+    rows, cols = shape
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + cols)
+    A = torch.randn(rows, cols, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn(rows, dtype=torch.float64, device="cuda", generator=g)
+    x = torch.randn(cols, dtype=torch.float64, device="cuda", generator=g)
+    monkeypatch.setenv("ZF_LASSO_RING", cluster)
+    out = {}
+    for rps in ("1", "2"):
+        monkeypatch.setenv("ZF_LASSO_RING_RPS", rps)
+        prob = DenseLasso(A, b, 0.02, scale=1 / (2 * rows))
+        assert prob.hbm_passes_per_gradient() == 1
+        grad, f = prob.gradient(x)
+        out[rps] = (grad.clone(), f.clone())
+        del prob
+    assert torch.equal(out["1"][0], out["2"][0])
+    assert torch.equal(out["1"][1], out["2"][1])
+    r = A @ x - b
+    torch.testing.assert_close(out["2"][0], (A.T @ r) / rows, rtol=1e-12, atol=1e-13)
 
 
 def test_reference_lasso_zero_and_return_all(gpu):

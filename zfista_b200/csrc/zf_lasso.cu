@@ -438,6 +438,9 @@ __device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, uns
 #ifndef ZF_RING_DEBUG
 #define ZF_RING_DEBUG 0
 #endif
+#ifndef ZF_RING_RPS_DEFAULT
+#define ZF_RING_RPS_DEFAULT 2     // rows per exchange step for row slices of <= 3 chunks
+#endif
 __device__ long long zf_ring_dbg[8][64];
 __device__ long long zf_ring_dbg2[8][64];
 #if ZF_RING_DEBUG
@@ -450,8 +453,8 @@ __device__ long long zf_ring_dbg2[8][64];
 #define RING_STAMP2(w, row) do { } while (0)
 #endif
 
-template <int NCH>
-__global__ void __maxnreg__(96)
+template <int NCH, int RPS>
+__global__ void __maxnreg__(96)   // 18 warps: 5 on one scheduler, whose register file holds 5 x 32 x 102
 lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__ b,
                         const double* __restrict__ v, long long n_rows, long long n_cols,
                         long long rows_per_cluster, long long pairs_per_cta,
@@ -465,8 +468,12 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
   const int csize = (int)cluster.num_blocks();
   const long long cid = blockIdx.x / csize;
   extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ double xslot[RING_NR][RING_MAX_CLUSTER];  // [row mod NR][cluster rank]
-  __shared__ double dpart[RING_NR][RING_WARPS];        // [row mod NR][dot warp]
+  // RPS rows per exchange STEP (2 for row slices of <= 3 chunks, else 1): the per-step fixed work
+  // -- the warp reduction, two barrier operations, the ready wait, the sum of the parts -- is paid
+  // once per step, and the dot warps run ahead by a whole row while the exchange is in flight
+  // (sustained clocks, interleaved A/B: +2..14 % at <= 3 chunks per row)
+  __shared__ double xslot[RING_NR][RPS][RING_MAX_CLUSTER];  // [step mod NR][row of the step][cluster rank]
+  __shared__ double dpart[RING_NR][RPS][RING_WARPS];        // [step mod NR][row of the step][dot warp]
   __shared__ __align__(8) unsigned long long full[RING_SLOTS];
   __shared__ __align__(8) unsigned long long empty[RING_SLOTS];
   __shared__ __align__(8) unsigned long long ready[RING_NR];   // the row's residual parts are here
@@ -532,33 +539,43 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
       }
     int s = 0, sl = 0;
     unsigned ph = 0;                          // phase parity of the ring slot
-    for (long long n = 0; n < my_rows; ++n) {
-      double accu[RING_U];                  // independent chains: a warp handles every chunk, its
+    for (long long n = 0; n < my_rows; n += RPS) {
+      double accu[RPS][RING_U];             // independent chains: a warp handles every chunk, its
 #pragma unroll                              // per-chunk latency is what bounds the dot warps
-      for (int u = 0; u < RING_U; ++u) accu[u] = 0.0;
+      for (int rr = 0; rr < RPS; ++rr)
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (c < nch) {
-          mbar_wait(&full[s], ph);
-          const double2* ch = ring + (size_t)s * RING_CH_PAIRS;
-          const int cp = my_pairs - c * RING_CH_PAIRS;           // valid pairs (may exceed a chunk)
+        for (int u = 0; u < RING_U; ++u) accu[rr][u] = 0.0;
 #pragma unroll
-          for (int u = 0; u < RING_U; ++u) {
-            const int p = u * RING_GROUP + tid;
-            if (p < cp) {                                        // stale shared memory past the copy
-              const double2 x = ch[p];
-              accu[u] += x.x * vreg[c][u].x + x.y * vreg[c][u].y;
+      for (int rr = 0; rr < RPS; ++rr) {
+        if (RPS > 1 && n + rr >= my_rows) break;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (c < nch) {
+            mbar_wait(&full[s], ph);
+            const double2* ch = ring + (size_t)s * RING_CH_PAIRS;
+            const int cp = my_pairs - c * RING_CH_PAIRS;         // valid pairs (may exceed a chunk)
+#pragma unroll
+            for (int u = 0; u < RING_U; ++u) {
+              const int p = u * RING_GROUP + tid;
+              if (p < cp) {                                      // stale shared memory past the copy
+                const double2 x = ch[p];
+                accu[rr][u] += x.x * vreg[c][u].x + x.y * vreg[c][u].y;
+              }
             }
+            if (++s == RING_SLOTS) { s = 0; ph ^= 1u; }
           }
-          if (++s == RING_SLOTS) { s = 0; ph ^= 1u; }
         }
       }
       if (tid == 0) RING_STAMP(1, n);
       if (lane == 0) RING_STAMP2(warp, n);
-      double acc = (accu[0] + accu[1]) + (accu[2] + accu[3]);
-      acc = warp_sum(acc);
+      double acc[RPS];
+#pragma unroll
+      for (int rr = 0; rr < RPS; ++rr) acc[rr] = (accu[rr][0] + accu[rr][1]) + (accu[rr][2] + accu[rr][3]);
+      if (RPS == 1) acc[0] = warp_sum(acc[0]);
+      else warp_sum_k<RPS>(acc);             // (bit-identical to one butterfly per value)
       if (lane == 0) {
-        dpart[sl][warp] = acc;
+#pragma unroll
+        for (int rr = 0; rr < RPS; ++rr) dpart[sl][rr][warp] = acc[rr];
         mbar_arrive_local(&dbar[sl]);
       }
       if (++sl == RING_NR) { sl = 0; }
@@ -573,20 +590,29 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
     const unsigned rd_base = smem_u32(&ready[0]);
     int sl = 0;
     unsigned rph = 0;
-    for (long long n = 0; n < my_rows; ++n) {
-      double bi = 0.0;
-      if (crank == 0) bi = __ldg(b + i0 + n);          // rank 0 folds -b_i into its part
-      if (lane == 0) mbar_expect_tx(&ready[sl], 8u * (unsigned)csize);
+    for (long long n = 0; n < my_rows; n += RPS) {
+      const int nr = (RPS > 1 && n + RPS > my_rows) ? (int)(my_rows - n) : RPS;   // rows of this step
+      double bi[RPS];
+#pragma unroll
+      for (int rr = 0; rr < RPS; ++rr)       // rank 0 folds -b_i into its part
+        bi[rr] = (crank == 0 && rr < nr) ? __ldg(b + i0 + n + rr) : 0.0;
+      if (lane == 0) mbar_expect_tx(&ready[sl], 8u * (unsigned)(csize * nr));
       mbar_wait(&dbar[sl], rph);
       if (lane == 0) RING_STAMP(6, n);
       if (lane < csize) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < RING_WARPS; ++w) t += dpart[sl][w];
-        t -= bi;
-        const unsigned ra = mapa_u32(xs_base + (unsigned)((sl * RING_MAX_CLUSTER + crank) * 8), (unsigned)lane);
         const unsigned rb = mapa_u32(rd_base + (unsigned)(sl * 8), (unsigned)lane);
-        st_async_f64(ra, t, rb);
+#pragma unroll
+        for (int rr = 0; rr < RPS; ++rr) {
+          if (rr < nr) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < RING_WARPS; ++w) t += dpart[sl][rr][w];
+            t -= bi[rr];
+            const unsigned ra = mapa_u32(
+                xs_base + (unsigned)((((sl * RPS + rr) * RING_MAX_CLUSTER) + crank) * 8), (unsigned)lane);
+            st_async_f64(ra, t, rb);
+          }
+        }
         if (lane == 0) RING_STAMP(2, n);
       }
       if (++sl == RING_NR) { sl = 0; rph ^= 1u; }
@@ -602,33 +628,43 @@ lasso_fused_ring_kernel(const double* __restrict__ A, const double* __restrict__
     double ss = 0.0;
     int s = 0, sl = 0;
     unsigned ph = 0, rph = 0;
-    for (long long n = 0; n < my_rows; ++n) {
-      double r = 0.0;
+    for (long long n = 0; n < my_rows; n += RPS) {
+      const int nr = (RPS > 1 && n + RPS > my_rows) ? (int)(my_rows - n) : RPS;
+      double r[RPS];
       {
         mbar_wait(&ready[sl], rph);
         if (ut == 0) RING_STAMP(3, n);
-        for (int c = 0; c < csize; ++c) r += xslot[sl][c];
+#pragma unroll
+        for (int rr = 0; rr < RPS; ++rr) {
+          r[rr] = 0.0;
+          if (rr < nr)
+            for (int c = 0; c < csize; ++c) r[rr] += xslot[sl][rr][c];
+          ss += r[rr] * r[rr];
+        }
       }
-      ss += r * r;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (c < nch) {
-          mbar_wait(&full[s], ph);                               // complete long ago: visibility
-          const double2* ch = ring + (size_t)s * RING_CH_PAIRS;
-          const int cp = my_pairs - c * RING_CH_PAIRS;
+      for (int rr = 0; rr < RPS; ++rr) {
+        if (RPS > 1 && rr >= nr) break;
 #pragma unroll
-          for (int u = 0; u < RING_U; ++u) {
-            const int p = u * RING_GROUP + ut;
-            if (p < cp) {
-              const double2 x = ch[p];
-              q[c][u].x += r * x.x;
-              q[c][u].y += r * x.y;
+        for (int c = 0; c < NCH; ++c) {
+          if (c < nch) {
+            mbar_wait(&full[s], ph);                             // complete long ago: visibility
+            const double2* ch = ring + (size_t)s * RING_CH_PAIRS;
+            const int cp = my_pairs - c * RING_CH_PAIRS;
+#pragma unroll
+            for (int u = 0; u < RING_U; ++u) {
+              const int p = u * RING_GROUP + ut;
+              if (p < cp) {
+                const double2 x = ch[p];
+                q[c][u].x += r[rr] * x.x;
+                q[c][u].y += r[rr] * x.y;
+              }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(&empty[s]);
+            if (ut == 0 && c == nch - 1) RING_STAMP(4, n);
+            if (++s == RING_SLOTS) { s = 0; ph ^= 1u; }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive_local(&empty[s]);
-          if (ut == 0 && c == nch - 1) RING_STAMP(4, n);
-          if (++s == RING_SLOTS) { s = 0; ph ^= 1u; }
         }
       }
       if (++sl == RING_NR) { sl = 0; rph ^= 1u; }
@@ -1266,6 +1302,7 @@ struct zf_lasso {
   zf::StepSums sums{};
   bool result_is_prev = false;
   const int* skip = nullptr;    // device flag the gradient-pass kernels test (device-decided loop)
+  int ring_rps = ZF_RING_RPS_DEFAULT;   // rows per exchange step of the chunk-ring kernel (create())
   // device-decided loop (zf_lasso_dev_*)
   zf::LassoDevOpts* d_opts = nullptr;
   zf::LassoDevState* d_state = nullptr;
@@ -1349,10 +1386,10 @@ struct RingLaunch {
   cudaStream_t stream;
 };
 
-template <int NCH>
+template <int NCH, int RPS>
 int launch_fused_ring_t(zf_lasso* h, const double* v, const RingLaunch& L, bool query_only,
                         int* max_clusters) {
-  auto k = zf::lasso_fused_ring_kernel<NCH>;
+  auto k = zf::lasso_fused_ring_kernel<NCH, RPS>;
   const size_t smem = (size_t)zf::RING_SLOTS * zf::RING_CH_PAIRS * 16;
   ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
@@ -1398,12 +1435,24 @@ int launch_fused_ring_t(zf_lasso* h, const double* v, const RingLaunch& L, bool 
 
 int launch_fused_ring_n(zf_lasso* h, const double* v, int nch, const RingLaunch& L, bool query_only,
                         int* max_clusters) {
+  // two rows per exchange step for narrow row slices (<= 3 chunks); ZF_LASSO_RING_RPS=1|2 overrides
+  // rows per exchange step: the chunks of one step stay in the ring until its update is done, so
+  // a step may hold at most 6 of the 13 slots or the producer runs out of prefetch depth
+  // (measured: 2 rows x 4 chunks drops from 1.00 to 0.66 of the copy bandwidth; 3 rows x <= 2
+  // chunks gains nothing over 2 rows, profiles/r02_ring_rows_per_step.txt)
+  if (h->ring_rps == 2 && nch <= 3) {
+    switch (nch) {
+      case 1: return launch_fused_ring_t<1, 2>(h, v, L, query_only, max_clusters);
+      case 2: return launch_fused_ring_t<2, 2>(h, v, L, query_only, max_clusters);
+      default: return launch_fused_ring_t<3, 2>(h, v, L, query_only, max_clusters);
+    }
+  }
   switch (nch) {                     // chunks per row slice
-    case 1: return launch_fused_ring_t<1>(h, v, L, query_only, max_clusters);
-    case 2: return launch_fused_ring_t<2>(h, v, L, query_only, max_clusters);
-    case 3: return launch_fused_ring_t<3>(h, v, L, query_only, max_clusters);
-    case 4: return launch_fused_ring_t<4>(h, v, L, query_only, max_clusters);
-    default: return launch_fused_ring_t<5>(h, v, L, query_only, max_clusters);
+    case 1: return launch_fused_ring_t<1, 1>(h, v, L, query_only, max_clusters);
+    case 2: return launch_fused_ring_t<2, 1>(h, v, L, query_only, max_clusters);
+    case 3: return launch_fused_ring_t<3, 1>(h, v, L, query_only, max_clusters);
+    case 4: return launch_fused_ring_t<4, 1>(h, v, L, query_only, max_clusters);
+    default: return launch_fused_ring_t<5, 1>(h, v, L, query_only, max_clusters);
   }
 }
 
@@ -1648,19 +1697,27 @@ namespace {
 // (and with it the summation order of A^T r) between two handles of the same shape.
 // ZF_LASSO_TUNE=0 switches the probe off, ZF_LASSO_TUNE=v prints the table.
 void ring_autotune(zf_lasso* h, int max_smem) {
-  struct Cand { int c; double rate2; float ms; };
+  // rps: rows per exchange step (it changes the schedule, not the arithmetic: results are
+  // bit-identical to rps 1)
+  struct Cand { int c; double rate2; int rps; float ms; };
   const int c_static = h->fused_cluster;
   const double r_static = h->ring2_ctas > 0 ? 0.57 : 0.0;
+  const int rps_static = h->ring_rps;
+  const bool rps_fixed = getenv("ZF_LASSO_RING_RPS") != nullptr;
   std::vector<Cand> cands;
-  cands.push_back(Cand{c_static, r_static, 0.f});
+  cands.push_back(Cand{c_static, r_static, rps_static, 0.f});
   const long long n2 = h->n_cols / 2;
   for (int c = 1; c <= zf::RING_MAX_CLUSTER; ++c) {
     const long long ppc = (n2 + c - 1) / c;
-    if ((ppc + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS > 4) continue;
+    const long long nch = (ppc + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
+    if (nch > 4) continue;
     for (double r : {0.0, 0.45, 0.57, 0.7}) {
       if (r > 0.0 && c != 4) continue;
-      if (c == c_static && r == r_static) continue;
-      cands.push_back(Cand{c, r, 0.f});
+      for (int rps = 1; rps <= 2; ++rps) {
+        if (rps_fixed ? rps != rps_static : rps * nch > 6) continue;
+        if (c == c_static && r == r_static && (rps == rps_static || nch > 3)) continue;
+        cands.push_back(Cand{c, r, rps, 0.f});
+      }
     }
   }
   const long long probe_rows = h->n_rows < 64LL * h->n_sm ? h->n_rows : 64LL * h->n_sm;
@@ -1677,6 +1734,7 @@ void ring_autotune(zf_lasso* h, int max_smem) {
     cd.ms = -1.f;
     if (!ring_plan(h, cd.c, cd.rate2, probe_rows, max_smem)) continue;
     if (cd.rate2 > 0.0 && h->ring2_ctas == 0) continue;           // the split did not apply
+    h->ring_rps = cd.rps;
     bool ok = launch_fused_ring(h, h->y, false, nullptr) == ZF_OK;
     ok = ok && cudaEventRecord(e0, h->st) == cudaSuccess;
     for (int rep = 0; rep < 2 && ok; ++rep) ok = launch_fused_ring(h, h->y, false, nullptr) == ZF_OK;
@@ -1693,13 +1751,17 @@ void ring_autotune(zf_lasso* h, int max_smem) {
   if (const char* ev = getenv("ZF_LASSO_TUNE")) {
     if (ev[0] == 'v') {
       for (size_t k = 0; k < cands.size(); ++k)
-        fprintf(stderr, "[zf_lasso tune %lldx%lld] cluster %d split %.2f : %.4f ms%s%s\n", h->n_rows,
-                h->n_cols, cands[k].c, cands[k].rate2, cands[k].ms, k == 0 ? " (static)" : "",
+        fprintf(stderr, "[zf_lasso tune %lldx%lld] cluster %d split %.2f rows/step %d : %.4f ms%s%s\n",
+                h->n_rows, h->n_cols, cands[k].c, cands[k].rate2, cands[k].rps, cands[k].ms,
+                k == 0 ? " (static)" : "",
                 (int)k == pick ? " <- chosen" : "");
     }
   }
-  if (!ring_plan(h, cands[pick].c, cands[pick].rate2, h->n_rows, max_smem))
+  h->ring_rps = cands[pick].rps;
+  if (!ring_plan(h, cands[pick].c, cands[pick].rate2, h->n_rows, max_smem)) {
+    h->ring_rps = rps_static;
     ring_plan(h, c_static, r_static, h->n_rows, max_smem);
+  }
   h->tuned_cluster = h->fused_cluster;
   h->tuned_rate2 = h->ring2_ctas > 0 ? cands[pick].rate2 : 0.0;
 }
@@ -1767,6 +1829,7 @@ extern "C" int zf_lasso_create(zf_lasso** out, const double* d_A, const double* 
     const bool big_enough = h->vec && n_rows >= 4LL * h->n_sm;
     const char* env_fused = getenv("ZF_LASSO_FUSED");
     const bool off = env_fused && env_fused[0] == '0';
+    if (const char* env_rps = getenv("ZF_LASSO_RING_RPS")) h->ring_rps = atoi(env_rps) == 2 ? 2 : 1;
     auto try_ring = [&](int c) -> bool {
       if (!big_enough) return false;
       const char* env_split = getenv("ZF_LASSO_RING_SPLIT");
