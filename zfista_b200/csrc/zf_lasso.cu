@@ -355,16 +355,32 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a protocol bug must trap, not hang the GPU
+// try_wait with a suspend-time hint: ptxas then emits TRYWAIT; @!p NANOSLEEP.SYNCS <ns>; PHASECHK --
+// the warp sleeps until the barrier's phase completes (or the hint runs out) instead of spinning.
+// Half of the ring kernel's 1.78 G warp instructions per pass at 100000 x 20000 were spin-loop
+// instructions of waiting warps (ncu source page: 100 M TRYWAITs, ~8 instructions per trip);
+// with the hint the kernel is 1 % faster at sustained clocks on every shape measured (0 = off).
+#ifndef ZF_MBAR_HINT_NS
+#define ZF_MBAR_HINT_NS 2000
+#endif
+// bounded wait: a protocol bug must trap, not hang the GPU (2^22 trips of at most 2 us)
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   unsigned done = 0;
   for (unsigned spin = 0; !done; ++spin) {
+#if ZF_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)ZF_MBAR_HINT_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (!done && spin > (1u << 26)) __trap();
+#endif
+    if (!done && spin > (ZF_MBAR_HINT_NS > 0 ? (1u << 22) : (1u << 26))) __trap();
   }
 }
 
