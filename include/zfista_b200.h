@@ -252,6 +252,22 @@ double* zf_lasso_multi_partial(zf_lasso_multi* h, int64_t* n_values);
 int zf_lasso_multi_step(zf_lasso_multi* h, int32_t* h_next);
 int zf_lasso_multi_finish(zf_lasso_multi* h, double* d_x, double* h_fun, int64_t* h_nit,
                           int32_t* h_status, double* h_lr, double* h_err);
+/* The device-decided rounds in pieces, for a caller that owns an exchange between the stages
+ * (row-sharded runs; the protocol and the stage numbers of zf_lasso_dev_* above): begin, all-reduce
+ * the residual norms (the last kp values of partial, zf_lasso_multi_layout), stage 0; per trial
+ * stage 1, all-reduce partial, stage 2 and -- if zf_lasso_multi_dev_needs_feval() -- stage 3,
+ * all-reduce the norms, stage 4; poll(slot, wait=0) enqueues a snapshot of the state,
+ * poll(slot, wait=1, &done) waits for it; after done: (stage 6, all-reduce the norms, if no
+ * feval), stage 5, finish.  Replaces the per-trial host decisions of proximal_gradient.py:474-538
+ * for every run of the lockstep batch.                                                    */
+int zf_lasso_multi_dev_begin(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                             int32_t x0_is_batched, const double* h_ab);
+int zf_lasso_multi_dev_stage(zf_lasso_multi* h, int32_t stage);
+int zf_lasso_multi_dev_needs_feval(zf_lasso_multi* h);
+int zf_lasso_multi_dev_poll(zf_lasso_multi* h, int32_t slot, int32_t wait, int32_t* done);
+int zf_lasso_multi_dev_finish(zf_lasso_multi* h, double* d_x, double* h_fun, int64_t* h_nit,
+                              int32_t* h_status, double* h_lr, double* h_err);
+int zf_lasso_multi_layout(zf_lasso_multi* h, int64_t* kp, int64_t* pitch_c);
 /* the closures at n_runs points: grad (n_runs x n_cols) = 2*scale*A^T(A x_k - b_k), f (n_runs) */
 int zf_lasso_multi_gradient_device(zf_lasso_multi* h, const double* d_X, double* d_grad,
                                    double* d_f);

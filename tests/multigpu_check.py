@@ -77,13 +77,23 @@ def main():
     grid = [(0.0, 0.25), (0.5, 1 / 16), (0.25, 17 / 128), (0.0, 0.0), (0.75, 0.25)]
     X0m = np.random.RandomState(5).standard_normal((len(grid), n_cols)) * 0.1
     msh = DenseLassoMulti(A[lo:hi], b[lo:hi], l1, len(grid), scale=scale, distributed=True)
-    for opts in (dict(nesterov=True), dict(nesterov=True, lr=0.2, decay_rate=1)):
+    for opts in (dict(nesterov=True), dict(nesterov=True, lr=0.2, decay_rate=1),
+                 dict(nesterov=False, lr=1e6, max_backtrack_iter=4), dict(nesterov=True, max_iter=7)):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
+            # device-decided rounds (default), then the host-decided rounds of round 1: bit-equal
             got = msh.minimize_proximal_gradient_batched(X0m, grid, **opts)
+            os.environ["ZF_LASSO_HOSTLOOP"] = "1"
+            try:
+                got_host = msh.minimize_proximal_gradient_batched(X0m, grid, **opts)
+            finally:
+                del os.environ["ZF_LASSO_HOSTLOOP"]
             for k, ab in enumerate(grid):
                 ref = zo.minimize_proximal_gradient(spec, X0m[k], nesterov_ratio=ab, **opts)
-                assert got[k].nit == ref["nit"], (k, got[k].nit, ref["nit"])
+                assert got[k].nit == got_host[k].nit == ref["nit"], (k, got[k].nit, got_host[k].nit, ref["nit"])
+                assert got[k].status == got_host[k].status == ref["status"]
+                np.testing.assert_array_equal(got[k].x, got_host[k].x)
+                assert got[k].fun == got_host[k].fun and got[k].lr == got_host[k].lr
                 np.testing.assert_allclose(got[k].x, ref["x"], rtol=1e-8, atol=1e-9)
                 np.testing.assert_allclose(got[k].fun, ref["fun"], rtol=1e-9)
     prob = zp.JOS1(n_features=20)

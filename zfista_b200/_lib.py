@@ -70,6 +70,8 @@ EXPORTED_SYMBOLS = [
     "zf_lasso_multi_begin", "zf_lasso_multi_grad", "zf_lasso_multi_partial",
     "zf_lasso_multi_step", "zf_lasso_multi_finish", "zf_lasso_multi_gradient_device",
     "zf_lasso_multi_pass_device",
+    "zf_lasso_multi_dev_begin", "zf_lasso_multi_dev_stage", "zf_lasso_multi_dev_needs_feval",
+    "zf_lasso_multi_dev_poll", "zf_lasso_multi_dev_finish", "zf_lasso_multi_layout",
     "zf_deblur_create", "zf_deblur_destroy", "zf_deblur_solve_host", "zf_deblur_solve_device",
     "zf_deblur_eval_host",
 ]
@@ -190,6 +192,18 @@ def _bind_lasso(L):
     L.zf_lasso_multi_gradient_device.restype = C.c_int
     L.zf_lasso_multi_pass_device.argtypes = [V, V, C.c_int]
     L.zf_lasso_multi_pass_device.restype = C.c_int
+    L.zf_lasso_multi_dev_begin.argtypes = [V, C.POINTER(ZfOptions), V, I32, V]
+    L.zf_lasso_multi_dev_begin.restype = C.c_int
+    L.zf_lasso_multi_dev_stage.argtypes = [V, I32]
+    L.zf_lasso_multi_dev_stage.restype = C.c_int
+    L.zf_lasso_multi_dev_needs_feval.argtypes = [V]
+    L.zf_lasso_multi_dev_needs_feval.restype = C.c_int
+    L.zf_lasso_multi_dev_poll.argtypes = [V, I32, I32, c_int32_p]
+    L.zf_lasso_multi_dev_poll.restype = C.c_int
+    L.zf_lasso_multi_dev_finish.argtypes = [V, V, V, V, V, V, V]
+    L.zf_lasso_multi_dev_finish.restype = C.c_int
+    L.zf_lasso_multi_layout.argtypes = [V, c_int64_p, c_int64_p]
+    L.zf_lasso_multi_layout.restype = C.c_int
     # deblurring handle API
     L.zf_deblur_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_void_p]

@@ -891,6 +891,7 @@ struct zf_lasso_multi {
   zf::multi::MultiDevState* d_state = nullptr;
   zf::multi::MultiDevState* h_state = nullptr;   // pinned, 2 snapshots
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+  int dev_need_F = 0, dev_cap = 0;               // of the device-decided solve in flight
   double* d_allerrs = nullptr;
   double* d_allfuns = nullptr;
   size_t dev_trace = 0;
@@ -1453,33 +1454,65 @@ int multi_dev_alloc(zf_lasso_multi* h) {
   return ZF_OK;
 }
 
-// one trial of the runs on trial
-int multi_dev_slot(zf_lasso_multi* h, bool need_F) {
+// Stages of a device-decided solve (the numbering of zf_lasso_dev_stage in zf_lasso.cu).  A trial
+// ("slot") is GRAD, PROX and -- with a line search or an F trace -- FEVAL, DECIDE.  A row-sharded
+// caller all-reduces `partial` after GRAD and its residual-norm tail after begin, FEVAL and
+// FEVAL_FINAL; every kernel that reads those values is skipped or reads its stored copy when the
+// pass before the exchange was skipped, so the exchange is unconditional.
+enum { MS_INIT = 0, MS_GRAD = 1, MS_PROX = 2, MS_FEVAL = 3, MS_DECIDE = 4, MS_FINAL = 5,
+       MS_FEVAL_FINAL = 6 };
+
+int multi_dev_stage(zf_lasso_multi* h, int stage) {
   using namespace zf::multi;
   const double* ss = h->partial + (long long)h->kp * h->pitch_c;
   dim3 vgrid(VEC_BLOCKS, (unsigned)h->n_runs);
-  h->skip = &h->d_state->skip_grad;
-  int rc = gradient_pass(h);                          // both DGEMM passes + collect (or nothing)
-  h->skip = nullptr;
-  if (rc != ZF_OK) return rc;
-  multi_dev_prox_kernel<<<vgrid, VEC_THREADS, 0, h->st>>>(h->d_opts, h->d_state, h->Y, h->Xn,
-                                                          h->partial, h->G, h->block_sums,
-                                                          h->counter, h->d_sums);
-  ZF_CUDA(cudaGetLastError());
-  zf::zf_count_launch();
-  multi_dev_after_prox_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss);
-  ZF_CUDA(cudaGetLastError());
-  zf::zf_count_launch();
-  if (need_F) {
-    h->skip = &h->d_state->done;
-    rc = launch_residual(h, 1);
-    h->skip = nullptr;
-    if (rc != ZF_OK) return rc;
-    rc = launch_collect(h, false);
-    if (rc != ZF_OK) return rc;
-    multi_dev_decide_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss);
-    ZF_CUDA(cudaGetLastError());
-    zf::zf_count_launch();
+  int rc = ZF_OK;
+  switch (stage) {
+    case MS_INIT:      // |x0|_1 of every run, then F(x0) from the (reduced) residual norms
+      rc = run_prox(h, h->active, false, true);
+      if (rc != ZF_OK) return rc;
+      multi_dev_init_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      return ZF_OK;
+    case MS_GRAD:      // both DGEMM passes + collect (or nothing while a retry is pending)
+      h->skip = &h->d_state->skip_grad;
+      rc = gradient_pass(h);
+      h->skip = nullptr;
+      return rc;
+    case MS_PROX:
+      multi_dev_prox_kernel<<<vgrid, VEC_THREADS, 0, h->st>>>(h->d_opts, h->d_state, h->Y, h->Xn,
+                                                              h->partial, h->G, h->block_sums,
+                                                              h->counter, h->d_sums);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      multi_dev_after_prox_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      if (h->dev_need_F) return ZF_OK;
+      break;           // fixed step, no F trace: the trial is accepted, momentum follows
+    case MS_FEVAL:
+      h->skip = &h->d_state->done;
+      rc = launch_residual(h, 1);
+      h->skip = nullptr;
+      if (rc != ZF_OK) return rc;
+      return launch_collect(h, false);
+    case MS_DECIDE:
+      multi_dev_decide_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      break;
+    case MS_FEVAL_FINAL:   // res.fun = F(x) of runs that never evaluated it: one residual pass
+      rc = launch_residual(h, 1);
+      if (rc != ZF_OK) return rc;
+      return launch_collect(h, false);
+    case MS_FINAL:
+      multi_dev_final_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss);
+      ZF_CUDA(cudaGetLastError());
+      zf::zf_count_launch();
+      return ZF_OK;
+    default:
+      return zf::zf_fail(ZF_ERR_INVALID, "unknown stage %d", stage);
   }
   multi_dev_momentum_kernel<<<vgrid, VEC_THREADS, 0, h->st>>>(h->d_opts, h->d_state, h->Xp, h->Xn, h->Y);
   ZF_CUDA(cudaGetLastError());
@@ -1487,10 +1520,20 @@ int multi_dev_slot(zf_lasso_multi* h, bool need_F) {
   return ZF_OK;
 }
 
-int multi_solve_dev(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
-                    int32_t x0_is_batched, const double* h_ab, double* d_x, double* h_fun,
-                    int64_t* h_nit, int32_t* h_status, double* h_lr, double* h_err,
-                    double* h_allerrs, double* h_allfuns) {
+// one trial of the runs on trial (single GPU: no exchange between the stages)
+int multi_dev_slot(zf_lasso_multi* h) {
+  int rc = multi_dev_stage(h, MS_GRAD);
+  if (rc == ZF_OK) rc = multi_dev_stage(h, MS_PROX);
+  if (rc == ZF_OK && h->dev_need_F) {
+    rc = multi_dev_stage(h, MS_FEVAL);
+    if (rc == ZF_OK) rc = multi_dev_stage(h, MS_DECIDE);
+  }
+  return rc;
+}
+
+// options and starts to the device, F(x0)'s residual pass enqueued (its norms are in `partial`)
+int multi_dev_begin(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                    int32_t x0_is_batched, const double* h_ab, bool want_errs, bool want_funs) {
   using namespace zf::multi;
   if (!h || !d_x0) return zf::zf_fail(ZF_ERR_INVALID, "NULL argument");
   int rc = check_options(opt);
@@ -1498,7 +1541,7 @@ int multi_solve_dev(zf_lasso_multi* h, const zf_options* opt, const double* d_x0
   rc = multi_dev_alloc(h);
   if (rc != ZF_OK) return rc;
   h->opt = *opt;
-  const int cap = (h_allerrs || h_allfuns) ? opt->trace_capacity : 0;
+  const int cap = (want_errs || want_funs) ? opt->trace_capacity : 0;
   const size_t need = (size_t)h->n_runs * ((size_t)cap + 1);
   if (cap > 0 && need > h->dev_trace) {
     cudaFree(h->d_allerrs);
@@ -1514,13 +1557,15 @@ int multi_solve_dev(zf_lasso_multi* h, const zf_options* opt, const double* d_x0
   o.scale = h->scale; o.l1 = h->l1; o.max_iter = opt->max_iter; o.pitch_c = h->pitch_c;
   o.n = h->n_cols; o.max_bt = opt->max_backtrack_iter; o.nesterov = opt->nesterov;
   o.deprecated = opt->deprecated; o.cap = cap; o.n_runs = h->n_runs; o.kp = h->kp;
-  o.need_F = (opt->decay_rate != 1.0) || (cap > 0 && h_allfuns != nullptr);
-  o.allerrs = (cap > 0 && h_allerrs) ? h->d_allerrs : nullptr;
-  o.allfuns = (cap > 0 && h_allfuns) ? h->d_allfuns : nullptr;
+  o.need_F = (opt->decay_rate != 1.0) || (cap > 0 && want_funs);
+  o.allerrs = (cap > 0 && want_errs) ? h->d_allerrs : nullptr;
+  o.allfuns = (cap > 0 && want_funs) ? h->d_allfuns : nullptr;
   for (int k = 0; k < h->n_runs; ++k) {
     o.na[k] = h_ab ? h_ab[2 * k] : opt->nesterov_a;
     o.nb[k] = h_ab ? h_ab[2 * k + 1] : opt->nesterov_b;
   }
+  h->dev_need_F = o.need_F;
+  h->dev_cap = cap;
   ZF_CUDA(cudaMemcpyAsync(h->d_opts, &o, sizeof(o), cudaMemcpyHostToDevice, h->st));
   if (cap > 0) {
     if (o.allerrs) ZF_CUDA(cudaMemsetAsync(h->d_allerrs, 0, sizeof(double) * (size_t)h->n_runs * cap, h->st));
@@ -1534,46 +1579,29 @@ int multi_solve_dev(zf_lasso_multi* h, const zf_options* opt, const double* d_x0
     ZF_CUDA(cudaMemcpyAsync(h->Xn + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
     ZF_CUDA(cudaMemcpyAsync(h->Y + off, src, nb, cudaMemcpyDeviceToDevice, h->st));
   }
-  // F(x0): residual norms and |x0|_1 of every run
-  const double* ss = h->partial + (long long)h->kp * h->pitch_c;
+  h->active = (h->n_runs == 32) ? 0xffffffffu : ((1u << h->n_runs) - 1u);
+  for (int k = 0; k < h->n_runs; ++k) h->run[k].lr = opt->lr;     // run_prox reads the host copy
+  // F(x0): residual norms of every run (all-reduced by the caller if the rows are sharded)
   rc = launch_residual(h, 0);
   if (rc == ZF_OK) rc = launch_collect(h, false);
   if (rc != ZF_OK) return rc;
-  h->active = (h->n_runs == 32) ? 0xffffffffu : ((1u << h->n_runs) - 1u);
-  for (int k = 0; k < h->n_runs; ++k) h->run[k].lr = opt->lr;     // run_prox reads the host copy
-  rc = run_prox(h, h->active, false, true);
-  if (rc != ZF_OK) return rc;
-  multi_dev_init_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, h->d_sums, ss);
-  ZF_CUDA(cudaGetLastError());
-  zf::zf_count_launch();
-  // chunks of slots, the poll one chunk behind
-  const int chunk = 8;
-  auto snapshot = [&](int slot) -> int {
-    ZF_CUDA(cudaMemcpyAsync(&h->h_state[slot], h->d_state, sizeof(MultiDevState),
-                            cudaMemcpyDeviceToHost, h->st));
-    ZF_CUDA(cudaEventRecord(h->ev_poll[slot], h->st));
-    return ZF_OK;
-  };
-  int cur = 0;
-  for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = multi_dev_slot(h, o.need_F != 0);
-  if (rc == ZF_OK) rc = snapshot(cur);
-  while (rc == ZF_OK) {
-    for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = multi_dev_slot(h, o.need_F != 0);
-    if (rc == ZF_OK) rc = snapshot(1 - cur);
-    if (rc != ZF_OK) break;
-    ZF_CUDA(cudaEventSynchronize(h->ev_poll[cur]));
-    if (h->h_state[cur].done) break;
-    cur = 1 - cur;
-  }
-  if (rc != ZF_OK) return rc;
-  if (!o.need_F) {                       // res.fun = F(x): one residual pass at the results
-    rc = launch_residual(h, 1);
-    if (rc == ZF_OK) rc = launch_collect(h, false);
-    if (rc != ZF_OK) return rc;
-  }
-  multi_dev_final_kernel<<<1, 32, 0, h->st>>>(h->d_opts, h->d_state, ss);
-  ZF_CUDA(cudaGetLastError());
-  zf::zf_count_launch();
+  h->phase = MP_INIT;
+  return ZF_OK;
+}
+
+int multi_dev_snapshot(zf_lasso_multi* h, int slot) {
+  ZF_CUDA(cudaMemcpyAsync(&h->h_state[slot], h->d_state, sizeof(zf::multi::MultiDevState),
+                          cudaMemcpyDeviceToHost, h->st));
+  ZF_CUDA(cudaEventRecord(h->ev_poll[slot], h->st));
+  return ZF_OK;
+}
+
+int multi_dev_finish(zf_lasso_multi* h, double* d_x, double* h_fun, int64_t* h_nit,
+                     int32_t* h_status, double* h_lr, double* h_err, double* h_allerrs,
+                     double* h_allfuns) {
+  using namespace zf::multi;
+  const int cap = h->dev_cap;
+  const size_t need = (size_t)h->n_runs * ((size_t)cap + 1);
   ZF_CUDA(cudaMemcpyAsync(&h->h_state[0], h->d_state, sizeof(MultiDevState), cudaMemcpyDeviceToHost,
                           h->st));
   ZF_CUDA(cudaStreamSynchronize(h->st));
@@ -1600,6 +1628,35 @@ int multi_solve_dev(zf_lasso_multi* h, const zf_options* opt, const double* d_x0
   ZF_CUDA(cudaStreamSynchronize(h->st));
   h->phase = MP_IDLE;
   return ZF_OK;
+}
+
+int multi_solve_dev(zf_lasso_multi* h, const zf_options* opt, const double* d_x0,
+                    int32_t x0_is_batched, const double* h_ab, double* d_x, double* h_fun,
+                    int64_t* h_nit, int32_t* h_status, double* h_lr, double* h_err,
+                    double* h_allerrs, double* h_allfuns) {
+  int rc = multi_dev_begin(h, opt, d_x0, x0_is_batched, h_ab, h_allerrs != nullptr,
+                           h_allfuns != nullptr);
+  if (rc == ZF_OK) rc = multi_dev_stage(h, MS_INIT);
+  // chunks of slots, the poll one chunk behind
+  const int chunk = 8;
+  int cur = 0;
+  for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = multi_dev_slot(h);
+  if (rc == ZF_OK) rc = multi_dev_snapshot(h, cur);
+  while (rc == ZF_OK) {
+    for (int k = 0; k < chunk && rc == ZF_OK; ++k) rc = multi_dev_slot(h);
+    if (rc == ZF_OK) rc = multi_dev_snapshot(h, 1 - cur);
+    if (rc != ZF_OK) break;
+    ZF_CUDA(cudaEventSynchronize(h->ev_poll[cur]));
+    if (h->h_state[cur].done) break;
+    cur = 1 - cur;
+  }
+  if (rc == ZF_OK && !h->dev_need_F) rc = multi_dev_stage(h, MS_FEVAL_FINAL);
+  if (rc == ZF_OK) rc = multi_dev_stage(h, MS_FINAL);
+  if (rc != ZF_OK) {
+    if (h) h->phase = MP_IDLE;
+    return rc;
+  }
+  return multi_dev_finish(h, d_x, h_fun, h_nit, h_status, h_lr, h_err, h_allerrs, h_allfuns);
 }
 
 }  // namespace
@@ -1629,6 +1686,42 @@ extern "C" int zf_lasso_multi_solve(zf_lasso_multi* h, const zf_options* opt, co
     return rc;
   }
   return zf_lasso_multi_finish(h, d_x, h_fun, h_nit, h_status, h_lr, h_err);
+}
+
+// ---- the device-decided solve in pieces, for a caller that owns an exchange between the stages
+// (row-sharded runs: zfista_b200/distributed.py run_device_lasso drives these exactly as it drives
+// zf_lasso_dev_*; same stage numbers)
+extern "C" int zf_lasso_multi_dev_begin(zf_lasso_multi* h, const zf_options* opt,
+                                        const double* d_x0, int32_t x0_is_batched,
+                                        const double* h_ab) {
+  return multi_dev_begin(h, opt, d_x0, x0_is_batched, h_ab, false, false);
+}
+extern "C" int zf_lasso_multi_dev_stage(zf_lasso_multi* h, int32_t stage) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (h->phase != MP_INIT) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_dev_stage outside a solve");
+  return multi_dev_stage(h, stage);
+}
+extern "C" int zf_lasso_multi_dev_needs_feval(zf_lasso_multi* h) { return h ? h->dev_need_F : 0; }
+extern "C" int zf_lasso_multi_dev_poll(zf_lasso_multi* h, int32_t slot, int32_t wait, int32_t* done) {
+  if (!h || slot < 0 || slot > 1) return zf::zf_fail(ZF_ERR_INVALID, "bad argument");
+  if (!wait) return multi_dev_snapshot(h, slot);
+  ZF_CUDA(cudaEventSynchronize(h->ev_poll[slot]));
+  if (done) *done = h->h_state[slot].done;
+  return ZF_OK;
+}
+extern "C" int zf_lasso_multi_dev_finish(zf_lasso_multi* h, double* d_x, double* h_fun,
+                                         int64_t* h_nit, int32_t* h_status, double* h_lr,
+                                         double* h_err) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (h->phase != MP_INIT) return zf::zf_fail(ZF_ERR_INVALID, "zf_lasso_multi_dev_finish outside a solve");
+  return multi_dev_finish(h, d_x, h_fun, h_nit, h_status, h_lr, h_err, nullptr, nullptr);
+}
+/* `partial` is [kp][pitch_c] gradients followed by kp residual norms */
+extern "C" int zf_lasso_multi_layout(zf_lasso_multi* h, int64_t* kp, int64_t* pitch_c) {
+  if (!h) return zf::zf_fail(ZF_ERR_INVALID, "NULL handle");
+  if (kp) *kp = h->kp;
+  if (pitch_c) *pitch_c = h->pitch_c;
+  return ZF_OK;
 }
 
 // the closure entries evaluate at caller-supplied points: they go through the y_k array (the

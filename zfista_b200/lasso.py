@@ -14,6 +14,7 @@ multi-GPU form -- ``torch.distributed`` all-reduce of ``A^T r``).  There is no C
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from warnings import warn
 
@@ -364,6 +365,9 @@ class DenseLassoMulti:
         n = C.c_int64()
         ptr = _lib.lib().zf_lasso_multi_partial(self._h, C.byref(n))
         self._partial = torch.as_tensor(_DevView(int(ptr), int(n.value)), device=self.device)
+        kp, pitch = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.lib().zf_lasso_multi_layout(self._h, C.byref(kp), C.byref(pitch)))
+        self._ss_offset = int(kp.value) * int(pitch.value)
 
     def __del__(self):
         try:
@@ -378,6 +382,13 @@ class DenseLassoMulti:
             import torch.distributed as dist
 
             dist.all_reduce(self._partial, group=self.group)
+
+    def _allreduce_ss(self):
+        """all-reduce of the residual norms alone (the last kp values of ``partial``)"""
+        if self.distributed:
+            import torch.distributed as dist
+
+            dist.all_reduce(self._partial[self._ss_offset:], group=self.group)
 
     def _use_current_stream(self):
         """as DenseLasso._use_current_stream: the library enqueues on torch's CURRENT stream"""
@@ -462,11 +473,11 @@ class DenseLassoMulti:
                 else:
                     if cap:
                         raise NotImplementedError("return_all is not available on the row-sharded path")
-                    from .distributed import run_split_lasso
+                    from .distributed import run_device_lasso, run_split_lasso
 
                     h = self._h
 
-                    class _Ops:
+                    class _Ops:            # host-decided rounds (ZF_LASSO_HOSTLOOP=1)
                         def begin(self_):
                             _lib.check(L.zf_lasso_multi_begin(h, C.byref(opts),
                                                               C.c_void_p(x0d.data_ptr()),
@@ -484,7 +495,35 @@ class DenseLassoMulti:
                             _lib.check(L.zf_lasso_multi_finish(h, C.c_void_p(xd.data_ptr()), p(fun),
                                                                p(nit), p(status), p(lrs), p(err)))
 
-                    run_split_lasso(_Ops(), self._allreduce)
+                    class _DevOps:         # device-decided rounds: the host only enqueues and polls
+                        def begin(self_):
+                            _lib.check(L.zf_lasso_multi_dev_begin(h, C.byref(opts),
+                                                                  C.c_void_p(x0d.data_ptr()),
+                                                                  int(batched), p(ab)))
+
+                        def stage(self_, k):
+                            _lib.check(L.zf_lasso_multi_dev_stage(h, int(k)))
+
+                        def needs_feval(self_):
+                            return bool(L.zf_lasso_multi_dev_needs_feval(h))
+
+                        def snapshot(self_, slot):
+                            _lib.check(L.zf_lasso_multi_dev_poll(h, int(slot), 0, None))
+
+                        def wait(self_, slot):
+                            done = C.c_int32(0)
+                            _lib.check(L.zf_lasso_multi_dev_poll(h, int(slot), 1, C.byref(done)))
+                            return bool(done.value)
+
+                        def finish(self_):
+                            _lib.check(L.zf_lasso_multi_dev_finish(h, C.c_void_p(xd.data_ptr()),
+                                                                   p(fun), p(nit), p(status), p(lrs),
+                                                                   p(err)))
+
+                    if os.environ.get("ZF_LASSO_HOSTLOOP", "0") == "1":
+                        run_split_lasso(_Ops(), self._allreduce)
+                    else:
+                        run_device_lasso(_DevOps(), self._allreduce, self._allreduce_ss, chunk=8)
             if cap and int(nit.max()) > cap and trace_capacity is None:
                 cap = int(nit.max())
                 continue
