@@ -1715,13 +1715,13 @@ namespace {
 void ring_autotune(zf_lasso* h, int max_smem) {
   // rps: rows per exchange step (it changes the schedule, not the arithmetic: results are
   // bit-identical to rps 1)
-  struct Cand { int c; double rate2; int rps; float ms; };
+  struct Cand { int c; double rate2; int rps; float ms; int ctas; };
   const int c_static = h->fused_cluster;
   const double r_static = h->ring2_ctas > 0 ? 0.57 : 0.0;
   const int rps_static = h->ring_rps;
   const bool rps_fixed = getenv("ZF_LASSO_RING_RPS") != nullptr;
   std::vector<Cand> cands;
-  cands.push_back(Cand{c_static, r_static, rps_static, 0.f});
+  cands.push_back(Cand{c_static, r_static, rps_static, 0.f, 0});
   const long long n2 = h->n_cols / 2;
   for (int c = 1; c <= zf::RING_MAX_CLUSTER; ++c) {
     const long long ppc = (n2 + c - 1) / c;
@@ -1732,7 +1732,7 @@ void ring_autotune(zf_lasso* h, int max_smem) {
       for (int rps = 1; rps <= 2; ++rps) {
         if (rps_fixed ? rps != rps_static : rps * nch > 6) continue;
         if (c == c_static && r == r_static && (rps == rps_static || nch > 3)) continue;
-        cands.push_back(Cand{c, r, rps, 0.f});
+        cands.push_back(Cand{c, r, rps, 0.f, 0});
       }
     }
   }
@@ -1751,6 +1751,7 @@ void ring_autotune(zf_lasso* h, int max_smem) {
     if (!ring_plan(h, cd.c, cd.rate2, probe_rows, max_smem)) continue;
     if (cd.rate2 > 0.0 && h->ring2_ctas == 0) continue;           // the split did not apply
     h->ring_rps = cd.rps;
+    cd.ctas = h->fused_ctas + h->ring2_ctas;
     bool ok = launch_fused_ring(h, h->y, false, nullptr) == ZF_OK;
     ok = ok && cudaEventRecord(e0, h->st) == cudaSuccess;
     for (int rep = 0; rep < 2 && ok; ++rep) ok = launch_fused_ring(h, h->y, false, nullptr) == ZF_OK;
@@ -1767,8 +1768,8 @@ void ring_autotune(zf_lasso* h, int max_smem) {
   if (const char* ev = getenv("ZF_LASSO_TUNE")) {
     if (ev[0] == 'v') {
       for (size_t k = 0; k < cands.size(); ++k)
-        fprintf(stderr, "[zf_lasso tune %lldx%lld] cluster %d split %.2f rows/step %d : %.4f ms%s%s\n",
-                h->n_rows, h->n_cols, cands[k].c, cands[k].rate2, cands[k].rps, cands[k].ms,
+        fprintf(stderr, "[zf_lasso tune %lldx%lld] cluster %d split %.2f rows/step %d on %3d SMs : %.4f ms%s%s\n",
+                h->n_rows, h->n_cols, cands[k].c, cands[k].rate2, cands[k].rps, cands[k].ctas, cands[k].ms,
                 k == 0 ? " (static)" : "",
                 (int)k == pick ? " <- chosen" : "");
     }
