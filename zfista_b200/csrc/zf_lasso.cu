@@ -1670,6 +1670,9 @@ bool ring_plan(zf_lasso* h, int c, double rate2, long long rows, int max_smem) {
   if (launch_fused_ring(h, nullptr, true, &active) == ZF_OK && active > 0 && active < n_clusters)
     n_clusters = active;
   const int idle = h->n_sm - n_clusters * c;
+  // (Only for 4-CTA clusters.  5- and 6-CTA clusters also leave 16-18 SMs idle, but a concurrent
+  // 2-CTA launch next to them was measured at 0.40-0.49 ms against 0.24 ms without it on the probe
+  // rows of 100000 x 20000: its clusters take SMs the wide clusters need to be co-resident.)
   const int c2 = c / 2;                                  // cluster size of the second launch
   const long long ppc2 = c2 > 0 ? (n2 + c2 - 1) / c2 : n2;
   const long long nch2 = (ppc2 + zf::RING_CH_PAIRS - 1) / zf::RING_CH_PAIRS;
