@@ -436,3 +436,234 @@ def test_device_decided_lasso_world2_matches_oracle(tmp_path):
                                    lambda: None, chunk=3)
         assert solo["nit"] == ref["nit"] and solo["status"] == ref["status"]
         np.testing.assert_allclose(solo["x"], ref["x"], rtol=1e-9, atol=1e-10)
+
+
+class NumpyDeviceLassoMulti:
+    """numpy model of the device-decided LOCKSTEP rounds of K runs sharing A (zf_lasso_multi_dev_*
+    in csrc/zf_lasso_multi.cu) on ONE row shard: per-run scalars and the run masks (active / on
+    trial / accepted / advancing) as the one-warp kernels keep them, a gradient stage that does
+    nothing while a retry is pending (so that the unconditional all-reduce after it re-reduces
+    stale values nobody reads), stages after the end that do nothing."""
+
+    def __init__(self, A, b, scale, l1, X0, ab, opts):
+        self.A, self.b, self.scale, self.l1 = A, b, scale, l1
+        self.X0, self.ab = np.array(X0, dtype=float), np.asarray(ab, dtype=float)
+        self.K, self.n = self.X0.shape
+        self.o = dict(lr=1.0, tol=1e-5, tol_internal=1e-12, max_iter=1000000,
+                      max_backtrack_iter=100, decay_rate=0.5, nesterov=False, deprecated=False)
+        self.o.update(opts)
+        self.partial = np.zeros(self.K * self.n + self.K)      # [K][n] gradients | K residual norms
+        self.snaps = [None, None]
+
+    # views into `partial`
+    def _g(self):
+        return self.partial[:self.K * self.n].reshape(self.K, self.n)
+
+    def _ss(self):
+        return self.partial[self.K * self.n:]
+
+    def _f(self, ss):
+        return np.sqrt(ss) ** 2 * self.scale
+
+    def needs_feval(self):
+        return self.o["decay_rate"] != 1
+
+    def _residual_norms(self, X):
+        R = X @ self.A.T - self.b
+        self._ss()[:] = np.einsum("kr,kr->k", R, R)
+        return R
+
+    def begin(self):
+        self.Xp, self.Xn, self.Y = self.X0.copy(), self.X0.copy(), self.X0.copy()
+        self.G = np.zeros_like(self.X0)
+        self._residual_norms(self.Y)
+        self.s = dict(done=False)
+
+    def _advance(self, accepted):
+        s, o = self.s, self.o
+        stop, adv = set(), set()
+        for k in accepted:
+            r = s["run"][k]
+            r["err"] = r["maxd"]
+            if r["err"] < o["tol"] or r["nit"] >= o["max_iter"]:
+                r["status"] = 1 if r["err"] < o["tol"] else 0
+                stop.add(k)
+            else:
+                mom = 0.0
+                if o["nesterov"]:
+                    a, b = self.ab[k]
+                    t = r["t"]
+                    tn = np.sqrt(t * t - a * t + b) + 0.5
+                    mom, r["t"] = (t - 1) / tn, tn
+                r.update(mom=mom, F_prev=r["F_x"], nit=r["nit"] + 1)
+                adv.add(k)
+        s["active"] -= stop
+        s.update(adv=adv, accepted=set(), trial=set())
+        if s["active"]:
+            s.update(phase="grad", skip_grad=False)
+        else:
+            s.update(phase="done", skip_grad=True, done=True)
+
+    def _momentum(self):
+        for k in self.s["adv"]:
+            xn = self.Xn[k]
+            self.Y[k] = xn + self.s["run"][k]["mom"] * (xn - self.Xp[k])
+            self.Xp[k] = xn.copy()
+
+    def stage(self, st):
+        s, o = self.s, self.o
+        if st == 0:
+            ss = self._ss()
+            s["run"] = []
+            for k in range(self.K):
+                abs1 = np.abs(self.X0[k]).sum()
+                F0 = self._f(ss[k]) + self.l1 * abs1
+                s["run"].append(dict(lr=o["lr"], t=1.0, F_prev=F0, F_x=F0, f_y=0.0, sub=0.0,
+                                     err=np.inf, mom=0.0, abs1=abs1, maxd=0.0, gd=0.0, dd=0.0,
+                                     nit=1, status=0, bt=0, F_known=False, result_is_prev=False))
+            s.update(active=set(range(self.K)), trial=set(), accepted=set(), adv=set(),
+                     phase="grad", skip_grad=False, done=False)
+        elif st == 1:
+            if s["skip_grad"]:
+                return                                   # `partial` keeps whatever it holds
+            R = self._residual_norms(self.Y)
+            self._g()[:] = R @ self.A
+        elif st == 2:
+            if s["done"]:
+                return                                   # (adv is empty once every run has stopped)
+            first = s["phase"] == "grad"
+            mask = set(s["active"] if first else s["trial"])
+            for k in mask:
+                r = s["run"][k]
+                if first:
+                    self.G[k] = self._g()[k] * (2 * self.scale)
+                g, lr, y = self.G[k], r["lr"], self.Y[k]
+                v = y - lr * g
+                xn = np.sign(v) * np.maximum(np.abs(v) - lr * self.l1, 0)
+                d = xn - y
+                self.Xn[k] = xn
+                r.update(gd=g @ d, dd=d @ d, abs1=np.abs(xn).sum(), maxd=np.max(np.abs(d)))
+                if first:
+                    r.update(bt=0, f_y=self._f(self._ss()[k]), F_known=False)
+                sub = r["gd"] + self.l1 * r["abs1"] + np.sqrt(r["dd"]) ** 2 / 2 / lr
+                if not o["deprecated"]:
+                    sub += r["f_y"] - r["F_prev"]
+                r["sub"] = sub
+            if not self.needs_feval():
+                self._advance(mask)
+                self._momentum()
+            else:
+                s.update(trial=mask, adv=set())
+        elif st in (3, 6):
+            if st == 3 and s["done"]:
+                return
+            self._residual_norms(self.Xn)
+        elif st == 4:
+            if not s["done"]:
+                acc, fail = set(), set()
+                for k in s["trial"]:
+                    r = s["run"][k]
+                    f_x = self._f(self._ss()[k])
+                    r["F_x"], r["F_known"] = f_x + self.l1 * r["abs1"], True
+                    if o["decay_rate"] == 1:
+                        ok = True
+                    elif o["deprecated"]:
+                        ok = f_x - r["f_y"] <= r["sub"] + o["tol_internal"]
+                    else:
+                        ok = r["F_x"] - r["F_prev"] <= r["sub"] + o["tol_internal"]
+                    if ok:
+                        acc.add(k)
+                        continue
+                    r["lr"] *= o["decay_rate"]
+                    r["bt"] += 1
+                    if r["bt"] >= o["max_backtrack_iter"]:
+                        r.update(result_is_prev=True, F_x=r["F_prev"], nit=r["nit"] - 1, status=-1)
+                        fail.add(k)
+                left = s["trial"] - acc - fail
+                accepted = s["accepted"] | acc
+                s["active"] -= fail
+                s.update(accepted=accepted, trial=left)
+                if left:
+                    s.update(phase="retry", skip_grad=True, adv=set())
+                else:
+                    self._advance(accepted)
+            self._momentum()
+        elif st == 5:
+            for k, r in enumerate(s["run"]):
+                if not r["F_known"] and not r["result_is_prev"]:
+                    r["F_x"] = self._f(self._ss()[k]) + self.l1 * r["abs1"]
+
+    def snapshot(self, slot):
+        self.snaps[slot] = self.s["done"]
+
+    def wait(self, slot):
+        return self.snaps[slot]
+
+    def finish(self):
+        s = self.s
+        assert s["done"]
+        runs = s["run"]
+        x = np.stack([self.Xp[k] if r["result_is_prev"] else self.Xn[k] for k, r in enumerate(runs)])
+        return dict(x=x, fun=np.array([r["F_x"] for r in runs]),
+                    nit=np.array([r["nit"] for r in runs]),
+                    status=np.array([r["status"] for r in runs]),
+                    lr=np.array([r["lr"] for r in runs]))
+
+
+MULTI_AB = [(0.0, 0.25), (0.5, 1 / 16), (0.25, 17 / 128), (0.0, 0.0), (0.75, 0.25)]
+MULTI_CASES = (("fista", dict(nesterov=True)), ("ista", dict(nesterov=False, max_iter=40)),
+               ("fixed", dict(nesterov=True, lr=0.5, decay_rate=1, max_iter=300)),
+               ("fail", dict(nesterov=True, lr=1e6, max_backtrack_iter=3)),
+               ("short", dict(nesterov=True, max_iter=7)))
+
+
+def _multi_starts():
+    return np.random.RandomState(8).standard_normal((len(MULTI_AB), 40)) * 0.2
+
+
+def _worker_device_lasso_multi(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    A, b, scale, l1, _ = _lasso_problem()
+    lo, hi = zd.shard_bounds(len(A), rank, world)
+    X0 = _multi_starts()
+    for tag, opts in MULTI_CASES:
+        ops = NumpyDeviceLassoMulti(A[lo:hi], b[lo:hi], scale, l1, X0, MULTI_AB, opts)
+        buf = torch.from_numpy(ops.partial)             # shares memory with ops.partial
+        res = zd.run_device_lasso(ops, lambda: dist.all_reduce(buf),
+                                  lambda: dist.all_reduce(buf[ops.K * ops.n:]), chunk=4)
+        np.savez(os.path.join(out_dir, f"mlasso_{tag}_{rank}.npz"), **res)
+    dist.destroy_process_group()
+
+
+def test_device_decided_multi_run_lasso_world2_matches_oracle(tmp_path):
+    """The lockstep rounds of several runs sharing A, decided "on the device", over two row
+    shards with the exchange after the gradient and the F stages: run by run the oracle's nit /
+    status / x / F (runs retry their line searches and stop at different rounds; one case fails
+    its line search, one stops at max_iter), ranks bit-equal, and the same through one shard."""
+    import torch.multiprocessing as mp
+
+    from oracle import zfista_oracle as zo
+
+    port = _free_port()
+    mp.spawn(_worker_device_lasso_multi, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    A, b, scale, l1, _ = _lasso_problem()
+    X0 = _multi_starts()
+    spec = zo.make_least_squares_l1(A, b, l1, scale=scale)
+    for tag, opts in MULTI_CASES:
+        outs = [np.load(tmp_path / f"mlasso_{tag}_{r}.npz") for r in range(2)]
+        np.testing.assert_array_equal(outs[0]["x"], outs[1]["x"])
+        solo = zd.run_device_lasso(NumpyDeviceLassoMulti(A, b, scale, l1, X0, MULTI_AB, opts),
+                                   lambda: None, lambda: None, chunk=3)
+        for k, ab in enumerate(MULTI_AB):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = zo.minimize_proximal_gradient(spec, X0[k], nesterov_ratio=ab, **opts)
+            for o in (outs[0], outs[1], solo):
+                assert int(o["nit"][k]) == ref["nit"], (tag, k, int(o["nit"][k]), ref["nit"])
+                assert int(o["status"][k]) == ref["status"], (tag, k)
+                np.testing.assert_allclose(o["x"][k], ref["x"], rtol=1e-9, atol=1e-10)
+                np.testing.assert_allclose(float(o["fun"][k]), ref["fun"], rtol=1e-10)
