@@ -385,25 +385,29 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 // ------------------------------------------------------------------------------------
-// Fused one-pass gradient, warp-specialised chunk ring (round-1 final form).
+// Fused one-pass gradient, warp-specialised chunk ring.
 // The roles are split over warps and nothing waits for a barrier it does not need:
 //   * producer warp: streams each row of the CTA's column slice as 16 KB
 //     chunks (1-D bulk TMA) into a ring of RING_SLOTS chunks -- rows simply follow each other
 //     through the ring, a slot is refilled as soon as the update warps release it, so HBM
 //     requests never pause;
-//   * dot warps (8): keep their part of v in REGISTERS, form the partial dot product of a row
-//     chunk by chunk as the chunks land; one warp per row (round-robin, the others move on)
-//     adds the warp partials and posts the CTA's part to every CTA of the cluster with
-//     st.async (remote shared-memory store that completes on the remote `ready` mbarrier);
-//   * update warps (8): wait for the row's `ready` mbarrier, sum the parts in rank order
-//     (rank 0's part carries -b_i), and apply the rank-1 update q += r * row from the
-//     SAME shared-memory chunks (q in registers), releasing each chunk to the producer.
+//   * dot warps (8): keep their part of v in REGISTERS, form the partial dot products of the
+//     RPS rows of an exchange step chunk by chunk as the chunks land, reduce them in one
+//     butterfly and hand the warp partials to
+//   * the exchange warp: adds the 8 warp partials in warp order (rank 0 folds -b_i in) and
+//     posts the CTA's part of every row of the step to every CTA of the cluster with st.async
+//     (remote shared-memory store that completes on the remote `ready` mbarrier);
+//   * update warps (8): wait for the step's `ready` mbarrier, sum the parts in rank order
+//     and apply the rank-1 updates q += r * row from the SAME shared-memory chunks (q in
+//     registers), releasing each chunk to the producer.
 // The dot warps run up to a ring ahead of the update warps, so the cluster exchange latency
-// is off the critical path.  Partial-dot slots and `ready` barriers are indexed by row modulo
+// is off the critical path.  Partial-dot slots and `ready` barriers are indexed by step modulo
 // RING_NR >= 2 * (rows a ring can hold) + 2, which is what makes reuse race-free: a peer can
-// post row n + RING_NR only after this CTA's update warps have consumed row n.
-// Cluster size 1, 2, 4 or 8: a row slice of at most 4 chunks (8192 columns) per CTA keeps three
-// rows in the ring; with 5 chunks (2.4 rows) the kernel drops to 0.64.
+// post step n + RING_NR only after this CTA's update warps have consumed step n.
+// Cluster sizes 1..8 (no power-of-two assumption); a row slice is at most 5 chunks: with 4
+// chunks (8192 columns) the ring keeps three rows, with 5 (2.4 rows) the kernel drops to 0.64.
+// RPS = 2 rows per step for slices of <= 3 chunks (a step's chunks stay in the ring until its
+// update is done: two rows of 4-5 chunks would leave the producer no prefetch depth).
 // ------------------------------------------------------------------------------------
 constexpr int RING_GROUP = 256;                    // threads of the dot / update group
 constexpr int RING_WARPS = RING_GROUP / 32;
@@ -412,7 +416,7 @@ constexpr int RING_THREADS = 2 * RING_GROUP + 64;  // 8 dot + 8 update warps, pr
 // the two service warps to the others with setmaxnreg -- 20 warps, 104 / 120 registers for the
 // dot / update warps -- was measured and is not used: 0.93 instead of 0.98 at 16384 columns.)
 constexpr int RING_CH_PAIRS = 1024;                // double2 per chunk: 2048 columns, 16 KB
-constexpr int RING_SLOTS = 13;                    // 208 KB ring + 4 KB static: the most that fits in 227 KB
+constexpr int RING_SLOTS = 13;                    // 208 KB ring + 4-8 KB static: the most that fits in 227 KB
 constexpr int RING_NR = 2 * RING_SLOTS + 2;
 constexpr int RING_U = RING_CH_PAIRS / RING_GROUP; // double2 per thread and chunk
 constexpr int RING_MAX_CLUSTER = 8;
